@@ -1,0 +1,57 @@
+"""ctypes binding of libladder_sm100.so (the C ABI declared in include/ladder_sm100.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libladder_sm100.so')
+
+_lib = None
+
+c_float_p = C.POINTER(C.c_float)
+c_double_p = C.POINTER(C.c_double)
+ptr = C.c_void_p          # device pointers travel as integers
+stream_t = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/ladder_sm100.h declares.
+SIGNATURES = {
+    'ladder_version': (C.c_int, []),
+    'ladder_last_error': (C.c_char_p, []),
+    'ladder_device_check': (C.c_int, [C.c_int]),
+    'ladder_mixture_table_stride': (C.c_int, [C.c_int, C.c_int]),
+    'ladder_mixture_pack_full': (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, c_float_p, c_float_p]),
+    'ladder_mixture_pack_diag': (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, C.c_int,
+                                           c_float_p, c_float_p, c_float_p]),
+    'ladder_mixture_workspace_bytes': (C.c_size_t, [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'ladder_mixture_logprob': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, C.c_int, C.c_int, C.c_float, C.c_float,
+                                         ptr, ptr, ptr, ptr, ptr, C.c_size_t, stream_t]),
+    'ladder_pipe_peak_launch': (C.c_int, [C.c_int, C.c_int, C.c_int, ptr, stream_t]),
+    'ladder_mixture_combine': (C.c_int, [ptr, ptr, ptr, C.c_int, C.c_longlong, C.c_int, ptr, ptr, stream_t]),
+}
+
+
+def load():
+    """Load the shared library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'libladder_sm100.so not found at %s -- build it with '
+            '`python -m ladder_latent_data_distribution_modelling_b200.build` '
+            '(there is no CPU or PyTorch fallback for the ELBO hot path)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code, what=''):
+    if code != 0:
+        msg = load().ladder_last_error().decode(errors='replace')
+        raise RuntimeError('libladder_sm100 %s failed (%d): %s' % (what, code, msg))

@@ -1,0 +1,147 @@
+"""GPU parity of the fused mixture kernel (K9) against the oracle and the golden fixture,
+called through the C ABI (ops -> ctypes -> libladder_sm100.so)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mixture as OM
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from ladder_latent_data_distribution_modelling_b200 import ops
+    return ops
+
+
+@pytest.fixture(scope='module')
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, 'gm_prior_golden.npz'))
+
+
+def _dev(a):
+    return torch.tensor(np.asarray(a, dtype=np.float32), device='cuda')
+
+
+@pytest.mark.parametrize('tag', ['full', 'active'])
+def test_reference_fixture_full_cov(ops, gold, tag):
+    """The reference's fitted 50-component hyper-prior incl. far outliers (rescue path)."""
+    t = gold['t_' + tag]
+    tab = ops.mixture_pack_full(gold['m_' + tag], gold['K_' + tag], gold['w_' + tag], 'cuda')
+    lp, g = ops.mixture_logprob(_dev(t), tab, want_grad=True)
+    mu, A, c = OM.canonical_from_full(gold['m_' + tag], gold['K_' + tag], gold['w_' + tag])
+    t32 = t.astype(np.float32).astype(np.float64)
+    ref, gref = OM.mixture_logprob(t32, mu, A, c, with_grad=True)
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    assert np.all(np.isfinite(lp))
+    # tolerance: fp32 arithmetic + ex2.approx (2 ulp); |logp| reaches 6e3 for the far outliers
+    np.testing.assert_allclose(lp, ref, rtol=2e-5, atol=2e-4)
+    np.testing.assert_allclose(lp, gold['logp_sklearn_' + tag], rtol=5e-5, atol=5e-4)
+    np.testing.assert_allclose(g, gref, rtol=2e-3, atol=2e-3 * np.abs(gref).max(axis=1, keepdims=True) + 1e-4)
+
+
+@pytest.mark.parametrize('D', [1, 2, 3, 4, 8, 16, 32, 64])
+@pytest.mark.parametrize('mode', ['iso', 'diag'])
+def test_diag_iso_all_dims(ops, D, mode):
+    rng = np.random.default_rng(D)
+    K, N = 77, 1000
+    m = rng.normal(size=(K, D)); t = rng.normal(size=(N, D)).astype(np.float32)
+    w = rng.uniform(0.1, 1.0, size=K)
+    if mode == 'iso':
+        std = 0.8
+        tab = ops.mixture_pack_diag(m, std, w, 'cuda')
+    else:
+        std = rng.uniform(0.5, 1.5, size=(K, D))
+        tab = ops.mixture_pack_diag(m, std, w, 'cuda')
+    lp, g = ops.mixture_logprob(_dev(t), tab, want_grad=True)
+    lp_only = ops.mixture_logprob(_dev(t), tab)
+    mu, A, c = OM.canonical_from_diag(m, std, w)
+    ref, gref = OM.mixture_logprob(t.astype(np.float64), mu, A, c, with_grad=True)
+    np.testing.assert_allclose(lp.cpu().numpy(), ref, rtol=1e-5, atol=1e-4 * max(1, D / 8))
+    np.testing.assert_allclose(lp_only.cpu().numpy(), lp.cpu().numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(g.cpu().numpy(), gref, rtol=2e-3, atol=2e-3)
+
+
+def test_full_cov_other_dims(ops):
+    rng = np.random.default_rng(0)
+    for D in (1, 3, 4):
+        K, N = 13, 500
+        m = rng.normal(size=(K, D)); a = rng.normal(size=(K, D, D))
+        cov = a @ a.transpose(0, 2, 1) + 0.2 * np.eye(D)
+        w = rng.uniform(0.1, 1, size=K)
+        t = rng.normal(size=(N, D)).astype(np.float32)
+        tab = ops.mixture_pack_full(m, cov, w, 'cuda')
+        lp, g = ops.mixture_logprob(_dev(t), tab, want_grad=True)
+        mu, A, c = OM.canonical_from_full(m, cov, w)
+        ref, gref = OM.mixture_logprob(t.astype(np.float64), mu, A, c, with_grad=True)
+        np.testing.assert_allclose(lp.cpu().numpy(), ref, rtol=2e-5, atol=2e-4)
+        np.testing.assert_allclose(g.cpu().numpy(), gref, rtol=2e-3, atol=2e-3)
+
+
+def test_split_components_large_k_and_ragged_sizes(ops):
+    """K large enough to be split over CTAs (deterministic partial reduce) and N not a tile multiple."""
+    rng = np.random.default_rng(3)
+    for N, K in ((1, 1), (129, 5000), (4097, 20011)):
+        m = rng.normal(size=(K, 2)) * 2; t = (rng.normal(size=(N, 2)) * 2).astype(np.float32)
+        tab = ops.mixture_pack_diag(m, 0.5, None, 'cuda')
+        lp1, g1 = ops.mixture_logprob(_dev(t), tab, want_grad=True)
+        lp2, g2 = ops.mixture_logprob(_dev(t), tab, want_grad=True)
+        assert torch.equal(lp1, lp2) and torch.equal(g1, g2)          # bitwise reproducible
+        mu, A, c = OM.canonical_from_diag(m, 0.5)
+        ref, gref = OM.mixture_logprob(t.astype(np.float64), mu, A, c, with_grad=True)
+        np.testing.assert_allclose(lp1.cpu().numpy(), ref, rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(g1.cpu().numpy(), gref, rtol=2e-3, atol=2e-3)
+
+
+def test_empty_input(ops):
+    tab = ops.mixture_pack_diag(np.zeros((3, 2)), 1.0, None, 'cuda')
+    lp = ops.mixture_logprob(torch.empty(0, 2, device='cuda'), tab)
+    assert lp.shape == (0,)
+
+
+def test_far_queries_stay_finite(ops):
+    """Queries far from every component underflow the fixed frame and must be rescued exactly."""
+    rng = np.random.default_rng(5)
+    m = rng.normal(size=(50, 2)); t = (rng.normal(size=(300, 2)) * 200).astype(np.float32)
+    tab = ops.mixture_pack_diag(m, 0.3, None, 'cuda')
+    lp, g = ops.mixture_logprob(_dev(t), tab, want_grad=True)
+    mu, A, c = OM.canonical_from_diag(m, 0.3)
+    ref, gref = OM.mixture_logprob(t.astype(np.float64), mu, A, c, with_grad=True)
+    assert torch.isfinite(lp).all() and torch.isfinite(g).all()
+    np.testing.assert_allclose(lp.cpu().numpy(), ref, rtol=1e-5)
+    np.testing.assert_allclose(g.cpu().numpy(), gref, rtol=1e-3, atol=1e-2)
+
+
+def test_component_sharded_partials_combine(ops, gold):
+    """ranks hold K/P components; (m, s, g) partials combine to the full answer."""
+    t = _dev(gold['t_full'])
+    tab = ops.mixture_pack_full(gold['m_full'], gold['K_full'], gold['w_full'], 'cuda')
+    full, gfull = ops.mixture_logprob(t, tab, want_grad=True)
+    for P in (2, 4, 8):
+        parts = [ops.mixture_logprob(t, tab.shard(r, P), want_grad=True, partial=True) for r in range(P)]
+        lp, g = ops.mixture_combine(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]),
+                                    torch.stack([p[2] for p in parts]))
+        np.testing.assert_allclose(lp.cpu().numpy(), full.cpu().numpy(), rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(g.cpu().numpy(), gfull.cpu().numpy(), rtol=1e-3, atol=1e-3)
+
+
+def test_full_size_properties(ops):
+    """BASELINE microbench size (65 536 x 65 536, D=2): size-independent checks -- a subsample
+    against the oracle, and the K copies of one component == that component identity."""
+    rng = np.random.default_rng(1234)
+    N = K = 65536
+    t = rng.normal(size=(N, 2)).astype(np.float32); m = rng.normal(size=(K, 2))
+    tab = ops.mixture_pack_diag(m, 1.0, None, 'cuda')
+    lp, g = ops.mixture_logprob(_dev(t), tab, want_grad=True)
+    idx = rng.choice(N, 256, replace=False)
+    mu, A, c = OM.canonical_from_diag(m, 1.0)
+    ref, gref = OM.mixture_logprob(t[idx].astype(np.float64), mu, A, c, with_grad=True)
+    np.testing.assert_allclose(lp.cpu().numpy()[idx], ref, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(g.cpu().numpy()[idx], gref, rtol=2e-3, atol=2e-3)
+    same = ops.mixture_pack_diag(np.tile(m[:1], (K, 1)), 1.0, None, 'cuda')
+    lp1 = ops.mixture_logprob(_dev(t), same).cpu().numpy()
+    want = -0.5 * ((t - m[:1]) ** 2).sum(1) - np.log(2 * np.pi)
+    np.testing.assert_allclose(lp1, want, rtol=1e-5, atol=1e-4)
