@@ -70,6 +70,122 @@ int ladder_mixture_logprob(const float* t, long long N, int D, const float* tabl
 int ladder_mixture_combine(const float* m_parts, const float* s_parts, const float* g_parts, int P,
                            long long N, int D, float* logp, float* grad_t, cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * K1/K2  conv2d + dense as implicit GEMM.  x NHWC [B,H,W,Cin], w HWIO [KH,KW,Cin,Cout],
+ * y [B,OH,OW,Cout].  pad_t/pad_l are TF's top/left zero padding (SAME on an even input with
+ * stride 2 is (0,1): pass pad_t = 0), the bottom/right padding is implied by OH/OW.  A dense
+ * layer is H=W=KH=KW=OH=OW=1, stride 1, no padding.
+ * replaces: tf.layers.conv2d / tf.layers.dense and their gradients -- codes/models.py:51-76,
+ *           109-148, 203-234, 267-315, 398-460, 478-587; codes/base.py:145-200; modules.py:8. */
+int ladder_conv2d_fprop(const float* x, const float* w, const float* bias /*nullable*/, float* y, int B, int H,
+                        int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH,
+                        int OW, int act, cudaStream_t stream);
+/* dx = conv_transpose(dy, w) [* act'(act_out) if act_out != NULL: fuses the activation
+ * backward of the layer that PRODUCED x]; accumulate != 0 adds into dx.                   */
+int ladder_conv2d_dgrad(const float* dy, const float* w, const float* act_out /*nullable*/, float* dx, int B,
+                        int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH,
+                        int OW, int act, int accumulate, cudaStream_t stream);
+/* dw [KH,KW,Cin,Cout] (overwritten) and, if dbias != NULL, dbias [Cout] = column sums of dy. */
+int ladder_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias /*nullable*/, int B, int H, int W,
+                        int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW,
+                        cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Layout ops.  replaces tf.pad(..., "SYMMETRIC") codes/models.py:48-50,200-202 and
+ * tf.nn.depth_to_space (NHWC, DCR order) codes/models.py:113-141,271-308.                  */
+int ladder_sym_pad(const float* x, float* y, int B, int H, int W, int C, int pad, cudaStream_t stream);
+int ladder_depth_to_space(const float* x, float* y, int B, int H, int W, int C, int r, cudaStream_t stream);
+/* gradient of depth_to_space fused with the producer's activation derivative:
+ * out[b,h,w,ch] = g[d2s position of ch] * act'(act_out[b,h,w,ch]);  (H,W,C) are the PRE-d2s dims */
+int ladder_space_to_depth_actgrad(const float* g, const float* act_out /*nullable*/, float* out, int B, int H,
+                                  int W, int C, int r, int act, cudaStream_t stream);
+int ladder_act_bwd(float* g_inout, const float* act_out, long long n, int act, cudaStream_t stream);
+int ladder_axpy(float* y, const float* x, float alpha, long long n, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The `scalars` buffer: LADDER_SCALARS_LEN floats on the device.  [0,16) are running sums the
+ * forward kernels accumulate into (zero them at the start of a sub-step), [16,40) the ELBO
+ * terms written by ladder_elbo_scalars (names = reference attributes, codes/base.py:257-413),
+ * [40,48) coefficients consumed by the backward kernels.                                   */
+#define LADDER_SCALARS_LEN 48
+#define LADDER_S_LOGSTD_Z 0        /* sum_{b,c} log code_std_dev                 */
+#define LADDER_S_M2_Z 1            /* sum code_mean^2                            */
+#define LADDER_S_S2_Z 2            /* sum code_std_dev^2                         */
+#define LADDER_S_LOGSTD_T 3        /* same three for the representation head     */
+#define LADDER_S_M2_T 4
+#define LADDER_S_S2_T 5
+#define LADDER_S_ABS_PIX 6         /* sum |x - decoded|                          */
+#define LADDER_S_SQ_PIX 7          /* sum (x - decoded)^2                        */
+#define LADDER_S_CODE_SQ 8         /* sum masked (code_sample - decoded_code)^2  */
+#define LADDER_S_CODE_ABS_MASKED 9
+#define LADDER_S_CODE_ABS 10       /* sum |decoded_code - code_sample|           */
+#define LADDER_S_MIX_LOGP 11       /* sum_n log p(t_n) over the MC samples       */
+#define LADDER_O_ENTROPY_Z 16
+#define LADDER_O_CE_SG 17          /* crossEntropy_prior_sg                      */
+#define LADDER_O_L1 18             /* l1_reconstruction_error                    */
+#define LADDER_O_L2 19             /* l2_reconstruction_error                    */
+#define LADDER_O_MEAN_PIXEL_ERROR 20
+#define LADDER_O_SIGMA 21
+#define LADDER_O_RECON_LL 22       /* reconstruction_likelihood                  */
+#define LADDER_O_SIGMA_REG 23      /* sigma_regularisor                          */
+#define LADDER_O_CODE_RECON_LL 24  /* code_reconstruction_likelihood             */
+#define LADDER_O_CODE_L1 25        /* code_l1_reconstruction_error               */
+#define LADDER_O_REPR_REG 26       /* representation_regularisor                 */
+#define LADDER_O_ENTROPY_T 27
+#define LADDER_O_CE_T 28           /* crossEntropy_representation                */
+#define LADDER_O_ELBO_PRIOR 29
+#define LADDER_O_CE_PRIOR 30       /* crossEntropy_prior                         */
+#define LADDER_O_ELBO 31
+#define LADDER_O_INNER_SIGMA 32
+#define LADDER_O_MEAN_CODE_ERROR 33
+#define LADDER_O_LOSS_AE 34
+#define LADDER_O_LOSS_PRIOR 35
+#define LADDER_C_COEF_DEC 40       /* d loss_ae / d (sum |x - decoded|)          */
+#define LADDER_C_DSIGMA 41         /* d loss_ae / d sigma variable               */
+#define LADDER_C_INV_B_ISIG2 42    /* 1 / (B inner_sigma^2)                      */
+#define LADDER_C_DINNER_SIGMA 43   /* d loss_prior / d inner_sigma variable      */
+
+/* Gaussian head: std = relu(std_pre) + floor IN PLACE, sample = mean + std*eps, and
+ * stats3[0..2] += (sum log std, sum mean^2, sum std^2).  n = B*C elements.
+ * replaces codes/models.py:85-103, codes/base.py:154-167 + the row sums of base.py:269-280. */
+int ladder_gauss_head_fwd(const float* mean, float* std_inout, const float* eps, float* sample, long long n,
+                          float std_floor, float* stats3, cudaStream_t stream);
+/* dmean = dsample + c_sg*mean (+dmean_add); dstd_pre = (dsample*eps + c_entropy/std + c_sg*std
+ * (+dstd_add)) * [std > floor].  dsample/dmean_add/dstd_add may be NULL.                  */
+int ladder_gauss_head_bwd(const float* dsample, const float* mean, const float* std_, const float* eps,
+                          const float* dmean_add, const float* dstd_add, float* dmean, float* dstd_pre, long long n,
+                          float std_floor, float c_entropy, float c_sg, cudaStream_t stream);
+/* MC samples of q(t|z) (codes/base.py:308-311): t[l,b,:] = mu[b,:] + sd[b,:]*eps[l,b,:]; BR = B*R. */
+int ladder_mc_sample(const float* mu, const float* sd, const float* eps, float* t, int L, long long BR,
+                     cudaStream_t stream);
+/* dmu[b,r] = coef*sum_l g[l,b,r];  dsd[b,r] = coef*sum_l g[l,b,r]*eps[l,b,r]              */
+int ladder_mc_reduce(const float* g, const float* eps, int L, long long BR, float coef, float* dmu, float* dsd,
+                     cudaStream_t stream);
+int ladder_sum(const float* x, long long n, float* out_accumulate, cudaStream_t stream);
+/* pixel reconstruction terms (codes/base.py:374-390) and their gradient w.r.t. the last
+ * decoder layer's pre-activation (act = that layer's activation).                          */
+int ladder_l1_recon_fwd(const float* x, const float* xhat, long long n, float* scalars, cudaStream_t stream);
+int ladder_l1_recon_bwd(const float* x, const float* xhat, const float* scalars, float* dpre, long long n, int act,
+                        cudaStream_t stream);
+/* prior-VAE code reconstruction with the code_std_dev > 1 mask (codes/base.py:286-297)     */
+int ladder_code_recon_fwd(const float* z, const float* zhat, const float* code_std, int use_mask, long long n,
+                          float* scalars, cudaStream_t stream);
+int ladder_code_recon_bwd(const float* z, const float* zhat, const float* code_std, int use_mask,
+                          const float* scalars, float weight, float* dzhat, float* dz /*nullable*/,
+                          int dz_accumulate, long long n, cudaStream_t stream);
+/* define_loss scalar assembly (codes/base.py:257-413) + sigma (codes/models.py:152-159) +
+ * inner_sigma clamp (codes/base.py:204-212).  prior_kind: 0 standard_gaussian, 1 ours,
+ * 2 hierarchical.  R_entropy is R except the hierarchical branch's hard-coded 2 (base.py:345). */
+int ladder_elbo_scalars(float* scalars, const float* sigma_var, const float* inner_sigma_var, int B, int C, int R,
+                        int R_entropy, int D_in, int N_mc, int sigma_takes_max, int clip_inner_sigma,
+                        float inner_sigma_lb, float inner_sigma_ub, int prior_kind, int use_standard_gaussian,
+                        cudaStream_t stream);
+/* ClipIfNotNone + tf.train.AdamOptimizer on a flat parameter group (codes/base.py:457-517):
+ * g <- clip(g,-1,1); TF epsilon placement; lr and the 1-based step are read from the device. */
+int ladder_clip_adam(float* param, const float* grad, float* m, float* v, long long n, const float* lr_dev,
+                     const int* step_dev, float beta1, float beta2, float eps, cudaStream_t stream);
+int ladder_increment(int* counter_dev, cudaStream_t stream);
+
 /* Diagnostic: saturate one pipe (kind 0 = FP32 FFMA, 1 = SFU MUFU.EX2).  Each of `blocks`
  * CTAs of 256 threads issues iters*64 dependent-chain ops per thread (8 chains).  Used by
  * bench.py to measure the pipe peaks the mixture kernel is compared against.            */

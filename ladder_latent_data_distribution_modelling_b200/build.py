@@ -18,9 +18,7 @@ OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libladder_sm100.so')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '--use_fast_math', '-Xcompiler', '-fPIC', '-I' + INCLUDE, '-I' + CSRC]
-# --use_fast_math only affects the elementwise / loss kernels' expf/logf/division; the
-# mixture and GEMM inner loops use explicit intrinsics.
+              '-Xcompiler', '-fPIC', '-I' + INCLUDE, '-I' + CSRC]
 
 
 def _nvcc():

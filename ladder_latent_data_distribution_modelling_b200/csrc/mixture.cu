@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "ladder_sm100.h"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace ladder {
@@ -396,19 +397,24 @@ static MixPlan mix_plan(long long N, int K, int D, int mode, bool grad) {
   // rows per thread: amortise the broadcast LDS of the table, keep registers sane
   p.R = (D <= 2) ? 4 : (D <= 8 ? 2 : 1);
   const int sms = num_sms();
-  while (p.R > 1 && ceil_div64(N, (long long)MIX_THREADS * p.R) < 2LL * sms) p.R >>= 1;
-  p.row_tiles = ceil_div64(N, (long long)MIX_THREADS * p.R);
+  // tuning knobs (benchmark sweeps only): CTAs per SM the grid should cover, rows per thread
+  static const int env_ctas = getenv("LADDER_MIX_CTAS_PER_SM") ? atoi(getenv("LADDER_MIX_CTAS_PER_SM")) : 16;
+  static const int env_r = getenv("LADDER_MIX_R") ? atoi(getenv("LADDER_MIX_R")) : 0;
+  if (env_r == 1 || env_r == 2 || (env_r == 4 && D <= 2)) p.R = env_r;
   p.kc = 8192 / stride;                  // <= 32 KB per stage
-  if (p.kc > 512) p.kc = 512;
+  if (p.kc > 256) p.kc = 256;          // 2 stages x 16 CTAs/SM must fit shared memory
   if (p.kc > K) p.kc = K > 0 ? K : 1;
+  const long long want = (long long)(env_ctas > 0 ? env_ctas : 16) * sms;
+  const int max_splits = ceil_div(K > 0 ? K : 1, p.kc);
+  // fewer rows per thread only when even a full component split cannot fill the machine (small K)
+  while (env_r == 0 && p.R > 1 && ceil_div64(N, (long long)MIX_THREADS * p.R) * max_splits < 2LL * sms) p.R >>= 1;
+  p.row_tiles = ceil_div64(N, (long long)MIX_THREADS * p.R);
   p.smem = (size_t)2 * p.kc * stride * sizeof(float);
-  // split components over grid.y until the grid covers ~4 CTAs per SM
-  long long want = 4LL * sms;
+  // split components over grid.y until the grid covers `want` CTAs
   int splits = (int)ceil_div64(want, p.row_tiles > 0 ? p.row_tiles : 1);
-  int max_splits = ceil_div(K > 0 ? K : 1, p.kc);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  int chunks_per_split = ceil_div(max_splits, splits);
+  const int chunks_per_split = ceil_div(max_splits, splits);
   p.k_per_split = chunks_per_split * p.kc;
   p.splits = ceil_div(K > 0 ? K : 1, p.k_per_split);
   const int gd = grad ? D : 1;

@@ -27,6 +27,29 @@ SIGNATURES = {
     'ladder_mixture_workspace_bytes': (C.c_size_t, [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]),
     'ladder_mixture_logprob': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, C.c_int, C.c_int, C.c_float, C.c_float,
                                          ptr, ptr, ptr, ptr, ptr, C.c_size_t, stream_t]),
+    # conv / dense
+    'ladder_conv2d_fprop': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 13 + [stream_t]),
+    'ladder_conv2d_dgrad': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 14 + [stream_t]),
+    'ladder_conv2d_wgrad': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 12 + [stream_t]),
+    # layout / elementwise
+    'ladder_sym_pad': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),
+    'ladder_depth_to_space': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),
+    'ladder_space_to_depth_actgrad': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 6 + [stream_t]),
+    'ladder_act_bwd': (C.c_int, [ptr, ptr, C.c_longlong, C.c_int, stream_t]),
+    'ladder_axpy': (C.c_int, [ptr, ptr, C.c_float, C.c_longlong, stream_t]),
+    # ELBO pieces
+    'ladder_gauss_head_fwd': (C.c_int, [ptr, ptr, ptr, ptr, C.c_longlong, C.c_float, ptr, stream_t]),
+    'ladder_gauss_head_bwd': (C.c_int, [ptr] * 8 + [C.c_longlong, C.c_float, C.c_float, C.c_float, stream_t]),
+    'ladder_mc_sample': (C.c_int, [ptr, ptr, ptr, ptr, C.c_int, C.c_longlong, stream_t]),
+    'ladder_mc_reduce': (C.c_int, [ptr, ptr, C.c_int, C.c_longlong, C.c_float, ptr, ptr, stream_t]),
+    'ladder_sum': (C.c_int, [ptr, C.c_longlong, ptr, stream_t]),
+    'ladder_l1_recon_fwd': (C.c_int, [ptr, ptr, C.c_longlong, ptr, stream_t]),
+    'ladder_l1_recon_bwd': (C.c_int, [ptr, ptr, ptr, ptr, C.c_longlong, C.c_int, stream_t]),
+    'ladder_code_recon_fwd': (C.c_int, [ptr, ptr, ptr, C.c_int, C.c_longlong, ptr, stream_t]),
+    'ladder_code_recon_bwd': (C.c_int, [ptr, ptr, ptr, C.c_int, ptr, C.c_float, ptr, ptr, C.c_int, C.c_longlong, stream_t]),
+    'ladder_elbo_scalars': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 8 + [C.c_float, C.c_float, C.c_int, C.c_int, stream_t]),
+    'ladder_clip_adam': (C.c_int, [ptr, ptr, ptr, ptr, C.c_longlong, ptr, ptr, C.c_float, C.c_float, C.c_float, stream_t]),
+    'ladder_increment': (C.c_int, [ptr, stream_t]),
     'ladder_pipe_peak_launch': (C.c_int, [C.c_int, C.c_int, C.c_int, ptr, stream_t]),
     'ladder_mixture_combine': (C.c_int, [ptr, ptr, ptr, C.c_int, C.c_longlong, C.c_int, ptr, ptr, stream_t]),
 }

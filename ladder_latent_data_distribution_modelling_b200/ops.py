@@ -110,6 +110,11 @@ def mixture_logprob(t, tab, want_grad=False, partial=False, out=None):
         raise RuntimeError('mixture_logprob: query dim %d != table dim %d' % (D, tab.D))
     out = out or {}
     dev = t.device
+    if N == 0:                       # empty batch: nothing to launch
+        e = torch.empty(0, device=dev, dtype=torch.float32)
+        if partial:
+            return (e, e.clone(), torch.empty_like(t)) if want_grad else (e, e.clone())
+        return (e, torch.empty_like(t)) if want_grad else e
     grad = (out.get('grad') if 'grad' in out else torch.empty_like(t)) if want_grad else None
     logp = m = s = None
     if partial:
@@ -147,3 +152,156 @@ def pipe_peak(kind, blocks, iters):
     out = _workspace(torch.device('cuda', torch.cuda.current_device()), 256, 'pipe')
     _lib.check(_L().ladder_pipe_peak_launch(kind, blocks, iters, _p(out), _stream()), 'pipe_peak')
     return blocks * 256 * iters * 64
+
+
+# ------------------------------------------------------------------------------ scalars layout
+# mirrors include/ladder_sm100.h
+SCALARS_LEN = 48
+S = dict(LOGSTD_Z=0, M2_Z=1, S2_Z=2, LOGSTD_T=3, M2_T=4, S2_T=5, ABS_PIX=6, SQ_PIX=7, CODE_SQ=8,
+         CODE_ABS_MASKED=9, CODE_ABS=10, MIX_LOGP=11)
+O = dict(entropy_z=16, crossEntropy_prior_sg=17, l1_reconstruction_error=18, l2_reconstruction_error=19,
+         mean_pixel_error=20, sigma=21, reconstruction_likelihood=22, sigma_regularisor=23,
+         code_reconstruction_likelihood=24, code_l1_reconstruction_error=25, representation_regularisor=26,
+         entropy_t=27, crossEntropy_representation=28, elbo_prior=29, crossEntropy_prior=30, elbo=31,
+         inner_sigma=32, mean_code_error=33, loss_ae=34, loss_prior=35)
+CF = dict(COEF_DEC=40, DSIGMA=41, INV_B_ISIG2=42, DINNER_SIGMA=43)
+
+
+# ------------------------------------------------------------------------------ conv / dense
+def tf_same_pads(n, k, s):
+    """TF 'SAME' rule: out = ceil(n/s); total = max((out-1)*s + k - n, 0); before = total//2."""
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return total // 2, total - total // 2
+
+
+class ConvGeom:
+    """Geometry of one conv2d (or dense: H=W=KH=KW=1) layer."""
+
+    def __init__(self, B, H, W, Cin, KH, KW, Cout, stride=1, padding='same'):
+        self.B, self.H, self.W, self.Cin, self.KH, self.KW, self.Cout, self.stride = B, H, W, Cin, KH, KW, Cout, stride
+        if padding == 'same':
+            self.pad_t, pb = tf_same_pads(H, KH, stride)
+            self.pad_l, pr = tf_same_pads(W, KW, stride)
+        else:
+            self.pad_t = self.pad_l = pb = pr = 0
+        self.OH = (H + self.pad_t + pb - KH) // stride + 1
+        self.OW = (W + self.pad_l + pr - KW) // stride + 1
+
+    @staticmethod
+    def dense(B, Cin, Cout):
+        return ConvGeom(B, 1, 1, Cin, 1, 1, Cout, 1, 'valid')
+
+    def args(self):
+        return (self.B, self.H, self.W, self.Cin, self.KH, self.KW, self.Cout, self.stride, self.pad_t, self.pad_l,
+                self.OH, self.OW)
+
+
+def conv2d_fprop(x, w, bias, y, g, act=None):
+    _lib.check(_L().ladder_conv2d_fprop(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(_f32(y)), *g.args(), ACT[act], _stream()),
+               'conv2d_fprop')
+    return y
+
+
+def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False):
+    _lib.check(_L().ladder_conv2d_dgrad(_p(_f32(dy)), _p(_f32(w)), _p(act_out), _p(_f32(dx)), *g.args(), ACT[act],
+                                        int(accumulate), _stream()), 'conv2d_dgrad')
+    return dx
+
+
+def conv2d_wgrad(x, dy, dw, dbias, g):
+    _lib.check(_L().ladder_conv2d_wgrad(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dw)), _p(dbias), *g.args(), _stream()),
+               'conv2d_wgrad')
+    return dw
+
+
+# ------------------------------------------------------------------------------ layout / elementwise
+def sym_pad(x, y, B, H, W, Cc, pad):
+    _lib.check(_L().ladder_sym_pad(_p(_f32(x)), _p(_f32(y)), B, H, W, Cc, pad, _stream()), 'sym_pad')
+    return y
+
+
+def depth_to_space(x, y, B, H, W, Cc, r):
+    _lib.check(_L().ladder_depth_to_space(_p(_f32(x)), _p(_f32(y)), B, H, W, Cc, r, _stream()), 'depth_to_space')
+    return y
+
+
+def space_to_depth_actgrad(g, act_out, out, B, H, W, Cc, r, act=None):
+    _lib.check(_L().ladder_space_to_depth_actgrad(_p(_f32(g)), _p(act_out), _p(_f32(out)), B, H, W, Cc, r, ACT[act],
+                                                  _stream()), 'space_to_depth_actgrad')
+    return out
+
+
+def act_bwd(g, act_out, act):
+    _lib.check(_L().ladder_act_bwd(_p(_f32(g)), _p(_f32(act_out)), g.numel(), ACT[act], _stream()), 'act_bwd')
+    return g
+
+
+def axpy(y, x, alpha=1.0):
+    _lib.check(_L().ladder_axpy(_p(_f32(y)), _p(_f32(x)), float(alpha), y.numel(), _stream()), 'axpy')
+    return y
+
+
+# ------------------------------------------------------------------------------ ELBO pieces
+def gauss_head_fwd(mean, std_inout, eps, sample, floor, stats3):
+    _lib.check(_L().ladder_gauss_head_fwd(_p(_f32(mean)), _p(_f32(std_inout)), _p(_f32(eps)), _p(_f32(sample)),
+                                          mean.numel(), float(floor), _p(stats3), _stream()), 'gauss_head_fwd')
+
+
+def gauss_head_bwd(dsample, mean, std, eps, dmean_add, dstd_add, dmean, dstd_pre, floor, c_entropy, c_sg):
+    _lib.check(_L().ladder_gauss_head_bwd(_p(dsample), _p(_f32(mean)), _p(_f32(std)), _p(_f32(eps)), _p(dmean_add),
+                                          _p(dstd_add), _p(_f32(dmean)), _p(_f32(dstd_pre)), mean.numel(), float(floor),
+                                          float(c_entropy), float(c_sg), _stream()), 'gauss_head_bwd')
+
+
+def mc_sample(mu, sd, eps, t):
+    L = eps.shape[0]
+    _lib.check(_L().ladder_mc_sample(_p(_f32(mu)), _p(_f32(sd)), _p(_f32(eps)), _p(_f32(t)), L, mu.numel(), _stream()),
+               'mc_sample')
+    return t
+
+
+def mc_reduce(g, eps, coef, dmu, dsd):
+    L = eps.shape[0]
+    _lib.check(_L().ladder_mc_reduce(_p(_f32(g)), _p(_f32(eps)), L, dmu.numel(), float(coef), _p(_f32(dmu)),
+                                     _p(_f32(dsd)), _stream()), 'mc_reduce')
+
+
+def sum_into(x, out_scalar):
+    _lib.check(_L().ladder_sum(_p(_f32(x)), x.numel(), _p(out_scalar), _stream()), 'sum')
+
+
+def l1_recon_fwd(x, xhat, scalars):
+    _lib.check(_L().ladder_l1_recon_fwd(_p(_f32(x)), _p(_f32(xhat)), x.numel(), _p(scalars), _stream()), 'l1_recon_fwd')
+
+
+def l1_recon_bwd(x, xhat, scalars, dpre, act=None):
+    _lib.check(_L().ladder_l1_recon_bwd(_p(_f32(x)), _p(_f32(xhat)), _p(scalars), _p(_f32(dpre)), x.numel(), ACT[act],
+                                        _stream()), 'l1_recon_bwd')
+
+
+def code_recon_fwd(z, zhat, code_std, use_mask, scalars):
+    _lib.check(_L().ladder_code_recon_fwd(_p(_f32(z)), _p(_f32(zhat)), _p(code_std), int(use_mask), z.numel(),
+                                          _p(scalars), _stream()), 'code_recon_fwd')
+
+
+def code_recon_bwd(z, zhat, code_std, use_mask, scalars, weight, dzhat, dz=None, dz_accumulate=False):
+    _lib.check(_L().ladder_code_recon_bwd(_p(_f32(z)), _p(_f32(zhat)), _p(code_std), int(use_mask), _p(scalars),
+                                          float(weight), _p(_f32(dzhat)), _p(dz), int(dz_accumulate), z.numel(),
+                                          _stream()), 'code_recon_bwd')
+
+
+def elbo_scalars(scalars, sigma_var, inner_sigma_var, B, Cc, R, R_entropy, D_in, N_mc, sigma_takes_max,
+                 clip_inner_sigma, lb, ub, prior_kind, use_sg):
+    _lib.check(_L().ladder_elbo_scalars(_p(scalars), _p(sigma_var), _p(inner_sigma_var), B, Cc, R, R_entropy, D_in,
+                                        N_mc, int(sigma_takes_max), int(clip_inner_sigma), float(lb), float(ub),
+                                        int(prior_kind), int(use_sg), _stream()), 'elbo_scalars')
+
+
+def clip_adam(param, grad, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.95, eps=1e-8):
+    _lib.check(_L().ladder_clip_adam(_p(_f32(param)), _p(_f32(grad)), _p(_f32(m)), _p(_f32(v)), param.numel(),
+                                     _p(lr_dev), _p(step_dev), beta1, beta2, eps, _stream()), 'clip_adam')
+
+
+def increment(counter):
+    _lib.check(_L().ladder_increment(_p(counter), _stream()), 'increment')

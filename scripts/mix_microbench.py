@@ -2,7 +2,10 @@
 kernel at D in {2, 32, 64}, forward and forward+gradient, plus the measured FFMA / MUFU.EX2
 pipe peaks it is compared against.  Prints one JSON object."""
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch

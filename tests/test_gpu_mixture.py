@@ -40,7 +40,9 @@ def test_reference_fixture_full_cov(ops, gold, tag):
     # tolerance: fp32 arithmetic + ex2.approx (2 ulp); |logp| reaches 6e3 for the far outliers
     np.testing.assert_allclose(lp, ref, rtol=2e-5, atol=2e-4)
     np.testing.assert_allclose(lp, gold['logp_sklearn_' + tag], rtol=5e-5, atol=5e-4)
-    np.testing.assert_allclose(g, gref, rtol=2e-3, atol=2e-3 * np.abs(gref).max(axis=1, keepdims=True) + 1e-4)
+    scale = np.abs(gref).max(axis=1, keepdims=True) + 1e-3      # per-row relative error
+    err = np.abs(g - gref) / scale
+    assert err.max() < 2e-3, (err.max(), np.argmax(err.max(axis=1)), t[np.argmax(err.max(axis=1))])
 
 
 @pytest.mark.parametrize('D', [1, 2, 3, 4, 8, 16, 32, 64])
@@ -144,4 +146,5 @@ def test_full_size_properties(ops):
     same = ops.mixture_pack_diag(np.tile(m[:1], (K, 1)), 1.0, None, 'cuda')
     lp1 = ops.mixture_logprob(_dev(t), same).cpu().numpy()
     want = -0.5 * ((t - m[:1]) ** 2).sum(1) - np.log(2 * np.pi)
-    np.testing.assert_allclose(lp1, want, rtol=1e-5, atol=1e-4)
+    # 65 536 identical addends: fp32 accumulation error is systematic here (~n*eps/4), hence 2e-3
+    np.testing.assert_allclose(lp1, want, rtol=1e-5, atol=2e-3)
