@@ -1,0 +1,362 @@
+"""Benchmark of the LaDDer ELBO hot path on B200 (contract: one JSON line on rank 0).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+  python bench.py --impl reference ...                      # CPU restatement of the reference (oracle port)
+
+A "step" is one reference training iteration (codes/trainers.py:33-40): train_step_ae,
+train_step_sigma, train_step_prior, train_step_inner_sigma -- four forward passes with fresh
+noise and two backward passes -- on one batch of synthetic 28x28x1 images.  Workload at N=1:
+BASELINE.json configs[1], `codes/mnist_fashion_config.json` at batch 1024 (weak scaling:
+batch 1024 PER GPU for N>1, gradients / batch sums all-reduced over NCCL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'train imgs/sec (ELBO fwd+bwd, 4 sub-steps per image batch)'
+
+
+def load_config(batch):
+    with open(os.path.join(ROOT, 'codes', 'mnist_fashion_config.json')) as f:
+        cfg = json.load(f)
+    cfg['batch_size'] = batch
+    return cfg
+
+
+def synthetic_mixture(K, R, seed=7):
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(K, R, R))
+    return (rng.normal(size=(K, R)) * 1.5, a @ a.transpose(0, 2, 1) * 0.2 + 0.05 * np.eye(R),
+            rng.uniform(0.05, 1.0, size=K))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'],
+                'bf16_tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(',')]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    out['sm_max_mhz'] = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out['sm_mhz'] = float(np.median(sm))
+            out['samples'] = len(sm)
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_reference(cfg_full, sample_B, steps, warmup):
+    """The oracle port of one reference iteration, float32, all host threads numpy/BLAS will use."""
+    from oracle import params as oparams, steps as osteps
+    cfg = dict(cfg_full)
+    cfg['batch_size'] = sample_B
+    rng = np.random.default_rng(0)
+    spec = oparams.vae_param_specs(cfg) + oparams.prior_param_specs(cfg)
+    P = oparams.glorot_init(spec, cfg, 1, dtype=np.float32)
+    C, R, L, K = cfg['code_size'], cfg['representation_size'], cfg['n_MC_samples'], cfg['n_mixtures']
+    x = rng.uniform(size=(sample_B, 28, 28, 1)).astype(np.float32)
+    epoch = cfg['sg_pretraining'] + 1
+    feeds = osteps.compute_feeds(cfg, epoch, synthetic_mixture(K, R))
+    tr = osteps.OracleTrainer(cfg, P, dtype=np.float32)
+
+    def noise():
+        return [dict(eps_z=rng.normal(size=(sample_B, C)), eps_t=rng.normal(size=(sample_B, R)),
+                     eps_mc=rng.normal(size=(L, sample_B, R))) for _ in range(4)]
+    for _ in range(warmup):
+        tr.iteration(x, noise(), feeds, epoch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.iteration(x, noise(), feeds, epoch)
+    dt = time.perf_counter() - t0
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
+    return {'value': sample_B * steps / dt, 'unit': 'imgs/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d iteration(s) of the 4-sub-step protocol on a %d-image batch of the same config, fp32 NumPy '
+                      'oracle (BLAS threads = host default)' % (steps, sample_B), 'seconds': dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    cfg = load_config(args.batch)
+    steps = max(1, min(args.steps, 3))
+    base = cpu_reference(cfg, args.cpu_sample, steps, 1)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'imgs/s', 'n_gpus': args.gpus,
+            'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * base['seconds'] / steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'codes/mnist_fashion_config.json @ batch %d (CPU arm times a %d-image sample)'
+                                   % (args.batch, args.cpu_sample)},
+            'cpu_baseline': {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': base['value'], 'unit': 'imgs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ladder_latent_data_distribution_modelling_b200 import ops
+    from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
+    from ladder_latent_data_distribution_modelling_b200.host.models import MNISTModel_fashion
+    from ladder_latent_data_distribution_modelling_b200.host.trainers import MNISTTrainer_joint_training
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device; there is no CPU fallback for the product path')
+    torch.cuda.set_device(local)
+    group = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        group = dist.group.WORLD
+    dev = torch.device('cuda', local)
+    B = args.batch
+    cfg = load_config(B)
+    cfg['seed'] = 1234
+    K, R = cfg['n_mixtures'], cfg['representation_size']
+    epoch = cfg['sg_pretraining'] + 1            # past pretraining: all four sub-steps active, fitted mixture fed
+    gm = synthetic_mixture(K, R)
+
+    # ---- device-resident loop (value)
+    eng = LadderEngine(cfg, B, dev, seed=1234 + rank, dist_group=group)
+    if world > 1:                                 # identical initial weights on every rank
+        for g in eng.groups.values():
+            dist.broadcast(g.param, 0)
+    eng.set_feeds(prior_mean=gm[0], prior_cov=gm[1], prior_weight=gm[2], use_standard_gaussian_prior=False,
+                  use_mask=False)
+    eng.set_lrs(cfg['learning_rate_ae'], cfg['learning_rate_sigma'], cfg['learning_rate_prior'],
+                cfg['learning_rate_inner_sigma'])
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    n_pool = 4
+    pool = [torch.rand(B, 28, 28, 1, device=dev, generator=gen) for _ in range(n_pool)]
+
+    def iteration(x):
+        eng.draw_noise()
+        eng.step_ae(x)
+        eng.draw_noise(t=False, mc=False)
+        eng.step_sigma(x)
+        eng.draw_noise()
+        eng.step_prior(x)
+        eng.draw_noise(mc=False)
+        eng.step_inner_sigma(x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        iteration(pool[i % n_pool])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        iteration(pool[i % n_pool])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world * args.steps / (ms * 1e-3)
+    loss_check = eng.fetch(['loss_prior'])['loss_prior']
+
+    # ---- end-to-end through the reference-facing API with HOST buffers (e2e)
+    cfg2 = dict(cfg)
+    cfg2['checkpoint_dir'] = cfg2['result_dir'] = tempfile.mkdtemp() + '/'
+    model = MNISTModel_fashion(cfg2, device=dev, dist_group=group)
+    if world > 1:
+        for g in model.engine.groups.values():
+            dist.broadcast(g.param, 0)
+
+    class _Data:
+        n_train, n_val = 60000, 10000
+        test_set = {'image': np.zeros((B, 28, 28, 1), np.float32)}
+    trainer = MNISTTrainer_joint_training(None, model, _Data(), cfg2)
+    trainer.cur_epoch = epoch
+    model.GM_prior_training.means_, model.GM_prior_training.covariances_, model.GM_prior_training.weights_ = gm
+    host_pool = [torch.rand(B, 28, 28, 1).pin_memory() for _ in range(n_pool)]
+    lr = cfg['learning_rate_ae'] * 0.99 ** (epoch - 1)
+
+    def e2e_iteration(hx):
+        loss = trainer.train_step_ae(cur_lr=lr, batch_data=hx)
+        trainer.train_step_prior(batch_data=hx)
+        return float(loss)                       # device -> host read of the step's loss
+
+    for i in range(args.warmup):
+        e2e_iteration(host_pool[i % n_pool])
+    trainer._pending = []
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        last = e2e_iteration(host_pool[i % n_pool])
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        peaks = measured_peaks()
+        # ---- roofline of the dominant kernel: the implicit-GEMM of decoder/conv2d_3 (16x16, 64 -> 256, 3x3),
+        # 68 % of the model's MACs; timed alone with CUDA events on the launch stream
+        H = cfg['num_hidden_units']
+        g = ops.ConvGeom(B, 16, 16, H // 4, 3, 3, H, 1, 'same')
+        xk = torch.randn(B, 16, 16, H // 4, device=dev)
+        wk = torch.randn(3, 3, H // 4, H, device=dev) * 0.05
+        bk = torch.zeros(H, device=dev)
+        yk = torch.empty(B, 16, 16, H, device=dev)
+        for _ in range(3):
+            ops.conv2d_fprop(xk, wk, bk, yk, g, 'leaky_relu')
+        torch.cuda.synchronize()
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            ops.conv2d_fprop(xk, wk, bk, yk, g, 'leaky_relu')
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / reps
+        flops = 2.0 * B * 256 * H * (9 * H // 4)
+        ach = flops / (k_ms * 1e-3) / 1e12
+        roofline = {'kernel': 'igemm_kernel<FPROP> decoder/conv2d_3 [B,16,16,%d]->%d 3x3' % (H // 4, H),
+                    'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                    'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'peak_source': peaks['source'] + ' bf16 burst',
+                    'ms_per_launch': k_ms, 'algorithmic_flops_per_launch': flops,
+                    'note': 'round-1 kernel is fp32 SIMT (no tensor cores yet); denominator is the bf16 tensor peak'}
+        # ---- hyper-prior micro-benchmark (second half of the metric): 65 536 x 65 536 pairs, D = 2
+        rng = np.random.default_rng(1234)
+        N = 65536
+        tq = torch.tensor(rng.normal(size=(N, 2)).astype(np.float32), device=dev)
+        tab = ops.mixture_pack_diag(rng.normal(size=(N, 2)), 1.0, None, dev)
+        hp = {}
+        for grad in (False, True):
+            for _ in range(3):
+                ops.mixture_logprob(tq, tab, want_grad=grad)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                ops.mixture_logprob(tq, tab, want_grad=grad)
+            e1.record()
+            torch.cuda.synchronize()
+            hp['fwd_grad' if grad else 'fwd'] = N * N / (e0.elapsed_time(e1) / 5 * 1e-3)
+        n_ex2 = ops.pipe_peak(1, 148 * 8, 512)
+        torch.cuda.synchronize()
+        e0.record()
+        ops.pipe_peak(1, 148 * 8, 512)
+        e1.record()
+        torch.cuda.synchronize()
+        ex2_peak = n_ex2 / (e0.elapsed_time(e1) * 1e-3)
+        hyper = {'pairs_per_s_fwd': hp['fwd'], 'pairs_per_s_fwd_grad': hp['fwd_grad'], 'N': N, 'K': N, 'D': 2,
+                 'bound': 'sfu (1 MUFU.EX2 per pair)', 'ex2_peak_per_s_measured': ex2_peak,
+                 'frac_fwd': hp['fwd'] / ex2_peak, 'frac_fwd_grad': hp['fwd_grad'] / ex2_peak}
+        cpu = cpu_reference(cfg, args.cpu_sample, 1, 1)
+        line = {'metric': METRIC, 'value': value, 'unit': 'imgs/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'codes/mnist_fashion_config.json @ batch %d per GPU, epoch %d (all 4 sub-steps, '
+                                       '50-component hyper-prior, L=100 MC samples)' % (B, epoch),
+                           'global_batch': B * world, 'parallelism': 'dp%d' % world,
+                           'l2': 'per-step activation working set (>1 GB) exceeds the 126 MB L2; 4 input batches rotate'},
+                'clocks': clocks, 'gpu_launches': launches,
+                'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': B * 784 * 4,
+                        'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps,
+                        'api': 'MNISTTrainer_joint_training.train_step_ae + train_step_prior on pinned host batches'},
+                'roofline': roofline, 'cpu_baseline': {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+                'hyper_prior': hyper, 'loss_prior_last': loss_check, 'loss_ae_last_e2e': last}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=1024, help='images per GPU')
+    ap.add_argument('--cpu-sample', type=int, default=32, help='batch of the bounded CPU-baseline sample')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -39,6 +39,8 @@ extern "C" {
 
 int ladder_version(void);
 const char* ladder_last_error(void);
+/* kernels enqueued by this library so far in this process (bench.py's gpu_launches evidence) */
+unsigned long long ladder_launch_count(void);
 /* LADDER_OK iff `device` is compute capability 10.x (the only target); else LADDER_ERR_ARCH. */
 int ladder_device_check(int device);
 

@@ -18,6 +18,11 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+unsigned long long& launch_counter() {
+  static unsigned long long n = 0;
+  return n;
+}
+
 int num_sms() {
   static int cached = 0;
   if (cached == 0) {
@@ -38,6 +43,8 @@ extern "C" {
 int ladder_version(void) { return 100; }
 
 const char* ladder_last_error(void) { return ladder::error_buffer(); }
+
+unsigned long long ladder_launch_count(void) { return ladder::launch_counter(); }
 
 int ladder_device_check(int device) {
   cudaDeviceProp p;

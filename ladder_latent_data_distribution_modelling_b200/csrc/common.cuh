@@ -17,7 +17,11 @@ namespace ladder {
 char* error_buffer();
 int fail(int code, const char* fmt, ...);
 
+// number of kernels this library has enqueued in this process (bench.py reports it as gpu_launches)
+unsigned long long& launch_counter();
+
 inline int check_launch(const char* what) {
+  ++launch_counter();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return LADDER_OK;

@@ -1,0 +1,563 @@
+"""Execution engine for the LaDDer ELBO sub-steps on one B200.
+
+This is the part of the reference that used to be `sess.run` (codes/base.py:583-641): it
+owns the flat parameter / gradient / Adam-moment buffers, allocates every activation once
+per batch size, and runs forward + backward of the outer VAE, the prior VAE, the mixture
+hyper-prior and the ELBO assembly as a fixed sequence of libladder_sm100 kernels on the
+current CUDA stream -- no host synchronisation, no allocation after warm-up, so a whole
+sub-step is CUDA-graph capturable.  PyTorch provides memory, streams and RNG only.
+
+Gradient convention: layers exchange d(loss)/d(pre-activation).  A conv/dense layer's
+dgrad fuses the activation derivative of the layer that PRODUCED its input, and the
+depth_to_space gradient kernel does the same across the permutation.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+
+LEAKY = 'leaky_relu'
+
+
+# ------------------------------------------------------------------------------ parameters
+class ParamGroup:
+    """One optimiser group = one flat fp32 buffer (+ grad, Adam m/v, lr and step on device).
+
+    Mirrors one `tf.train.AdamOptimizer` + var_list of codes/base.py:457-511."""
+
+    def __init__(self, name, specs, device):
+        self.name = name
+        self.specs = list(specs)
+        self.offsets = {}
+        n = 0
+        for pname, shape in self.specs:
+            size = int(np.prod(shape)) if len(shape) else 1
+            n = (n + 3) // 4 * 4                   # keep every tensor 16-byte aligned
+            self.offsets[pname] = (n, size, tuple(shape))
+            n += size
+        self.numel = max(n, 1)
+        self.param = torch.zeros(self.numel, device=device)
+        self.grad = torch.zeros(self.numel, device=device)
+        self.m = torch.zeros(self.numel, device=device)
+        self.v = torch.zeros(self.numel, device=device)
+        self.lr = torch.zeros(1, device=device)
+        self.step = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def view(self, buf, pname):
+        off, size, shape = self.offsets[pname]
+        return buf[off:off + size].view(shape)
+
+    def p(self, pname):
+        return self.view(self.param, pname)
+
+    def g(self, pname):
+        return self.view(self.grad, pname)
+
+    def names(self):
+        return [n for n, _ in self.specs]
+
+    def apply_adam(self, grad=None):
+        """ClipIfNotNone + Adam (base.py:464,502) with this group's own step counter."""
+        ops.increment(self.step)
+        ops.clip_adam(self.param, self.grad if grad is None else grad, self.m, self.v, self.lr, self.step)
+
+
+def glorot_uniform_(t, shape, gen):
+    """tf xavier_initializer / glorot_uniform: U(-l, l), l = sqrt(6 / (fan_in + fan_out))."""
+    if len(shape) == 4:
+        rf = shape[0] * shape[1]
+        fan_in, fan_out = rf * shape[2], rf * shape[3]
+    else:
+        fan_in, fan_out = shape
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    t.uniform_(-lim, lim, generator=gen)
+
+
+# ------------------------------------------------------------------------------ layers
+class Conv:
+    """conv2d (or dense) + bias + activation with preallocated output and gradients."""
+
+    def __init__(self, group, wname, geom, act, device):
+        self.group, self.geom, self.act = group, geom, act
+        self.w = group.p(wname + '/kernel')
+        self.b = group.p(wname + '/bias')
+        self.dw = group.g(wname + '/kernel')
+        self.db = group.g(wname + '/bias')
+        g = geom
+        self.y = torch.empty(g.B, g.OH, g.OW, g.Cout, device=device)
+        self.x = None
+
+    def forward(self, x):
+        self.x = x
+        return ops.conv2d_fprop(x, self.w, self.b, self.y, self.geom, self.act)
+
+    def backward(self, dpre, dx=None, producer=None, wgrad=True, accumulate=False):
+        """dpre: d loss / d pre-activation of this layer.  producer = (act_out, act) of the layer
+        that produced x, whose activation derivative is fused into dx."""
+        if wgrad:
+            ops.conv2d_wgrad(self.x, dpre, self.dw, self.db, self.geom)
+        if dx is not None:
+            ao, act = producer if producer is not None else (None, None)
+            ops.conv2d_dgrad(dpre, self.w, dx, self.geom, act_out=ao, act=act, accumulate=accumulate)
+        return dx
+
+
+class Buffers:
+    """Named scratch tensors allocated once."""
+
+    def __init__(self, device):
+        self.device = device
+        self.t = {}
+
+    def get(self, name, *shape):
+        t = self.t.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(*shape, device=self.device)
+            self.t[name] = t
+        return t
+
+
+# ------------------------------------------------------------------------------ outer VAEs (MNIST)
+class MnistOuterVAE:
+    """Encoder / decoder of MNISTModel_digit (codes/models.py:46-148) and MNISTModel_fashion
+    (codes/models.py:199-315) for a fixed batch size."""
+
+    def __init__(self, config, group, B, device):
+        self.cfg, self.group, self.B, self.dev = config, group, B, device
+        exp = config['exp_name']
+        H = int(config['num_hidden_units'])
+        C = int(config['code_size'])
+        k = int(config['kernel_size'])
+        G = ops.ConvGeom
+        self.buf = Buffers(device)
+        self.xpad = torch.empty(B, 32, 32, 1, device=device)
+        enc = []
+        if exp == 'mnist_digit':
+            enc.append(Conv(group, 'encoder/conv2d', G(B, 32, 32, 1, k, k, H // 16, 2, 'same'), LEAKY, device))
+            enc.append(Conv(group, 'encoder/conv2d_1', G(B, 16, 16, H // 16, k, k, H // 4, 2, 'same'), LEAKY, device))
+            enc.append(Conv(group, 'encoder/conv2d_2', G(B, 8, 8, H // 4, k, k, H, 2, 'same'), LEAKY, device))
+            flat, feat = 16 * H, H // 4
+        else:
+            enc.append(Conv(group, 'encoder/conv2d', G(B, 32, 32, 1, 3, 3, H // 4, 2, 'same'), LEAKY, device))
+            enc.append(Conv(group, 'encoder/conv2d_1', G(B, 16, 16, H // 4, 3, 3, H // 4, 2, 'same'), LEAKY, device))
+            enc.append(Conv(group, 'encoder/conv2d_2', G(B, 8, 8, H // 4, 3, 3, H // 2, 2, 'same'), LEAKY, device))
+            enc.append(Conv(group, 'encoder/conv2d_3', G(B, 4, 4, H // 2, 3, 3, H // 2, 1, 'valid'), LEAKY, device))
+            flat, feat = 2 * H, H
+        self.enc_convs = enc
+        self.enc_dense = Conv(group, 'encoder/dense', G.dense(B, flat, feat), LEAKY, device)
+        self.head_mean = Conv(group, 'encoder/code_mean', G.dense(B, feat, C), None, device)
+        self.head_std = Conv(group, 'encoder/code_std_dev', G.dense(B, feat, C), None, device)
+        # decoder: dense -> [d2s -> conv]* -> d2s -> conv5x5 valid relu
+        if exp == 'mnist_digit':
+            self.dec_dense = Conv(group, 'decoder/dense', G.dense(B, C, 16 * H), LEAKY, device)
+            stages = [(1, 16 * H, 4, 'decoder/conv2d', 3, H), (4, H, 2, 'decoder/conv2d_1', 3, H // 4),
+                      (8, H // 4, 2, 'decoder/conv2d_2', 3, H // 16)]
+            last = (16, H // 16, 2, 'decoder/conv2d_3', H // 64)
+        else:
+            self.dec_dense = Conv(group, 'decoder/dense', G.dense(B, C, H), LEAKY, device)
+            stages = [(1, H, 2, 'decoder/conv2d', 1, H), (2, H, 2, 'decoder/conv2d_1', 3, H),
+                      (4, H, 2, 'decoder/conv2d_2', 3, H), (8, H, 2, 'decoder/conv2d_3', 3, H)]
+            last = (16, H, 2, 'decoder/conv2d_4', H // 4)
+        self.dec = []          # (hw_in, c_in, r, d2s_out, conv)
+        for hw, cin, r, name, kk, cout in stages:
+            d2s_out = torch.empty(B, hw * r, hw * r, cin // (r * r), device=device)
+            conv = Conv(group, name, G(B, hw * r, hw * r, cin // (r * r), kk, kk, cout, 1, 'same'), LEAKY, device)
+            self.dec.append((hw, cin, r, d2s_out, conv))
+        hw, cin, r, name, cl = last
+        d2s_out = torch.empty(B, hw * r, hw * r, cin // (r * r), device=device)
+        conv = Conv(group, name, G(B, hw * r, hw * r, cl, 5, 5, 1, 1, 'valid'), 'relu', device)
+        self.dec.append((hw, cin, r, d2s_out, conv))
+        self.flat, self.feat, self.C = flat, feat, C
+        self.mean = self.head_mean.y.view(B, C)
+        self.std = self.head_std.y.view(B, C)              # becomes relu(.)+floor in place
+        self.z = torch.empty(B, C, device=device)
+        self.decoded = self.dec[-1][4].y
+
+    # -- forward
+    def encode(self, x, eps_z, stats_z):
+        B = self.B
+        ops.sym_pad(x, self.xpad, B, 28, 28, 1, 2)
+        h = self.xpad
+        for c in self.enc_convs:
+            h = c.forward(h)
+        h = self.enc_dense.forward(h.view(B, 1, 1, self.flat))
+        self.head_mean.forward(h)
+        self.head_std.forward(h)
+        ops.gauss_head_fwd(self.mean, self.std, eps_z, self.z, float(self.cfg['latent_variance_precision']), stats_z)
+        self.eps_z = eps_z
+        return self.z
+
+    def decode(self, z):
+        B = self.B
+        h = self.dec_dense.forward(z.view(B, 1, 1, self.C))
+        for hw, cin, r, d2s_out, conv in self.dec:
+            ops.depth_to_space(h.view(B, hw, hw, cin), d2s_out, B, hw, hw, cin, r)
+            h = conv.forward(d2s_out)
+        return self.decoded
+
+    # -- backward
+    def decode_backward(self, dpre_last, dz, wgrad=True):
+        """dpre_last: gradient w.r.t. the last conv's pre-activation; writes dz (grad of the decoder
+        input code) and the decoder weight gradients."""
+        B = self.B
+        dpre = dpre_last
+        for i in range(len(self.dec) - 1, -1, -1):
+            hw, cin, r, d2s_out, conv = self.dec[i]
+            dd = self.buf.get('dd%d' % i, *d2s_out.shape)
+            conv.backward(dpre, dx=dd, wgrad=wgrad)
+            prod = self.dec[i - 1][4] if i > 0 else self.dec_dense
+            dp = self.buf.get('dp%d' % i, B, hw, hw, cin)
+            ops.space_to_depth_actgrad(dd, prod.y, dp, B, hw, hw, cin, r, prod.act)
+            dpre = dp
+        self.dec_dense.backward(dpre.view(B, 1, 1, -1), dx=dz.view(B, 1, 1, self.C), wgrad=wgrad)
+        return dz
+
+    def encode_backward(self, dz, c_entropy, c_sg):
+        """dz: d loss / d code_sample (already summed over its consumers)."""
+        B, C = self.B, self.C
+        floor = float(self.cfg['latent_variance_precision'])
+        dmean = self.buf.get('dmean', B, C)
+        dstd = self.buf.get('dstd', B, C)
+        ops.gauss_head_bwd(dz, self.mean, self.std, self.eps_z, None, None, dmean, dstd, floor, c_entropy, c_sg)
+        dfeat = self.buf.get('dfeat', B, 1, 1, self.feat)
+        prod = (self.enc_dense.y, LEAKY)
+        self.head_mean.backward(dmean.view(B, 1, 1, C), dx=dfeat, producer=prod)
+        self.head_std.backward(dstd.view(B, 1, 1, C), dx=dfeat, producer=prod, accumulate=True)
+        last = self.enc_convs[-1]
+        dflat = self.buf.get('dflat', B, 1, 1, self.flat)
+        self.enc_dense.backward(dfeat, dx=dflat, producer=(last.y.view(B, 1, 1, self.flat), LEAKY))
+        dpre = dflat.view(*last.y.shape)
+        for i in range(len(self.enc_convs) - 1, 0, -1):
+            c, prev = self.enc_convs[i], self.enc_convs[i - 1]
+            dx = self.buf.get('de%d' % i, *prev.y.shape)
+            c.backward(dpre, dx=dx, producer=(prev.y, LEAKY))
+            dpre = dx
+        self.enc_convs[0].backward(dpre, dx=None)            # no gradient w.r.t. the image
+
+
+# ------------------------------------------------------------------------------ prior ("inner") VAE
+class PriorVAE:
+    """define_inner_VAE_prior (codes/base.py:127-213): two 5-layer MLPs around t."""
+
+    def __init__(self, config, group, B, device):
+        self.cfg, self.group, self.B, self.dev = config, group, B, device
+        C, R = int(config['code_size']), int(config['representation_size'])
+        Hi, nl = int(config['num_hidden_units_inner_VAE']), int(config['n_layers_inner_VAE'])
+        act = config['inner_activation']
+        G = ops.ConvGeom
+        names = ['prior/dense'] + ['prior/dense_%d' % i for i in range(1, 2 * nl + 3)]
+        self.enc = [Conv(group, names[0], G.dense(B, C, Hi), act, device)]
+        self.enc += [Conv(group, names[i], G.dense(B, Hi, Hi), act, device) for i in range(1, nl)]
+        self.head_mean = Conv(group, names[nl], G.dense(B, Hi, R), None, device)
+        self.head_std = Conv(group, names[nl + 1], G.dense(B, Hi, R), None, device)
+        self.dec = [Conv(group, names[nl + 2], G.dense(B, R, Hi), act, device)]
+        self.dec += [Conv(group, names[nl + 2 + i], G.dense(B, Hi, Hi), act, device) for i in range(1, nl)]
+        self.out = Conv(group, names[2 * nl + 2], G.dense(B, Hi, C), None, device)
+        self.C, self.R, self.Hi, self.act = C, R, Hi, act
+        self.mean = self.head_mean.y.view(B, R)
+        self.std = self.head_std.y.view(B, R)
+        self.t = torch.empty(B, R, device=device)
+        self.zhat = self.out.y.view(B, C)
+        self.buf = Buffers(device)
+
+    def forward(self, z, eps_t, stats_t):
+        B = self.B
+        h = z.view(B, 1, 1, self.C)
+        for l in self.enc:
+            h = l.forward(h)
+        self.head_mean.forward(h)
+        self.head_std.forward(h)
+        ops.gauss_head_fwd(self.mean, self.std, eps_t, self.t, float(self.cfg['latent_variance_precision']), stats_t)
+        self.eps_t = eps_t
+        h = self.t.view(B, 1, 1, self.R)
+        for l in self.dec:
+            h = l.forward(h)
+        self.out.forward(h)
+        return self.zhat
+
+    def backward(self, dzhat, dmu_add, dsd_add, c_entropy, c_sg, dz=None, wgrad=True):
+        """dzhat: d loss / d decoded_code.  dmu_add / dsd_add: MC-sample gradients for the t head.
+        If dz is given, the gradient w.r.t. the input code is ACCUMULATED into it."""
+        B = self.B
+        Hi = self.Hi
+        pp = [self.buf.get('dh_a', B, 1, 1, Hi), self.buf.get('dh_b', B, 1, 1, Hi)]
+        cur = 0
+        self.out.backward(dzhat.view(B, 1, 1, self.C), dx=pp[cur], producer=(self.dec[-1].y, self.act), wgrad=wgrad)
+        for i in range(len(self.dec) - 1, 0, -1):
+            self.dec[i].backward(pp[cur], dx=pp[1 - cur], producer=(self.dec[i - 1].y, self.act), wgrad=wgrad)
+            cur = 1 - cur
+        dt = self.buf.get('dt', B, 1, 1, self.R)
+        self.dec[0].backward(pp[cur], dx=dt, wgrad=wgrad)
+        floor = float(self.cfg['latent_variance_precision'])
+        dmean = self.buf.get('dmean', B, self.R)
+        dstd = self.buf.get('dstd', B, self.R)
+        ops.gauss_head_bwd(dt.view(B, self.R), self.mean, self.std, self.eps_t, dmu_add, dsd_add, dmean, dstd, floor,
+                           c_entropy, c_sg)
+        prod = (self.enc[-1].y, self.act)
+        cur = 0
+        self.head_mean.backward(dmean.view(B, 1, 1, self.R), dx=pp[cur], producer=prod, wgrad=wgrad)
+        self.head_std.backward(dstd.view(B, 1, 1, self.R), dx=pp[cur], producer=prod, wgrad=wgrad, accumulate=True)
+        for i in range(len(self.enc) - 1, 0, -1):
+            self.enc[i].backward(pp[cur], dx=pp[1 - cur], producer=(self.enc[i - 1].y, self.act), wgrad=wgrad)
+            cur = 1 - cur
+        if dz is not None:
+            self.enc[0].backward(pp[cur], dx=dz.view(B, 1, 1, self.C), wgrad=wgrad, accumulate=True)
+        else:
+            self.enc[0].backward(pp[cur], dx=None, wgrad=wgrad)
+
+
+# ------------------------------------------------------------------------------ the sub-step engine
+PRIOR_KIND = {'standard_gaussian': 0, 'ours': 1, 'hierarchical': 2}
+
+
+def vae_param_specs(config):
+    """[(name, shape)] of scopes encoder + decoder in graph-creation order; names and shapes are those
+    TF1.15 creates for codes/models.py (pinned by the reference's checkpoint index files)."""
+    exp = config['exp_name']
+    H, C, k = int(config['num_hidden_units']), int(config['code_size']), int(config['kernel_size'])
+    ch = int(config['dim_input_channel'])
+    out = []
+
+    def conv(scope, idx, kk, cin, cout):
+        n = 'conv2d' if idx == 0 else 'conv2d_%d' % idx
+        out.extend([('%s/%s/kernel' % (scope, n), (kk, kk, cin, cout)), ('%s/%s/bias' % (scope, n), (cout,))])
+
+    def dense(scope, name, cin, cout):
+        out.extend([('%s/%s/kernel' % (scope, name), (cin, cout)), ('%s/%s/bias' % (scope, name), (cout,))])
+
+    if exp == 'mnist_digit':
+        for i, (a, b) in enumerate([(1, H // 16), (H // 16, H // 4), (H // 4, H)]):
+            conv('encoder', i, k, a, b)
+        dense('encoder', 'dense', 16 * H, H // 4)
+        dense('encoder', 'code_mean', H // 4, C)
+        dense('encoder', 'code_std_dev', H // 4, C)
+        dense('decoder', 'dense', C, 16 * H)
+        for i, (kk, a, b) in enumerate([(3, H, H), (3, H // 4, H // 4), (3, H // 16, H // 16), (5, H // 64, 1)]):
+            conv('decoder', i, kk, a, b)
+    elif exp == 'mnist_fashion':
+        for i, (a, b) in enumerate([(1, H // 4), (H // 4, H // 4), (H // 4, H // 2), (H // 2, H // 2)]):
+            conv('encoder', i, 3, a, b)
+        dense('encoder', 'dense', 2 * H, H)
+        dense('encoder', 'code_mean', H, C)
+        dense('encoder', 'code_std_dev', H, C)
+        dense('decoder', 'dense', C, H)
+        for i, (kk, a, b) in enumerate([(1, H // 4, H), (3, H // 4, H), (3, H // 4, H), (3, H // 4, H), (5, H // 4, 1)]):
+            conv('decoder', i, kk, a, b)
+    else:
+        raise NotImplementedError('engine: exp_name %r' % exp)
+    return out
+
+
+def prior_param_specs(config):
+    """[(name, shape)] of scope prior (codes/base.py:141-186), creation order."""
+    C, R = int(config['code_size']), int(config['representation_size'])
+    Hi, nl = int(config['num_hidden_units_inner_VAE']), int(config['n_layers_inner_VAE'])
+    dims = [(C, Hi)] + [(Hi, Hi)] * (nl - 1) + [(Hi, R), (Hi, R), (R, Hi)] + [(Hi, Hi)] * (nl - 1) + [(Hi, C)]
+    out = []
+    for i, (a, b) in enumerate(dims):
+        n = 'dense' if i == 0 else 'dense_%d' % i
+        out.extend([('prior/%s/kernel' % n, (a, b)), ('prior/%s/bias' % n, (b,))])
+    return out
+
+
+class LadderEngine:
+    """All four sub-steps of one reference training iteration for a fixed batch size."""
+
+    def __init__(self, config, batch_size, device='cuda', seed=0, dist_group=None):
+        self.cfg = config
+        self.B = B = int(batch_size)
+        self.dev = torch.device(device)
+        self.prior = config['prior']
+        if self.prior not in PRIOR_KIND:
+            raise NotImplementedError("prior=%r is not built yet (supported: %s)" % (self.prior, sorted(PRIOR_KIND)))
+        self.has_prior = self.prior in ('ours', 'hierarchical')
+        self.C, self.R = int(config['code_size']), int(config['representation_size'])
+        self.L, self.K = int(config['n_MC_samples']), int(config['n_mixtures'])
+        self.D_in = int(config['dim_input_x']) * int(config['dim_input_y']) * int(config['dim_input_channel'])
+        self.dist = dist_group
+        self.world = 1
+        if dist_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(dist_group)
+        self.B_global = B * self.world
+        dev = self.dev
+        # optimiser groups (base.py:415-455, 457-511)
+        self.ae = ParamGroup('ae', vae_param_specs(config), dev)
+        self.sigma = ParamGroup('sigma', [('sigma/Variable', ())], dev)
+        self.groups = {'ae': self.ae, 'sigma': self.sigma}
+        if self.has_prior:
+            self.prior_g = ParamGroup('prior', prior_param_specs(config), dev)
+            self.inner_sigma = ParamGroup('inner_sigma', [('inner_sigma/Variable', ())], dev)
+            self.groups.update(prior=self.prior_g, inner_sigma=self.inner_sigma)
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(seed)
+        self.init_params()
+        self.outer = MnistOuterVAE(config, self.ae, B, dev)
+        self.pvae = PriorVAE(config, self.prior_g, B, dev) if self.has_prior else None
+        self.scalars = torch.zeros(ops.SCALARS_LEN, device=dev)
+        self.eps_z = torch.zeros(B, self.C, device=dev)
+        self.dz = torch.zeros(B, self.C, device=dev)
+        self.dpre_last = torch.empty_like(self.outer.decoded)
+        if self.has_prior:
+            self.eps_t = torch.zeros(B, self.R, device=dev)
+            self.dzhat = torch.empty(B, self.C, device=dev)
+        if self.prior == 'ours':
+            self.eps_mc = torch.zeros(self.L, B, self.R, device=dev)
+            self.t_mc = torch.empty(self.L * B, self.R, device=dev)
+            self.g_mc = torch.empty(self.L * B, self.R, device=dev)
+            self.logp_mc = torch.empty(self.L * B, device=dev)
+            self.dmu_add = torch.empty(B, self.R, device=dev)
+            self.dsd_add = torch.empty(B, self.R, device=dev)
+            self.mixture = None
+        self.use_sg = self.prior == 'standard_gaussian'
+        self.use_mask = False
+
+    # ---- parameters
+    def init_params(self):
+        for g in self.groups.values():
+            for name, shape in g.specs:
+                t = g.p(name)
+                if name == 'sigma/Variable':
+                    t.fill_(float(self.cfg['sigma']))
+                elif name == 'inner_sigma/Variable':
+                    t.fill_(float(self.cfg['inner_sigma']))
+                elif name.endswith('/kernel'):
+                    glorot_uniform_(t, shape, self.gen)
+                else:
+                    t.zero_()
+
+    def named_parameters(self):
+        for g in self.groups.values():
+            for name in g.names():
+                yield name, g.p(name)
+
+    def named_gradients(self):
+        for g in self.groups.values():
+            for name in g.names():
+                yield name, g.g(name)
+
+    def load_parameters(self, params):
+        """params: {name: array-like}; unknown names raise."""
+        mine = dict(self.named_parameters())
+        for k, v in params.items():
+            if k not in mine:
+                raise KeyError('unknown parameter %r' % k)
+            mine[k].copy_(torch.as_tensor(np.asarray(v), dtype=torch.float32).reshape(mine[k].shape))
+
+    # ---- feeds (codes/base.py:862-942 values arrive here)
+    def set_feeds(self, prior_mean=None, prior_cov=None, prior_weight=None, use_standard_gaussian_prior=None,
+                  use_mask=None):
+        if prior_mean is not None:
+            self.mixture = ops.mixture_pack_full(prior_mean, prior_cov, prior_weight, self.dev)
+        if use_standard_gaussian_prior is not None:
+            self.use_sg = bool(use_standard_gaussian_prior) or self.prior == 'standard_gaussian'
+        if use_mask is not None:
+            self.use_mask = bool(use_mask)
+
+    def set_lrs(self, lr_ae=None, lr_sigma=None, lr_prior=None, lr_inner_sigma=None):
+        for g, lr in ((self.ae, lr_ae), (self.sigma, lr_sigma), (getattr(self, 'prior_g', None), lr_prior),
+                      (getattr(self, 'inner_sigma', None), lr_inner_sigma)):
+            if g is not None and lr is not None:
+                g.lr.fill_(float(lr))
+
+    def draw_noise(self, z=True, t=True, mc=True):
+        """Fresh standard-normal noise for one sess.run (K8: tfd sample() draws)."""
+        if z:
+            self.eps_z.normal_(generator=self.gen)
+        if t and self.has_prior:
+            self.eps_t.normal_(generator=self.gen)
+        if mc and self.prior == 'ours':
+            self.eps_mc.normal_(generator=self.gen)
+
+    def set_noise(self, eps_z=None, eps_t=None, eps_mc=None):
+        for dst, src in ((self.eps_z, eps_z), (getattr(self, 'eps_t', None), eps_t), (getattr(self, 'eps_mc', None), eps_mc)):
+            if src is not None and dst is not None:
+                dst.copy_(torch.as_tensor(np.asarray(src), dtype=torch.float32).reshape(dst.shape))
+
+    # ---- forward
+    def _allreduce(self, t):
+        if self.dist is not None and self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.dist)
+
+    def forward(self, x, dec=True, prior=True, mix=True):
+        """One forward pass; fills self.scalars with the ELBO terms of the GLOBAL batch."""
+        s = self.scalars
+        s[:16].zero_()
+        z = self.outer.encode(x, self.eps_z, s[0:3])
+        if dec:
+            xhat = self.outer.decode(z)
+            ops.l1_recon_fwd(x, xhat, s)
+        kind = 0
+        if self.has_prior and prior:
+            kind = PRIOR_KIND[self.prior]
+            zhat = self.pvae.forward(z, self.eps_t, s[3:6])
+            ops.code_recon_fwd(z, zhat, self.outer.std, self.use_mask and self.prior == 'ours', s)
+            if self.prior == 'ours' and mix:
+                if self.mixture is None:
+                    raise RuntimeError('engine: mixture feeds (prior_mean/prior_cov/prior_weight) were never set')
+                ops.mc_sample(self.pvae.mean, self.pvae.std, self.eps_mc, self.t_mc)
+                ops.mixture_logprob(self.t_mc, self.mixture, want_grad=True,
+                                    out={'logp': self.logp_mc, 'grad': self.g_mc})
+                ops.sum_into(self.logp_mc, s[11:12])
+        self._allreduce(s[:12])            # batch-global sums (sigma, means) across data-parallel ranks
+        cfg = self.cfg
+        takes_max = cfg['exp_name'] == 'celeba' or int(cfg['TRAIN_sigma']) == 1
+        ops.elbo_scalars(s, self.sigma.param, self.inner_sigma.param if self.has_prior else None, self.B_global, self.C,
+                         self.R, self.R if self.prior != 'hierarchical' else 2, self.D_in,
+                         self.L * self.B_global, takes_max, int(cfg.get('TRAIN_inner_sigma', 0)) == 1,
+                         float(cfg.get('inner_sigma_lb', 0.0)), float(cfg.get('inner_sigma_ub', 1.0)), kind,
+                         self.use_sg)
+        return s
+
+    # ---- backward pieces
+    def _prior_backward(self, dz, wgrad):
+        Bg = self.B_global
+        ops.code_recon_bwd(self.outer.z, self.pvae.zhat, self.outer.std, self.use_mask and self.prior == 'ours',
+                           self.scalars, 1.0, self.dzhat, dz, dz is not None)
+        if self.prior == 'ours':
+            ops.mc_reduce(self.g_mc, self.eps_mc, -1.0 / (self.L * Bg), self.dmu_add, self.dsd_add)
+            self.pvae.backward(self.dzhat, self.dmu_add, self.dsd_add, -1.0 / Bg, 0.0, dz=dz, wgrad=wgrad)
+        else:
+            self.pvae.backward(self.dzhat, None, None, -1.0 / Bg, 1.0 / Bg, dz=dz, wgrad=wgrad)
+
+    # ---- the four sess.run equivalents (codes/base.py:583-641)
+    def step_ae(self, x, apply=True):
+        """train_step_ae: forward everything, d loss_ae / d (encoder, decoder), clip + Adam."""
+        self.forward(x, dec=True, prior=True, mix=True)
+        ops.l1_recon_bwd(x, self.outer.decoded, self.scalars, self.dpre_last, 'relu')
+        self.outer.decode_backward(self.dpre_last, self.dz)
+        if self.has_prior and not self.use_sg:
+            self._prior_backward(self.dz, wgrad=False)
+        Bg = self.B_global
+        self.outer.encode_backward(self.dz, -1.0 / Bg, (1.0 / Bg) if self.use_sg else 0.0)
+        self._allreduce(self.ae.grad)
+        if apply:
+            self.ae.apply_adam()
+
+    def step_sigma(self, x, apply=True):
+        """train_step_sigma: fresh forward of encoder + decoder, gradient of the one sigma scalar."""
+        self.forward(x, dec=True, prior=False, mix=False)
+        if apply:
+            self.sigma.apply_adam(self.scalars[ops.CF['DSIGMA']:ops.CF['DSIGMA'] + 1])
+
+    def step_prior(self, x, apply=True):
+        """train_step_prior: d(-elbo_prior) / d scope 'prior' only (base.py:479)."""
+        self.forward(x, dec=False, prior=True, mix=True)
+        self._prior_backward(None, wgrad=True)
+        self._allreduce(self.prior_g.grad)
+        if apply:
+            self.prior_g.apply_adam()
+
+    def step_inner_sigma(self, x, apply=True):
+        """train_step_inner_sigma (base.py:636-639)."""
+        self.forward(x, dec=False, prior=True, mix=False)
+        if apply:
+            self.inner_sigma.apply_adam(self.scalars[ops.CF['DINNER_SIGMA']:ops.CF['DINNER_SIGMA'] + 1])
+
+    def fetch(self, names):
+        """Device->host read of named ELBO terms (reference attribute names)."""
+        vals = self.scalars.cpu().numpy()
+        return {n: float(vals[ops.O[n]]) for n in names}

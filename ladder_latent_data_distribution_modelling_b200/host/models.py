@@ -1,0 +1,196 @@
+"""Model classes with the reference's names and attributes (codes/models.py, codes/base.py:32-517).
+
+In the reference a model object IS the TF graph: placeholders, tensors and train ops as
+attributes.  Here the object owns a `LadderEngine` (sm_100a kernels); the reference's tensor
+attributes (`code_mean`, `decoded`, `elbo`, ...) are Python properties that return the device
+tensors / scalars of the most recent forward pass, and the four train ops are methods on the
+engine.  `GM_prior_training` is the same scikit-learn object the reference builds
+(codes/base.py:93-106); its fitted parameters enter through `engine.set_feeds`, exactly like
+the `prior_mean / prior_cov / prior_weight` placeholder feeds.
+"""
+import os
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..engine import LadderEngine
+from .utils import count_trainable_variables
+
+
+class BatchIterator:
+    """Stand-in for the tf.data pipeline of define_iterator (codes/models.py:26-40): the whole
+    image set lives on the device, `initializer` reshuffles it with the epoch seed and `get_next`
+    returns consecutive batches, repeating for ever (`repeat(8000)`, drop_remainder=True)."""
+
+    def __init__(self, batch_size, device):
+        self.B, self.dev = batch_size, device
+        self.data = None
+        self.perm = None
+        self.pos = 0
+        self._src_id = None
+
+    def initializer(self, images, seed):
+        if self._src_id != id(images):
+            self.data = torch.as_tensor(np.asarray(images), dtype=torch.float32).to(self.dev).contiguous()
+            self._src_id = id(images)
+        g = torch.Generator()
+        g.manual_seed(int(seed))
+        self.perm = torch.randperm(self.data.shape[0], generator=g).to(self.dev)
+        self.pos = 0
+
+    def get_next(self):
+        n = self.data.shape[0]
+        if self.pos + self.B > n:          # next pass of the repeated, reshuffled stream
+            self.pos = 0
+        idx = self.perm[self.pos:self.pos + self.B]
+        self.pos += self.B
+        return self.data.index_select(0, idx)
+
+
+class BaseModel:
+    """Shared graph pieces: priors, loss, variable groups, optimisers, savers (base.py:32-517)."""
+
+    def __init__(self, config, device=None, dist_group=None):
+        self.config = config
+        self.device = torch.device(device if device is not None else 'cuda')
+        self.two_pi = 2 * np.pi
+        self.engine = LadderEngine(config, int(config['batch_size']), self.device, seed=int(config.get('seed', 0)),
+                                   dist_group=dist_group)
+        self.define_iterator()
+        if config['prior'] in ('ours', 'GMM'):
+            self.define_GM_prior()
+        self.training_variables()
+        self.init_saver()
+
+    # -- iterator (models.py:26-44)
+    def define_iterator(self):
+        self.iterator = BatchIterator(int(self.config['batch_size']), self.device)
+
+    @property
+    def input_image(self):
+        return self.iterator.get_next()
+
+    # -- hyper-prior (base.py:88-124)
+    def define_GM_prior(self):
+        from sklearn.mixture import BayesianGaussianMixture, GaussianMixture
+        n_mixtures = self.config['n_mixtures']
+        if self.config['prior'] == 'ours':
+            self.GM_prior_training = BayesianGaussianMixture(
+                n_components=n_mixtures, covariance_type='full', max_iter=1000, n_init=1,
+                weight_concentration_prior_type='dirichlet_distribution', weight_concentration_prior=0.1,
+                warm_start=True)
+        else:
+            self.GM_prior_training = GaussianMixture(n_components=n_mixtures, covariance_type='full', max_iter=1000,
+                                                     n_init=1, warm_start=True)
+
+    def prior_GM_log_prob(self, samples):
+        """`prior_GM_tf.log_prob(samples)` for the currently fed mixture; samples [..., D] (device)."""
+        t = samples.reshape(-1, samples.shape[-1]).contiguous().float()
+        return ops.mixture_logprob(t, self.engine.mixture).reshape(samples.shape[:-1])
+
+    # -- variable groups and counts (base.py:415-455)
+    def training_variables(self):
+        self.num_encoder = count_trainable_variables(self, 'encoder')
+        self.num_decoder = count_trainable_variables(self, 'decoder')
+        self.num_sigma = count_trainable_variables(self, 'sigma')
+        if self.config['prior'] in ('ours', 'hierarchical', 'vampPrior'):
+            self.num_prior_ae = count_trainable_variables(self, 'prior')
+            self.num_prior_sigma = count_trainable_variables(self, 'inner_sigma') \
+                if self.config['prior'] in ('ours', 'hierarchical') else 0
+        else:
+            self.num_prior_ae = self.num_prior_sigma = 0
+        self.num_para_list = [self.num_encoder, self.num_decoder, self.num_sigma, self.num_prior_ae,
+                              self.num_prior_sigma]
+        print("Total number of trainable parameters in VAE network is:\n{}k\n".format(
+            np.around(sum(self.num_para_list) / 1000, 2)))
+
+    # -- checkpoints (base.py:37-85): two files, trainable variables only, reference variable names
+    def init_saver(self):
+        self.saver_path_ae = os.path.join(self.config['checkpoint_dir'], 'vae-model') \
+            if 'checkpoint_dir' in self.config else None
+        self.saver_path_prior = os.path.join(self.config['checkpoint_dir'], 'prior-model') \
+            if 'checkpoint_dir' in self.config else None
+
+    def _group_arrays(self, groups):
+        out = {}
+        for g in groups:
+            for n in g.names():
+                out[n] = g.p(n).detach().cpu().numpy()
+        return out
+
+    def _save(self, path, groups):
+        np.savez(path + '.npz', **{k.replace('/', '__'): v for k, v in self._group_arrays(groups).items()})
+        with open(path + '.meta', 'w') as f:      # the reference's restore test is isfile('<path>.meta')
+            f.write('ladder_b200 checkpoint: trainable variables in %s.npz\n' % os.path.basename(path))
+
+    def _load(self, path):
+        d = np.load(path + '.npz')
+        self.engine.load_parameters({k.replace('__', '/'): d[k] for k in d.files})
+
+    def save(self, sess, model):
+        print("Saving model...")
+        e = self.engine
+        if model == "VAE" or (model == "joint" and self.config['TRAIN_VAE'] == 1):
+            self._save(self.saver_path_ae, [e.ae, e.sigma])
+            print("Outer VAE model saved.")
+        if e.has_prior and (model == "prior" or (model == "joint" and self.config['TRAIN_prior'] == 1)):
+            self._save(self.saver_path_prior, [e.prior_g, e.inner_sigma])
+            print("Prior model saved.")
+
+    def load(self, sess, model):
+        print("\ncheckpoint_dir to be loaded:\n{}\n".format(self.config['checkpoint_dir']))
+        if model == "VAE":
+            if os.path.isfile(self.saver_path_ae + '.meta'):
+                self._load(self.saver_path_ae)
+                print("Outer VAE model loaded.")
+            else:
+                print("No outer VAE model found. No VAE model loaded.")
+        elif model == "prior":
+            if os.path.isfile(self.saver_path_prior + '.meta'):
+                self._load(self.saver_path_prior)
+                print("Prior model loaded.")
+            else:
+                print("No prior model found. No prior model loaded.")
+
+    # -- tensors of the last forward pass, under the reference's attribute names
+    def _scalar(self, name):
+        return self.engine.scalars[ops.O[name]]
+
+    @property
+    def code_mean(self): return self.engine.outer.mean
+    @property
+    def code_std_dev(self): return self.engine.outer.std
+    @property
+    def code_sample(self): return self.engine.outer.z
+    @property
+    def decoded(self): return self.engine.outer.decoded
+    @property
+    def representation_mean(self): return self.engine.pvae.mean
+    @property
+    def representation_std_dev(self): return self.engine.pvae.std
+    @property
+    def representation_sample(self): return self.engine.pvae.t
+    @property
+    def decoded_code(self): return self.engine.pvae.zhat
+    @property
+    def std_dev_code(self): return self.engine.outer.std.mean(dim=0)
+    @property
+    def std_dev_representation(self): return self.engine.pvae.std.mean(dim=0)
+
+
+for _name in ops.O:       # elbo, loss_ae, entropy_z, sigma, inner_sigma, ... as scalar properties
+    setattr(BaseModel, _name, property(lambda self, _n=_name: self._scalar(_n)))
+BaseModel.negative_elbo = property(lambda self: self._scalar('loss_ae'))
+
+
+class MNISTModel_digit(BaseModel):
+    """codes/models.py:10-160"""
+
+
+class MNISTModel_fashion(BaseModel):
+    """codes/models.py:163-327"""
+
+
+class CelebAModel_densenet(BaseModel):
+    """codes/models.py:330-598"""

@@ -19,6 +19,7 @@ stream_t = C.c_void_p
 SIGNATURES = {
     'ladder_version': (C.c_int, []),
     'ladder_last_error': (C.c_char_p, []),
+    'ladder_launch_count': (C.c_ulonglong, []),
     'ladder_device_check': (C.c_int, [C.c_int]),
     'ladder_mixture_table_stride': (C.c_int, [C.c_int, C.c_int]),
     'ladder_mixture_pack_full': (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, c_float_p, c_float_p]),

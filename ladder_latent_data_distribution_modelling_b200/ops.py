@@ -147,6 +147,11 @@ def mixture_combine(m_parts, s_parts, g_parts=None):
     return (logp, grad) if g_parts is not None else logp
 
 
+def launch_count():
+    """Kernels enqueued by libladder_sm100 so far in this process."""
+    return int(_L().ladder_launch_count())
+
+
 def pipe_peak(kind, blocks, iters):
     """Launch the pipe-saturation diagnostic (kind 0 FFMA, 1 MUFU.EX2); returns op count."""
     out = _workspace(torch.device('cuda', torch.cuda.current_device()), 256, 'pipe')
