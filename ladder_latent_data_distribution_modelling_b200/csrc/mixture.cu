@@ -400,7 +400,7 @@ static MixPlan mix_plan(long long N, int K, int D, int mode, bool grad) {
   // tuning knobs (benchmark sweeps only): CTAs per SM the grid should cover, rows per thread
   static const int env_ctas = getenv("LADDER_MIX_CTAS_PER_SM") ? atoi(getenv("LADDER_MIX_CTAS_PER_SM")) : 16;
   static const int env_r = getenv("LADDER_MIX_R") ? atoi(getenv("LADDER_MIX_R")) : 0;
-  if (env_r == 1 || env_r == 2 || (env_r == 4 && D <= 2)) p.R = env_r;
+  if (env_r == 1 || env_r == 2 || ((env_r == 4 || env_r == 8) && D <= 2)) p.R = env_r;
   p.kc = 8192 / stride;                  // <= 32 KB per stage
   if (p.kc > 256) p.kc = 256;          // 2 stages x 16 CTAs/SM must fit shared memory
   if (p.kc > K) p.kc = K > 0 ? K : 1;
@@ -435,6 +435,7 @@ static int mix_launch_r(const MixArgs& a, const MixPlan& p, cudaStream_t st) {
 
 template <int D, int MODE, bool GRAD>
 static int mix_launch(const MixArgs& a, const MixPlan& p, cudaStream_t st) {
+  if constexpr (D <= 2) { if (p.R == 8) return mix_launch_r<D, MODE, 8, GRAD>(a, p, st); }
   if constexpr (D <= 2) { if (p.R == 4) return mix_launch_r<D, MODE, 4, GRAD>(a, p, st); }
   if constexpr (D <= 8) { if (p.R == 2) return mix_launch_r<D, MODE, 2, GRAD>(a, p, st); }
   return mix_launch_r<D, MODE, 1, GRAD>(a, p, st);
