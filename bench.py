@@ -233,7 +233,9 @@ def run_ours(args):
     # ---- end-to-end through the reference-facing API with HOST buffers (e2e)
     cfg2 = dict(cfg)
     cfg2['checkpoint_dir'] = cfg2['result_dir'] = tempfile.mkdtemp() + '/'
-    model = MNISTModel_fashion(cfg2, device=dev, dist_group=group)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # keep stdout to the single JSON line
+        model = MNISTModel_fashion(cfg2, device=dev, dist_group=group)
     if world > 1:
         for g in model.engine.groups.values():
             dist.broadcast(g.param, 0)

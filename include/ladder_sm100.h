@@ -79,9 +79,12 @@ int ladder_mixture_combine(const float* m_parts, const float* s_parts, const flo
  * layer is H=W=KH=KW=OH=OW=1, stride 1, no padding.
  * replaces: tf.layers.conv2d / tf.layers.dense and their gradients -- codes/models.py:51-76,
  *           109-148, 203-234, 267-315, 398-460, 478-587; codes/base.py:145-200; modules.py:8. */
+/* scratch needed by fprop / wgrad of this geometry (0 for most layers; single-output-channel
+ * KHxKW convs are evaluated as tap-GEMMs and stage a [B*H*W, KH*KW] fp32 matrix).          */
+size_t ladder_conv2d_workspace_bytes(int B, int H, int W, int Cin, int KH, int KW, int Cout);
 int ladder_conv2d_fprop(const float* x, const float* w, const float* bias /*nullable*/, float* y, int B, int H,
                         int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH,
-                        int OW, int act, cudaStream_t stream);
+                        int OW, int act, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* dx = conv_transpose(dy, w) [* act'(act_out) if act_out != NULL: fuses the activation
  * backward of the layer that PRODUCED x]; accumulate != 0 adds into dx.                   */
 int ladder_conv2d_dgrad(const float* dy, const float* w, const float* act_out /*nullable*/, float* dx, int B,
@@ -90,7 +93,7 @@ int ladder_conv2d_dgrad(const float* dy, const float* w, const float* act_out /*
 /* dw [KH,KW,Cin,Cout] (overwritten) and, if dbias != NULL, dbias [Cout] = column sums of dy. */
 int ladder_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias /*nullable*/, int B, int H, int W,
                         int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW,
-                        cudaStream_t stream);
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Layout ops.  replaces tf.pad(..., "SYMMETRIC") codes/models.py:48-50,200-202 and

@@ -324,6 +324,61 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g
   }
 }
 
+
+// ---------------------------------------------------------------- single-output-channel convs as tap-GEMMs
+// A KHxKW conv with Cout == 1 (the MNIST decoders' last layer) is decomposed as
+//   Z[p_in, tap] = sum_c x[p_in, c] * w[tap, c]        (dense GEMM over the INPUT pixels)
+//   y[p_out]     = act(bias + sum_tap Z[p_out + tap, tap])
+// and its weight gradient as  dw[tap, c] = sum_{p_in} DYS[p_in, tap] * x[p_in, c]  with
+// DYS[p_in, tap] = dy[p_in - tap] -- so both ride on the tiled GEMM instead of a warp-per-pixel loop.
+__global__ void tap_sum_kernel(const float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ y, ConvArgs a) {
+  const long long pixels = (long long)a.B * a.OH * a.OW;
+  const int T = a.KH * a.KW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % a.OW);
+    long long r = p / a.OW;
+    const int oy = (int)(r % a.OH);
+    const int b = (int)(r / a.OH);
+    float acc = bias != nullptr ? __ldg(bias) : 0.f;
+    for (int kh = 0; kh < a.KH; ++kh) {
+      const int iy = oy * a.stride - a.pad_t + kh;
+      if (iy < 0 || iy >= a.H) continue;
+      for (int kw = 0; kw < a.KW; ++kw) {
+        const int ix = ox * a.stride - a.pad_l + kw;
+        if (ix < 0 || ix >= a.W) continue;
+        acc += __ldg(z + (((long long)b * a.H + iy) * a.W + ix) * T + kh * a.KW + kw);
+      }
+    }
+    y[p] = act_apply(acc, a.act);
+  }
+}
+
+__global__ void tap_scatter_kernel(const float* __restrict__ dy, float* __restrict__ dys, ConvArgs a) {
+  const int T = a.KH * a.KW;
+  const long long n = (long long)a.B * a.H * a.W * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % T);
+    long long r = i / T;
+    const int ix = (int)(r % a.W); r /= a.W;
+    const int iy = (int)(r % a.H);
+    const int b = (int)(r / a.H);
+    int ny = iy + a.pad_t - tap / a.KW, nx = ix + a.pad_l - tap % a.KW;
+    float v = 0.f;
+    if (ny >= 0 && nx >= 0 && ny % a.stride == 0 && nx % a.stride == 0) {
+      ny /= a.stride; nx /= a.stride;
+      if (ny < a.OH && nx < a.OW) v = __ldg(dy + ((long long)b * a.OH + ny) * a.OW + nx);
+    }
+    dys[i] = v;
+  }
+}
+
+static bool use_tap_gemm(const ConvArgs& a) { return a.Cout == 1 && a.KH * a.KW > 1 && a.Cin >= 4; }
+
+static ConvArgs dense_view(const float* src, const float* wgt, float* out, long long rows, int cin, int cout) {
+  ConvArgs d{src, wgt, nullptr, nullptr, out, (int)rows, 1, 1, cin, 1, 1, cout, 1, 0, 0, 1, 1, 0, 0, 0};
+  return d;
+}
+
 static int validate(const ConvArgs& a, const char* what) {
   if (a.B < 1 || a.H < 1 || a.W < 1 || a.Cin < 1 || a.Cout < 1 || a.KH < 1 || a.KW < 1 || a.stride < 1 ||
       a.OH < 1 || a.OW < 1 || a.pad_t < 0 || a.pad_l < 0)
@@ -343,14 +398,34 @@ using namespace ladder;
 
 extern "C" {
 
+size_t ladder_conv2d_workspace_bytes(int B, int H, int W, int Cin, int KH, int KW, int Cout) {
+  ConvArgs a{};
+  a.Cin = Cin; a.KH = KH; a.KW = KW; a.Cout = Cout;
+  return use_tap_gemm(a) ? (size_t)B * H * W * KH * KW * sizeof(float) : 0;
+}
+
 int ladder_conv2d_fprop(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
                         int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
-                        cudaStream_t stream) {
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   ConvArgs a{x, w, bias, nullptr, y, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, act, 0, 0};
   int rc = validate(a, "conv2d_fprop");
   if (rc) return rc;
   const long long pixels = (long long)B * OH * OW;
-  if (Cout <= 4) {
+  if (use_tap_gemm(a)) {
+    const long long p_in = (long long)B * H * W;
+    const int T = KH * KW;
+    if (workspace == nullptr || workspace_bytes < (size_t)p_in * T * sizeof(float))
+      return fail(LADDER_ERR_WORKSPACE, "conv2d_fprop: workspace %zu < %zu bytes", workspace_bytes, (size_t)p_in * T * sizeof(float));
+    float* z = static_cast<float*>(workspace);
+    ConvArgs d = dense_view(x, w, z, p_in, T, Cin);            // Z = X * W^T via the transposed-B (dgrad) gather
+    dim3 grid((unsigned)ceil_div64(p_in, BM), (unsigned)ceil_div(T, BN));
+    igemm_kernel<DGRAD><<<grid, NT, 0, stream>>>(d);
+    rc = check_launch("conv2d_fprop tap gemm");
+    if (rc) return rc;
+    long long blocks = ceil_div64(pixels, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tap_sum_kernel<<<(unsigned)blocks, 256, 0, stream>>>(z, bias, y, a);
+  } else if (Cout <= 4) {
     thin_fprop_kernel<<<(unsigned)ceil_div64(pixels, 8), 256, 0, stream>>>(a);
   } else {
     dim3 grid((unsigned)ceil_div64(pixels, BM), (unsigned)ceil_div(Cout, BN));
@@ -372,7 +447,7 @@ int ladder_conv2d_dgrad(const float* dy, const float* w, const float* act_out, f
 
 int ladder_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cin,
                         int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW,
-                        cudaStream_t stream) {
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   ConvArgs a{x, dy, nullptr, nullptr, dw, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, 0, 0, 0};
   int rc = validate(a, "conv2d_wgrad");
   if (rc) return rc;
@@ -381,7 +456,27 @@ int ladder_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias
   const int sms = num_sms();
   cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)patch * Cout * sizeof(float), stream);
   if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "conv2d_wgrad memset: %s", cudaGetErrorString(e));
-  if (Cout <= 4) {
+  if (use_tap_gemm(a)) {
+    const long long p_in = (long long)B * H * W;
+    const int T = KH * KW;
+    if (workspace == nullptr || workspace_bytes < (size_t)p_in * T * sizeof(float))
+      return fail(LADDER_ERR_WORKSPACE, "conv2d_wgrad: workspace %zu < %zu bytes", workspace_bytes, (size_t)p_in * T * sizeof(float));
+    float* dys = static_cast<float*>(workspace);
+    long long blocks = ceil_div64(p_in * T, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tap_scatter_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dy, dys, a);
+    rc = check_launch("conv2d_wgrad tap scatter");
+    if (rc) return rc;
+    ConvArgs d = dense_view(dys, x, dw, p_in, T, Cin);         // dw[tap, c] = DYS^T * X
+    const int gx = ceil_div(T, BM), gy = ceil_div(Cin, BN);
+    long long splits = ceil_div64(2LL * sms, (long long)gx * gy);
+    const long long max_splits = ceil_div64(p_in, 4 * BK);
+    if (splits > max_splits) splits = max_splits;
+    long long per = ceil_div64(ceil_div64(p_in, splits), BK) * BK;
+    d.m_per_split = (int)per;
+    dim3 grid(gx, gy, (unsigned)ceil_div64(p_in, per));
+    igemm_kernel<WGRAD><<<grid, NT, 0, stream>>>(d);
+  } else if (Cout <= 4) {
     const int gx = ceil_div(patch, 256);
     long long splits = ceil_div64(4LL * sms, gx);
     if (splits > pixels) splits = pixels;

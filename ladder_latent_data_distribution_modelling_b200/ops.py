@@ -202,9 +202,18 @@ class ConvGeom:
                 self.OH, self.OW)
 
 
+def _conv_ws(x, g):
+    n = _L().ladder_conv2d_workspace_bytes(g.B, g.H, g.W, g.Cin, g.KH, g.KW, g.Cout)
+    if n == 0:
+        return None, 0
+    ws = _workspace(x.device, n, 'conv')
+    return ws, ws.numel()
+
+
 def conv2d_fprop(x, w, bias, y, g, act=None):
-    _lib.check(_L().ladder_conv2d_fprop(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(_f32(y)), *g.args(), ACT[act], _stream()),
-               'conv2d_fprop')
+    ws, n = _conv_ws(x, g)
+    _lib.check(_L().ladder_conv2d_fprop(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(_f32(y)), *g.args(), ACT[act],
+                                        _p(ws), n, _stream()), 'conv2d_fprop')
     return y
 
 
@@ -215,8 +224,9 @@ def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False):
 
 
 def conv2d_wgrad(x, dy, dw, dbias, g):
-    _lib.check(_L().ladder_conv2d_wgrad(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dw)), _p(dbias), *g.args(), _stream()),
-               'conv2d_wgrad')
+    ws, n = _conv_ws(x, g)
+    _lib.check(_L().ladder_conv2d_wgrad(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dw)), _p(dbias), *g.args(), _p(ws), n,
+                                        _stream()), 'conv2d_wgrad')
     return dw
 
 
