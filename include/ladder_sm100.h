@@ -95,6 +95,24 @@ int ladder_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias
                         int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+int ladder_colsum(const float* g, long long rows, int cols, float* out, cudaStream_t stream);
+
+/* bf16 tensor-core (tcgen05.mma, TMEM accumulators) versions of the three conv/dense GEMMs:
+ * same geometry arguments and fp32 NHWC / HWIO tensors in HBM; operands are converted to bf16
+ * while being staged into shared memory, accumulation is fp32.  `workspace` receives the
+ * per-call bf16 K-major repack of the weights (ladder_conv2d_tc_workspace_bytes).  wgrad_tc
+ * overwrites dw; the bias gradient is ladder_colsum(dy).                                   */
+size_t ladder_conv2d_tc_workspace_bytes(int B, int H, int W, int Cin, int KH, int KW, int Cout);
+int ladder_conv2d_fprop_tc(const float* x, const float* w, const float* bias /*nullable*/, float* y, int B, int H,
+                           int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH,
+                           int OW, int act, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int ladder_conv2d_dgrad_tc(const float* dy, const float* w, const float* act_out /*nullable*/, float* dx, int B,
+                           int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l,
+                           int OH, int OW, int act, int accumulate, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream);
+int ladder_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int KH, int KW,
+                           int Cout, int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Layout ops.  replaces tf.pad(..., "SYMMETRIC") codes/models.py:48-50,200-202 and
  * tf.nn.depth_to_space (NHWC, DCR order) codes/models.py:113-141,271-308.                  */

@@ -511,4 +511,19 @@ int ladder_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias
   return rc;
 }
 
+// out[c] = sum_r g[r, c]  (bias gradient of a conv / dense layer whose dy is g)
+int ladder_colsum(const float* g, long long rows, int cols, float* out, cudaStream_t stream) {
+  LADDER_REQUIRE(g && out && rows >= 0 && cols > 0, "colsum: bad arguments");
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), stream);
+  if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "colsum memset: %s", cudaGetErrorString(e));
+  if (rows == 0) return LADDER_OK;
+  const int gx = ceil_div(cols, 32);
+  long long blocks = ceil_div64(2LL * num_sms(), gx);
+  long long per = ceil_div64(rows, blocks);
+  if (per < 64) per = 64;
+  dim3 grid(gx, (unsigned)ceil_div64(rows, per));
+  colsum_kernel<<<grid, 256, 0, stream>>>(g, rows, cols, per, out);
+  return check_launch("colsum");
+}
+
 }  // extern "C"

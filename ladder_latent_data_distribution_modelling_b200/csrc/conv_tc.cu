@@ -1,0 +1,510 @@
+// K1/K2 on the 5th-generation tensor cores: conv2d / dense as implicit GEMM with tcgen05.mma.
+//
+// Same three gather modes and the same C-ABI geometry as conv_igemm.cu (fp32 SIMT), but the
+// mainloop is  D[tmem] += A[smem] * B[smem]  in bf16 with fp32 accumulation in TMEM:
+//
+//   * 4 producer warps gather the A operand (im2col rows for FPROP/DGRAD, transposed patch
+//     columns for WGRAD) straight from the fp32 NHWC activations, convert to bf16 in registers
+//     and store into the canonical K-major SWIZZLE_128B shared-memory layout (16-byte chunk
+//     index XOR row&7) -- TF padding, stride, zero-insertion for strided dgrad all resolved in
+//     the gather, so no im2col matrix and no bf16 copy of the activations ever exists in HBM.
+//     The B operand is the per-call bf16 K-major repack of the weights (FPROP/DGRAD) or the
+//     transposed dy tile (WGRAD).
+//   * generic-proxy stores are published to the async proxy with fence.proxy.async, then an
+//     mbarrier hand-off (full/empty ring, 4 stages) to
+//   * 1 MMA warp: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN,
+//     K=16) x4 per 64-wide k-block against shared-memory descriptors; tcgen05.commit releases
+//     the stage, a final commit signals
+//   * 4 epilogue warps: tcgen05.ld 32x32b.x32 TMEM -> registers, fused bias + activation
+//     (FPROP), activation-derivative of the producer layer + accumulate (DGRAD) or split-K
+//     red.global.add (WGRAD), vectorised stores.
+#include "common.cuh"
+#include "ladder_sm100.h"
+#include <cuda_bf16.h>
+
+namespace ladder {
+namespace tc {
+
+constexpr int BM = 128;            // UMMA M (TMEM lanes)
+constexpr int BK = 64;             // bf16 per k-block = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int PRODUCERS = 128;     // threads
+constexpr int NTHREADS = 288;      // 4 producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
+
+struct TcArgs {
+  const float* src;            // gathered activations: x (FPROP/WGRAD) or dy (DGRAD), fp32 NHWC
+  const float* src2;           // WGRAD: dy [pixels, Cout]
+  const __nv_bfloat16* wt;     // FPROP/DGRAD: packed weights Bt[N][Kpad], K-major bf16
+  const float* bias;
+  const float* aux;
+  float* out;
+  int B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW;
+  int act, accumulate;
+  int k_per_split;             // WGRAD: pixels per grid.z slice (multiple of BK)
+  int Kpad;                    // FPROP/DGRAD: padded reduction length (multiple of BK)
+  int m_valid;                 // rows of the output that exist (WGRAD with padded taps)
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 encoding):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (1024 B between 8-row
+// groups) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
+// a/b K-major (0), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]);
+  __nv_bfloat162 p1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]);
+  __nv_bfloat162 p3 = __floats2bfloat162_rn(f[6], f[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&p0);
+  u.y = *reinterpret_cast<uint32_t*>(&p1);
+  u.z = *reinterpret_cast<uint32_t*>(&p2);
+  u.w = *reinterpret_cast<uint32_t*>(&p3);
+  return u;
+}
+
+// ------------------------------------------------------------------ gather (same index math as conv_igemm.cu)
+struct Geo {
+  int B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW;
+};
+template <bool FROM_DY>
+__device__ __forceinline__ long long tap_offset(const TcArgs& a, int b, int y, int x, int kh, int kw, int c) {
+  if (FROM_DY) {
+    int ny = y + a.pad_t - kh, nx = x + a.pad_l - kw;
+    if (ny < 0 || nx < 0) return -1;
+    if (a.stride > 1) {
+      if (ny % a.stride || nx % a.stride) return -1;
+      ny /= a.stride; nx /= a.stride;
+    }
+    if (ny >= a.OH || nx >= a.OW) return -1;
+    return (((long long)b * a.OH + ny) * a.OW + nx) * a.Cout + c;
+  } else {
+    const int iy = y * a.stride - a.pad_t + kh, ix = x * a.stride - a.pad_l + kw;
+    if (iy < 0 || ix < 0 || iy >= a.H || ix >= a.W) return -1;
+    return (((long long)b * a.H + iy) * a.W + ix) * a.Cin + c;
+  }
+}
+// 8 consecutive patch entries q0..q0+7 of pixel (b, y, x) -> f[8] (zeros outside)
+template <bool FROM_DY>
+__device__ __forceinline__ void gather8(const TcArgs& a, int b, int y, int x, long long q0, int patch, int C, bool vec,
+                                        float (&f)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  if (q0 >= patch) return;
+  if (vec) {
+    const int tap = (int)(q0 / C), c = (int)(q0 % C);
+    const long long off = tap_offset<FROM_DY>(a, b, y, x, tap / a.KW, tap % a.KW, c);
+    if (off >= 0) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(a.src + off));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(a.src + off + 4));
+      f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long q = q0 + j;
+      if (q < patch) {
+        const int tap = (int)(q / C), c = (int)(q % C);
+        const long long off = tap_offset<FROM_DY>(a, b, y, x, tap / a.KW, tap % a.KW, c);
+        if (off >= 0) f[j] = __ldg(a.src + off);
+      }
+    }
+  }
+}
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + STAGES * A_STAGE_BYTES;
+  const uint32_t bars = sB + STAGES * B_STAGE_BYTES;            // full[STAGES], empty[STAGES], tmem_full (8 B each)
+  const uint32_t slot = bars + (2 * STAGES + 1) * 8;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (slot - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long pixels = MODE == DGRAD ? (long long)a.B * a.H * a.W : (long long)a.B * a.OH * a.OW;
+  const int C = MODE == DGRAD ? a.Cout : a.Cin;                  // channels of the gathered tensor
+  const int patch = a.KH * a.KW * C;
+  const long long Mg = MODE == WGRAD ? patch : pixels;
+  const int Ng = MODE == DGRAD ? a.Cin : a.Cout;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  long long k_lo = 0, k_hi = a.Kpad;
+  if (MODE == WGRAD) {
+    k_lo = (long long)blockIdx.z * a.k_per_split;
+    k_hi = min(pixels, k_lo + a.k_per_split);
+  }
+  const int num_kb = (int)((k_hi - k_lo + BK - 1) / BK);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + s * 8, PRODUCERS);
+      mbar_init(bars + (STAGES + s) * 8, 1);
+    }
+    mbar_init(bars + 2 * STAGES * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+
+  if (warp < 4) {
+    // ===================================================== producers
+    const bool vec = (C % 8 == 0);
+    if (MODE != WGRAD) {
+      const long long p = m0 + tid;
+      const bool row_ok = p < pixels;
+      int pb = 0, py = 0, px = 0;
+      if (row_ok) {
+        const int gw = MODE == DGRAD ? a.W : a.OW, gh = MODE == DGRAD ? a.H : a.OH;
+        px = (int)(p % gw);
+        const long long r = p / gw;
+        py = (int)(r % gh);
+        pb = (int)(r / gh);
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(bars + (STAGES + s) * 8, ((kb / STAGES) & 1) ^ 1);
+        const uint32_t rowA = sA + s * A_STAGE_BYTES + tid * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float f[8];
+          if (row_ok) gather8<MODE == DGRAD>(a, pb, py, px, (long long)kb * BK + 8 * j, patch, C, vec, f);
+          else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+          }
+          const uint4 u = pack8(f);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowA + ((j ^ (tid & 7)) << 4)), "r"(u.x), "r"(u.y),
+                       "r"(u.z), "r"(u.w) : "memory");
+        }
+        for (int rr = tid; rr < BN; rr += PRODUCERS) {
+          const int n = n0 + rr;
+          const uint32_t rowB = sB + s * B_STAGE_BYTES + rr * 128;
+          const uint4* g = reinterpret_cast<const uint4*>(a.wt + (size_t)n * a.Kpad + (size_t)kb * BK);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (n < Ng) u = __ldg(g + j);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowB + ((j ^ (rr & 7)) << 4)), "r"(u.x), "r"(u.y),
+                         "r"(u.z), "r"(u.w) : "memory");
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bars + s * 8);
+      }
+    } else {
+      // WGRAD: the reduction runs over pixels; both operands are transposed while staging
+      const int pcol = tid & 63, half = tid >> 6;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(bars + (STAGES + s) * 8, ((kb / STAGES) & 1) ^ 1);
+        const long long p = k_lo + (long long)kb * BK + pcol;
+        const bool ok = p < k_hi;
+        int pb = 0, py = 0, px = 0;
+        if (ok) {
+          px = (int)(p % a.OW);
+          const long long r = p / a.OW;
+          py = (int)(r % a.OH);
+          pb = (int)(r / a.OH);
+        }
+        const uint32_t tileA = sA + s * A_STAGE_BYTES, tileB = sB + s * B_STAGE_BYTES;
+        const uint32_t colbyte = (pcol & 7) * 2, colchunk = pcol >> 3;
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int R0 = half * 64 + 8 * i;
+          float f[8];
+          if (ok) gather8<false>(a, pb, py, px, m0 + R0, patch, C, vec, f);
+          else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(f[jj]));
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(tileA + (R0 + jj) * 128 + ((colchunk ^ jj) << 4) + colbyte), "h"(h) : "memory");
+          }
+        }
+        const bool vecn = (a.Cout % 8 == 0);
+        for (int i = 0; i < BN / 16; ++i) {
+          const int R0 = half * (BN / 2) + 8 * i;
+          const int co = n0 + R0;
+          float f[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) f[q] = 0.f;
+          if (ok && co < a.Cout) {
+            const float* g = a.src2 + p * a.Cout + co;
+            if (vecn) {
+              const float4 v0 = __ldg(reinterpret_cast<const float4*>(g)), v1 = __ldg(reinterpret_cast<const float4*>(g + 4));
+              f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (co + q < a.Cout) f[q] = __ldg(g + q);
+            }
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(f[jj]));
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(tileB + (R0 + jj) * 128 + ((colchunk ^ jj) << 4) + colbyte), "h"(h) : "memory");
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bars + s * 8);
+      }
+    }
+  } else if (warp == 4) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(bars + s * 8, (kb / STAGES) & 1);
+        tc_fence_after();
+        const uint64_t adesc = make_desc(sA + s * A_STAGE_BYTES);
+        const uint64_t bdesc = make_desc(sB + s * B_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)          // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle atom
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(bars + (STAGES + s) * 8);      // stage is free once these MMAs retire
+      }
+      umma_commit(bars + 2 * STAGES * 8);          // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue (TMEM -> registers -> global)
+    mbar_wait(bars + 2 * STAGES * 8, 0);
+    tc_fence_after();
+    const int quad = warp & 3;                     // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
+    const int row = quad * 32 + lane;
+    const long long m = m0 + row;
+    const bool row_ok = m < Mg && (MODE != WGRAD || m < a.m_valid);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, v);
+      if (num_kb == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+      if (!row_ok) continue;
+      const int nb = n0 + c0;
+      float* o = a.out + m * Ng + nb;
+      if (MODE == FPROP) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (nb + i < Ng) v[i] = act_apply(v[i] + (a.bias != nullptr ? __ldg(a.bias + nb + i) : 0.f), a.act);
+      } else if (MODE == DGRAD) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (nb + i < Ng) {
+            if (a.aux != nullptr) v[i] *= act_grad_from_out(__ldg(a.aux + m * Ng + nb + i), a.act);
+            if (a.accumulate) v[i] += o[i];
+          }
+      }
+      if (MODE == WGRAD) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (nb + i < Ng) atomicAdd(o + i, v[i]);
+      } else if ((Ng & 3) == 0 && nb + 32 <= Ng) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (nb + i < Ng) o[i] = v[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ weight repack (fp32 HWIO -> bf16 K-major)
+// FPROP: Bt[n][k] = w[k*N + n];  DGRAD: Bt[ci][tap*Cout + co] = w[(tap*Cin + ci)*Cout + co]
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ bt, int mode, int taps, int Cin,
+                                    int Cout, int Kpad) {
+  const int N = mode == FPROP ? Cout : Cin;
+  const int K = taps * (mode == FPROP ? Cin : Cout);
+  const long long total = (long long)N * Kpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad), n = (int)(i / Kpad);
+    float v = 0.f;
+    if (k < K) {
+      if (mode == FPROP) v = w[(long long)k * Cout + n];
+      else {
+        const int tap = k / Cout, co = k % Cout;
+        v = w[((long long)tap * Cin + n) * Cout + co];
+      }
+    }
+    bt[i] = __float2bfloat16_rn(v);
+  }
+}
+
+template <int MODE>
+static int launch(const TcArgs& a, long long Mg, int Ng, int splits, cudaStream_t st) {
+  const int bn = Ng <= 32 ? 32 : (Ng <= 64 ? 64 : (Ng <= 128 ? 128 : 256));
+  dim3 grid((unsigned)ceil_div64(Mg, BM), (unsigned)ceil_div(Ng, bn), (unsigned)splits);
+  auto go = [&](auto kern, int BNv) {
+    const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, NTHREADS, smem, st>>>(a);
+  };
+  switch (bn) {
+    case 32: go(tc_kernel<MODE, 32>, 32); break;
+    case 64: go(tc_kernel<MODE, 64>, 64); break;
+    case 128: go(tc_kernel<MODE, 128>, 128); break;
+    default: go(tc_kernel<MODE, 256>, 256); break;
+  }
+  return check_launch("tcgen05 conv kernel");
+}
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace tc
+}  // namespace ladder
+
+using namespace ladder;
+using namespace ladder::tc;
+
+extern "C" {
+
+size_t ladder_conv2d_tc_workspace_bytes(int B, int H, int W, int Cin, int KH, int KW, int Cout) {
+  (void)B; (void)H; (void)W;
+  const size_t f = (size_t)Cout * round_up(KH * KW * Cin, BK) * 2;     // FPROP pack
+  const size_t d = (size_t)Cin * round_up(KH * KW * Cout, BK) * 2;     // DGRAD pack
+  return (f > d ? f : d) + 256;
+}
+
+static int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, int Kpad, cudaStream_t st) {
+  const int N = mode == FPROP ? Cout : Cin;
+  const size_t need = (size_t)N * Kpad * 2;
+  if (ws == nullptr || ws_bytes < need) return fail(LADDER_ERR_WORKSPACE, "conv2d_tc: workspace %zu < %zu bytes", ws_bytes, need);
+  if ((uintptr_t)ws & 15) return fail(LADDER_ERR_ARG, "conv2d_tc: workspace must be 16-byte aligned");
+  long long blocks = ceil_div64((long long)N * Kpad, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(ws), mode, taps, Cin, Cout, Kpad);
+  return check_launch("conv2d_tc weight pack");
+}
+
+int ladder_conv2d_fprop_tc(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
+                           int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  LADDER_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
+                 "conv2d_fprop_tc: bad arguments");
+  const int Kpad = round_up(KH * KW * Cin, BK);
+  int rc = pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, Kpad, stream);
+  if (rc) return rc;
+  TcArgs a{x, nullptr, static_cast<const __nv_bfloat16*>(workspace), bias, nullptr, y, B, H, W, Cin, KH, KW, Cout, stride,
+           pad_t, pad_l, OH, OW, act, 0, 0, Kpad, 0};
+  return launch<FPROP>(a, (long long)B * OH * OW, Cout, 1, stream);
+}
+
+int ladder_conv2d_dgrad_tc(const float* dy, const float* w, const float* act_out, float* dx, int B, int H, int W, int Cin,
+                           int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
+                           int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  LADDER_REQUIRE(dy && w && dx && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
+                 "conv2d_dgrad_tc: bad arguments");
+  const int Kpad = round_up(KH * KW * Cout, BK);
+  int rc = pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, Kpad, stream);
+  if (rc) return rc;
+  TcArgs a{dy, nullptr, static_cast<const __nv_bfloat16*>(workspace), nullptr, act_out, dx, B, H, W, Cin, KH, KW, Cout, stride,
+           pad_t, pad_l, OH, OW, act, accumulate, 0, Kpad, 0};
+  return launch<DGRAD>(a, (long long)B * H * W, Cin, 1, stream);
+}
+
+// dw must be zero on entry is NOT required: it is cleared here; dbias is left to ladder_conv2d_wgrad's column sum.
+int ladder_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int KH, int KW, int Cout,
+                           int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream) {
+  LADDER_REQUIRE(x && dy && dw && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
+                 "conv2d_wgrad_tc: bad arguments");
+  const int patch = KH * KW * Cin;
+  const long long pixels = (long long)B * OH * OW;
+  cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)patch * Cout * sizeof(float), stream);
+  if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "conv2d_wgrad_tc memset: %s", cudaGetErrorString(e));
+  const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
+  const long long tiles = ceil_div64(patch, BM) * ceil_div(Cout, bn);
+  long long splits = ceil_div64(2LL * num_sms(), tiles);
+  const long long max_splits = ceil_div64(pixels, 2 * BK);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  long long per = ceil_div64(ceil_div64(pixels, splits), BK) * BK;
+  TcArgs a{x, dy, nullptr, nullptr, nullptr, dw, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, 0, 0, (int)per, 0, patch};
+  return launch<WGRAD>(a, patch, Cout, (int)ceil_div64(pixels, per), stream);
+}
+
+}  // extern "C"

@@ -367,6 +367,8 @@ class LadderEngine:
 
     def __init__(self, config, batch_size, device='cuda', seed=0, dist_group=None):
         self.cfg = config
+        # optional key: 'bf16' = tcgen05 tensor-core GEMMs (default), 'fp32' = SIMT GEMMs (strict parity)
+        ops.set_math_mode(config.get('compute_dtype', ops.MATH_MODE))
         self.B = B = int(batch_size)
         self.dev = torch.device(device)
         self.prior = config['prior']

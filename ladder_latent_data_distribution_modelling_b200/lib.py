@@ -33,6 +33,11 @@ SIGNATURES = {
     'ladder_conv2d_fprop': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 13 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_dgrad': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 14 + [stream_t]),
     'ladder_conv2d_wgrad': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 12 + [ptr, C.c_size_t, stream_t]),
+    'ladder_colsum': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, stream_t]),
+    'ladder_conv2d_tc_workspace_bytes': (C.c_size_t, [C.c_int] * 7),
+    'ladder_conv2d_fprop_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 13 + [ptr, C.c_size_t, stream_t]),
+    'ladder_conv2d_dgrad_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 14 + [ptr, C.c_size_t, stream_t]),
+    'ladder_conv2d_wgrad_tc': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [stream_t]),
     # layout / elementwise
     'ladder_sym_pad': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),
     'ladder_depth_to_space': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),

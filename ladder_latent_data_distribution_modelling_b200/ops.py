@@ -5,6 +5,7 @@ stream and never synchronises.  No fallback exists: calling any op without the b
 library or on a non-sm_100 device raises.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -202,6 +203,22 @@ class ConvGeom:
                 self.OH, self.OW)
 
 
+# 'fp32': SIMT implicit GEMM (csrc/conv_igemm.cu); 'bf16': tcgen05 tensor-core implicit GEMM (csrc/conv_tc.cu)
+MATH_MODE = os.environ.get('LADDER_MATH_MODE', 'bf16')
+
+
+def set_math_mode(mode):
+    global MATH_MODE
+    if mode not in ('fp32', 'bf16'):
+        raise ValueError("math mode must be 'fp32' or 'bf16'")
+    MATH_MODE = mode
+
+
+def _use_tc(g):
+    # single-output-channel KxK convs stay on the tap-GEMM decomposition of the fp32 path
+    return MATH_MODE == 'bf16' and not (g.Cout == 1 and g.KH * g.KW > 1)
+
+
 def _conv_ws(x, g):
     n = _L().ladder_conv2d_workspace_bytes(g.B, g.H, g.W, g.Cin, g.KH, g.KW, g.Cout)
     if n == 0:
@@ -210,7 +227,18 @@ def _conv_ws(x, g):
     return ws, ws.numel()
 
 
+def _tc_ws(x, g):
+    n = _L().ladder_conv2d_tc_workspace_bytes(g.B, g.H, g.W, g.Cin, g.KH, g.KW, g.Cout)
+    ws = _workspace(x.device, n, 'conv_tc')
+    return ws, ws.numel()
+
+
 def conv2d_fprop(x, w, bias, y, g, act=None):
+    if _use_tc(g):
+        ws, n = _tc_ws(x, g)
+        _lib.check(_L().ladder_conv2d_fprop_tc(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(_f32(y)), *g.args(), ACT[act],
+                                               _p(ws), n, _stream()), 'conv2d_fprop_tc')
+        return y
     ws, n = _conv_ws(x, g)
     _lib.check(_L().ladder_conv2d_fprop(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(_f32(y)), *g.args(), ACT[act],
                                         _p(ws), n, _stream()), 'conv2d_fprop')
@@ -218,12 +246,23 @@ def conv2d_fprop(x, w, bias, y, g, act=None):
 
 
 def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False):
+    if _use_tc(g):
+        ws, n = _tc_ws(dy, g)
+        _lib.check(_L().ladder_conv2d_dgrad_tc(_p(_f32(dy)), _p(_f32(w)), _p(act_out), _p(_f32(dx)), *g.args(), ACT[act],
+                                               int(accumulate), _p(ws), n, _stream()), 'conv2d_dgrad_tc')
+        return dx
     _lib.check(_L().ladder_conv2d_dgrad(_p(_f32(dy)), _p(_f32(w)), _p(act_out), _p(_f32(dx)), *g.args(), ACT[act],
                                         int(accumulate), _stream()), 'conv2d_dgrad')
     return dx
 
 
 def conv2d_wgrad(x, dy, dw, dbias, g):
+    if _use_tc(g):
+        _lib.check(_L().ladder_conv2d_wgrad_tc(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dw)), *g.args(), _stream()),
+                   'conv2d_wgrad_tc')
+        if dbias is not None:
+            _lib.check(_L().ladder_colsum(_p(dy), g.B * g.OH * g.OW, g.Cout, _p(dbias), _stream()), 'colsum')
+        return dw
     ws, n = _conv_ws(x, g)
     _lib.check(_L().ladder_conv2d_wgrad(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dw)), _p(dbias), *g.args(), _p(ws), n,
                                         _stream()), 'conv2d_wgrad')

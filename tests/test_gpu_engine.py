@@ -20,6 +20,7 @@ SCALARS_PRIOR = ['elbo_prior', 'code_l1_reconstruction_error', 'code_reconstruct
 
 
 def make_case(exp, B, seed, prior='ours', epoch=None, **over):
+    over.setdefault('compute_dtype', 'fp32')
     cfg = load_config(exp, batch_size=B, n_MC_samples=10, prior=prior, **over)
     rng = np.random.default_rng(seed)
     spec = oparams.vae_param_specs(cfg) + (oparams.prior_param_specs(cfg) if prior in ('ours', 'hierarchical') else [])
@@ -180,3 +181,21 @@ def test_full_iteration_matches_oracle_trainer(exp):
     got = eng.fetch(SCALARS_AE + SCALARS_PRIOR)
     for k in SCALARS_AE + SCALARS_PRIOR:
         assert rel(got[k], float(o[k].v)) < 2e-3, (k, got[k], float(o[k].v))
+
+
+@pytest.mark.parametrize('exp', ['mnist_digit', 'mnist_fashion'])
+def test_bf16_tensor_core_engine(exp):
+    """Same sub-step through the tcgen05 GEMMs (compute_dtype=bf16): operands rounded to bf16, fp32
+    accumulation.  Stated tolerance: ELBO terms 1e-2 relative, gradients 6e-2 of the tensor's max."""
+    cfg, P, x, noises, feeds, epoch = make_case(exp, 6, 21, compute_dtype='bf16')
+    eng = make_engine(cfg, P, feeds, 6)
+    xd = torch.tensor(x, device='cuda')
+    eng.set_noise(**noises[0])
+    eng.step_ae(xd, apply=False)
+    Pv, o = nets.build(cfg, P, x, noises[0], feeds)
+    got = eng.fetch(SCALARS_AE + SCALARS_PRIOR)
+    for k in SCALARS_AE + SCALARS_PRIOR:
+        assert rel(got[k], float(o[k].v)) < 1e-2, (k, got[k], float(o[k].v))
+    grad_check(eng, eng.ae, nets.grads_of(o['loss_ae'], Pv, eng.ae.names()), tol=6e-2)
+    eng.step_prior(xd, apply=False)
+    grad_check(eng, eng.prior_g, nets.grads_of(o['loss_prior'], Pv, eng.prior_g.names()), tol=6e-2)

@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope='module')
 def ops():
     from ladder_latent_data_distribution_modelling_b200 import ops
+    ops.set_math_mode('fp32')
     return ops
 
 

@@ -1,0 +1,84 @@
+"""GPU parity of the tcgen05 (bf16 tensor-core) conv / dense kernels against the float64 oracle.
+Tolerance: operands are rounded to bf16 (2^-9 relative) with fp32 accumulation -> 1.5e-2 of the output scale."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tape as T
+from test_gpu_layers import CASES, dev
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.5e-2
+
+
+@pytest.fixture()
+def ops():
+    from ladder_latent_data_distribution_modelling_b200 import ops
+    ops.set_math_mode('bf16')
+    yield ops
+    ops.set_math_mode('fp32')
+
+
+def close(got, want, tol=TOL):
+    got = got.cpu().numpy().astype(np.float64)
+    scale = np.abs(want).max() + 1e-12
+    err = np.abs(got - want).max() / scale
+    assert err < tol, err
+    return err
+
+
+TC_CASES = CASES + [
+    (4, 16, 16, 64, 3, 256, 1, 'same', 'leaky_relu'),     # the dominant fashion decoder layer
+    (2, 16, 16, 128, 3, 128, 1, 'same', 'leaky_relu'),    # CelebA-like
+    (300, 1, 1, 512, 1, 512, 1, 'valid', 'leaky_relu'),   # dense, M not a tile multiple, several k-blocks
+    (3, 8, 8, 64, 3, 300, 2, 'same', None),               # N > 256: two N tiles with a ragged tail
+]
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+def test_tc_conv_fprop_dgrad_wgrad(ops, case):
+    B, H, W, Cin, k, Cout, stride, padding, act = case
+    rng = np.random.default_rng(hash(case) % 2**32)
+    x = rng.normal(size=(B, H, W, Cin)); w = rng.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)
+    b = rng.normal(size=(Cout,))
+    X, Wv, Bv = T.Var(x), T.Var(w), T.Var(b)
+    pre = T.conv2d(X, Wv, Bv, stride=stride, padding=padding)
+    actf = {None: lambda v: v, 'leaky_relu': T.leaky_relu, 'relu': T.relu, 'tanh': T.tanh}[act]
+    y = actf(pre)
+    up = rng.normal(size=y.shape)
+    T.backward(y, seed=up)
+    g = ops.ConvGeom(B, H, W, Cin, k, k, Cout, stride, padding)
+    xd, wd, bd = dev(x), dev(w), dev(b)
+    yd = torch.full((B, g.OH, g.OW, Cout), 5.0, device='cuda')
+    ops.conv2d_fprop(xd, wd, bd, yd, g, act)
+    close(yd, y.v)
+    dyd = dev(pre.g)                       # exact d(pre-activation) so each GEMM is checked in isolation
+    dwd = torch.full_like(wd, 7.0); dbd = torch.full_like(bd, 7.0)
+    ops.conv2d_wgrad(xd, dyd, dwd, dbd, g)
+    close(dwd, Wv.g)
+    close(dbd, Bv.g, 1e-4)
+    dxd = torch.full_like(xd, 3.0)
+    ops.conv2d_dgrad(dyd, wd, dxd, g)
+    close(dxd, X.g)
+    prod = dev(rng.normal(size=x.shape)); base = dev(rng.normal(size=x.shape))
+    out = base.clone()
+    ops.conv2d_dgrad(dyd, wd, out, g, act_out=prod, act='leaky_relu', accumulate=True)
+    close(out, base.cpu().numpy() + X.g * np.where(prod.cpu().numpy() > 0, 1.0, 0.2))
+
+
+def test_tc_large_gemm_matches_fp32_kernel(ops):
+    """Full-size dominant layer (batch 64): tensor-core result vs the fp32 SIMT kernel of the same library."""
+    B, H = 64, 256
+    g = ops.ConvGeom(B, 16, 16, H // 4, 3, 3, H, 1, 'same')
+    gen = torch.Generator(device='cuda'); gen.manual_seed(0)
+    x = torch.randn(B, 16, 16, H // 4, device='cuda', generator=gen)
+    w = torch.randn(3, 3, H // 4, H, device='cuda', generator=gen) * 0.05
+    b = torch.randn(H, device='cuda', generator=gen)
+    y_tc = torch.empty(B, 16, 16, H, device='cuda')
+    ops.conv2d_fprop(x, w, b, y_tc, g, 'leaky_relu')
+    ops.set_math_mode('fp32')
+    y_ref = torch.empty_like(y_tc)
+    ops.conv2d_fprop(x, w, b, y_ref, g, 'leaky_relu')
+    err = (y_tc - y_ref).abs().max().item() / y_ref.abs().max().item()
+    assert err < TOL, err
