@@ -110,6 +110,7 @@ int ladder_conv2d_dgrad_tc(const float* dy, const float* w, const float* act_out
                            int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l,
                            int OH, int OW, int act, int accumulate, void* workspace, size_t workspace_bytes,
                            cudaStream_t stream);
+int ladder_conv2d_wgrad_tc_supported(int Cin, int Cout);   /* 1 iff Cin % 64 == 0 */
 int ladder_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int KH, int KW,
                            int Cout, int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream);
 
@@ -124,6 +125,34 @@ int ladder_space_to_depth_actgrad(const float* g, const float* act_out /*nullabl
                                   int W, int C, int r, int act, cudaStream_t stream);
 int ladder_act_bwd(float* g_inout, const float* act_out, long long n, int act, cudaStream_t stream);
 int ladder_axpy(float* y, const float* x, float alpha, long long n, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * CelebA-only layers (codes/models.py:392-598, codes/modules.py:6-10), NHWC fp32.
+ * Batch norm with TRAINING statistics (is_training is the constant True, models.py:471), eps 1e-3,
+ * fused with the activation that follows it.  x is [P, C] (P = B*H*W).  `count` is the number of
+ * rows the sums cover: P on one GPU, the global P after the caller all-reduced sums2c.         */
+int ladder_bn_stats(const float* x, long long P, int C, float* sums2c, cudaStream_t stream);
+int ladder_bn_apply(const float* x, const float* sums2c, const float* gamma, const float* beta, float* y,
+                    long long P, int C, long long count, float eps, int act, cudaStream_t stream);
+/* dsums2c = [dbeta | dgamma] (sums over this rank's rows; all-reduce them for cross-replica BN) */
+int ladder_bn_bwd_stats(const float* dout, const float* y, const float* x, const float* sums2c, long long P, int C,
+                        long long count, float eps, int act, float* dsums2c, cudaStream_t stream);
+int ladder_bn_bwd_apply(const float* dout, const float* y, const float* x, const float* sums2c,
+                        const float* dsums2c, const float* gamma, float* dx, long long P, int C, long long count,
+                        float eps, int act, cudaStream_t stream);
+/* tf.contrib.layers.instance_norm(center=False, scale=False) -> style_mod -> activation in one pass:
+ * y = act(xhat * (style[:, :C] + 1) + style[:, C:]);  stats [2, B, C] receives (mean, rstd).
+ * backward: dstyle [B, 2C] and dx.                                                             */
+int ladder_instnorm_style_fwd(const float* x, const float* style, float* stats, float* y, int B, int HW, int C,
+                              float eps, int act, cudaStream_t stream);
+int ladder_instnorm_style_bwd(const float* dout, const float* y, const float* x, const float* stats,
+                              const float* style, float* dstyle, float* dx, int B, int HW, int C, int act,
+                              cudaStream_t stream);
+/* tf.image.resize_images of TF1 (legacy bilinear, align_corners=False, no half-pixel centres) */
+int ladder_resize_bilinear_fwd(const float* x, float* y, int B, int H, int W, int C, int OH, int OW,
+                               cudaStream_t stream);
+int ladder_resize_bilinear_bwd(const float* dy, float* dx, int B, int H, int W, int C, int OH, int OW,
+                               cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * The `scalars` buffer: LADDER_SCALARS_LEN floats on the device.  [0,16) are running sums the

@@ -56,6 +56,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk TMA global -> shared, completion on an mbarrier (SASS UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -111,10 +119,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major SWIZZLE_128B descriptor: 64 MN-elements (128 B) contiguous per K row, 8 K rows per 1024-byte atom
+// (SBO = 1024 B between K groups of 8), next 64-element MN block at LBO bytes.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
 // a/b K-major (0), N>>3 [17,23), M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
@@ -179,6 +192,12 @@ __device__ __forceinline__ void gather8(const TcArgs& a, int b, int y, int x, lo
   }
 }
 
+__device__ __forceinline__ void sts64(uint32_t addr, float4 v) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t*>(&p0)),
+               "r"(*reinterpret_cast<uint32_t*>(&p1)) : "memory");
+}
+
 template <int MODE, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -191,6 +210,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
   const uint32_t bars = sB + STAGES * B_STAGE_BYTES;            // full[STAGES], empty[STAGES], tmem_full (8 B each)
   const uint32_t slot = bars + (2 * STAGES + 1) * 8;
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (slot - base));
+  int* rowinfo = reinterpret_cast<int*>(smem + (slot + 16 - base));     // [2][128][3] (b, y, x) of tile rows / pixels
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long pixels = MODE == DGRAD ? (long long)a.B * a.H * a.W : (long long)a.B * a.OH * a.OW;
@@ -206,6 +226,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
     k_hi = min(pixels, k_lo + a.k_per_split);
   }
   const int num_kb = (int)((k_hi - k_lo + BK - 1) / BK);
+  const int gw = MODE == DGRAD ? a.W : a.OW, gh = MODE == DGRAD ? a.H : a.OH;   // pixel grid of the rows
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -215,6 +236,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
     mbar_init(bars + 2 * STAGES * 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (MODE != WGRAD && tid < BM) {            // (b, y, x) of every tile row, shared by the coalesced gather
+    const long long p = m0 + tid;
+    int b = -1, y = 0, x = 0;
+    if (p < pixels) {
+      x = (int)(p % gw);
+      const long long r = p / gw;
+      y = (int)(r % gh);
+      b = (int)(r / gh);
+    }
+    rowinfo[tid * 3] = b; rowinfo[tid * 3 + 1] = y; rowinfo[tid * 3 + 2] = x;
+  }
   if (warp == 4) tmem_alloc(slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -223,103 +255,139 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
 
   if (warp < 4) {
     // ===================================================== producers
-    const bool vec = (C % 8 == 0);
     if (MODE != WGRAD) {
-      const long long p = m0 + tid;
-      const bool row_ok = p < pixels;
-      int pb = 0, py = 0, px = 0;
-      if (row_ok) {
-        const int gw = MODE == DGRAD ? a.W : a.OW, gh = MODE == DGRAD ? a.H : a.OH;
-        px = (int)(p % gw);
-        const long long r = p / gw;
-        py = (int)(r % gh);
-        pb = (int)(r / gh);
-      }
+      const bool fast = (C % BK == 0);         // a 64-wide k-block = 64 contiguous channels of one tap
+      const bool vec = (C % 8 == 0);
+      int pb = rowinfo[tid * 3], py = rowinfo[tid * 3 + 1], px = rowinfo[tid * 3 + 2];
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         mbar_wait(bars + (STAGES + s) * 8, ((kb / STAGES) & 1) ^ 1);
-        const uint32_t rowA = sA + s * A_STAGE_BYTES + tid * 128;
+        const uint32_t tileA = sA + s * A_STAGE_BYTES;
+        if (fast) {
+          // coalesced: 16 lanes cover the 256 B (64 fp32 channels) of one row, 2 rows per warp instruction
+          const int q0 = kb * BK, tap = q0 / C, c0 = q0 % C, kh = tap / a.KW, kw = tap % a.KW;
+          const int f4 = lane & 15;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float f[8];
-          if (row_ok) gather8<MODE == DGRAD>(a, pb, py, px, (long long)kb * BK + 8 * j, patch, C, vec, f);
-          else {
+          for (int half = 0; half < 2; ++half) {
+            float4 v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            for (int it = 0; it < 8; ++it) {
+              const int row = warp * 32 + (half * 8 + it) * 2 + (lane >> 4);
+              const int b = rowinfo[row * 3], y = rowinfo[row * 3 + 1], x = rowinfo[row * 3 + 2];
+              v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (b >= 0) {
+                const long long off = tap_offset<MODE == DGRAD>(a, b, y, x, kh, kw, c0 + 4 * f4);
+                if (off >= 0) v[it] = __ldg(reinterpret_cast<const float4*>(a.src + off));
+              }
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int row = warp * 32 + (half * 8 + it) * 2 + (lane >> 4);
+              sts64(tileA + row * 128 + (((f4 >> 1) ^ (row & 7)) << 4) + (f4 & 1) * 8, v[it]);
+            }
           }
-          const uint4 u = pack8(f);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowA + ((j ^ (tid & 7)) << 4)), "r"(u.x), "r"(u.y),
-                       "r"(u.z), "r"(u.w) : "memory");
-        }
-        for (int rr = tid; rr < BN; rr += PRODUCERS) {
-          const int n = n0 + rr;
-          const uint32_t rowB = sB + s * B_STAGE_BYTES + rr * 128;
-          const uint4* g = reinterpret_cast<const uint4*>(a.wt + (size_t)n * a.Kpad + (size_t)kb * BK);
+        } else {
+          const uint32_t rowA = tileA + tid * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            uint4 u = make_uint4(0u, 0u, 0u, 0u);
-            if (n < Ng) u = __ldg(g + j);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowB + ((j ^ (rr & 7)) << 4)), "r"(u.x), "r"(u.y),
+            float f[8];
+            if (pb >= 0) gather8<MODE == DGRAD>(a, pb, py, px, (long long)kb * BK + 8 * j, patch, C, vec, f);
+            else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) f[q] = 0.f;
+            }
+            const uint4 u = pack8(f);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowA + ((j ^ (tid & 7)) << 4)), "r"(u.x), "r"(u.y),
                          "r"(u.z), "r"(u.w) : "memory");
           }
         }
         fence_proxy_async();
-        mbar_arrive(bars + s * 8);
+        if (tid == 0) {
+          // B tile: one bulk TMA copy of the pre-swizzled bf16 weight tile image
+          mbar_arrive_expect_tx(bars + s * 8, B_STAGE_BYTES);
+          tma_bulk_g2s(sB + s * B_STAGE_BYTES,
+                       reinterpret_cast<const uint8_t*>(a.wt) + ((size_t)blockIdx.y * num_kb + kb) * B_STAGE_BYTES,
+                       B_STAGE_BYTES, bars + s * 8);
+        } else {
+          mbar_arrive(bars + s * 8);
+        }
       }
     } else {
-      // WGRAD: the reduction runs over pixels; both operands are transposed while staging
-      const int pcol = tid & 63, half = tid >> 6;
+      // WGRAD: reduction over pixels.  Both operands are staged MN-major: row = pixel, 64 contiguous
+      // channels (128 B of bf16) per row, one [64 pixels x 128 B] swizzled block per 64 M- (or N-) elements.
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         mbar_wait(bars + (STAGES + s) * 8, ((kb / STAGES) & 1) ^ 1);
-        const long long p = k_lo + (long long)kb * BK + pcol;
-        const bool ok = p < k_hi;
-        int pb = 0, py = 0, px = 0;
-        if (ok) {
-          px = (int)(p % a.OW);
-          const long long r = p / a.OW;
-          py = (int)(r % a.OH);
-          pb = (int)(r / a.OH);
+        int* ri = rowinfo + (kb & 1) * (BK * 3);
+        if (tid < BK) {
+          const long long p = k_lo + (long long)kb * BK + tid;
+          int b = -1, y = 0, x = 0;
+          if (p < k_hi) {
+            x = (int)(p % a.OW);
+            const long long r = p / a.OW;
+            y = (int)(r % a.OH);
+            b = (int)(r / a.OH);
+          }
+          ri[tid * 3] = b; ri[tid * 3 + 1] = y; ri[tid * 3 + 2] = x;
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         const uint32_t tileA = sA + s * A_STAGE_BYTES, tileB = sB + s * B_STAGE_BYTES;
-        const uint32_t colbyte = (pcol & 7) * 2, colchunk = pcol >> 3;
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-          const int R0 = half * 64 + 8 * i;
-          float f[8];
-          if (ok) gather8<false>(a, pb, py, px, m0 + R0, patch, C, vec, f);
-          else {
+        const int f4 = lane & 15;
+        // A: 2 M-blocks of 64 patch entries (one tap's 64 channels each)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = 0.f;
-          }
+        for (int mb = 0; mb < 2; ++mb) {
+          const long long kd0 = m0 + mb * 64;
+          const bool blk_ok = kd0 < patch;
+          const int tap = blk_ok ? (int)(kd0 / C) : 0, c0 = blk_ok ? (int)(kd0 % C) : 0, kh = tap / a.KW, kw = tap % a.KW;
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(f[jj]));
-            asm volatile("st.shared.b16 [%0], %1;" ::"r"(tileA + (R0 + jj) * 128 + ((colchunk ^ jj) << 4) + colbyte), "h"(h) : "memory");
-          }
-        }
-        const bool vecn = (a.Cout % 8 == 0);
-        for (int i = 0; i < BN / 16; ++i) {
-          const int R0 = half * (BN / 2) + 8 * i;
-          const int co = n0 + R0;
-          float f[8];
+          for (int half = 0; half < 2; ++half) {
+            float4 v[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) f[q] = 0.f;
-          if (ok && co < a.Cout) {
-            const float* g = a.src2 + p * a.Cout + co;
-            if (vecn) {
-              const float4 v0 = __ldg(reinterpret_cast<const float4*>(g)), v1 = __ldg(reinterpret_cast<const float4*>(g + 4));
-              f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
-            } else {
+            for (int it = 0; it < 4; ++it) {
+              const int k = warp * 16 + (half * 4 + it) * 2 + (lane >> 4);
+              const int b = ri[k * 3], y = ri[k * 3 + 1], x = ri[k * 3 + 2];
+              v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (blk_ok && b >= 0) {
+                const long long off = tap_offset<false>(a, b, y, x, kh, kw, c0 + 4 * f4);
+                if (off >= 0) v[it] = __ldg(reinterpret_cast<const float4*>(a.src + off));
+              }
+            }
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                if (co + q < a.Cout) f[q] = __ldg(g + q);
+            for (int it = 0; it < 4; ++it) {
+              const int k = warp * 16 + (half * 4 + it) * 2 + (lane >> 4);
+              sts64(tileA + mb * 8192 + k * 128 + (((f4 >> 1) ^ (k & 7)) << 4) + (f4 & 1) * 8, v[it]);
             }
           }
+        }
+        // B: BN/64 N-blocks of 64 output channels of dy
+        const bool vecn = (a.Cout & 3) == 0;
+#pragma unroll 1
+        for (int nb = 0; nb < BN / 64; ++nb) {
+          const int co = n0 + nb * 64 + 4 * f4;
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(f[jj]));
-            asm volatile("st.shared.b16 [%0], %1;" ::"r"(tileB + (R0 + jj) * 128 + ((colchunk ^ jj) << 4) + colbyte), "h"(h) : "memory");
+          for (int half = 0; half < 2; ++half) {
+            float4 v[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int k = warp * 16 + (half * 4 + it) * 2 + (lane >> 4);
+              const long long p = k_lo + (long long)kb * BK + k;
+              v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p < k_hi && co < a.Cout) {
+                const float* g = a.src2 + p * a.Cout + co;
+                if (vecn) v[it] = __ldg(reinterpret_cast<const float4*>(g));
+                else {
+                  v[it].x = __ldg(g);
+                  if (co + 1 < a.Cout) v[it].y = __ldg(g + 1);
+                  if (co + 2 < a.Cout) v[it].z = __ldg(g + 2);
+                  if (co + 3 < a.Cout) v[it].w = __ldg(g + 3);
+                }
+              }
+            }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int k = warp * 16 + (half * 4 + it) * 2 + (lane >> 4);
+              sts64(tileB + nb * 8192 + k * 128 + (((f4 >> 1) ^ (k & 7)) << 4) + (f4 & 1) * 8, v[it]);
+            }
           }
         }
         fence_proxy_async();
@@ -329,16 +397,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
   } else if (warp == 4) {
     // ===================================================== MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc = make_idesc(BM, BN, MODE == WGRAD);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         mbar_wait(bars + s * 8, (kb / STAGES) & 1);
         tc_fence_after();
-        const uint64_t adesc = make_desc(sA + s * A_STAGE_BYTES);
-        const uint64_t bdesc = make_desc(sB + s * B_STAGE_BYTES);
+        const uint32_t tA = sA + s * A_STAGE_BYTES, tB = sB + s * B_STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)          // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle atom
-          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        for (int k = 0; k < BK / 16; ++k) {
+          if (MODE == WGRAD)       // 16 pixels = two 8-row groups = 2048 B per K step; 64-element MN blocks 8192 B apart
+            umma_bf16(tmem_base, make_desc_mn(tA + k * 2048, 8192), make_desc_mn(tB + k * 2048, 8192), idesc, (kb | k) != 0);
+          else                     // +32 bytes per 16-element K step inside the swizzle atom
+            umma_bf16(tmem_base, make_desc(tA + k * 32), make_desc(tB + k * 32), idesc, (kb | k) != 0);
+        }
         umma_commit(bars + (STAGES + s) * 8);      // stage is free once these MMAs retire
       }
       umma_commit(bars + 2 * STAGES * 8);          // accumulator complete
@@ -362,6 +433,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
       }
       if (!row_ok) continue;
       const int nb = n0 + c0;
+      if (nb >= Ng) continue;
       float* o = a.out + m * Ng + nb;
       if (MODE == FPROP) {
 #pragma unroll
@@ -394,38 +466,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
   if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// ------------------------------------------------------------------ weight repack (fp32 HWIO -> bf16 K-major)
-// FPROP: Bt[n][k] = w[k*N + n];  DGRAD: Bt[ci][tap*Cout + co] = w[(tap*Cin + ci)*Cout + co]
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ bt, int mode, int taps, int Cin,
-                                    int Cout, int Kpad) {
+static int pick_bn(int Ng) { return Ng <= 32 ? 32 : (Ng <= 64 ? 64 : (Ng <= 128 ? 128 : 256)); }
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------ weight repack (fp32 HWIO -> bf16 tile images)
+// Logical K-major matrix  FPROP: Bt[n][k] = w[k*Cout + n];  DGRAD: Bt[ci][tap*Cout + co] = w[(tap*Cin + ci)*Cout + co]
+// stored as consecutive [BN x 64] tiles (tile index = n_tile * num_kb + kb), each already in the SWIZZLE_128B
+// shared-memory image (row rr at rr*128, 16-byte chunk j at ((j ^ (rr & 7)) << 4)), so one bulk TMA copy stages it.
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img, int mode, int taps, int Cin,
+                                    int Cout, int bn, int num_kb, int n_tiles) {
   const int N = mode == FPROP ? Cout : Cin;
   const int K = taps * (mode == FPROP ? Cin : Cout);
-  const long long total = (long long)N * Kpad;
+  const long long total = (long long)n_tiles * num_kb * bn * BK;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % Kpad), n = (int)(i / Kpad);
+    const int kk = (int)(i % BK);
+    long long r = i / BK;
+    const int rr = (int)(r % bn); r /= bn;
+    const int kb = (int)(r % num_kb);
+    const int nt = (int)(r / num_kb);
+    const int n = nt * bn + rr, k = kb * BK + kk;
     float v = 0.f;
-    if (k < K) {
+    if (n < N && k < K) {
       if (mode == FPROP) v = w[(long long)k * Cout + n];
       else {
         const int tap = k / Cout, co = k % Cout;
         v = w[((long long)tap * Cin + n) * Cout + co];
       }
     }
-    bt[i] = __float2bfloat16_rn(v);
+    const long long tile = (long long)nt * num_kb + kb;
+    img[tile * bn * BK + rr * BK + ((((kk >> 3) ^ (rr & 7))) << 3) + (kk & 7)] = __float2bfloat16_rn(v);
   }
 }
 
 template <int MODE>
 static int launch(const TcArgs& a, long long Mg, int Ng, int splits, cudaStream_t st) {
-  const int bn = Ng <= 32 ? 32 : (Ng <= 64 ? 64 : (Ng <= 128 ? 128 : 256));
+  int bn = pick_bn(Ng);
+  if (MODE == WGRAD && bn < 64) bn = 64;       // MN-major blocks are 64 elements wide
   dim3 grid((unsigned)ceil_div64(Mg, BM), (unsigned)ceil_div(Ng, bn), (unsigned)splits);
   auto go = [&](auto kern, int BNv) {
-    const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256;
+    const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256 + 2 * BM * 3 * sizeof(int);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, NTHREADS, smem, st>>>(a);
   };
   switch (bn) {
-    case 32: go(tc_kernel<MODE, 32>, 32); break;
+    case 32: if constexpr (MODE != WGRAD) { go(tc_kernel<MODE, 32>, 32); } break;
     case 64: go(tc_kernel<MODE, 64>, 64); break;
     case 128: go(tc_kernel<MODE, 128>, 128); break;
     default: go(tc_kernel<MODE, 256>, 256); break;
@@ -433,44 +517,49 @@ static int launch(const TcArgs& a, long long Mg, int Ng, int splits, cudaStream_
   return check_launch("tcgen05 conv kernel");
 }
 
-static int round_up(int x, int m) { return (x + m - 1) / m * m; }
-
 }  // namespace tc
 }  // namespace ladder
 
 using namespace ladder;
 using namespace ladder::tc;
 
+static size_t pack_bytes(int N, int K) {
+  const int bn = pick_bn(N);
+  return (size_t)ceil_div(N, bn) * ceil_div(K, BK) * bn * BK * 2;
+}
+
+static int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, cudaStream_t st) {
+  const int N = mode == FPROP ? Cout : Cin, K = taps * (mode == FPROP ? Cin : Cout);
+  const size_t need = pack_bytes(N, K);
+  if (ws == nullptr || ws_bytes < need) return fail(LADDER_ERR_WORKSPACE, "conv2d_tc: workspace %zu < %zu bytes", ws_bytes, need);
+  if ((uintptr_t)ws & 127) return fail(LADDER_ERR_ARG, "conv2d_tc: workspace must be 128-byte aligned");
+  const int bn = pick_bn(N), num_kb = ceil_div(K, BK), n_tiles = ceil_div(N, bn);
+  long long blocks = ceil_div64((long long)n_tiles * num_kb * bn * BK, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(ws), mode, taps, Cin, Cout, bn, num_kb, n_tiles);
+  return check_launch("conv2d_tc weight pack");
+}
+
 extern "C" {
 
 size_t ladder_conv2d_tc_workspace_bytes(int B, int H, int W, int Cin, int KH, int KW, int Cout) {
   (void)B; (void)H; (void)W;
-  const size_t f = (size_t)Cout * round_up(KH * KW * Cin, BK) * 2;     // FPROP pack
-  const size_t d = (size_t)Cin * round_up(KH * KW * Cout, BK) * 2;     // DGRAD pack
+  const size_t f = pack_bytes(Cout, KH * KW * Cin), d = pack_bytes(Cin, KH * KW * Cout);
   return (f > d ? f : d) + 256;
 }
 
-static int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, int Kpad, cudaStream_t st) {
-  const int N = mode == FPROP ? Cout : Cin;
-  const size_t need = (size_t)N * Kpad * 2;
-  if (ws == nullptr || ws_bytes < need) return fail(LADDER_ERR_WORKSPACE, "conv2d_tc: workspace %zu < %zu bytes", ws_bytes, need);
-  if ((uintptr_t)ws & 15) return fail(LADDER_ERR_ARG, "conv2d_tc: workspace must be 16-byte aligned");
-  long long blocks = ceil_div64((long long)N * Kpad, 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(ws), mode, taps, Cin, Cout, Kpad);
-  return check_launch("conv2d_tc weight pack");
-}
+/* 1 if wgrad of this geometry runs on the tensor cores (64-channel-aligned input), else 0 (use the fp32 kernel) */
+int ladder_conv2d_wgrad_tc_supported(int Cin, int Cout) { (void)Cout; return Cin % BK == 0 ? 1 : 0; }
 
 int ladder_conv2d_fprop_tc(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
                            int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
                            void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   LADDER_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
                  "conv2d_fprop_tc: bad arguments");
-  const int Kpad = round_up(KH * KW * Cin, BK);
-  int rc = pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, Kpad, stream);
+  int rc = pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, stream);
   if (rc) return rc;
   TcArgs a{x, nullptr, static_cast<const __nv_bfloat16*>(workspace), bias, nullptr, y, B, H, W, Cin, KH, KW, Cout, stride,
-           pad_t, pad_l, OH, OW, act, 0, 0, Kpad, 0};
+           pad_t, pad_l, OH, OW, act, 0, 0, round_up(KH * KW * Cin, BK), 0};
   return launch<FPROP>(a, (long long)B * OH * OW, Cout, 1, stream);
 }
 
@@ -479,24 +568,25 @@ int ladder_conv2d_dgrad_tc(const float* dy, const float* w, const float* act_out
                            int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   LADDER_REQUIRE(dy && w && dx && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
                  "conv2d_dgrad_tc: bad arguments");
-  const int Kpad = round_up(KH * KW * Cout, BK);
-  int rc = pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, Kpad, stream);
+  int rc = pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, stream);
   if (rc) return rc;
   TcArgs a{dy, nullptr, static_cast<const __nv_bfloat16*>(workspace), nullptr, act_out, dx, B, H, W, Cin, KH, KW, Cout, stride,
-           pad_t, pad_l, OH, OW, act, accumulate, 0, Kpad, 0};
+           pad_t, pad_l, OH, OW, act, accumulate, 0, round_up(KH * KW * Cout, BK), 0};
   return launch<DGRAD>(a, (long long)B * H * W, Cin, 1, stream);
 }
 
-// dw must be zero on entry is NOT required: it is cleared here; dbias is left to ladder_conv2d_wgrad's column sum.
+// dw is overwritten; the bias gradient is ladder_colsum(dy).  Requires Cin % 64 == 0 (ladder_conv2d_wgrad_tc_supported).
 int ladder_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int KH, int KW, int Cout,
                            int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream) {
   LADDER_REQUIRE(x && dy && dw && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
                  "conv2d_wgrad_tc: bad arguments");
+  LADDER_REQUIRE(Cin % BK == 0, "conv2d_wgrad_tc: Cin must be a multiple of 64 (got %d)", Cin);
   const int patch = KH * KW * Cin;
   const long long pixels = (long long)B * OH * OW;
   cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)patch * Cout * sizeof(float), stream);
   if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "conv2d_wgrad_tc memset: %s", cudaGetErrorString(e));
-  const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
+  int bn = pick_bn(Cout);
+  if (bn < 64) bn = 64;
   const long long tiles = ceil_div64(patch, BM) * ceil_div(Cout, bn);
   long long splits = ceil_div64(2LL * num_sms(), tiles);
   const long long max_splits = ceil_div64(pixels, 2 * BK);

@@ -123,6 +123,7 @@ class Buffers:
 class MnistOuterVAE:
     """Encoder / decoder of MNISTModel_digit (codes/models.py:46-148) and MNISTModel_fashion
     (codes/models.py:199-315) for a fixed batch size."""
+    last_act = 'relu'
 
     def __init__(self, config, group, B, device):
         self.cfg, self.group, self.B, self.dev = config, group, B, device
@@ -237,6 +238,200 @@ class MnistOuterVAE:
         self.enc_convs[0].backward(dpre, dx=None)            # no gradient w.r.t. the image
 
 
+# ------------------------------------------------------------------------------ outer VAE (CelebA)
+class BNBlock:
+    """conv -> batch_norm(training statistics) -> leaky_relu (codes/models.py:398-460)."""
+
+    def __init__(self, group, idx, geom, device, allreduce):
+        cname = 'encoder/conv2d' if idx == 0 else 'encoder/conv2d_%d' % idx
+        bname = 'encoder/batch_normalization' if idx == 0 else 'encoder/batch_normalization_%d' % idx
+        self.conv = Conv(group, cname, geom, None, device)
+        self.gamma, self.beta = group.p(bname + '/gamma'), group.p(bname + '/beta')
+        self.dgamma, self.dbeta = group.g(bname + '/gamma'), group.g(bname + '/beta')
+        C = geom.Cout
+        self.C = C
+        self.sums = torch.zeros(2 * C, device=device)
+        self.dsums = torch.zeros(2 * C, device=device)
+        self.y = torch.empty_like(self.conv.y)
+        self.dconv = torch.empty_like(self.conv.y)
+        self.allreduce = allreduce
+        self.count = geom.B * geom.OH * geom.OW       # rows per rank; x world for cross-replica statistics
+
+    def forward(self, x, world):
+        c = self.conv.forward(x)
+        ops.bn_stats(c, self.sums)
+        self.allreduce(self.sums)
+        return ops.bn_apply(c, self.sums, self.gamma, self.beta, self.y, self.count * world, LEAKY)
+
+    def backward(self, dout, dx, world):
+        c = self.conv.y
+        ops.bn_bwd_stats(dout, self.y, c, self.sums, self.dsums, self.count * world, LEAKY)
+        self.allreduce(self.dsums)
+        self.dbeta.copy_(self.dsums[:self.C])
+        self.dgamma.copy_(self.dsums[self.C:])
+        ops.bn_bwd_apply(dout, self.y, c, self.sums, self.dsums, self.gamma, self.dconv, self.count * world, LEAKY)
+        self.conv.backward(self.dconv, dx=dx)
+
+
+class StyleBlock:
+    """conv -> instance_norm -> style_mod(dlatent) -> leaky_relu (codes/models.py:522-528, modules.py:6-10)."""
+
+    def __init__(self, group, conv_idx, style_idx, geom, B, H, device):
+        self.conv = Conv(group, 'decoder/conv2d_%d' % conv_idx, geom, None, device)
+        Cx = geom.Cout
+        self.Cx = Cx
+        self.style = Conv(group, 'decoder/StyleMod_%d/dense' % style_idx, ops.ConvGeom.dense(B, H, 2 * Cx), None, device)
+        self.stats = torch.empty(2, B, Cx, device=device)
+        self.y = torch.empty_like(self.conv.y)
+        self.dstyle = torch.empty(B, 2 * Cx, device=device)
+        self.dconv = torch.empty_like(self.conv.y)
+
+    def forward(self, x, dlatent):
+        c = self.conv.forward(x)
+        s = self.style.forward(dlatent)
+        return ops.instnorm_style_fwd(c, s.view(s.shape[0], -1), self.stats, self.y, LEAKY)
+
+    def backward(self, dout, dx, d_dlatent_pre, dlatent_out, first, conv_producer=None):
+        """dout: grad w.r.t. this block's output.  Accumulates into d_dlatent_pre (pre-activation gradient of
+        the last mapping layer) unless `first`, and writes the gradient of the conv input into dx."""
+        B = self.dstyle.shape[0]
+        ops.instnorm_style_bwd(dout, self.y, self.conv.y, self.stats, self.style.y.view(B, -1), self.dstyle, self.dconv, LEAKY)
+        self.style.backward(self.dstyle.view(B, 1, 1, -1), dx=d_dlatent_pre, producer=(dlatent_out, LEAKY),
+                            accumulate=not first)
+        self.conv.backward(self.dconv, dx=dx, producer=conv_producer)
+
+
+class CelebAOuterVAE:
+    """CelebAModel_densenet encoder / decoder (codes/models.py:392-587) for a fixed batch size."""
+    last_act = None
+
+    def __init__(self, config, group, B, device, allreduce, world):
+        self.cfg, self.group, self.B, self.dev, self.world = config, group, B, device, world
+        H, C, k = int(config['num_hidden_units']), int(config['code_size']), int(config['kernel_size'])
+        ch, S = int(config['dim_input_channel']), int(config['dim_input_x'])
+        G = ops.ConvGeom
+        self.buf = Buffers(device)
+        widths = [H // 4, H // 4, H // 2, H // 2, H, H]
+        self.enc = []
+        cin, hw = ch, S
+        for i, w in enumerate(widths):
+            g = G(B, hw, hw, cin, k, k, w, 2 if i < 5 else 1, 'same' if i < 5 else 'valid')
+            self.enc.append(BNBlock(group, i, g, device, allreduce))
+            cin, hw = w, g.OH
+        self.flat, self.C, self.H = hw * hw * cin, C, H
+        self.head_mean = Conv(group, 'encoder/code_mean', G.dense(B, self.flat, C), None, device)
+        self.head_std = Conv(group, 'encoder/code_std_dev', G.dense(B, self.flat, C), None, device)
+        self.mean = self.head_mean.y.view(B, C)
+        self.std = self.head_std.y.view(B, C)
+        self.z = torch.empty(B, C, device=device)
+        # decoder
+        self.dec_dense = Conv(group, 'decoder/dense', G.dense(B, C, H), LEAKY, device)
+        self.mapping = [Conv(group, 'decoder/dense_%d' % i, G.dense(B, H, H), LEAKY, device) for i in range(1, 9)]
+        self.conv0 = Conv(group, 'decoder/conv2d', G(B, 1, 1, H, 1, 1, H, 1, 'same'), None, device)
+        self.sb1 = StyleBlock(group, 1, 0, G(B, 2, 2, H, 3, 3, H, 1, 'same'), B, H, device)
+        self.sb2 = StyleBlock(group, 2, 1, G(B, 2, 2, H, 3, 3, H, 1, 'same'), B, H, device)
+        self.conv3 = Conv(group, 'decoder/conv2d_3', G(B, 8, 8, H, 3, 3, H, 1, 'same'), LEAKY, device)
+        self.sb4 = StyleBlock(group, 4, 2, G(B, 16, 16, H, 3, 3, H // 2, 1, 'same'), B, H, device)
+        self.conv5 = Conv(group, 'decoder/conv2d_5', G(B, 32, 32, H // 2, 3, 3, H // 2, 1, 'same'), LEAKY, device)
+        self.sb6 = StyleBlock(group, 6, 3, G(B, 64, 64, H // 2, 3, 3, H // 4, 1, 'same'), B, H, device)
+        self.conv7 = Conv(group, 'decoder/conv2d_7', G(B, 128, 128, H // 4, 3, 3, H // 4, 1, 'same'), LEAKY, device)
+        self.conv8 = Conv(group, 'decoder/conv2d_8', G(B, 128, 128, H // 4, 1, 1, ch, 1, 'same'), None, device)
+        self.decoded = self.conv8.y
+        E = lambda *shape: torch.empty(*shape, device=device)           # noqa: E731
+        self.r0, self.r2, self.r3 = E(B, 2, 2, H), E(B, 8, 8, H), E(B, 16, 16, H)
+        self.r4, self.r5, self.r6 = E(B, 32, 32, H // 2), E(B, 64, 64, H // 2), E(B, 128, 128, H // 4)
+
+    def encode(self, x, eps_z, stats_z):
+        B = self.B
+        h = x
+        for blk in self.enc:
+            h = blk.forward(h, self.world)
+        h = h.view(B, 1, 1, self.flat)
+        self.head_mean.forward(h)
+        self.head_std.forward(h)
+        ops.gauss_head_fwd(self.mean, self.std, eps_z, self.z, float(self.cfg['latent_variance_precision']), stats_z)
+        self.eps_z = eps_z
+        return self.z
+
+    def decode(self, z):
+        B, H = self.B, self.H
+        enc = self.dec_dense.forward(z.view(B, 1, 1, self.C))
+        dl = enc
+        for m in self.mapping:
+            dl = m.forward(dl)
+        h = self.conv0.forward(enc)
+        h = ops.resize_bilinear_fwd(h, self.r0)
+        h = self.sb1.forward(h, dl)
+        h = self.sb2.forward(h, dl)
+        h = self.conv3.forward(ops.resize_bilinear_fwd(h, self.r2))
+        h = self.sb4.forward(ops.resize_bilinear_fwd(h, self.r3), dl)
+        h = self.conv5.forward(ops.resize_bilinear_fwd(h, self.r4))
+        h = self.sb6.forward(ops.resize_bilinear_fwd(h, self.r5), dl)
+        h = self.conv7.forward(ops.resize_bilinear_fwd(h, self.r6))
+        return self.conv8.forward(h)
+
+    def decode_backward(self, dpre_last, dz, wgrad=True):
+        B, H = self.B, self.H
+        g = self.buf.get
+        dl_out = self.mapping[-1].y
+        d_dl = g('d_dl', B, 1, 1, H)                      # pre-activation gradient of the last mapping layer
+        d7 = g('d7', *self.conv7.y.shape)
+        self.conv8.backward(dpre_last, dx=d7, producer=(self.conv7.y, LEAKY), wgrad=wgrad)
+        dr6 = g('dr6', *self.r6.shape)
+        self.conv7.backward(d7, dx=dr6, wgrad=wgrad)
+        da6 = g('da6', *self.sb6.y.shape)
+        ops.resize_bilinear_bwd(dr6, da6)
+        dr5 = g('dr5', *self.r5.shape)
+        self.sb6.backward(da6, dr5, d_dl, dl_out, first=True)
+        da5 = g('da5', *self.conv5.y.shape)
+        ops.resize_bilinear_bwd(dr5, da5)
+        ops.act_bwd(da5, self.conv5.y, LEAKY)
+        dr4 = g('dr4', *self.r4.shape)
+        self.conv5.backward(da5, dx=dr4, wgrad=wgrad)
+        da4 = g('da4', *self.sb4.y.shape)
+        ops.resize_bilinear_bwd(dr4, da4)
+        dr3 = g('dr3', *self.r3.shape)
+        self.sb4.backward(da4, dr3, d_dl, dl_out, first=False)
+        da3 = g('da3', *self.conv3.y.shape)
+        ops.resize_bilinear_bwd(dr3, da3)
+        ops.act_bwd(da3, self.conv3.y, LEAKY)
+        dr2 = g('dr2', *self.r2.shape)
+        self.conv3.backward(da3, dx=dr2, wgrad=wgrad)
+        da2 = g('da2', *self.sb2.y.shape)
+        ops.resize_bilinear_bwd(dr2, da2)
+        da1 = g('da1', *self.sb1.y.shape)
+        self.sb2.backward(da2, da1, d_dl, dl_out, first=False)
+        dr0 = g('dr0', *self.r0.shape)
+        self.sb1.backward(da1, dr0, d_dl, dl_out, first=False)
+        dh0 = g('dh0', B, 1, 1, H)
+        ops.resize_bilinear_bwd(dr0, dh0)
+        d_enc = g('d_enc', B, 1, 1, H)                    # pre-activation gradient of decoder/dense
+        enc = self.dec_dense.y
+        self.conv0.backward(dh0, dx=d_enc, producer=(enc, LEAKY), wgrad=wgrad)
+        dcur = d_dl
+        for i in range(len(self.mapping) - 1, 0, -1):
+            nxt = g('dmap%d' % (i % 2), B, 1, 1, H)
+            self.mapping[i].backward(dcur, dx=nxt, producer=(self.mapping[i - 1].y, LEAKY), wgrad=wgrad)
+            dcur = nxt
+        self.mapping[0].backward(dcur, dx=d_enc, producer=(enc, LEAKY), wgrad=wgrad, accumulate=True)
+        self.dec_dense.backward(d_enc, dx=dz.view(B, 1, 1, self.C), wgrad=wgrad)
+        return dz
+
+    def encode_backward(self, dz, c_entropy, c_sg):
+        B, C = self.B, self.C
+        floor = float(self.cfg['latent_variance_precision'])
+        dmean, dstd = self.buf.get('dmean', B, C), self.buf.get('dstd', B, C)
+        ops.gauss_head_bwd(dz, self.mean, self.std, self.eps_z, None, None, dmean, dstd, floor, c_entropy, c_sg)
+        dflat = self.buf.get('dflat', B, 1, 1, self.flat)
+        self.head_mean.backward(dmean.view(B, 1, 1, C), dx=dflat)
+        self.head_std.backward(dstd.view(B, 1, 1, C), dx=dflat, accumulate=True)
+        dout = dflat.view(*self.enc[-1].y.shape)
+        for i in range(len(self.enc) - 1, -1, -1):
+            dx = self.buf.get('de%d' % i, *self.enc[i - 1].y.shape) if i > 0 else None
+            self.enc[i].backward(dout, dx, self.world)
+            dout = dx
+
+
 # ------------------------------------------------------------------------------ prior ("inner") VAE
 class PriorVAE:
     """define_inner_VAE_prior (codes/base.py:127-213): two 5-layer MLPs around t."""
@@ -345,6 +540,32 @@ def vae_param_specs(config):
         dense('decoder', 'dense', C, H)
         for i, (kk, a, b) in enumerate([(1, H // 4, H), (3, H // 4, H), (3, H // 4, H), (3, H // 4, H), (5, H // 4, 1)]):
             conv('decoder', i, kk, a, b)
+    elif exp == 'celeba':
+        widths = [H // 4, H // 4, H // 2, H // 2, H, H]
+        cin = ch
+        for i, wd in enumerate(widths):
+            conv('encoder', i, k, cin, wd)
+            bn = 'batch_normalization' if i == 0 else 'batch_normalization_%d' % i
+            out.extend([('encoder/%s/gamma' % bn, (wd,)), ('encoder/%s/beta' % bn, (wd,))])
+            cin = wd
+        dense('encoder', 'code_mean', 4 * H, C)
+        dense('encoder', 'code_std_dev', 4 * H, C)
+        dense('decoder', 'dense', C, H)
+        for i in range(1, 9):
+            dense('decoder', 'dense_%d' % i, H, H)
+        conv('decoder', 0, 1, H, H)
+        conv('decoder', 1, 3, H, H)
+        dense('decoder/StyleMod_0', 'dense', H, 2 * H)
+        conv('decoder', 2, 3, H, H)
+        dense('decoder/StyleMod_1', 'dense', H, 2 * H)
+        conv('decoder', 3, 3, H, H)
+        conv('decoder', 4, 3, H, H // 2)
+        dense('decoder/StyleMod_2', 'dense', H, H)
+        conv('decoder', 5, 3, H // 2, H // 2)
+        conv('decoder', 6, 3, H // 2, H // 4)
+        dense('decoder/StyleMod_3', 'dense', H, H // 2)
+        conv('decoder', 7, 3, H // 4, H // 4)
+        conv('decoder', 8, 1, H // 4, ch)
     else:
         raise NotImplementedError('engine: exp_name %r' % exp)
     return out
@@ -396,7 +617,10 @@ class LadderEngine:
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(seed)
         self.init_params()
-        self.outer = MnistOuterVAE(config, self.ae, B, dev)
+        if config['exp_name'] == 'celeba':
+            self.outer = CelebAOuterVAE(config, self.ae, B, dev, self._allreduce, self.world)
+        else:
+            self.outer = MnistOuterVAE(config, self.ae, B, dev)
         self.pvae = PriorVAE(config, self.prior_g, B, dev) if self.has_prior else None
         self.scalars = torch.zeros(ops.SCALARS_LEN, device=dev)
         self.eps_z = torch.zeros(B, self.C, device=dev)
@@ -427,6 +651,8 @@ class LadderEngine:
                     t.fill_(float(self.cfg['inner_sigma']))
                 elif name.endswith('/kernel'):
                     glorot_uniform_(t, shape, self.gen)
+                elif name.endswith('/gamma'):
+                    t.fill_(1.0)
                 else:
                     t.zero_()
 
@@ -529,7 +755,7 @@ class LadderEngine:
     def step_ae(self, x, apply=True):
         """train_step_ae: forward everything, d loss_ae / d (encoder, decoder), clip + Adam."""
         self.forward(x, dec=True, prior=True, mix=True)
-        ops.l1_recon_bwd(x, self.outer.decoded, self.scalars, self.dpre_last, 'relu')
+        ops.l1_recon_bwd(x, self.outer.decoded, self.scalars, self.dpre_last, self.outer.last_act)
         self.outer.decode_backward(self.dpre_last, self.dz)
         if self.has_prior and not self.use_sg:
             self._prior_backward(self.dz, wgrad=False)

@@ -37,6 +37,7 @@ SIGNATURES = {
     'ladder_conv2d_tc_workspace_bytes': (C.c_size_t, [C.c_int] * 7),
     'ladder_conv2d_fprop_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 13 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_dgrad_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 14 + [ptr, C.c_size_t, stream_t]),
+    'ladder_conv2d_wgrad_tc_supported': (C.c_int, [C.c_int, C.c_int]),
     'ladder_conv2d_wgrad_tc': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [stream_t]),
     # layout / elementwise
     'ladder_sym_pad': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),
@@ -44,6 +45,15 @@ SIGNATURES = {
     'ladder_space_to_depth_actgrad': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 6 + [stream_t]),
     'ladder_act_bwd': (C.c_int, [ptr, ptr, C.c_longlong, C.c_int, stream_t]),
     'ladder_axpy': (C.c_int, [ptr, ptr, C.c_float, C.c_longlong, stream_t]),
+    # CelebA-only layers
+    'ladder_bn_stats': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, stream_t]),
+    'ladder_bn_apply': (C.c_int, [ptr, ptr, ptr, ptr, ptr, C.c_longlong, C.c_int, C.c_longlong, C.c_float, C.c_int, stream_t]),
+    'ladder_bn_bwd_stats': (C.c_int, [ptr, ptr, ptr, ptr, C.c_longlong, C.c_int, C.c_longlong, C.c_float, C.c_int, ptr, stream_t]),
+    'ladder_bn_bwd_apply': (C.c_int, [ptr] * 7 + [C.c_longlong, C.c_int, C.c_longlong, C.c_float, C.c_int, stream_t]),
+    'ladder_instnorm_style_fwd': (C.c_int, [ptr, ptr, ptr, ptr, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, stream_t]),
+    'ladder_instnorm_style_bwd': (C.c_int, [ptr] * 7 + [C.c_int, C.c_int, C.c_int, C.c_int, stream_t]),
+    'ladder_resize_bilinear_fwd': (C.c_int, [ptr, ptr] + [C.c_int] * 6 + [stream_t]),
+    'ladder_resize_bilinear_bwd': (C.c_int, [ptr, ptr] + [C.c_int] * 6 + [stream_t]),
     # ELBO pieces
     'ladder_gauss_head_fwd': (C.c_int, [ptr, ptr, ptr, ptr, C.c_longlong, C.c_float, ptr, stream_t]),
     'ladder_gauss_head_bwd': (C.c_int, [ptr] * 8 + [C.c_longlong, C.c_float, C.c_float, C.c_float, stream_t]),

@@ -257,7 +257,7 @@ def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False):
 
 
 def conv2d_wgrad(x, dy, dw, dbias, g):
-    if _use_tc(g):
+    if _use_tc(g) and g.Cin % 64 == 0:
         _lib.check(_L().ladder_conv2d_wgrad_tc(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dw)), *g.args(), _stream()),
                    'conv2d_wgrad_tc')
         if dbias is not None:
@@ -359,3 +359,61 @@ def clip_adam(param, grad, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.95, eps=1e
 
 def increment(counter):
     _lib.check(_L().ladder_increment(_p(counter), _stream()), 'increment')
+
+
+# ------------------------------------------------------------------------------ CelebA-only layers
+BN_EPS = 1e-3        # tf.layers.batch_normalization default epsilon
+IN_EPS = 1e-6        # tf.contrib.layers.instance_norm default epsilon
+
+
+def bn_stats(x, sums2c):
+    Cc = x.shape[-1]
+    _lib.check(_L().ladder_bn_stats(_p(_f32(x)), x.numel() // Cc, Cc, _p(sums2c), _stream()), 'bn_stats')
+
+
+def bn_apply(x, sums2c, gamma, beta, y, count, act='leaky_relu'):
+    Cc = x.shape[-1]
+    _lib.check(_L().ladder_bn_apply(_p(_f32(x)), _p(sums2c), _p(gamma), _p(beta), _p(_f32(y)), x.numel() // Cc, Cc,
+                                    int(count), BN_EPS, ACT[act], _stream()), 'bn_apply')
+    return y
+
+
+def bn_bwd_stats(dout, y, x, sums2c, dsums2c, count, act='leaky_relu'):
+    Cc = x.shape[-1]
+    _lib.check(_L().ladder_bn_bwd_stats(_p(_f32(dout)), _p(y), _p(x), _p(sums2c), x.numel() // Cc, Cc, int(count), BN_EPS,
+                                        ACT[act], _p(dsums2c), _stream()), 'bn_bwd_stats')
+
+
+def bn_bwd_apply(dout, y, x, sums2c, dsums2c, gamma, dx, count, act='leaky_relu'):
+    Cc = x.shape[-1]
+    _lib.check(_L().ladder_bn_bwd_apply(_p(_f32(dout)), _p(y), _p(x), _p(sums2c), _p(dsums2c), _p(gamma), _p(_f32(dx)),
+                                        x.numel() // Cc, Cc, int(count), BN_EPS, ACT[act], _stream()), 'bn_bwd_apply')
+    return dx
+
+
+def instnorm_style_fwd(x, style, stats, y, act='leaky_relu'):
+    B, H, W, Cc = x.shape
+    _lib.check(_L().ladder_instnorm_style_fwd(_p(_f32(x)), _p(_f32(style)), _p(stats), _p(_f32(y)), B, H * W, Cc, IN_EPS,
+                                              ACT[act], _stream()), 'instnorm_style_fwd')
+    return y
+
+
+def instnorm_style_bwd(dout, y, x, stats, style, dstyle, dx, act='leaky_relu'):
+    B, H, W, Cc = x.shape
+    _lib.check(_L().ladder_instnorm_style_bwd(_p(_f32(dout)), _p(y), _p(x), _p(stats), _p(style), _p(_f32(dstyle)),
+                                              _p(_f32(dx)), B, H * W, Cc, ACT[act], _stream()), 'instnorm_style_bwd')
+    return dx
+
+
+def resize_bilinear_fwd(x, y):
+    B, H, W, Cc = x.shape
+    _lib.check(_L().ladder_resize_bilinear_fwd(_p(_f32(x)), _p(_f32(y)), B, H, W, Cc, y.shape[1], y.shape[2], _stream()),
+               'resize_bilinear_fwd')
+    return y
+
+
+def resize_bilinear_bwd(dy, dx):
+    B, H, W, Cc = dx.shape
+    _lib.check(_L().ladder_resize_bilinear_bwd(_p(_f32(dy)), _p(_f32(dx)), B, H, W, Cc, dy.shape[1], dy.shape[2],
+                                               _stream()), 'resize_bilinear_bwd')
+    return dx
