@@ -175,6 +175,8 @@ def run_ours(args):
     cfg = load_config(B)
     cfg['seed'] = 1234
     cfg['compute_dtype'] = args.dtype
+    if args.no_graphs:
+        cfg['cuda_graphs'] = False
     K, R = cfg['n_mixtures'], cfg['representation_size']
     epoch = cfg['sg_pretraining'] + 1            # past pretraining: all four sub-steps active, fitted mixture fed
     gm = synthetic_mixture(K, R)
@@ -194,14 +196,8 @@ def run_ours(args):
     pool = [torch.rand(B, 28, 28, 1, device=dev, generator=gen) for _ in range(n_pool)]
 
     def iteration(x):
-        eng.draw_noise()
-        eng.step_ae(x)
-        eng.draw_noise(t=False, mc=False)
-        eng.step_sigma(x)
-        eng.draw_noise()
-        eng.step_prior(x)
-        eng.draw_noise(mc=False)
-        eng.step_inner_sigma(x)
+        for name in ('ae', 'sigma', 'prior', 'inner_sigma'):
+            eng.run_step(name, x)
 
     def barrier():
         if world > 1:
@@ -334,7 +330,7 @@ def run_ours(args):
                 'vs_baseline': None, 'dtype': 'bf16' if args.dtype == 'bf16' else 'f32', 'data': 'synthetic',
                 'config': {'workload': 'codes/mnist_fashion_config.json @ batch %d per GPU, epoch %d (all 4 sub-steps, '
                                        '50-component hyper-prior, L=100 MC samples)' % (B, epoch),
-                           'global_batch': B * world, 'parallelism': 'dp%d' % world,
+                           'global_batch': B * world, 'parallelism': 'dp%d' % world, 'cuda_graphs': bool(eng.use_graphs),
                            'l2': 'per-step activation working set (>1 GB) exceeds the 126 MB L2; 4 input batches rotate'},
                 'clocks': clocks, 'gpu_launches': launches,
                 'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': B * 784 * 4,
@@ -356,6 +352,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1024, help='images per GPU')
+    ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of CUDA-graph replay')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'], help='GEMM math: bf16 tcgen05 or fp32 SIMT')
     ap.add_argument('--cpu-sample', type=int, default=32, help='batch of the bounded CPU-baseline sample')
     args = ap.parse_args()

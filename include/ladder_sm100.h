@@ -112,7 +112,8 @@ int ladder_conv2d_dgrad_tc(const float* dy, const float* w, const float* act_out
                            cudaStream_t stream);
 int ladder_conv2d_wgrad_tc_supported(int Cin, int Cout);   /* 1 iff Cin % 64 == 0 */
 int ladder_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int KH, int KW,
-                           int Cout, int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream);
+                           int Cout, int stride, int pad_t, int pad_l, int OH, int OW, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Layout ops.  replaces tf.pad(..., "SYMMETRIC") codes/models.py:48-50,200-202 and

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "ladder_sm100.h"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace ladder {
 namespace tc {
@@ -28,8 +29,10 @@ namespace tc {
 constexpr int BM = 128;            // UMMA M (TMEM lanes)
 constexpr int BK = 64;             // bf16 per k-block = one 128-byte swizzle row
 constexpr int STAGES = 4;
-constexpr int PRODUCERS = 128;     // threads
-constexpr int NTHREADS = 288;      // 4 producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int PROD_WARPS = 8;
+constexpr int PRODUCERS = PROD_WARPS * 32;   // threads
+constexpr int MMA_WARP = PROD_WARPS;         // warp 8
+constexpr int NTHREADS = (PROD_WARPS + 1 + 4) * 32;   // 8 producer warps, 1 MMA warp, 4 epilogue warps = 416
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
@@ -43,9 +46,11 @@ struct TcArgs {
   float* out;
   int B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW;
   int act, accumulate;
-  int k_per_split;             // WGRAD: pixels per grid.z slice (multiple of BK)
+  int k_per_split;             // WGRAD: pixels per split (multiple of BK)
   int Kpad;                    // FPROP/DGRAD: padded reduction length (multiple of BK)
   int m_valid;                 // rows of the output that exist (WGRAD with padded taps)
+  int m_tiles, n_tiles, splits;   // persistent tile space
+  int debug;                   // bring-up only (LADDER_TC_DEBUG): 1 skip A loads, 2 skip B copies, 4 skip epilogue stores
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -198,19 +203,55 @@ __device__ __forceinline__ void sts64(uint32_t addr, float4 v) {
                "r"(*reinterpret_cast<uint32_t*>(&p1)) : "memory");
 }
 
+// One unit of persistent work: output tile (m_tile, n_tile) and, for WGRAD, a slice of the pixel reduction.
+struct Tile {
+  long long t;
+  int m_tile, n_tile, nkb;
+  long long k_lo;     // WGRAD: first pixel of the slice
+  bool valid;
+};
+
+template <int MODE>
+__device__ __forceinline__ void decode_tile(const TcArgs& a, long long t, long long total, long long pixels, Tile& c) {
+  c.t = t;
+  c.valid = t < total;
+  if (!c.valid) { c.nkb = 0; return; }
+  c.n_tile = (int)(t % a.n_tiles);
+  const long long r = t / a.n_tiles;
+  if (MODE == WGRAD) {
+    c.m_tile = (int)(r % a.m_tiles);
+    const long long split = r / a.m_tiles;
+    c.k_lo = split * a.k_per_split;
+    const long long k_hi = min(pixels, c.k_lo + a.k_per_split);
+    c.nkb = (int)((k_hi - c.k_lo + BK - 1) / BK);
+  } else {
+    c.m_tile = (int)r;
+    c.k_lo = 0;
+    c.nkb = a.Kpad / BK;
+  }
+}
+
+// Persistent warp-specialised implicit GEMM.  grid = min(#tiles, #SMs); each CTA walks tiles blockIdx.x, +gridDim.x, ...
+//   warps 0-7  producers: gather fp32 activations (coalesced: 16 lanes = 256 B = 64 channels of one row), keep TWO
+//              k-blocks in flight in registers, convert to bf16, store the SWIZZLE_128B operand tile; one thread
+//              also issues the bulk-TMA copy of the pre-packed bf16 B tile (weights, or dy for WGRAD)
+//   warp  8    MMA issuer (tcgen05.mma, accumulators double-buffered in TMEM so the epilogue of tile i overlaps
+//              the mainloop of tile i+1)
+//   warps 9-12 epilogue (tcgen05.ld -> fused bias/activation | act'-multiply/accumulate | split-K red.add)
 template <int MODE, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t sA = base, sB = base + STAGES * A_STAGE_BYTES;
-  const uint32_t bars = sB + STAGES * B_STAGE_BYTES;            // full[STAGES], empty[STAGES], tmem_full (8 B each)
-  const uint32_t slot = bars + (2 * STAGES + 1) * 8;
+  const uint32_t bars = sB + STAGES * B_STAGE_BYTES;            // full[S], empty[S], tfull[2], tempty[2]
+  const uint32_t bar_full = bars, bar_empty = bars + STAGES * 8, bar_tfull = bars + 2 * STAGES * 8,
+                 bar_tempty = bars + (2 * STAGES + 2) * 8;
+  const uint32_t slot = bars + (2 * STAGES + 4) * 8;
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (slot - base));
-  int* rowinfo = reinterpret_cast<int*>(smem + (slot + 16 - base));     // [2][128][3] (b, y, x) of tile rows / pixels
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long pixels = MODE == DGRAD ? (long long)a.B * a.H * a.W : (long long)a.B * a.OH * a.OW;
@@ -218,259 +259,304 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
   const int patch = a.KH * a.KW * C;
   const long long Mg = MODE == WGRAD ? patch : pixels;
   const int Ng = MODE == DGRAD ? a.Cin : a.Cout;
-  const long long m0 = (long long)blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
-  long long k_lo = 0, k_hi = a.Kpad;
-  if (MODE == WGRAD) {
-    k_lo = (long long)blockIdx.z * a.k_per_split;
-    k_hi = min(pixels, k_lo + a.k_per_split);
-  }
-  const int num_kb = (int)((k_hi - k_lo + BK - 1) / BK);
+  const long long total = (long long)a.m_tiles * a.n_tiles * a.splits;
   const int gw = MODE == DGRAD ? a.W : a.OW, gh = MODE == DGRAD ? a.H : a.OH;   // pixel grid of the rows
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bars + s * 8, PRODUCERS);
-      mbar_init(bars + (STAGES + s) * 8, 1);
+      mbar_init(bar_full + s * 8, PRODUCERS);
+      mbar_init(bar_empty + s * 8, 1);
     }
-    mbar_init(bars + 2 * STAGES * 8, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + i * 8, 1);
+      mbar_init(bar_tempty + i * 8, 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (MODE != WGRAD && tid < BM) {            // (b, y, x) of every tile row, shared by the coalesced gather
-    const long long p = m0 + tid;
-    int b = -1, y = 0, x = 0;
-    if (p < pixels) {
-      x = (int)(p % gw);
-      const long long r = p / gw;
-      y = (int)(r % gh);
-      b = (int)(r / gh);
-    }
-    rowinfo[tid * 3] = b; rowinfo[tid * 3 + 1] = y; rowinfo[tid * 3 + 2] = x;
-  }
-  if (warp == 4) tmem_alloc(slot, TMEM_COLS);
+  if (warp == MMA_WARP) tmem_alloc(slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *slot_ptr;
 
-  if (warp < 4) {
+  if (warp < PROD_WARPS) {
     // ===================================================== producers
-    if (MODE != WGRAD) {
-      const bool fast = (C % BK == 0);         // a 64-wide k-block = 64 contiguous channels of one tap
-      const bool vec = (C % 8 == 0);
-      int pb = rowinfo[tid * 3], py = rowinfo[tid * 3 + 1], px = rowinfo[tid * 3 + 2];
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(bars + (STAGES + s) * 8, ((kb / STAGES) & 1) ^ 1);
-        const uint32_t tileA = sA + s * A_STAGE_BYTES;
-        if (fast) {
-          // coalesced: 16 lanes cover the 256 B (64 fp32 channels) of one row, 2 rows per warp instruction
-          const int q0 = kb * BK, tap = q0 / C, c0 = q0 % C, kh = tap / a.KW, kw = tap % a.KW;
-          const int f4 = lane & 15;
+    const int f4 = lane & 15, rsel = lane >> 4;
+    const bool fast = (C % BK == 0);
+    Tile L, S;                       // load cursor (two k-blocks ahead) and store cursor
+    int lkb = 0, skb = 0;
+    decode_tile<MODE>(a, blockIdx.x, total, pixels, L);
+    S = L;
+    // Affine fast path (64-aligned channels; FPROP any stride, DGRAD stride 1): the source offset of (row, tap, c)
+    // is rbase[row] + tapoff(tap) + c with a per-row validity mask per tap row / column, so a k-block costs one
+    // add + one predicate per 16-byte load instead of re-deriving (b, y, x) -> offset every time.
+    const bool affine = fast && (MODE == FPROP || (MODE == DGRAD && a.stride == 1));
+    long long rbase[8];
+    unsigned rvy[8], rvx[8];
+    auto pixel_affine = [&](long long p, long long lim, long long& base, unsigned& vy, unsigned& vx) {
+      base = 0; vy = 0; vx = 0;
+      if (p >= lim) return;
+      const unsigned pu = (unsigned)p;
+      const int x = (int)(pu % (unsigned)gw);
+      const unsigned r = pu / (unsigned)gw;
+      const int y = (int)(r % (unsigned)gh), b = (int)(r / (unsigned)gh);
+      if (MODE == DGRAD) {            // ny = y + pad_t - kh, nx = x + pad_l - kw  (stride 1)
+        base = (((long long)b * a.OH + y + a.pad_t) * a.OW + x + a.pad_l) * a.Cout;
+        for (int k = 0; k < a.KH; ++k) { const int ny = y + a.pad_t - k; vy |= (unsigned)(ny >= 0 && ny < a.OH) << k; }
+        for (int k = 0; k < a.KW; ++k) { const int nx = x + a.pad_l - k; vx |= (unsigned)(nx >= 0 && nx < a.OW) << k; }
+      } else {                        // iy = y*s - pad_t + kh, ix = x*s - pad_l + kw
+        base = (((long long)b * a.H + y * a.stride - a.pad_t) * a.W + x * a.stride - a.pad_l) * a.Cin;
+        for (int k = 0; k < a.KH; ++k) { const int iy = y * a.stride - a.pad_t + k; vy |= (unsigned)(iy >= 0 && iy < a.H) << k; }
+        for (int k = 0; k < a.KW; ++k) { const int ix = x * a.stride - a.pad_l + k; vx |= (unsigned)(ix >= 0 && ix < a.W) << k; }
+      }
+    };
+    auto tap_delta = [&](int kh, int kw) -> long long {
+      return MODE == DGRAD ? -((long long)kh * a.OW + kw) * a.Cout : ((long long)kh * a.W + kw) * a.Cin;
+    };
+    auto row_coords = [&]() {
+      if (MODE == WGRAD || !L.valid || !affine) return;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float4 v[8];
+      for (int i = 0; i < 8; ++i)
+        pixel_affine((long long)L.m_tile * BM + warp * 16 + i * 2 + rsel, pixels, rbase[i], rvy[i], rvx[i]);
+    };
+    row_coords();
+    auto load = [&](float4 (&v)[8]) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = warp * 32 + (half * 8 + it) * 2 + (lane >> 4);
-              const int b = rowinfo[row * 3], y = rowinfo[row * 3 + 1], x = rowinfo[row * 3 + 2];
-              v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (b >= 0) {
-                const long long off = tap_offset<MODE == DGRAD>(a, b, y, x, kh, kw, c0 + 4 * f4);
-                if (off >= 0) v[it] = __ldg(reinterpret_cast<const float4*>(a.src + off));
+      for (int i = 0; i < 8; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!L.valid || (a.debug & 1)) return;
+      if (MODE != WGRAD) {
+        if (affine) {
+          const int q0 = lkb * BK, tap = q0 / C, c0 = q0 % C, kh = tap / a.KW, kw = tap % a.KW;
+          const float* srck = a.src + tap_delta(kh, kw) + c0 + 4 * f4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if ((rvy[i] >> kh) & (rvx[i] >> kw) & 1u) v[i] = __ldg(reinterpret_cast<const float4*>(srck + rbase[i]));
+        } else {
+          // general gather (narrow / ragged channel counts, strided dgrad): 4 patch entries per lane, element-wise
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long p = (long long)L.m_tile * BM + warp * 16 + i * 2 + rsel;
+            if (p >= pixels) continue;
+            const unsigned pu = (unsigned)p;
+            const int x = (int)(pu % (unsigned)gw);
+            const unsigned r = pu / (unsigned)gw;
+            const int y = (int)(r % (unsigned)gh), b = (int)(r / (unsigned)gh);
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int q = lkb * BK + 4 * f4 + j;
+              if (q < patch) {
+                const int tap = q / C, c = q % C;
+                const long long off = tap_offset<MODE == DGRAD>(a, b, y, x, tap / a.KW, tap % a.KW, c);
+                if (off >= 0) e[j] = __ldg(a.src + off);
               }
             }
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int row = warp * 32 + (half * 8 + it) * 2 + (lane >> 4);
-              sts64(tileA + row * 128 + (((f4 >> 1) ^ (row & 7)) << 4) + (f4 & 1) * 8, v[it]);
-            }
-          }
-        } else {
-          const uint32_t rowA = tileA + tid * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float f[8];
-            if (pb >= 0) gather8<MODE == DGRAD>(a, pb, py, px, (long long)kb * BK + 8 * j, patch, C, vec, f);
-            else {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) f[q] = 0.f;
-            }
-            const uint4 u = pack8(f);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowA + ((j ^ (tid & 7)) << 4)), "r"(u.x), "r"(u.y),
-                         "r"(u.z), "r"(u.w) : "memory");
+            v[i] = make_float4(e[0], e[1], e[2], e[3]);
           }
         }
-        fence_proxy_async();
-        if (tid == 0) {
-          // B tile: one bulk TMA copy of the pre-swizzled bf16 weight tile image
-          mbar_arrive_expect_tx(bars + s * 8, B_STAGE_BYTES);
-          tma_bulk_g2s(sB + s * B_STAGE_BYTES,
-                       reinterpret_cast<const uint8_t*>(a.wt) + ((size_t)blockIdx.y * num_kb + kb) * B_STAGE_BYTES,
-                       B_STAGE_BYTES, bars + s * 8);
-        } else {
-          mbar_arrive(bars + s * 8);
+      } else {
+        // WGRAD A: 2 M-blocks (64 patch entries = 64 channels of one tap) x 64 pixels; i -> (block i/4, pixel (i%4)*16 + ..)
+        const long long lim = min(pixels, L.k_lo + a.k_per_split);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = j * 16 + warp * 2 + rsel;
+          long long base; unsigned vy, vx;
+          pixel_affine(L.k_lo + (long long)lkb * BK + k, lim, base, vy, vx);
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) {
+            const long long kd0 = (long long)L.m_tile * BM + mb * 64;
+            if (kd0 < patch) {
+              const int tap = (int)(kd0 / C), c0 = (int)(kd0 % C), kh = tap / a.KW, kw = tap % a.KW;
+              if ((vy >> kh) & (vx >> kw) & 1u)
+                v[mb * 4 + j] = __ldg(reinterpret_cast<const float4*>(a.src + base + tap_delta(kh, kw) + c0 + 4 * f4));
+            }
+          }
         }
       }
-    } else {
-      // WGRAD: reduction over pixels.  Both operands are staged MN-major: row = pixel, 64 contiguous
-      // channels (128 B of bf16) per row, one [64 pixels x 128 B] swizzled block per 64 M- (or N-) elements.
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(bars + (STAGES + s) * 8, ((kb / STAGES) & 1) ^ 1);
-        int* ri = rowinfo + (kb & 1) * (BK * 3);
-        if (tid < BK) {
-          const long long p = k_lo + (long long)kb * BK + tid;
-          int b = -1, y = 0, x = 0;
-          if (p < k_hi) {
-            x = (int)(p % a.OW);
-            const long long r = p / a.OW;
-            y = (int)(r % a.OH);
-            b = (int)(r / a.OH);
-          }
-          ri[tid * 3] = b; ri[tid * 3 + 1] = y; ri[tid * 3 + 2] = x;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const uint32_t tileA = sA + s * A_STAGE_BYTES, tileB = sB + s * B_STAGE_BYTES;
-        const int f4 = lane & 15;
-        // A: 2 M-blocks of 64 patch entries (one tap's 64 channels each)
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          const long long kd0 = m0 + mb * 64;
-          const bool blk_ok = kd0 < patch;
-          const int tap = blk_ok ? (int)(kd0 / C) : 0, c0 = blk_ok ? (int)(kd0 % C) : 0, kh = tap / a.KW, kw = tap % a.KW;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float4 v[4];
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int k = warp * 16 + (half * 4 + it) * 2 + (lane >> 4);
-              const int b = ri[k * 3], y = ri[k * 3 + 1], x = ri[k * 3 + 2];
-              v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (blk_ok && b >= 0) {
-                const long long off = tap_offset<false>(a, b, y, x, kh, kw, c0 + 4 * f4);
-                if (off >= 0) v[it] = __ldg(reinterpret_cast<const float4*>(a.src + off));
-              }
-            }
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int k = warp * 16 + (half * 4 + it) * 2 + (lane >> 4);
-              sts64(tileA + mb * 8192 + k * 128 + (((f4 >> 1) ^ (k & 7)) << 4) + (f4 & 1) * 8, v[it]);
-            }
-          }
-        }
-        // B: BN/64 N-blocks of 64 output channels of dy
-        const bool vecn = (a.Cout & 3) == 0;
-#pragma unroll 1
-        for (int nb = 0; nb < BN / 64; ++nb) {
-          const int co = n0 + nb * 64 + 4 * f4;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float4 v[4];
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int k = warp * 16 + (half * 4 + it) * 2 + (lane >> 4);
-              const long long p = k_lo + (long long)kb * BK + k;
-              v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p < k_hi && co < a.Cout) {
-                const float* g = a.src2 + p * a.Cout + co;
-                if (vecn) v[it] = __ldg(reinterpret_cast<const float4*>(g));
-                else {
-                  v[it].x = __ldg(g);
-                  if (co + 1 < a.Cout) v[it].y = __ldg(g + 1);
-                  if (co + 2 < a.Cout) v[it].z = __ldg(g + 2);
-                  if (co + 3 < a.Cout) v[it].w = __ldg(g + 3);
-                }
-              }
-            }
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int k = warp * 16 + (half * 4 + it) * 2 + (lane >> 4);
-              sts64(tileB + nb * 8192 + k * 128 + (((f4 >> 1) ^ (k & 7)) << 4) + (f4 & 1) * 8, v[it]);
-            }
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(bars + s * 8);
+    };
+    auto advance_load = [&]() {
+      if (!L.valid) return;
+      if (++lkb == L.nkb) {
+        lkb = 0;
+        decode_tile<MODE>(a, L.t + gridDim.x, total, pixels, L);
+        row_coords();
       }
+    };
+    unsigned it = 0;                 // global k-block counter -> stage / phase
+    auto store = [&](const float4 (&v)[8]) {
+      const int s = it % STAGES;
+      mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
+      const uint32_t tileA = sA + s * A_STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (MODE != WGRAD) {
+          const int row = warp * 16 + i * 2 + rsel;
+          sts64(tileA + row * 128 + (((f4 >> 1) ^ (row & 7)) << 4) + (f4 & 1) * 8, v[i]);
+        } else {
+          const int mb = i >> 2, k = (i & 3) * 16 + warp * 2 + rsel;
+          sts64(tileA + mb * 8192 + k * 128 + (((f4 >> 1) ^ (k & 7)) << 4) + (f4 & 1) * 8, v[i]);
+        }
+      }
+      // NOTE: the generic->async proxy fence is issued by the MMA thread after it has acquired the stage
+      // (see below).  A writer-side fence.proxy.async lowers to MEMBAR.ALL.CTA, which would drain this
+      // thread's in-flight prefetch loads and serialise the pipeline on HBM latency.
+      if (tid == 0 && !(a.debug & 2)) {
+        // B tile image: weights [n_tile][kb], or dy [global k-block][n_tile] for WGRAD
+        const size_t tile_idx = MODE == WGRAD ? ((size_t)(S.k_lo / BK + skb) * a.n_tiles + S.n_tile)
+                                              : ((size_t)S.n_tile * S.nkb + skb);
+        mbar_arrive_expect_tx(bar_full + s * 8, B_STAGE_BYTES);
+        tma_bulk_g2s(sB + s * B_STAGE_BYTES, reinterpret_cast<const uint8_t*>(a.wt) + tile_idx * B_STAGE_BYTES,
+                     B_STAGE_BYTES, bar_full + s * 8);
+      } else {
+        mbar_arrive(bar_full + s * 8);
+      }
+      ++it;
+      if (++skb == S.nkb) {
+        skb = 0;
+        decode_tile<MODE>(a, S.t + gridDim.x, total, pixels, S);
+      }
+    };
+    float4 va[8], vb[8];
+    load(va); advance_load();
+    load(vb); advance_load();
+    while (S.valid) {
+      store(va);
+      load(va); advance_load();
+      if (!S.valid) break;
+      store(vb);
+      load(vb); advance_load();
     }
-  } else if (warp == 4) {
+  } else if (warp == MMA_WARP) {
     // ===================================================== MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN, MODE == WGRAD);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(bars + s * 8, (kb / STAGES) & 1);
+      Tile T;
+      decode_tile<MODE>(a, blockIdx.x, total, pixels, T);
+      unsigned it = 0, j = 0;
+      while (T.valid) {
+        const uint32_t acc = j & 1;
+        mbar_wait(bar_tempty + acc * 8, ((j >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tA = sA + s * A_STAGE_BYTES, tB = sB + s * B_STAGE_BYTES;
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < T.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(bar_full + s * 8, (it / STAGES) & 1);   // acquire: all producers' st.shared of this stage
+          fence_proxy_async();                               // ... made visible to the async proxy (tcgen05.mma reads)
+          tc_fence_after();
+          const uint32_t tA = sA + s * A_STAGE_BYTES, tB = sB + s * B_STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          if (MODE == WGRAD)       // 16 pixels = two 8-row groups = 2048 B per K step; 64-element MN blocks 8192 B apart
-            umma_bf16(tmem_base, make_desc_mn(tA + k * 2048, 8192), make_desc_mn(tB + k * 2048, 8192), idesc, (kb | k) != 0);
-          else                     // +32 bytes per 16-element K step inside the swizzle atom
-            umma_bf16(tmem_base, make_desc(tA + k * 32), make_desc(tB + k * 32), idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            if (MODE == WGRAD)     // 16 pixels = two 8-row groups = 2048 B per K step; 64-element MN blocks 8192 B apart
+              umma_bf16(tmem_d, make_desc_mn(tA + k * 2048, 8192), make_desc_mn(tB + k * 2048, 8192), idesc, (kb | k) != 0);
+            else                   // +32 bytes per 16-element K step inside the swizzle atom
+              umma_bf16(tmem_d, make_desc(tA + k * 32), make_desc(tB + k * 32), idesc, (kb | k) != 0);
+          }
+          umma_commit(bar_empty + s * 8);          // stage is free once these MMAs retire
         }
-        umma_commit(bars + (STAGES + s) * 8);      // stage is free once these MMAs retire
+        umma_commit(bar_tfull + acc * 8);          // accumulator complete
+        ++j;
+        decode_tile<MODE>(a, T.t + gridDim.x, total, pixels, T);
       }
-      umma_commit(bars + 2 * STAGES * 8);          // accumulator complete
     }
     __syncwarp();
   } else {
-    // ===================================================== epilogue (TMEM -> registers -> global)
-    mbar_wait(bars + 2 * STAGES * 8, 0);
-    tc_fence_after();
+    // ===================================================== epilogue (TMEM -> registers -> smem transpose -> global)
+    // tcgen05.ld hands every thread one accumulator ROW; stores of that shape are 32 scattered 16-byte pieces per
+    // instruction.  Each warp therefore transposes its 32x32 chunk through a private padded smem tile so that 8
+    // lanes cover 128 contiguous bytes of one output row (coalesced 16-byte loads/stores, 4 rows per instruction).
     const int quad = warp & 3;                     // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
-    const int row = quad * 32 + lane;
-    const long long m = m0 + row;
-    const bool row_ok = m < Mg && (MODE != WGRAD || m < a.m_valid);
+    float* stage = reinterpret_cast<float*>(smem + (slot + 16 - base)) + quad * (32 * 36);
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    Tile T;
+    decode_tile<MODE>(a, blockIdx.x, total, pixels, T);
+    unsigned j = 0;
+    while (T.valid) {
+      const uint32_t acc = j & 1;
+      mbar_wait(bar_tfull + acc * 8, (j >> 1) & 1);
+      tc_fence_after();
+      const long long mrow0 = (long long)T.m_tile * BM + quad * 32;
+      const int n0 = T.n_tile * BN;
+      const long long mlim = MODE == WGRAD ? min(Mg, (long long)a.m_valid) : Mg;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + c0, v);
-      if (num_kb == 0) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c0, v);
+        const int nb = n0 + c0;
+        if (nb >= Ng || (a.debug & 4)) continue;            // warp-uniform
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-      }
-      if (!row_ok) continue;
-      const int nb = n0 + c0;
-      if (nb >= Ng) continue;
-      float* o = a.out + m * Ng + nb;
-      if (MODE == FPROP) {
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        __syncwarp();
+        const int col = nb + c4;
+        const bool vec_ok = (Ng & 3) == 0 && col + 4 <= Ng;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == FPROP && a.bias != nullptr) {
+          if (col < Ng) bias4.x = __ldg(a.bias + col);
+          if (col + 1 < Ng) bias4.y = __ldg(a.bias + col + 1);
+          if (col + 2 < Ng) bias4.z = __ldg(a.bias + col + 2);
+          if (col + 3 < Ng) bias4.w = __ldg(a.bias + col + 3);
+        }
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (nb + i < Ng) v[i] = act_apply(v[i] + (a.bias != nullptr ? __ldg(a.bias + nb + i) : 0.f), a.act);
-      } else if (MODE == DGRAD) {
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + sub;
+          const long long m = mrow0 + r;
+          float4 q = *reinterpret_cast<const float4*>(stage + r * 36 + c4);
+          if (m >= mlim || col >= Ng) continue;
+          float* o = a.out + m * Ng + col;
+          float e[4] = {q.x, q.y, q.z, q.w};
+          if (MODE == FPROP) {
+            e[0] = act_apply(e[0] + bias4.x, a.act); e[1] = act_apply(e[1] + bias4.y, a.act);
+            e[2] = act_apply(e[2] + bias4.z, a.act); e[3] = act_apply(e[3] + bias4.w, a.act);
+          } else if (MODE == DGRAD) {
+            if (vec_ok) {
+              if (a.aux != nullptr) {
+                const float4 ax = __ldg(reinterpret_cast<const float4*>(a.aux + m * Ng + col));
+                e[0] *= act_grad_from_out(ax.x, a.act); e[1] *= act_grad_from_out(ax.y, a.act);
+                e[2] *= act_grad_from_out(ax.z, a.act); e[3] *= act_grad_from_out(ax.w, a.act);
+              }
+              if (a.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(o);
+                e[0] += old.x; e[1] += old.y; e[2] += old.z; e[3] += old.w;
+              }
+            } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (nb + i < Ng) {
-            if (a.aux != nullptr) v[i] *= act_grad_from_out(__ldg(a.aux + m * Ng + nb + i), a.act);
-            if (a.accumulate) v[i] += o[i];
+              for (int t = 0; t < 4; ++t)
+                if (col + t < Ng) {
+                  if (a.aux != nullptr) e[t] *= act_grad_from_out(__ldg(a.aux + m * Ng + col + t), a.act);
+                  if (a.accumulate) e[t] += o[t];
+                }
+            }
           }
+          if (MODE == WGRAD) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (col + t < Ng) atomicAdd(o + t, e[t]);
+          } else if (vec_ok) {
+            *reinterpret_cast<float4*>(o) = make_float4(e[0], e[1], e[2], e[3]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              if (col + t < Ng) o[t] = e[t];
+          }
+        }
+        __syncwarp();
       }
-      if (MODE == WGRAD) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (nb + i < Ng) atomicAdd(o + i, v[i]);
-      } else if ((Ng & 3) == 0 && nb + 32 <= Ng) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (nb + i < Ng) o[i] = v[i];
-      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + acc * 8);           // this thread's TMEM reads of the buffer are complete
+      ++j;
+      decode_tile<MODE>(a, T.t + gridDim.x, total, pixels, T);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 static int pick_bn(int Ng) { return Ng <= 32 ? 32 : (Ng <= 64 ? 64 : (Ng <= 128 ? 128 : 256)); }
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// ------------------------------------------------------------------ weight repack (fp32 HWIO -> bf16 tile images)
-// Logical K-major matrix  FPROP: Bt[n][k] = w[k*Cout + n];  DGRAD: Bt[ci][tap*Cout + co] = w[(tap*Cin + ci)*Cout + co]
+// ------------------------------------------------------------------ operand repack (fp32 -> bf16 tile images)
+// Weights: logical K-major matrix  FPROP: Bt[n][k] = w[k*Cout + n];  DGRAD: Bt[ci][tap*Cout + co] = w[(tap*Cin + ci)*Cout + co]
 // stored as consecutive [BN x 64] tiles (tile index = n_tile * num_kb + kb), each already in the SWIZZLE_128B
 // shared-memory image (row rr at rr*128, 16-byte chunk j at ((j ^ (rr & 7)) << 4)), so one bulk TMA copy stages it.
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img, int mode, int taps, int Cin,
@@ -498,13 +584,50 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+// dy [P, Cout] fp32 -> MN-major bf16 tile images for WGRAD's B operand: image index = kblock * n_tiles + n_tile, each
+// [bn/64 blocks][64 pixels][64 channels] with the 16-byte chunk swizzle (chunk ^ (pixel & 7)).  One thread = one chunk.
+__global__ void pack_dy_kernel(const float* __restrict__ dy, uint4* __restrict__ img, long long P, int Cout, int bn, int n_tiles,
+                               long long n_kblocks) {
+  const int chunks_n = n_tiles * bn / 8;
+  const long long total = n_kblocks * BK * chunks_n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cn = (int)(i % chunks_n);          // 8-channel chunk along the (padded) Cout axis
+    const long long p = i / chunks_n;            // pixel (padded to a multiple of 64)
+    const int co = cn * 8;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p < P && co < Cout) {
+      const float* g = dy + p * Cout + co;
+      if ((Cout & 3) == 0 && co + 8 <= Cout) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(g)), v1 = __ldg(reinterpret_cast<const float4*>(g + 4));
+        f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (co + q < Cout) f[q] = __ldg(g + q);
+      }
+    }
+    const long long kbg = p / BK;
+    const int k = (int)(p % BK);
+    const int nt = co / bn, nb = (co % bn) / 64, chunk = (co % 64) / 8;
+    const long long dst = (((kbg * n_tiles + nt) * (bn / 64) + nb) * 64 + k) * 8 + (chunk ^ (k & 7));
+    img[dst] = pack8(f);
+  }
+}
+
 template <int MODE>
-static int launch(const TcArgs& a, long long Mg, int Ng, int splits, cudaStream_t st) {
+static int launch(TcArgs& a, long long Mg, int Ng, int splits, cudaStream_t st) {
   int bn = pick_bn(Ng);
   if (MODE == WGRAD && bn < 64) bn = 64;       // MN-major blocks are 64 elements wide
-  dim3 grid((unsigned)ceil_div64(Mg, BM), (unsigned)ceil_div(Ng, bn), (unsigned)splits);
+  a.m_tiles = (int)ceil_div64(Mg, BM);
+  a.n_tiles = ceil_div(Ng, bn);
+  a.splits = splits;
+  static const int dbg = getenv("LADDER_TC_DEBUG") ? atoi(getenv("LADDER_TC_DEBUG")) : 0;
+  a.debug = dbg;
+  const long long total = (long long)a.m_tiles * a.n_tiles * splits;
+  const int sms = num_sms();
+  const unsigned grid = (unsigned)(total < sms ? total : sms);
   auto go = [&](auto kern, int BNv) {
-    const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256 + 2 * BM * 3 * sizeof(int);
+    const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256 + 4 * 32 * 36 * sizeof(float);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, NTHREADS, smem, st>>>(a);
   };
@@ -527,6 +650,11 @@ static size_t pack_bytes(int N, int K) {
   const int bn = pick_bn(N);
   return (size_t)ceil_div(N, bn) * ceil_div(K, BK) * bn * BK * 2;
 }
+static size_t pack_dy_bytes(long long P, int Cout) {
+  int bn = pick_bn(Cout);
+  if (bn < 64) bn = 64;
+  return (size_t)ceil_div64(P, BK) * BK * ceil_div(Cout, bn) * bn * 2;
+}
 
 static int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, cudaStream_t st) {
   const int N = mode == FPROP ? Cout : Cin, K = taps * (mode == FPROP ? Cin : Cout);
@@ -543,9 +671,12 @@ static int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, i
 extern "C" {
 
 size_t ladder_conv2d_tc_workspace_bytes(int B, int H, int W, int Cin, int KH, int KW, int Cout) {
-  (void)B; (void)H; (void)W;
+  const int OHmax = H, OWmax = W;                       // OH*OW <= H*W for every geometry the library accepts
   const size_t f = pack_bytes(Cout, KH * KW * Cin), d = pack_bytes(Cin, KH * KW * Cout);
-  return (f > d ? f : d) + 256;
+  const size_t g = Cin % BK == 0 ? pack_dy_bytes((long long)B * OHmax * OWmax, Cout) : 0;
+  size_t m = f > d ? f : d;
+  if (g > m) m = g;
+  return m + 256;
 }
 
 /* 1 if wgrad of this geometry runs on the tensor cores (64-channel-aligned input), else 0 (use the fp32 kernel) */
@@ -556,10 +687,11 @@ int ladder_conv2d_fprop_tc(const float* x, const float* w, const float* bias, fl
                            void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   LADDER_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
                  "conv2d_fprop_tc: bad arguments");
+  LADDER_REQUIRE((long long)B * OH * OW < (1LL << 31) && (long long)B * H * W < (1LL << 31), "conv2d_fprop_tc: too many pixels");
   int rc = pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, stream);
   if (rc) return rc;
   TcArgs a{x, nullptr, static_cast<const __nv_bfloat16*>(workspace), bias, nullptr, y, B, H, W, Cin, KH, KW, Cout, stride,
-           pad_t, pad_l, OH, OW, act, 0, 0, round_up(KH * KW * Cin, BK), 0};
+           pad_t, pad_l, OH, OW, act, 0, 0, round_up(KH * KW * Cin, BK), 0, 0, 0, 0};
   return launch<FPROP>(a, (long long)B * OH * OW, Cout, 1, stream);
 }
 
@@ -568,32 +700,49 @@ int ladder_conv2d_dgrad_tc(const float* dy, const float* w, const float* act_out
                            int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   LADDER_REQUIRE(dy && w && dx && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
                  "conv2d_dgrad_tc: bad arguments");
+  LADDER_REQUIRE((long long)B * OH * OW < (1LL << 31) && (long long)B * H * W < (1LL << 31), "conv2d_dgrad_tc: too many pixels");
   int rc = pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, stream);
   if (rc) return rc;
   TcArgs a{dy, nullptr, static_cast<const __nv_bfloat16*>(workspace), nullptr, act_out, dx, B, H, W, Cin, KH, KW, Cout, stride,
-           pad_t, pad_l, OH, OW, act, accumulate, 0, round_up(KH * KW * Cout, BK), 0};
+           pad_t, pad_l, OH, OW, act, accumulate, 0, round_up(KH * KW * Cout, BK), 0, 0, 0, 0};
   return launch<DGRAD>(a, (long long)B * H * W, Cin, 1, stream);
 }
 
 // dw is overwritten; the bias gradient is ladder_colsum(dy).  Requires Cin % 64 == 0 (ladder_conv2d_wgrad_tc_supported).
 int ladder_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int KH, int KW, int Cout,
-                           int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream) {
+                           int stride, int pad_t, int pad_l, int OH, int OW, void* workspace, size_t workspace_bytes,
+                           cudaStream_t stream) {
   LADDER_REQUIRE(x && dy && dw && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
                  "conv2d_wgrad_tc: bad arguments");
   LADDER_REQUIRE(Cin % BK == 0, "conv2d_wgrad_tc: Cin must be a multiple of 64 (got %d)", Cin);
   const int patch = KH * KW * Cin;
   const long long pixels = (long long)B * OH * OW;
+  LADDER_REQUIRE(pixels < (1LL << 31) && (long long)B * H * W < (1LL << 31), "conv2d_wgrad_tc: too many pixels");
+  const size_t need = pack_dy_bytes(pixels, Cout);
+  if (workspace == nullptr || workspace_bytes < need)
+    return fail(LADDER_ERR_WORKSPACE, "conv2d_wgrad_tc: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)patch * Cout * sizeof(float), stream);
   if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "conv2d_wgrad_tc memset: %s", cudaGetErrorString(e));
   int bn = pick_bn(Cout);
   if (bn < 64) bn = 64;
-  const long long tiles = ceil_div64(patch, BM) * ceil_div(Cout, bn);
+  const int n_tiles = ceil_div(Cout, bn);
+  const long long n_kblocks = ceil_div64(pixels, BK);
+  {
+    const long long chunks = n_kblocks * BK * (n_tiles * bn / 8);
+    long long blocks = ceil_div64(chunks, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pack_dy_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dy, static_cast<uint4*>(workspace), pixels, Cout, bn, n_tiles, n_kblocks);
+    int rc = check_launch("conv2d_wgrad_tc dy pack");
+    if (rc) return rc;
+  }
+  const long long tiles = ceil_div64(patch, BM) * n_tiles;
   long long splits = ceil_div64(2LL * num_sms(), tiles);
-  const long long max_splits = ceil_div64(pixels, 2 * BK);
+  const long long max_splits = ceil_div64(pixels, 4 * BK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   long long per = ceil_div64(ceil_div64(pixels, splits), BK) * BK;
-  TcArgs a{x, dy, nullptr, nullptr, nullptr, dw, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, 0, 0, (int)per, 0, patch};
+  TcArgs a{x, nullptr, static_cast<const __nv_bfloat16*>(workspace), nullptr, nullptr, dw, B, H, W, Cin, KH, KW, Cout, stride,
+           pad_t, pad_l, OH, OW, 0, 0, (int)per, 0, patch, 0, 0, 0};
   return launch<WGRAD>(a, patch, Cout, (int)ceil_div64(pixels, per), stream);
 }
 

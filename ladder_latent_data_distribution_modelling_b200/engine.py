@@ -639,6 +639,9 @@ class LadderEngine:
             self.mixture = None
         self.use_sg = self.prior == 'standard_gaussian'
         self.use_mask = False
+        # CUDA graphs: on by default on one GPU (optional config key `cuda_graphs`)
+        self.use_graphs = bool(config.get('cuda_graphs', self.world == 1))
+        self._graphs, self._static_x, self._feed_version = {}, None, 0
 
     # ---- parameters
     def init_params(self):
@@ -677,12 +680,16 @@ class LadderEngine:
     # ---- feeds (codes/base.py:862-942 values arrive here)
     def set_feeds(self, prior_mean=None, prior_cov=None, prior_weight=None, use_standard_gaussian_prior=None,
                   use_mask=None):
+        before = (self.use_sg, self.use_mask)
         if prior_mean is not None:
             self.mixture = ops.mixture_pack_full(prior_mean, prior_cov, prior_weight, self.dev)
+            self._feed_version += 1          # table pointer / frame are baked into captured graphs
         if use_standard_gaussian_prior is not None:
             self.use_sg = bool(use_standard_gaussian_prior) or self.prior == 'standard_gaussian'
         if use_mask is not None:
             self.use_mask = bool(use_mask)
+        if (self.use_sg, self.use_mask) != before:
+            self._feed_version += 1
 
     def set_lrs(self, lr_ae=None, lr_sigma=None, lr_prior=None, lr_inner_sigma=None):
         for g, lr in ((self.ae, lr_ae), (self.sigma, lr_sigma), (getattr(self, 'prior_g', None), lr_prior),
@@ -784,6 +791,46 @@ class LadderEngine:
         self.forward(x, dec=False, prior=True, mix=False)
         if apply:
             self.inner_sigma.apply_adam(self.scalars[ops.CF['DINNER_SIGMA']:ops.CF['DINNER_SIGMA'] + 1])
+
+    # ---- CUDA-graph replay of the sub-steps
+    _STEP_NOISE = {'ae': dict(z=True, t=True, mc=True), 'sigma': dict(z=True, t=False, mc=False),
+                   'prior': dict(z=True, t=True, mc=True), 'inner_sigma': dict(z=True, t=True, mc=False)}
+
+    def run_step(self, name, x, graph=None):
+        """One sess.run equivalent: fresh noise + step `name` in {'ae','sigma','prior','inner_sigma'} on batch x.
+        With CUDA graphs the whole sub-step (noise, ~100 kernels, clip+Adam) is one graph launch; graphs are
+        re-captured when the feeds (mixture, use_sg, use_mask) change."""
+        fn = getattr(self, 'step_' + name)
+        use_graph = self.use_graphs if graph is None else graph
+        if not use_graph:
+            self.draw_noise(**self._STEP_NOISE[name])
+            fn(x)
+            return
+        key = (name, self._feed_version)
+        g = self._graphs.get(key)
+        if g is None:
+            if self._static_x is None:
+                self._static_x = torch.empty_like(x)
+            self._static_x.copy_(x)
+            # eager warm-up WITHOUT the parameter update (allocates every buffer), then capture with it
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.draw_noise(**self._STEP_NOISE[name])
+                fn(self._static_x, apply=False)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            if hasattr(g, 'register_generator_state'):
+                g.register_generator_state(self.gen)
+            with torch.cuda.graph(g):
+                self.draw_noise(**self._STEP_NOISE[name])
+                fn(self._static_x)
+            self._graphs = {k: v for k, v in self._graphs.items() if k[1] == self._feed_version}
+            self._graphs[key] = g
+        else:
+            self._static_x.copy_(x)
+        g.replay()
 
     def fetch(self, names):
         """Device->host read of named ELBO terms (reference attribute names)."""

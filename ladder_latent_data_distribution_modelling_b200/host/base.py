@@ -111,14 +111,12 @@ class BaseTrain:
         eng = self.model.engine
         x = self._apply_feeds(batch_data, "VAE")
         eng.set_lrs(lr_ae=cur_lr)
-        eng.draw_noise()
-        eng.step_ae(x)
+        eng.run_step('ae', x)
         self._snapshot('train_ae')
         loss = eng.scalars[ops.O['loss_ae']].clone()
         if self.config['TRAIN_sigma'] == 1:
             eng.set_lrs(lr_sigma=self.config['learning_rate_sigma'] * (0.99 ** (self.cur_epoch - 1)))
-            eng.draw_noise(t=False, mc=False)
-            eng.step_sigma(x)
+            eng.run_step('sigma', x)
             self._snapshot('train_sigma')
         return loss
 
@@ -126,13 +124,11 @@ class BaseTrain:
         eng = self.model.engine
         x = self._apply_feeds(batch_data, "prior")
         eng.set_lrs(lr_prior=self.config['learning_rate_prior'] * (1.01 ** (self.cur_epoch - 1)))
-        eng.draw_noise()
-        eng.step_prior(x)
+        eng.run_step('prior', x)
         self._snapshot('train_prior')
         if self.config['prior'] in ("ours", "hierarchical") and self.config['TRAIN_inner_sigma'] == 1:
             eng.set_lrs(lr_inner_sigma=self.config['learning_rate_inner_sigma'] * (1.01 ** (self.cur_epoch - 1)))
-            eng.draw_noise(mc=False)
-            eng.step_inner_sigma(x)
+            eng.run_step('inner_sigma', x)
 
     def val_step(self, model_to_train, batch_data):
         eng = self.model.engine

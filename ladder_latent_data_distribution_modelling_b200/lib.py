@@ -38,7 +38,7 @@ SIGNATURES = {
     'ladder_conv2d_fprop_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 13 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_dgrad_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 14 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_wgrad_tc_supported': (C.c_int, [C.c_int, C.c_int]),
-    'ladder_conv2d_wgrad_tc': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [stream_t]),
+    'ladder_conv2d_wgrad_tc': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [ptr, C.c_size_t, stream_t]),
     # layout / elementwise
     'ladder_sym_pad': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),
     'ladder_depth_to_space': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),

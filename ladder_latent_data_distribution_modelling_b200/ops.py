@@ -258,7 +258,8 @@ def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False):
 
 def conv2d_wgrad(x, dy, dw, dbias, g):
     if _use_tc(g) and g.Cin % 64 == 0:
-        _lib.check(_L().ladder_conv2d_wgrad_tc(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dw)), *g.args(), _stream()),
+        ws, n = _tc_ws(x, g)
+        _lib.check(_L().ladder_conv2d_wgrad_tc(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dw)), *g.args(), _p(ws), n, _stream()),
                    'conv2d_wgrad_tc')
         if dbias is not None:
             _lib.check(_L().ladder_colsum(_p(dy), g.B * g.OH * g.OW, g.Cout, _p(dbias), _stream()), 'colsum')

@@ -82,3 +82,34 @@ def test_tc_large_gemm_matches_fp32_kernel(ops):
     ops.conv2d_fprop(x, w, b, y_ref, g, 'leaky_relu')
     err = (y_tc - y_ref).abs().max().item() / y_ref.abs().max().item()
     assert err < TOL, err
+
+
+def test_tc_repeatability_stress(ops):
+    """Race detector for the warp-specialised pipeline (generic-proxy stores -> async-proxy MMA reads, TMEM
+    double buffering, split-K atomics): the same launch repeated 30 times must reproduce the first result
+    bit-for-bit (fprop / dgrad) or to fp32 summation-order noise (wgrad), and match the fp32 kernel."""
+    B, H = 256, 256
+    g = ops.ConvGeom(B, 16, 16, H // 4, 3, 3, H, 1, 'same')
+    gen = torch.Generator(device='cuda'); gen.manual_seed(1)
+    x = torch.randn(B, 16, 16, H // 4, device='cuda', generator=gen)
+    w = torch.randn(3, 3, H // 4, H, device='cuda', generator=gen) * 0.05
+    b = torch.randn(H, device='cuda', generator=gen)
+    dy = torch.randn(B, 16, 16, H, device='cuda', generator=gen)
+    y0 = torch.empty(B, 16, 16, H, device='cuda'); dx0 = torch.empty_like(x); dw0 = torch.empty_like(w)
+    ops.conv2d_fprop(x, w, b, y0, g, 'leaky_relu')
+    ops.conv2d_dgrad(dy, w, dx0, g)
+    ops.conv2d_wgrad(x, dy, dw0, None, g)
+    y = torch.empty_like(y0); dx = torch.empty_like(dx0); dw = torch.empty_like(dw0)
+    for _ in range(30):
+        ops.conv2d_fprop(x, w, b, y, g, 'leaky_relu')
+        ops.conv2d_dgrad(dy, w, dx, g)
+        ops.conv2d_wgrad(x, dy, dw, None, g)
+        assert torch.equal(y, y0) and torch.equal(dx, dx0)
+        assert (dw - dw0).abs().max().item() <= 1e-4 * dw0.abs().max().item()
+    ops.set_math_mode('fp32')
+    yr = torch.empty_like(y0); dxr = torch.empty_like(dx0); dwr = torch.empty_like(dw0)
+    ops.conv2d_fprop(x, w, b, yr, g, 'leaky_relu')
+    ops.conv2d_dgrad(dy, w, dxr, g)
+    ops.conv2d_wgrad(x, dy, dwr, None, g)
+    for a, r in ((y0, yr), (dx0, dxr), (dw0, dwr)):
+        assert (a - r).abs().max().item() < TOL * r.abs().max().item()
