@@ -68,6 +68,17 @@ size_t ladder_mixture_workspace_bytes(long long N, int K, int D, int mode, int w
 int ladder_mixture_logprob(const float* t, long long N, int D, const float* table, int K, int mode,
                            float iso_scale, float ref_log2, float* logp, float* grad_t, float* m_out,
                            float* s_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* Tensor-core path (tcgen05.mma kind::tf32, accumulators and the exp/sum epilogue in TMEM) for an isotropic
+ * mixture with D in {32, 64}: forward log-density only.  `image_host` is packed on the host
+ * (ladder_mixture_tc_image_bytes bytes), copied to the device by the caller; `simt_table` is the mode-0 table of
+ * ladder_mixture_pack_diag (used to recompute, exactly, rows whose fixed-frame sum underflows).   */
+size_t ladder_mixture_tc_image_bytes(int K, int D);
+int ladder_mixture_tc_pack_iso(const double* mean_host, double std_, const double* weight_host /*nullable*/, int K,
+                               int D, float* image_host, float* ref_log2, float* iso_scale);
+size_t ladder_mixture_tc_workspace_bytes(long long N, int K);
+int ladder_mixture_logprob_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
+                              float iso_scale, float ref_log2, float* logp, void* workspace,
+                              size_t workspace_bytes, cudaStream_t stream);
 /* (max, sum-exp) combine of P shard partials laid out [P,N] (+ [P,N,D] gradients). */
 int ladder_mixture_combine(const float* m_parts, const float* s_parts, const float* g_parts, int P,
                            long long N, int D, float* logp, float* grad_t, cudaStream_t stream);

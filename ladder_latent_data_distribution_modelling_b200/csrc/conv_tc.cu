@@ -28,7 +28,8 @@ namespace tc {
 
 constexpr int BM = 128;            // UMMA M (TMEM lanes)
 constexpr int BK = 64;             // bf16 per k-block = one 128-byte swizzle row
-constexpr int STAGES = 4;
+// smem ring depth per N tile width (A 16 KB + B BN*128 B per stage, ~192 KB total)
+__host__ __device__ constexpr int stages_for(int bn) { return bn >= 256 ? 4 : 4; }
 constexpr int PROD_WARPS = 8;
 constexpr int PRODUCERS = PROD_WARPS * 32;   // threads
 constexpr int MMA_WARP = PROD_WARPS;         // warp 8
@@ -240,6 +241,7 @@ __device__ __forceinline__ void decode_tile(const TcArgs& a, long long t, long l
 //   warps 9-12 epilogue (tcgen05.ld -> fused bias/activation | act'-multiply/accumulate | split-K red.add)
 template <int MODE, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
+  constexpr int STAGES = stages_for(BN);
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -326,7 +328,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
       if (!L.valid || (a.debug & 1)) return;
       if (MODE != WGRAD) {
         if (affine) {
-          const int q0 = lkb * BK, tap = q0 / C, c0 = q0 % C, kh = tap / a.KW, kw = tap % a.KW;
+          // K order on the fast path: 64-channel chunk major, tap minor -- the KH*KW consecutive k-blocks of one
+          // chunk re-read the same [pixels x 64 channels] slab shifted by one pixel, so all but the first hit L1
+          const int taps = a.KH * a.KW, tap = lkb % taps, c0 = (lkb / taps) * BK, kh = tap / a.KW, kw = tap % a.KW;
           const float* srck = a.src + tap_delta(kh, kw) + c0 + 4 * f4;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -346,7 +350,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
             for (int j = 0; j < 4; ++j) {
               const int q = lkb * BK + 4 * f4 + j;
               if (q < patch) {
-                const int tap = q / C, c = q % C;
+                int tap = q / C, c = q % C;
+                if (fast) {            // same channel-chunk-major K order as the weight image (strided dgrad lands here)
+                  const int taps = a.KH * a.KW;
+                  tap = lkb % taps;
+                  c = (lkb / taps) * BK + 4 * f4 + j;
+                }
                 const long long off = tap_offset<MODE == DGRAD>(a, b, y, x, tap / a.KW, tap % a.KW, c);
                 if (off >= 0) e[j] = __ldg(a.src + off);
               }
@@ -389,6 +398,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
       const uint32_t tileA = sA + s * A_STAGE_BYTES;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
+        if (a.debug & 16) break;
         if (MODE != WGRAD) {
           const int row = warp * 16 + i * 2 + rsel;
           sts64(tileA + row * 128 + (((f4 >> 1) ^ (row & 7)) << 4) + (f4 & 1) * 8, v[i]);
@@ -441,7 +451,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
         for (int kb = 0; kb < T.nkb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_full + s * 8, (it / STAGES) & 1);   // acquire: all producers' st.shared of this stage
-          fence_proxy_async();                               // ... made visible to the async proxy (tcgen05.mma reads)
+          if (!(a.debug & 8)) fence_proxy_async();            // ... made visible to the async proxy (tcgen05.mma reads)
           tc_fence_after();
           const uint32_t tA = sA + s * A_STAGE_BYTES, tB = sB + s * B_STAGE_BYTES;
 #pragma unroll
@@ -562,7 +572,8 @@ static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img, int mode, int taps, int Cin,
                                     int Cout, int bn, int num_kb, int n_tiles) {
   const int N = mode == FPROP ? Cout : Cin;
-  const int K = taps * (mode == FPROP ? Cin : Cout);
+  const int Cg = mode == FPROP ? Cin : Cout;        // channels of the gathered (A) tensor
+  const int K = taps * Cg;
   const long long total = (long long)n_tiles * num_kb * bn * BK;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int kk = (int)(i % BK);
@@ -570,7 +581,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     const int rr = (int)(r % bn); r /= bn;
     const int kb = (int)(r % num_kb);
     const int nt = (int)(r / num_kb);
-    const int n = nt * bn + rr, k = kb * BK + kk;
+    const int n = nt * bn + rr;
+    int k = kb * BK + kk;
+    if (Cg % BK == 0) {            // channel-chunk-major K order of the affine fast path (see the producer)
+      const int tap = kb % taps, c = (kb / taps) * BK + kk;
+      k = tap * Cg + c;
+    }
     float v = 0.f;
     if (n < N && k < K) {
       if (mode == FPROP) v = w[(long long)k * Cout + n];
@@ -627,7 +643,7 @@ static int launch(TcArgs& a, long long Mg, int Ng, int splits, cudaStream_t st) 
   const int sms = num_sms();
   const unsigned grid = (unsigned)(total < sms ? total : sms);
   auto go = [&](auto kern, int BNv) {
-    const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256 + 4 * 32 * 36 * sizeof(float);
+    const size_t smem = (size_t)stages_for(BNv) * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256 + 4 * 32 * 36 * sizeof(float);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, NTHREADS, smem, st>>>(a);
   };

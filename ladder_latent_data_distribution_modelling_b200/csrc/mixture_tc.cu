@@ -1,0 +1,406 @@
+// K9 on the tensor cores: hyper-prior mixture log-density for latent dim D in {32, 64}, shared isotropic
+// sigma (the BASELINE.json micro-benchmark form; reference codes/base.py:109-124 generalised).
+//
+//   e2[n,k] = c2'_k - |t'_n - mu'_k|^2 = (c2'_k - |mu'_k|^2) - |t'_n|^2 + t'_n . (2 mu'_k)          (log2 domain)
+//
+// The cross term is a [256 x D] x [D x 128] GEMM per (query block, component chunk) on tcgen05.mma
+// kind::tf32 (fp32 operands read as tf32, fp32 accumulation in TMEM); the rank-1 corrections ck, tn are
+// added exactly in fp32 by the consumer warps, which then do the MUFU.EX2 + sum of the fixed-frame
+// log-sum-exp straight out of TMEM (one thread = one query row, so no cross-thread reduction).  The
+// N x K matrix never leaves the SM.  Per pair: 2*D tensor flops + 2 FADD + 1 MUFU.EX2 + 1 FADD.
+//
+//   warp 0      : bulk-TMA producer of the pre-swizzled component tiles (+ their ck constants), 4-stage ring
+//   warp 1      : MMA issuer: 2 query sub-tiles (M=128 each) x D/8 k-steps per chunk, accumulators double
+//                 buffered in TMEM (2 sub-tiles x 2 buffers x 128 columns = all 512 columns)
+//   warps 4-11  : consumers (quadrant = warp % 4, sub-tile = (warp - 4) / 4)
+//
+// Accuracy: tf32 rounds the operands of the cross term to 11 bits: |d logp| <= 3e-2 (D = 32) / 5e-2 (D = 64) for
+// unit-scale data with |logp| ~ 1e2 (tested); exact fp32 evaluation remains available through the SIMT kernel (mixture.cu), which is
+// also what rescues rows whose fixed-frame sum underflows.
+#include "common.cuh"
+#include "ladder_sm100.h"
+#include <cmath>
+#include <vector>
+
+namespace ladder {
+namespace mixtc {
+
+constexpr int BN = 128;               // components per chunk (UMMA N)
+constexpr int QROWS = 256;            // queries per CTA work unit (2 x UMMA M=128)
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 12 * 32;     // warps 0-3 control, 4-11 consumers
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// K-major SWIZZLE_128B descriptor (see conv_tc.cu): one 128-byte row = 32 tf32 elements
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: c = F32 (1), a = b = TF32 (2), K-major, N >> 3, M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Args {
+  const float* t;        // [N, D] queries
+  const float* bimg;     // component tiles: per chunk [ATOMS][128 rows][32 fp32, swizzled] then ck[128]
+  float* part;           // [splits, N] partial sums in the fixed frame
+  long long N;
+  int n_chunks;          // ceil(K / 128)
+  int chunks_per_split, splits;
+  float iso_scale;
+};
+
+template <int D>
+__global__ void __launch_bounds__(NTHREADS, 1) mix_tc_kernel(Args a) {
+  constexpr int ATOMS = D / 32;                       // 128-byte K atoms per row
+  constexpr int A_BYTES = 2 * ATOMS * 128 * 128;      // 2 query sub-tiles
+  constexpr int B_BYTES = ATOMS * BN * 128;           // one component chunk
+  constexpr int B_STAGE = B_BYTES + BN * 4;           // + ck
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + A_BYTES;
+  constexpr int B_STRIDE = (B_STAGE + 1023) / 1024 * 1024;
+  const uint32_t bars = sB + STAGES * B_STRIDE;
+  const uint32_t bar_full = bars, bar_empty = bars + STAGES * 8, bar_tfull = bars + 2 * STAGES * 8,   // [2 sub][2 buf]
+                 bar_tempty = bar_tfull + 4 * 8, bar_a = bar_tempty + 4 * 8, bar_adone = bar_a + 8;
+  const uint32_t slot = bar_adone + 8;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (slot - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long row_tiles = (a.N + QROWS - 1) / QROWS;
+  const long long units = row_tiles * a.splits;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1 + 8);            // MMA commit + one lane of each consumer warp (ck is read from the stage)
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar_tfull + i * 8, 1);
+      mbar_init(bar_tempty + i * 8, 128);
+    }
+    mbar_init(bar_a, 256);                             // consumers staged their query rows
+    mbar_init(bar_adone, 1);                           // MMAs of the unit retired: A tile reusable
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      unsigned it = 0;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = (int)(u % a.splits);
+        const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
+        for (int c = c_lo; c < c_hi; ++c, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full + s * 8, B_STAGE);
+          tma_bulk_g2s(sB + s * B_STRIDE, reinterpret_cast<const uint8_t*>(a.bimg) + (size_t)c * B_STAGE, B_STAGE, bar_full + s * 8);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BN);
+      unsigned it = 0, g = 0, un = 0;     // stage counter, accumulator-use counter, unit counter
+      for (long long u = blockIdx.x; u < units; u += gridDim.x, ++un) {
+        const int split = (int)(u % a.splits);
+        const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
+        mbar_wait(bar_a, un & 1);                          // query tile staged by the consumers (generic proxy)
+        fence_proxy_async();
+        for (int c = c_lo; c < c_hi; ++c, ++it, ++g) {
+          const int s = it % STAGES;
+          const uint32_t buf = g & 1;
+          mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            mbar_wait(bar_tempty + (sub * 2 + buf) * 8, ((g >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (sub * 2 + buf) * BN;
+#pragma unroll
+            for (int k = 0; k < D / 8; ++k) {
+              const int atom = k / 4, kk = k % 4;          // 4 k-steps of 8 tf32 (32 B) per 128-byte atom
+              const uint64_t ad = make_desc(sA + (sub * ATOMS + atom) * (128 * 128) + kk * 32);
+              const uint64_t bd = make_desc(sB + s * B_STRIDE + atom * (BN * 128) + kk * 32);
+              umma_tf32(tmem_d, ad, bd, idesc, k != 0);
+            }
+            umma_commit(bar_tfull + (sub * 2 + buf) * 8);
+          }
+          umma_commit(bar_empty + s * 8);
+        }
+        umma_commit(bar_adone);                            // all MMAs reading this unit's A tile have retired
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================== consumers: one query row per thread
+    const int sub = (warp - 4) >> 2, quad = warp & 3;
+    const int row = sub * 128 + quad * 32 + lane;          // row within the 256-query unit
+    unsigned it = 0, g = 0, un = 0;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x, ++un) {
+      const long long rt = u / a.splits;
+      const int split = (int)(u % a.splits);
+      const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
+      const long long n = rt * QROWS + row;
+      // ---- stage this thread's query row (scaled) into the K-major swizzled A tile, tn = |t'|^2 in fp32
+      if (un > 0) mbar_wait(bar_adone, (un - 1) & 1);      // previous unit's MMAs no longer read the A tile
+      float tn = 0.f;
+      {
+        const int r = quad * 32 + lane;                    // row within the sub-tile
+#pragma unroll
+        for (int atom = 0; atom < ATOMS; ++atom) {
+          const uint32_t rowaddr = sA + (sub * ATOMS + atom) * (128 * 128) + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < a.N) v = __ldg(reinterpret_cast<const float4*>(a.t + n * D + atom * 32 + j * 4));
+            v.x *= a.iso_scale; v.y *= a.iso_scale; v.z *= a.iso_scale; v.w *= a.iso_scale;
+            tn = fmaf(v.x, v.x, tn); tn = fmaf(v.y, v.y, tn); tn = fmaf(v.z, v.z, tn); tn = fmaf(v.w, v.w, tn);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((j ^ (r & 7)) << 4)), "f"(v.x), "f"(v.y),
+                         "f"(v.z), "f"(v.w) : "memory");
+          }
+        }
+      }
+      mbar_arrive(bar_a);
+      float S = 0.f;
+      for (int c = c_lo; c < c_hi; ++c, ++it, ++g) {
+        const int s = it % STAGES;
+        const uint32_t buf = g & 1;
+        const float* ck = reinterpret_cast<const float*>(smem + (sB + s * B_STRIDE + B_BYTES - base));
+        mbar_wait(bar_full + s * 8, (it / STAGES) & 1);             // the stage's ck constants (async-proxy write) are visible
+        mbar_wait(bar_tfull + (sub * 2 + buf) * 8, (g >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (sub * 2 + buf) * BN + c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(ck + c0 + i);
+            S += ex2((v[i] + k4.x) - tn);
+            S += ex2((v[i + 1] + k4.y) - tn);
+            S += ex2((v[i + 2] + k4.z) - tn);
+            S += ex2((v[i + 3] + k4.w) - tn);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty + (sub * 2 + buf) * 8);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + s * 8);     // this warp is done with the stage's ck
+      }
+      if (n < a.N) a.part[(size_t)split * a.N + n] = S;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// log p = ln2 * (M + log2 sum_splits S); rows that underflowed the fixed frame are recomputed exactly (two-pass)
+// from the SIMT table (iso layout [mu'(D), c2'], stride padded to 4).
+template <int D>
+__global__ void mix_tc_finalize_kernel(const float* __restrict__ part, int splits, long long N, const float* __restrict__ t,
+                                       const float* __restrict__ table, int K, float iso_scale, float ref_log2,
+                                       float* __restrict__ logp) {
+  constexpr int STRIDE = (D + 1 + 3) / 4 * 4;
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int i = 0; i < splits; ++i) s += part[(size_t)i * N + n];
+  float frame = ref_log2;
+  if (!(s >= 1e-30f)) {
+    float mx = -INFINITY;
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) s = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float* c = table + (size_t)k * STRIDE;
+        float e = c[D];
+        for (int d = 0; d < D; ++d) {
+          const float y = t[n * D + d] * iso_scale - c[d];
+          e = fmaf(-y, y, e);
+        }
+        if (pass == 0) mx = fmaxf(mx, e);
+        else s += exp2f(e - mx);
+      }
+    }
+    frame += mx;
+  }
+  logp[n] = LN2 * (frame + log2f(s));
+}
+
+}  // namespace mixtc
+}  // namespace ladder
+
+using namespace ladder;
+using namespace ladder::mixtc;
+
+extern "C" {
+
+/* bytes of the device image ladder_mixture_tc_pack_iso produces (0 if D is not 32 / 64) */
+size_t ladder_mixture_tc_image_bytes(int K, int D) {
+  if (D != 32 && D != 64) return 0;
+  const size_t chunks = (size_t)(K + BN - 1) / BN;
+  return chunks * ((size_t)(D / 32) * BN * 128 + BN * 4);
+}
+
+/* Host-side pack (double precision) of an isotropic mixture for the tensor-core kernel: per chunk of 128
+ * components the K-major SWIZZLE_128B tile image of 2*mu' followed by ck = c2' - |mu'|^2 (padding: -1e30). */
+int ladder_mixture_tc_pack_iso(const double* mean, double std_, const double* weight, int K, int D, float* image,
+                               float* ref_log2, float* iso_scale) {
+  LADDER_REQUIRE(mean && image && ref_log2 && iso_scale && K >= 1, "mixture_tc_pack_iso: bad arguments");
+  LADDER_REQUIRE(D == 32 || D == 64, "mixture_tc_pack_iso: D must be 32 or 64 (got %d)", D);
+  LADDER_REQUIRE(std_ > 0, "mixture_tc_pack_iso: std must be positive");
+  const double LOG2E = 1.4426950408889634, HALF_LOG_2PI = 0.9189385332046727;
+  const double sc = std::sqrt(0.5 * LOG2E) / std_;
+  double wsum = 0;
+  for (int k = 0; k < K; ++k) wsum += weight ? weight[k] : 1.0;
+  std::vector<double> c2(K);
+  double M = -INFINITY;
+  for (int k = 0; k < K; ++k) {
+    const double w = weight ? weight[k] : 1.0;
+    c2[k] = (std::log(w / wsum) - D * HALF_LOG_2PI - D * std::log(std_)) * LOG2E;
+    if (c2[k] > M) M = c2[k];
+  }
+  if (!(M > -INFINITY)) return fail(LADDER_ERR_ARG, "mixture_tc_pack_iso: all weights are zero");
+  const int atoms = D / 32, chunks = (K + BN - 1) / BN;
+  const size_t stage_floats = (size_t)atoms * BN * 32 + BN;
+  for (int c = 0; c < chunks; ++c) {
+    float* img = image + (size_t)c * stage_floats;
+    float* ck = img + (size_t)atoms * BN * 32;
+    for (int r = 0; r < BN; ++r) {
+      const int k = c * BN + r;
+      double m2 = 0;
+      for (int d = 0; d < D; ++d) {
+        const double mu = k < K ? sc * mean[(size_t)k * D + d] : 0.0;
+        m2 += mu * mu;
+        const int atom = d / 32, e = d % 32, chunk16 = e / 4;
+        img[(size_t)atom * BN * 32 + r * 32 + ((chunk16 ^ (r & 7)) << 2) + (e & 3)] = (float)(2.0 * mu);
+      }
+      ck[r] = k < K ? (float)(c2[k] - M - m2) : -1e30f;
+    }
+  }
+  *ref_log2 = (float)M;
+  *iso_scale = (float)sc;
+  return LADDER_OK;
+}
+
+size_t ladder_mixture_tc_workspace_bytes(long long N, int K) {
+  const int n_chunks = (K + BN - 1) / BN;
+  const long long row_tiles = (N + QROWS - 1) / QROWS;
+  long long splits = ceil_div64(2LL * num_sms(), row_tiles > 0 ? row_tiles : 1);
+  if (splits > n_chunks) splits = n_chunks;
+  if (splits < 1) splits = 1;
+  return (size_t)splits * (N > 0 ? N : 1) * sizeof(float) + 256;
+}
+
+/* log p(t_n) for an isotropic mixture with D in {32, 64} on the tensor cores.  `image` from
+ * ladder_mixture_tc_pack_iso (device copy), `simt_table` the mode-0 table of ladder_mixture_pack_diag (for the
+ * exact rescue of underflowed rows).                                                              */
+int ladder_mixture_logprob_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
+                              float iso_scale, float ref_log2, float* logp, void* workspace, size_t workspace_bytes,
+                              cudaStream_t stream) {
+  LADDER_REQUIRE(D == 32 || D == 64, "mixture_logprob_tc: D must be 32 or 64 (got %d)", D);
+  LADDER_REQUIRE(N >= 0 && K >= 1, "mixture_logprob_tc: bad sizes");
+  if (N == 0) return LADDER_OK;
+  LADDER_REQUIRE(t && image && simt_table && logp, "mixture_logprob_tc: null pointer");
+  LADDER_REQUIRE(((uintptr_t)image & 127) == 0 && ((uintptr_t)t & 15) == 0, "mixture_logprob_tc: misaligned input");
+  const int n_chunks = (K + BN - 1) / BN;
+  const long long row_tiles = (N + QROWS - 1) / QROWS;
+  const int sms = num_sms();
+  long long splits = ceil_div64(2LL * sms, row_tiles);
+  if (splits > n_chunks) splits = n_chunks;
+  if (splits < 1) splits = 1;
+  const int cps = ceil_div(n_chunks, (int)splits);
+  splits = ceil_div(n_chunks, cps);
+  const size_t need = (size_t)splits * N * sizeof(float);
+  if (workspace == nullptr || workspace_bytes < need)
+    return fail(LADDER_ERR_WORKSPACE, "mixture_logprob_tc: workspace %zu < %zu bytes", workspace_bytes, need);
+  Args a{t, image, static_cast<float*>(workspace), N, n_chunks, cps, (int)splits, iso_scale};
+  const long long units = row_tiles * splits;
+  const unsigned grid = (unsigned)(units < sms ? units : sms);
+  auto go = [&](auto kern, int Dv) {
+    const int atoms = Dv / 32;
+    const size_t b_stride = ((size_t)atoms * BN * 128 + BN * 4 + 1023) / 1024 * 1024;
+    const size_t smem = (size_t)2 * atoms * 128 * 128 + STAGES * b_stride + 1024 + 256;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, NTHREADS, smem, stream>>>(a);
+  };
+  if (D == 32) go(mix_tc_kernel<32>, 32); else go(mix_tc_kernel<64>, 64);
+  int rc = check_launch("mixture tc kernel");
+  if (rc) return rc;
+  const unsigned fb = (unsigned)ceil_div64(N, 256);
+  if (D == 32) mix_tc_finalize_kernel<32><<<fb, 256, 0, stream>>>(a.part, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp);
+  else mix_tc_finalize_kernel<64><<<fb, 256, 0, stream>>>(a.part, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp);
+  return check_launch("mixture tc finalize");
+}
+
+}  // extern "C"

@@ -642,6 +642,7 @@ class LadderEngine:
         # CUDA graphs: on by default on one GPU (optional config key `cuda_graphs`)
         self.use_graphs = bool(config.get('cuda_graphs', self.world == 1))
         self._graphs, self._static_x, self._feed_version = {}, None, 0
+        self._graph_launches, self.replayed_launches = {}, 0     # kernels of libladder_sm100 replayed through graphs
 
     # ---- parameters
     def init_params(self):
@@ -821,6 +822,7 @@ class LadderEngine:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
             if hasattr(g, 'register_generator_state'):
                 g.register_generator_state(self.gen)
             with torch.cuda.graph(g):
@@ -828,9 +830,11 @@ class LadderEngine:
                 fn(self._static_x)
             self._graphs = {k: v for k, v in self._graphs.items() if k[1] == self._feed_version}
             self._graphs[key] = g
+            self._graph_launches[key] = ops.launch_count() - n0      # kernels captured in this graph
         else:
             self._static_x.copy_(x)
         g.replay()
+        self.replayed_launches += self._graph_launches[key]
 
     def fetch(self, names):
         """Device->host read of named ELBO terms (reference attribute names)."""

@@ -193,4 +193,32 @@ class MNISTModel_fashion(BaseModel):
 
 
 class CelebAModel_densenet(BaseModel):
-    """codes/models.py:330-598"""
+    """codes/models.py:330-598.  The reference streams `celebA_{train,val,test}.tfrecords` ('X' = raw uint8
+    128x128x3, scaled by 1/255) through tf.data; TFRecord parsing is outside the hot path, so the image pools
+    come from `<data_path>/celeba_{train,val,test}.npy` (uint8 [N,128,128,3]) when present and are synthetic
+    otherwise.  The iterator reshuffles the pool every epoch and repeats it, like `shuffle(...).repeat(8000)`."""
+
+    def _pool(self, split, n_default):
+        cfg = self.config
+        path = os.path.join(cfg.get('data_path', '') or '', 'celeba_%s.npy' % split)
+        if not cfg.get('synthetic', False) and os.path.isfile(path):
+            return np.load(path, mmap_mode='r').astype(np.float32) * (1.0 / 255)
+        key = '_pool_' + split
+        if not hasattr(self, key):
+            n = int(cfg.get('synthetic_pool', n_default))
+            rng = np.random.default_rng({'train': 1, 'val': 2, 'test': 3}[split])
+            s, c = int(cfg['dim_input_x']), int(cfg['dim_input_channel'])
+            low = rng.uniform(size=(n, s // 8, s // 8, c)).astype(np.float32)      # smooth, image-like blobs
+            setattr(self, key, np.clip(np.repeat(np.repeat(low, 8, axis=1), 8, axis=2) +
+                                       0.05 * rng.normal(size=(n, s, s, c)).astype(np.float32), 0, 1))
+            print("[data] no dataset file found ({}); using a synthetic pool of {} images".format(path, n))
+        return getattr(self, key)
+
+    def train_images(self):
+        return self._pool('train', 1024)
+
+    def val_images(self):
+        return self._pool('val', 256)
+
+    def test_image(self):
+        return self._pool('test', 256)[:int(self.config['batch_size'])]

@@ -54,15 +54,17 @@ def _workspace(device, nbytes, tag):
 class MixtureTable:
     """Packed canonical form of a Gaussian mixture on the device (see csrc/mixture.cu)."""
 
-    def __init__(self, table, K, D, mode, iso_scale, ref_log2):
+    def __init__(self, table, K, D, mode, iso_scale, ref_log2, tc_image=None):
         self.table, self.K, self.D, self.mode = table, K, D, mode
         self.iso_scale, self.ref_log2 = iso_scale, ref_log2
+        self.tc_image = tc_image          # tensor-core operand image (isotropic, D in {32, 64}); forward only
 
     def shard(self, rank, world):
         """Contiguous component shard for rank `rank` of `world` (same frame)."""
         per = -(-self.K // world)
         lo, hi = min(rank * per, self.K), min((rank + 1) * per, self.K)
         return MixtureTable(self.table[lo:hi].contiguous(), hi - lo, self.D, self.mode, self.iso_scale, self.ref_log2)
+
 
 
 def _dptr(a):
@@ -97,11 +99,26 @@ def mixture_pack_diag(mean, std, weight=None, device='cuda'):
     _lib.check(_L().ladder_mixture_pack_diag(_dptr(mean), _dptr(std), _dptr(w) if w is not None else None, K, D,
                                              int(scalar), table.ctypes.data_as(_lib.c_float_p), C.byref(ref),
                                              C.byref(iso)), 'mixture_pack_diag')
-    return MixtureTable(torch.from_numpy(table).to(device), K, D, mode, iso.value, ref.value)
+    tc_image = None
+    if scalar and D in (32, 64):
+        nbytes = _L().ladder_mixture_tc_image_bytes(K, D)
+        img = np.zeros(nbytes // 4, dtype=np.float32)
+        ref2, iso2 = C.c_float(), C.c_float()
+        _lib.check(_L().ladder_mixture_tc_pack_iso(_dptr(mean), float(std[0]), _dptr(w) if w is not None else None, K, D,
+                                                   img.ctypes.data_as(_lib.c_float_p), C.byref(ref2), C.byref(iso2)),
+                   'mixture_tc_pack_iso')
+        tc_image = torch.from_numpy(img).to(device)
+    return MixtureTable(torch.from_numpy(table).to(device), K, D, mode, iso.value, ref.value, tc_image)
 
 
-def mixture_logprob(t, tab, want_grad=False, partial=False, out=None):
+MIXTURE_TC = True      # use the tcgen05 kernel for isotropic D in {32, 64} forward evaluations
+
+
+def mixture_logprob(t, tab, want_grad=False, partial=False, out=None, exact=False):
     """log p(t_n) under the packed mixture; optionally d log p / d t.
+
+    Isotropic mixtures with D in {32, 64} evaluate the forward pass on the tensor cores (tf32 cross term,
+    |d logp| <= 3e-2 / 5e-2); pass exact=True for the fp32 SIMT kernel.
 
     partial=True returns the component-shard partial (m, s[, g_unnormalised]) instead.
     `out` may carry preallocated tensors {'logp','grad','m','s'} (for CUDA-graph capture)."""
@@ -111,6 +128,14 @@ def mixture_logprob(t, tab, want_grad=False, partial=False, out=None):
         raise RuntimeError('mixture_logprob: query dim %d != table dim %d' % (D, tab.D))
     out = out or {}
     dev = t.device
+    if (MIXTURE_TC and not exact and not want_grad and not partial and tab.tc_image is not None and N > 0):
+        logp = out.get('logp') if 'logp' in out else torch.empty(N, device=dev, dtype=torch.float32)
+        nbytes = _L().ladder_mixture_tc_workspace_bytes(N, tab.K)
+        ws = _workspace(dev, nbytes, 'mixture_tc')
+        _lib.check(_L().ladder_mixture_logprob_tc(_p(t), N, D, _p(tab.tc_image), _p(tab.table), tab.K, tab.iso_scale,
+                                                  tab.ref_log2, _p(logp), _p(ws), ws.numel(), _stream()),
+                   'mixture_logprob_tc')
+        return logp
     if N == 0:                       # empty batch: nothing to launch
         e = torch.empty(0, device=dev, dtype=torch.float32)
         if partial:

@@ -148,3 +148,38 @@ def test_full_size_properties(ops):
     want = -0.5 * ((t - m[:1]) ** 2).sum(1) - np.log(2 * np.pi)
     # 65 536 identical addends: fp32 accumulation error is systematic here (~n*eps/4), hence 2e-3
     np.testing.assert_allclose(lp1, want, rtol=1e-5, atol=2e-3)
+
+
+@pytest.mark.parametrize('D', [32, 64])
+def test_tensor_core_path_iso(ops, D):
+    """tcgen05 (tf32) forward path for isotropic D in {32, 64}: against the float64 oracle and the exact fp32
+    SIMT kernel.  Stated tolerance: |d logp| <= 3e-2 at D=32 and 5e-2 at D=64 for unit-scale data with
+    |logp| ~ 1e2 (tf32 rounds the operands of the cross term to 11 bits)."""
+    rng = np.random.default_rng(D)
+    for N, K in ((1000, 777), (4096, 4096), (257, 129)):
+        m = rng.normal(size=(K, D)); t = rng.normal(size=(N, D)).astype(np.float32)
+        w = rng.uniform(0.1, 1.0, size=K)
+        tab = ops.mixture_pack_diag(m, 0.9, w, 'cuda')
+        assert tab.tc_image is not None
+        lp_tc = ops.mixture_logprob(_dev(t), tab)
+        lp_exact = ops.mixture_logprob(_dev(t), tab, exact=True)
+        mu, A, c = OM.canonical_from_diag(m, 0.9, w)
+        ref = OM.mixture_logprob(t.astype(np.float64), mu, A, c)
+        assert torch.isfinite(lp_tc).all()
+        np.testing.assert_allclose(lp_exact.cpu().numpy(), ref, rtol=1e-5, atol=2e-3)
+        err = np.abs(lp_tc.cpu().numpy() - ref).max()
+        assert err < (3e-2 if D == 32 else 5e-2), err
+        lp2 = ops.mixture_logprob(_dev(t), tab)
+        assert torch.equal(lp_tc, lp2)                               # deterministic
+
+
+def test_tensor_core_path_far_queries_rescued(ops):
+    rng = np.random.default_rng(9)
+    D, K, N = 32, 300, 512
+    m = rng.normal(size=(K, D)); t = (rng.normal(size=(N, D)) * 30).astype(np.float32)
+    tab = ops.mixture_pack_diag(m, 0.5, None, 'cuda')
+    lp = ops.mixture_logprob(_dev(t), tab)
+    mu, A, c = OM.canonical_from_diag(m, 0.5)
+    ref = OM.mixture_logprob(t.astype(np.float64), mu, A, c)
+    assert torch.isfinite(lp).all()
+    np.testing.assert_allclose(lp.cpu().numpy(), ref, rtol=2e-5)
