@@ -26,11 +26,18 @@ sys.path.insert(0, ROOT)
 METRIC = 'train imgs/sec (ELBO fwd+bwd, 4 sub-steps per image batch)'
 
 
+WORKLOAD = 'mnist_fashion'       # set from --workload; the default is BASELINE.json configs[1]
+
+
 def load_config(batch):
-    with open(os.path.join(ROOT, 'codes', 'mnist_fashion_config.json')) as f:
+    with open(os.path.join(ROOT, 'codes', WORKLOAD + '_config.json')) as f:
         cfg = json.load(f)
     cfg['batch_size'] = batch
     return cfg
+
+
+def image_shape(cfg):
+    return (int(cfg['dim_input_x']), int(cfg['dim_input_y']), int(cfg['dim_input_channel']))
 
 
 def synthetic_mixture(K, R, seed=7):
@@ -114,7 +121,7 @@ def cpu_reference(cfg_full, sample_B, steps, warmup):
     spec = oparams.vae_param_specs(cfg) + oparams.prior_param_specs(cfg)
     P = oparams.glorot_init(spec, cfg, 1, dtype=np.float32)
     C, R, L, K = cfg['code_size'], cfg['representation_size'], cfg['n_MC_samples'], cfg['n_mixtures']
-    x = rng.uniform(size=(sample_B, 28, 28, 1)).astype(np.float32)
+    x = rng.uniform(size=(sample_B,) + image_shape(cfg)).astype(np.float32)
     epoch = cfg['sg_pretraining'] + 1
     feeds = osteps.compute_feeds(cfg, epoch, synthetic_mixture(K, R))
     tr = osteps.OracleTrainer(cfg, P, dtype=np.float32)
@@ -144,8 +151,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'imgs/s', 'n_gpus': args.gpus,
             'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * base['seconds'] / steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'codes/mnist_fashion_config.json @ batch %d (CPU arm times a %d-image sample)'
-                                   % (args.batch, args.cpu_sample)},
+            'config': {'workload': 'codes/%s_config.json @ batch %d (CPU arm times a %d-image sample)'
+                                   % (WORKLOAD, args.batch, args.cpu_sample)},
             'cpu_baseline': {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
             'e2e': {'value': base['value'], 'unit': 'imgs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -157,8 +164,7 @@ def run_ours(args):
     import torch.distributed as dist
     from ladder_latent_data_distribution_modelling_b200 import ops
     from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
-    from ladder_latent_data_distribution_modelling_b200.host.models import MNISTModel_fashion
-    from ladder_latent_data_distribution_modelling_b200.host.trainers import MNISTTrainer_joint_training
+    from ladder_latent_data_distribution_modelling_b200.host import models as hmodels, trainers as htrainers
 
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
@@ -193,7 +199,8 @@ def run_ours(args):
     gen = torch.Generator(device=dev)
     gen.manual_seed(99 + rank)
     n_pool = 4
-    pool = [torch.rand(B, 28, 28, 1, device=dev, generator=gen) for _ in range(n_pool)]
+    shp = image_shape(cfg)
+    pool = [torch.rand(B, *shp, device=dev, generator=gen) for _ in range(n_pool)]
 
     def iteration(x):
         for name in ('ae', 'sigma', 'prior', 'inner_sigma'):
@@ -232,18 +239,25 @@ def run_ours(args):
     cfg2['checkpoint_dir'] = cfg2['result_dir'] = tempfile.mkdtemp() + '/'
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):      # keep stdout to the single JSON line
-        model = MNISTModel_fashion(cfg2, device=dev, dist_group=group)
+        model_cls = {'mnist_fashion': hmodels.MNISTModel_fashion, 'mnist_digit': hmodels.MNISTModel_digit,
+                     'celeba': hmodels.CelebAModel_densenet}[WORKLOAD]
+        model = model_cls(cfg2, device=dev, dist_group=group)
     if world > 1:
         for g in model.engine.groups.values():
             dist.broadcast(g.param, 0)
 
     class _Data:
         n_train, n_val = 60000, 10000
-        test_set = {'image': np.zeros((B, 28, 28, 1), np.float32)}
-    trainer = MNISTTrainer_joint_training(None, model, _Data(), cfg2)
+        test_set = {'image': np.zeros((B,) + shp, np.float32)}
+    if WORKLOAD == 'celeba':
+        cfg2['synthetic_pool'] = B
+        with contextlib.redirect_stdout(sys.stderr):
+            trainer = htrainers.CelebATrainer_joint_training(None, model, _Data(), cfg2)
+    else:
+        trainer = htrainers.MNISTTrainer_joint_training(None, model, _Data(), cfg2)
     trainer.cur_epoch = epoch
     model.GM_prior_training.means_, model.GM_prior_training.covariances_, model.GM_prior_training.weights_ = gm
-    host_pool = [torch.rand(B, 28, 28, 1).pin_memory() for _ in range(n_pool)]
+    host_pool = [torch.rand(B, *shp).pin_memory() for _ in range(n_pool)]
     lr = cfg['learning_rate_ae'] * 0.99 ** (epoch - 1)
 
     def e2e_iteration(hx):
@@ -272,11 +286,14 @@ def run_ours(args):
         # ---- roofline of the dominant kernel: the implicit-GEMM of decoder/conv2d_3 (16x16, 64 -> 256, 3x3),
         # 68 % of the model's MACs; timed alone with CUDA events on the launch stream
         H = cfg['num_hidden_units']
-        g = ops.ConvGeom(B, 16, 16, H // 4, 3, 3, H, 1, 'same')
-        xk = torch.randn(B, 16, 16, H // 4, device=dev)
-        wk = torch.randn(3, 3, H // 4, H, device=dev) * 0.05
-        bk = torch.zeros(H, device=dev)
-        yk = torch.empty(B, 16, 16, H, device=dev)
+        # (name, HW, Cin, Cout) of the layer that carries the most MACs of the model
+        dom_name, hw, ci, co = {'mnist_fashion': ('decoder/conv2d_3', 16, H // 4, H), 'mnist_digit': ('decoder/conv2d', 4, H, H),
+                                'celeba': ('decoder/conv2d_7', 128, H // 4, H // 4)}[WORKLOAD]
+        g = ops.ConvGeom(B, hw, hw, ci, 3, 3, co, 1, 'same')
+        xk = torch.randn(B, hw, hw, ci, device=dev)
+        wk = torch.randn(3, 3, ci, co, device=dev) * 0.05
+        bk = torch.zeros(co, device=dev)
+        yk = torch.empty(B, hw, hw, co, device=dev)
         for _ in range(3):
             ops.conv2d_fprop(xk, wk, bk, yk, g, 'leaky_relu')
         torch.cuda.synchronize()
@@ -287,11 +304,11 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / reps
-        flops = 2.0 * B * 256 * H * (9 * H // 4)
+        flops = 2.0 * B * hw * hw * co * 9 * ci
         ach = flops / (k_ms * 1e-3) / 1e12
         ops.set_math_mode(args.dtype)
         kname = 'tc_kernel<FPROP,256> (tcgen05)' if args.dtype == 'bf16' else 'igemm_kernel<FPROP> (fp32 SIMT)'
-        roofline = {'kernel': kname + ' decoder/conv2d_3 [B,16,16,%d]->%d 3x3' % (H // 4, H),
+        roofline = {'kernel': kname + ' %s [B,%d,%d,%d]->%d 3x3' % (dom_name, hw, hw, ci, co),
                     'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                     'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'peak_source': peaks['source'] + ' bf16 burst',
                     'ms_per_launch': k_ms, 'algorithmic_flops_per_launch': flops,
@@ -328,14 +345,14 @@ def run_ours(args):
         line = {'metric': METRIC, 'value': value, 'unit': 'imgs/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16' if args.dtype == 'bf16' else 'f32', 'data': 'synthetic',
-                'config': {'workload': 'codes/mnist_fashion_config.json @ batch %d per GPU, epoch %d (all 4 sub-steps, '
-                                       '50-component hyper-prior, L=100 MC samples)' % (B, epoch),
+                'config': {'workload': 'codes/%s_config.json @ batch %d per GPU, epoch %d (all 4 sub-steps, '
+                                       '50-component hyper-prior, L=100 MC samples)' % (WORKLOAD, B, epoch),
                            'global_batch': B * world, 'parallelism': 'dp%d' % world, 'cuda_graphs': bool(eng.use_graphs),
                            'l2': 'per-step activation working set (>1 GB) exceeds the 126 MB L2; 4 input batches rotate'},
                 'clocks': clocks, 'gpu_launches': launches,
-                'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': B * 784 * 4,
+                'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': B * int(np.prod(shp)) * 4,
                         'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps,
-                        'api': 'MNISTTrainer_joint_training.train_step_ae + train_step_prior on pinned host batches'},
+                        'api': '*Trainer_joint_training.train_step_ae + train_step_prior on pinned host batches'},
                 'roofline': roofline, 'cpu_baseline': {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
                 'hyper_prior': hyper, 'loss_prior_last': loss_check, 'loss_ae_last_e2e': last}
     if world > 1:
@@ -355,7 +372,11 @@ def main():
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of CUDA-graph replay')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'], help='GEMM math: bf16 tcgen05 or fp32 SIMT')
     ap.add_argument('--cpu-sample', type=int, default=32, help='batch of the bounded CPU-baseline sample')
+    ap.add_argument('--workload', default='mnist_fashion', choices=['mnist_fashion', 'mnist_digit', 'celeba'],
+                    help='config file under codes/ (default: BASELINE.json configs[1])')
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
         run_reference(args)

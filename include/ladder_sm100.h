@@ -95,18 +95,30 @@ int ladder_mixture_combine(const float* m_parts, const float* s_parts, const flo
 size_t ladder_conv2d_workspace_bytes(int B, int H, int W, int Cin, int KH, int KW, int Cout);
 int ladder_conv2d_fprop(const float* x, const float* w, const float* bias /*nullable*/, float* y, int B, int H,
                         int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH,
-                        int OW, int act, void* workspace, size_t workspace_bytes, cudaStream_t stream);
-/* dx = conv_transpose(dy, w) [* act'(act_out) if act_out != NULL: fuses the activation
+                        int OW, int act, int out_d2s, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* out_d2s = r > 0: y is written directly in tf.nn.depth_to_space(r) layout [B, OH*r, OW*r, Cout/r^2] (the
+ * permutation of codes/models.py:113-141 fused into the epilogue).
+ * dx = conv_transpose(dy, w) [* act'(act_out) if act_out != NULL: fuses the activation
  * backward of the layer that PRODUCED x]; accumulate != 0 adds into dx.                   */
 int ladder_conv2d_dgrad(const float* dy, const float* w, const float* act_out /*nullable*/, float* dx, int B,
                         int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH,
-                        int OW, int act, int accumulate, cudaStream_t stream);
+                        int OW, int act, int accumulate, int out_s2d, cudaStream_t stream);
+/* out_s2d = r > 0: x was the depth_to_space(r) of the producer's output; dx is written at the producer-side
+ * position [B, H/r, W/r, Cin*r^2] (the gradient of depth_to_space fused into the epilogue; act_out is then
+ * the producer output in the d2s layout, i.e. indexed like x).                                          */
 /* dw [KH,KW,Cin,Cout] (overwritten) and, if dbias != NULL, dbias [Cout] = column sums of dy. */
 int ladder_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias /*nullable*/, int B, int H, int W,
                         int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW,
                         void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 int ladder_colsum(const float* g, long long rows, int cols, float* out, cudaStream_t stream);
+
+/* Element-wise halves of the tap-GEMM evaluation of a single-output-channel KHxKW conv (Z, DYS are
+ * [B*H*W, ldz], ldz >= KH*KW):  y = act(bias + sum_tap Z[p + tap, tap]);  DYS[p, tap] = dy[p - tap].   */
+int ladder_tap_sum(const float* z, int ldz, const float* bias /*nullable*/, float* y, int B, int H, int W, int KH,
+                   int KW, int stride, int pad_t, int pad_l, int OH, int OW, int act, cudaStream_t stream);
+int ladder_tap_scatter(const float* dy, float* dys, int ldz, int B, int H, int W, int KH, int KW, int stride,
+                       int pad_t, int pad_l, int OH, int OW, cudaStream_t stream);
 
 /* bf16 tensor-core (tcgen05.mma, TMEM accumulators) versions of the three conv/dense GEMMs:
  * same geometry arguments and fp32 NHWC / HWIO tensors in HBM; operands are converted to bf16
@@ -116,11 +128,11 @@ int ladder_colsum(const float* g, long long rows, int cols, float* out, cudaStre
 size_t ladder_conv2d_tc_workspace_bytes(int B, int H, int W, int Cin, int KH, int KW, int Cout);
 int ladder_conv2d_fprop_tc(const float* x, const float* w, const float* bias /*nullable*/, float* y, int B, int H,
                            int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH,
-                           int OW, int act, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                           int OW, int act, int out_d2s, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int ladder_conv2d_dgrad_tc(const float* dy, const float* w, const float* act_out /*nullable*/, float* dx, int B,
                            int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l,
-                           int OH, int OW, int act, int accumulate, void* workspace, size_t workspace_bytes,
-                           cudaStream_t stream);
+                           int OH, int OW, int act, int accumulate, int out_s2d, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream);
 int ladder_conv2d_wgrad_tc_supported(int Cin, int Cout);   /* 1 iff Cin % 64 == 0 */
 int ladder_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, int H, int W, int Cin, int KH, int KW,
                            int Cout, int stride, int pad_t, int pad_l, int OH, int OW, void* workspace,

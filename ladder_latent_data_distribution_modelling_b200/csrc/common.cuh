@@ -56,4 +56,28 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
   }
 }
 
+
+// Output permutations fused into the GEMM epilogues (r = block size, 0 = none):
+//  * forward:  y is written directly in depth_to_space (NHWC, DCR) layout -- row (b,h,w), col (i*r+j)*C'+c  ->
+//              element (b, h*r+i, w*r+j, c) of [B, GH*r, GW*r, C']
+//  * backward: the gradient w.r.t. a depth_to_space OUTPUT (row (b,y2,x2) of the [B,GH,GW,C] grid, col c) is
+//              written at the position of the matching depth_to_space INPUT element
+//              (b, y2/r, x2/r, ((y2%r)*r + x2%r)*C + c) of [B, GH/r, GW/r, C*r*r]
+__device__ __forceinline__ long long d2s_dest(long long m, int n, int GH, int GW, int Ncols, int r) {
+  const int Cp = Ncols / (r * r);
+  const int w = (int)(m % GW);
+  const long long q = m / GW;
+  const int h = (int)(q % GH);
+  const long long b = q / GH;
+  const int ij = n / Cp, c = n % Cp, i = ij / r, j = ij % r;
+  return ((b * GH * r + h * r + i) * ((long long)GW * r) + w * r + j) * Cp + c;
+}
+__device__ __forceinline__ long long s2d_dest(long long m, int n, int GH, int GW, int Ncols, int r) {
+  const int x2 = (int)(m % GW);
+  const long long q = m / GW;
+  const int y2 = (int)(q % GH);
+  const long long b = q / GH;
+  return ((b * (GH / r) + y2 / r) * (GW / r) + x2 / r) * ((long long)Ncols * r * r) + ((y2 % r) * r + x2 % r) * Ncols + n;
+}
+
 }  // namespace ladder

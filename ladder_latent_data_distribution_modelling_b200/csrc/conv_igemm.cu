@@ -27,6 +27,7 @@ struct ConvArgs {
   int act;             // FPROP: activation; DGRAD: activation whose derivative multiplies dx
   int accumulate;      // DGRAD: out += result (tensor with two consumers)
   int m_per_split;     // WGRAD: reduction rows per grid.z slice
+  int perm_r;          // FPROP: write y in depth_to_space(r) layout; DGRAD: write dx at the d2s-input position (0 = off)
 };
 
 enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
@@ -237,6 +238,8 @@ __global__ void __launch_bounds__(NT) igemm_kernel(ConvArgs a) {
       if (n >= Ng) continue;
       float v = acc[i][j];
       float* o = a.out + m * Ng + n;
+      if (MODE == FPROP && a.perm_r > 0) o = a.out + d2s_dest(m, n, a.OH, a.OW, Ng, a.perm_r);
+      if (MODE == DGRAD && a.perm_r > 0) o = a.out + s2d_dest(m, n, a.H, a.W, Ng, a.perm_r);
       if (MODE == FPROP) {
         if (a.bias != nullptr) v += __ldg(a.bias + n);
         *o = act_apply(v, a.act);
@@ -406,10 +409,12 @@ size_t ladder_conv2d_workspace_bytes(int B, int H, int W, int Cin, int KH, int K
 
 int ladder_conv2d_fprop(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
                         int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
-                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  ConvArgs a{x, w, bias, nullptr, y, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, act, 0, 0};
+                        int out_d2s, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  ConvArgs a{x, w, bias, nullptr, y, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, act, 0, 0, out_d2s};
   int rc = validate(a, "conv2d_fprop");
   if (rc) return rc;
+  LADDER_REQUIRE(out_d2s == 0 || (out_d2s > 0 && Cout % (out_d2s * out_d2s) == 0 && Cout > 4),
+                 "conv2d_fprop: depth_to_space(%d) output needs Cout %% r^2 == 0 (Cout=%d)", out_d2s, Cout);
   const long long pixels = (long long)B * OH * OW;
   if (use_tap_gemm(a)) {
     const long long p_in = (long long)B * H * W;
@@ -436,10 +441,12 @@ int ladder_conv2d_fprop(const float* x, const float* w, const float* bias, float
 
 int ladder_conv2d_dgrad(const float* dy, const float* w, const float* act_out, float* dx, int B, int H, int W,
                         int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW,
-                        int act, int accumulate, cudaStream_t stream) {
-  ConvArgs a{dy, w, nullptr, act_out, dx, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, act, accumulate, 0};
+                        int act, int accumulate, int out_s2d, cudaStream_t stream) {
+  ConvArgs a{dy, w, nullptr, act_out, dx, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, act, accumulate, 0, out_s2d};
   int rc = validate(a, "conv2d_dgrad");
   if (rc) return rc;
+  LADDER_REQUIRE(out_s2d == 0 || (out_s2d > 0 && H % out_s2d == 0 && W % out_s2d == 0),
+                 "conv2d_dgrad: space_to_depth(%d) output needs H, W divisible by r", out_s2d);
   dim3 grid((unsigned)ceil_div64((long long)B * H * W, BM), (unsigned)ceil_div(Cin, BN));
   igemm_kernel<DGRAD><<<grid, NT, 0, stream>>>(a);
   return check_launch("conv2d_dgrad");
@@ -524,6 +531,71 @@ int ladder_colsum(const float* g, long long rows, int cols, float* out, cudaStre
   dim3 grid(gx, (unsigned)ceil_div64(rows, per));
   colsum_kernel<<<grid, 256, 0, stream>>>(g, rows, cols, per, out);
   return check_launch("colsum");
+}
+
+// The two element-wise halves of the tap-GEMM decomposition of a single-output-channel conv, exposed so the
+// GEMM half can run on either GEMM backend:  y = act(bias + sum_tap Z[p + tap, tap])  and  DYS[p, tap] = dy[p - tap].
+// Z / DYS are [B*H*W, ldz] with ldz >= KH*KW (columns beyond KH*KW are ignored / zero-filled).
+__global__ void tap_sum_ld_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ bias, float* __restrict__ y, ConvArgs a) {
+  const long long pixels = (long long)a.B * a.OH * a.OW;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % a.OW);
+    long long r = p / a.OW;
+    const int oy = (int)(r % a.OH);
+    const int b = (int)(r / a.OH);
+    float acc = bias != nullptr ? __ldg(bias) : 0.f;
+    for (int kh = 0; kh < a.KH; ++kh) {
+      const int iy = oy * a.stride - a.pad_t + kh;
+      if (iy < 0 || iy >= a.H) continue;
+      for (int kw = 0; kw < a.KW; ++kw) {
+        const int ix = ox * a.stride - a.pad_l + kw;
+        if (ix < 0 || ix >= a.W) continue;
+        acc += __ldg(z + (((long long)b * a.H + iy) * a.W + ix) * ldz + kh * a.KW + kw);
+      }
+    }
+    y[p] = act_apply(acc, a.act);
+  }
+}
+
+__global__ void tap_scatter_ld_kernel(const float* __restrict__ dy, float* __restrict__ dys, int ldz, ConvArgs a) {
+  const int T = a.KH * a.KW;
+  const long long n = (long long)a.B * a.H * a.W * ldz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % ldz);
+    long long r = i / ldz;
+    const int ix = (int)(r % a.W); r /= a.W;
+    const int iy = (int)(r % a.H);
+    const int b = (int)(r / a.H);
+    float v = 0.f;
+    if (tap < T) {
+      int ny = iy + a.pad_t - tap / a.KW, nx = ix + a.pad_l - tap % a.KW;
+      if (ny >= 0 && nx >= 0 && ny % a.stride == 0 && nx % a.stride == 0) {
+        ny /= a.stride; nx /= a.stride;
+        if (ny < a.OH && nx < a.OW) v = __ldg(dy + ((long long)b * a.OH + ny) * a.OW + nx);
+      }
+    }
+    dys[i] = v;
+  }
+}
+
+int ladder_tap_sum(const float* z, int ldz, const float* bias, float* y, int B, int H, int W, int KH, int KW, int stride,
+                   int pad_t, int pad_l, int OH, int OW, int act, cudaStream_t stream) {
+  LADDER_REQUIRE(z && y && ldz >= KH * KW && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && stride > 0, "tap_sum: bad arguments");
+  ConvArgs a{z, nullptr, bias, nullptr, y, B, H, W, 1, KH, KW, 1, stride, pad_t, pad_l, OH, OW, act, 0, 0};
+  long long blocks = ceil_div64((long long)B * OH * OW, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tap_sum_ld_kernel<<<(unsigned)blocks, 256, 0, stream>>>(z, ldz, bias, y, a);
+  return check_launch("tap_sum");
+}
+
+int ladder_tap_scatter(const float* dy, float* dys, int ldz, int B, int H, int W, int KH, int KW, int stride, int pad_t,
+                       int pad_l, int OH, int OW, cudaStream_t stream) {
+  LADDER_REQUIRE(dy && dys && ldz >= KH * KW && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && stride > 0, "tap_scatter: bad arguments");
+  ConvArgs a{dy, nullptr, nullptr, nullptr, dys, B, H, W, 1, KH, KW, 1, stride, pad_t, pad_l, OH, OW, 0, 0, 0};
+  long long blocks = ceil_div64((long long)B * H * W * ldz, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tap_scatter_ld_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dy, dys, ldz, a);
+  return check_launch("tap_scatter");
 }
 
 }  // extern "C"

@@ -51,6 +51,7 @@ struct TcArgs {
   int Kpad;                    // FPROP/DGRAD: padded reduction length (multiple of BK)
   int m_valid;                 // rows of the output that exist (WGRAD with padded taps)
   int m_tiles, n_tiles, splits;   // persistent tile space
+  int perm_r;                  // FPROP: y in depth_to_space(r) layout; DGRAD: dx at the d2s-input position (0 = off)
   int debug;                   // bring-up only (LADDER_TC_DEBUG): 1 skip A loads, 2 skip B copies, 4 skip epilogue stores
 };
 
@@ -487,6 +488,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
       const long long mrow0 = (long long)T.m_tile * BM + quad * 32;
       const int n0 = T.n_tile * BN;
       const long long mlim = MODE == WGRAD ? min(Mg, (long long)a.m_valid) : Mg;
+      // destination offset of column 0 of this lane's 8 rows (once per tile; the fused depth_to_space /
+      // space_to_depth permutations only change this row term and, for FPROP, a small per-chunk column term)
+      long long rowoff[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const long long m = mrow0 + it * 4 + sub;
+        rowoff[it] = m * Ng;
+        if (a.perm_r > 0 && m < mlim) {
+          if (MODE == FPROP) rowoff[it] = d2s_dest(m, 0, a.OH, a.OW, Ng, a.perm_r);
+          if (MODE == DGRAD) rowoff[it] = s2d_dest(m, 0, a.H, a.W, Ng, a.perm_r);
+        }
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
@@ -498,7 +511,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
           *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         __syncwarp();
         const int col = nb + c4;
-        const bool vec_ok = (Ng & 3) == 0 && col + 4 <= Ng;
+        bool vec_ok = (Ng & 3) == 0 && col + 4 <= Ng;
+        long long coloff = col;
+        if (MODE == FPROP && a.perm_r > 0) {      // col = (i*r + j)*C' + c  ->  (i * OW*r + j) * C' + c
+          const int r = a.perm_r, Cp = Ng / (r * r), ij = col / Cp, c = col % Cp;
+          coloff = ((long long)(ij / r) * a.OW * r + ij % r) * Cp + c;
+          vec_ok = vec_ok && (Cp & 3) == 0;
+        }
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODE == FPROP && a.bias != nullptr) {
           if (col < Ng) bias4.x = __ldg(a.bias + col);
@@ -512,7 +531,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
           const long long m = mrow0 + r;
           float4 q = *reinterpret_cast<const float4*>(stage + r * 36 + c4);
           if (m >= mlim || col >= Ng) continue;
-          float* o = a.out + m * Ng + col;
+          float* o = a.out + rowoff[it] + coloff;
           float e[4] = {q.x, q.y, q.z, q.w};
           if (MODE == FPROP) {
             e[0] = act_apply(e[0] + bias4.x, a.act); e[1] = act_apply(e[1] + bias4.y, a.act);
@@ -546,7 +565,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
           } else {
 #pragma unroll
             for (int t = 0; t < 4; ++t)
-              if (col + t < Ng) o[t] = e[t];
+              if (col + t < Ng) {
+                if (MODE == FPROP && a.perm_r > 0) a.out[d2s_dest(m, col + t, a.OH, a.OW, Ng, a.perm_r)] = e[t];
+                else o[t] = e[t];
+              }
           }
         }
         __syncwarp();
@@ -700,27 +722,31 @@ int ladder_conv2d_wgrad_tc_supported(int Cin, int Cout) { (void)Cout; return Cin
 
 int ladder_conv2d_fprop_tc(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
                            int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
-                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                           int out_d2s, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  LADDER_REQUIRE(out_d2s == 0 || (out_d2s > 0 && Cout % (out_d2s * out_d2s) == 0),
+                 "conv2d_fprop_tc: depth_to_space(%d) output needs Cout %% r^2 == 0", out_d2s);
   LADDER_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
                  "conv2d_fprop_tc: bad arguments");
   LADDER_REQUIRE((long long)B * OH * OW < (1LL << 31) && (long long)B * H * W < (1LL << 31), "conv2d_fprop_tc: too many pixels");
   int rc = pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, stream);
   if (rc) return rc;
   TcArgs a{x, nullptr, static_cast<const __nv_bfloat16*>(workspace), bias, nullptr, y, B, H, W, Cin, KH, KW, Cout, stride,
-           pad_t, pad_l, OH, OW, act, 0, 0, round_up(KH * KW * Cin, BK), 0, 0, 0, 0};
+           pad_t, pad_l, OH, OW, act, 0, 0, round_up(KH * KW * Cin, BK), 0, 0, 0, 0, out_d2s};
   return launch<FPROP>(a, (long long)B * OH * OW, Cout, 1, stream);
 }
 
 int ladder_conv2d_dgrad_tc(const float* dy, const float* w, const float* act_out, float* dx, int B, int H, int W, int Cin,
                            int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
-                           int accumulate, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                           int accumulate, int out_s2d, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  LADDER_REQUIRE(out_s2d == 0 || (out_s2d > 0 && H % out_s2d == 0 && W % out_s2d == 0),
+                 "conv2d_dgrad_tc: space_to_depth(%d) output needs H, W divisible by r", out_s2d);
   LADDER_REQUIRE(dy && w && dx && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
                  "conv2d_dgrad_tc: bad arguments");
   LADDER_REQUIRE((long long)B * OH * OW < (1LL << 31) && (long long)B * H * W < (1LL << 31), "conv2d_dgrad_tc: too many pixels");
   int rc = pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, stream);
   if (rc) return rc;
   TcArgs a{dy, nullptr, static_cast<const __nv_bfloat16*>(workspace), nullptr, act_out, dx, B, H, W, Cin, KH, KW, Cout, stride,
-           pad_t, pad_l, OH, OW, act, accumulate, 0, round_up(KH * KW * Cout, BK), 0, 0, 0, 0};
+           pad_t, pad_l, OH, OW, act, accumulate, 0, round_up(KH * KW * Cout, BK), 0, 0, 0, 0, out_s2d};
   return launch<DGRAD>(a, (long long)B * H * W, Cin, 1, stream);
 }
 

@@ -89,18 +89,21 @@ class Conv:
         self.y = torch.empty(g.B, g.OH, g.OW, g.Cout, device=device)
         self.x = None
 
-    def forward(self, x):
+    def forward(self, x, d2s=0):
+        """d2s = r: the output is written directly in depth_to_space(r) layout (self.y must then be viewed as
+        [B, OH*r, OW*r, Cout/r^2] by the caller)."""
         self.x = x
-        return ops.conv2d_fprop(x, self.w, self.b, self.y, self.geom, self.act)
+        return ops.conv2d_fprop(x, self.w, self.b, self.y, self.geom, self.act, out_d2s=d2s)
 
-    def backward(self, dpre, dx=None, producer=None, wgrad=True, accumulate=False):
+    def backward(self, dpre, dx=None, producer=None, wgrad=True, accumulate=False, s2d=0):
         """dpre: d loss / d pre-activation of this layer.  producer = (act_out, act) of the layer
-        that produced x, whose activation derivative is fused into dx."""
+        that produced x, whose activation derivative is fused into dx.  s2d = r: x was the depth_to_space(r)
+        of the producer's output, so dx is scattered back to the producer's layout in the epilogue."""
         if wgrad:
             ops.conv2d_wgrad(self.x, dpre, self.dw, self.db, self.geom)
         if dx is not None:
             ao, act = producer if producer is not None else (None, None)
-            ops.conv2d_dgrad(dpre, self.w, dx, self.geom, act_out=ao, act=act, accumulate=accumulate)
+            ops.conv2d_dgrad(dpre, self.w, dx, self.geom, act_out=ao, act=act, accumulate=accumulate, out_s2d=s2d)
         return dx
 
 
@@ -161,20 +164,20 @@ class MnistOuterVAE:
             stages = [(1, H, 2, 'decoder/conv2d', 1, H), (2, H, 2, 'decoder/conv2d_1', 3, H),
                       (4, H, 2, 'decoder/conv2d_2', 3, H), (8, H, 2, 'decoder/conv2d_3', 3, H)]
             last = (16, H, 2, 'decoder/conv2d_4', H // 4)
-        self.dec = []          # (hw_in, c_in, r, d2s_out, conv)
+        # decoder chain: every layer writes its activation straight in depth_to_space layout (fused epilogue), which
+        # is the input of the next conv; stage = (hw_in, c_in, r, conv) with conv consuming [B, hw*r, hw*r, c_in/r^2]
+        self.dec = []
         for hw, cin, r, name, kk, cout in stages:
-            d2s_out = torch.empty(B, hw * r, hw * r, cin // (r * r), device=device)
             conv = Conv(group, name, G(B, hw * r, hw * r, cin // (r * r), kk, kk, cout, 1, 'same'), LEAKY, device)
-            self.dec.append((hw, cin, r, d2s_out, conv))
+            self.dec.append((hw, cin, r, conv))
         hw, cin, r, name, cl = last
-        d2s_out = torch.empty(B, hw * r, hw * r, cin // (r * r), device=device)
         conv = Conv(group, name, G(B, hw * r, hw * r, cl, 5, 5, 1, 1, 'valid'), 'relu', device)
-        self.dec.append((hw, cin, r, d2s_out, conv))
+        self.dec.append((hw, cin, r, conv))
         self.flat, self.feat, self.C = flat, feat, C
         self.mean = self.head_mean.y.view(B, C)
         self.std = self.head_std.y.view(B, C)              # becomes relu(.)+floor in place
         self.z = torch.empty(B, C, device=device)
-        self.decoded = self.dec[-1][4].y
+        self.decoded = self.dec[-1][3].y
 
     # -- forward
     def encode(self, x, eps_z, stats_z):
@@ -192,25 +195,26 @@ class MnistOuterVAE:
 
     def decode(self, z):
         B = self.B
-        h = self.dec_dense.forward(z.view(B, 1, 1, self.C))
-        for hw, cin, r, d2s_out, conv in self.dec:
-            ops.depth_to_space(h.view(B, hw, hw, cin), d2s_out, B, hw, hw, cin, r)
-            h = conv.forward(d2s_out)
+        prod = self.dec_dense
+        r0 = self.dec[0][2]
+        h = prod.forward(z.view(B, 1, 1, self.C), d2s=r0)          # y holds the d2s layout from here on
+        for i, (hw, cin, r, conv) in enumerate(self.dec):
+            nxt_r = self.dec[i + 1][2] if i + 1 < len(self.dec) else 0
+            h = conv.forward(h.view(B, hw * r, hw * r, cin // (r * r)), d2s=nxt_r)
         return self.decoded
 
     # -- backward
     def decode_backward(self, dpre_last, dz, wgrad=True):
         """dpre_last: gradient w.r.t. the last conv's pre-activation; writes dz (grad of the decoder
-        input code) and the decoder weight gradients."""
+        input code) and the decoder weight gradients.  Each dgrad scatters straight back into the producer's
+        (pre-depth_to_space) layout and applies the producer's activation derivative."""
         B = self.B
         dpre = dpre_last
         for i in range(len(self.dec) - 1, -1, -1):
-            hw, cin, r, d2s_out, conv = self.dec[i]
-            dd = self.buf.get('dd%d' % i, *d2s_out.shape)
-            conv.backward(dpre, dx=dd, wgrad=wgrad)
-            prod = self.dec[i - 1][4] if i > 0 else self.dec_dense
-            dp = self.buf.get('dp%d' % i, B, hw, hw, cin)
-            ops.space_to_depth_actgrad(dd, prod.y, dp, B, hw, hw, cin, r, prod.act)
+            hw, cin, r, conv = self.dec[i]
+            prod = self.dec[i - 1][3] if i > 0 else self.dec_dense
+            dp = self.buf.get('dp%d' % i, B, hw, hw, cin)              # producer layout
+            conv.backward(dpre, dx=dp, producer=(prod.y, prod.act), wgrad=wgrad, s2d=r)
             dpre = dp
         self.dec_dense.backward(dpre.view(B, 1, 1, -1), dx=dz.view(B, 1, 1, self.C), wgrad=wgrad)
         return dz

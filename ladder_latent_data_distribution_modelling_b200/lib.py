@@ -30,13 +30,15 @@ SIGNATURES = {
                                          ptr, ptr, ptr, ptr, ptr, C.c_size_t, stream_t]),
     # conv / dense
     'ladder_conv2d_workspace_bytes': (C.c_size_t, [C.c_int] * 7),
-    'ladder_conv2d_fprop': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 13 + [ptr, C.c_size_t, stream_t]),
-    'ladder_conv2d_dgrad': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 14 + [stream_t]),
+    'ladder_conv2d_fprop': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 14 + [ptr, C.c_size_t, stream_t]),
+    'ladder_conv2d_dgrad': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 15 + [stream_t]),
     'ladder_conv2d_wgrad': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 12 + [ptr, C.c_size_t, stream_t]),
+    'ladder_tap_sum': (C.c_int, [ptr, C.c_int, ptr, ptr] + [C.c_int] * 11 + [stream_t]),
+    'ladder_tap_scatter': (C.c_int, [ptr, ptr] + [C.c_int] * 11 + [stream_t]),
     'ladder_colsum': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, stream_t]),
     'ladder_conv2d_tc_workspace_bytes': (C.c_size_t, [C.c_int] * 7),
-    'ladder_conv2d_fprop_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 13 + [ptr, C.c_size_t, stream_t]),
-    'ladder_conv2d_dgrad_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 14 + [ptr, C.c_size_t, stream_t]),
+    'ladder_conv2d_fprop_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 14 + [ptr, C.c_size_t, stream_t]),
+    'ladder_conv2d_dgrad_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 15 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_wgrad_tc_supported': (C.c_int, [C.c_int, C.c_int]),
     'ladder_conv2d_wgrad_tc': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [ptr, C.c_size_t, stream_t]),
     # layout / elementwise

@@ -240,8 +240,45 @@ def set_math_mode(mode):
 
 
 def _use_tc(g):
-    # single-output-channel KxK convs stay on the tap-GEMM decomposition of the fp32 path
-    return MATH_MODE == 'bf16' and not (g.Cout == 1 and g.KH * g.KW > 1)
+    # tiny reductions (e.g. the 3x3 conv on a 1-channel image, K = 9) stay on the fp32 SIMT kernel: padding K to a
+    # 64-wide k-block would waste the gather; single-output-channel KxK convs go through _tap_gemm_*.
+    return MATH_MODE == 'bf16' and g.KH * g.KW * g.Cin >= 32 and not _is_tap_gemm(g)
+
+
+def _is_tap_gemm(g):
+    return g.Cout == 1 and g.KH * g.KW > 1 and g.Cin >= 4
+
+
+def _tap_ld(g):
+    return (g.KH * g.KW + 7) // 8 * 8          # leading dimension of Z / DYS (vectorisable, zero padded)
+
+
+def _tap_gemm_fprop_tc(x, w, bias, y, g, act):
+    """Single-output-channel conv on the tensor cores: Z[p, tap] = x[p, :] . w[tap, :] as a dense GEMM over the
+    INPUT pixels (dgrad-form: B^T operand = w), then the shifted tap sum."""
+    P, ld = g.B * g.H * g.W, _tap_ld(g)
+    z = _workspace(x.device, P * ld * 4, 'tap_z').view(torch.float32)[:P * ld].view(P, 1, 1, ld)
+    wpad = _workspace(x.device, ld * g.Cin * 4, 'tap_w').view(torch.float32)[:ld * g.Cin].view(1, 1, ld, g.Cin)
+    wpad.zero_()
+    wpad.view(ld, g.Cin)[:g.KH * g.KW].copy_(w.view(g.KH * g.KW, g.Cin))
+    conv2d_dgrad(x.view(P, 1, 1, g.Cin), wpad, z, ConvGeom.dense(P, ld, g.Cin))
+    _lib.check(_L().ladder_tap_sum(_p(z), ld, _p(bias), _p(_f32(y)), g.B, g.H, g.W, g.KH, g.KW, g.stride, g.pad_t,
+                                   g.pad_l, g.OH, g.OW, ACT[act], _stream()), 'tap_sum')
+    return y
+
+
+def _tap_gemm_wgrad_tc(x, dy, dw, dbias, g):
+    """dw[tap, c] = sum_p DYS[p, tap] x[p, c]: shifted copy of dy, then a dense wgrad with x as the (64-aligned) input."""
+    P, ld, T = g.B * g.H * g.W, _tap_ld(g), g.KH * g.KW
+    dys = _workspace(x.device, P * ld * 4, 'tap_z').view(torch.float32)[:P * ld].view(P, 1, 1, ld)
+    _lib.check(_L().ladder_tap_scatter(_p(_f32(dy)), _p(dys), ld, g.B, g.H, g.W, g.KH, g.KW, g.stride, g.pad_t, g.pad_l,
+                                       g.OH, g.OW, _stream()), 'tap_scatter')
+    dwt = _workspace(x.device, g.Cin * ld * 4, 'tap_w').view(torch.float32)[:g.Cin * ld].view(1, 1, g.Cin, ld)
+    conv2d_wgrad(x.view(P, 1, 1, g.Cin), dys, dwt, None, ConvGeom.dense(P, g.Cin, ld))
+    dw.view(T, g.Cin).copy_(dwt.view(g.Cin, ld)[:, :T].t())
+    if dbias is not None:
+        _lib.check(_L().ladder_colsum(_p(dy), g.B * g.OH * g.OW, 1, _p(dbias), _stream()), 'colsum')
+    return dw
 
 
 def _conv_ws(x, g):
@@ -258,30 +295,36 @@ def _tc_ws(x, g):
     return ws, ws.numel()
 
 
-def conv2d_fprop(x, w, bias, y, g, act=None):
+def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0):
+    """y = act(conv(x, w) + bias); out_d2s = r writes y directly in depth_to_space(r) layout."""
+    if MATH_MODE == 'bf16' and _is_tap_gemm(g) and g.Cin % 64 == 0 and not out_d2s:
+        return _tap_gemm_fprop_tc(x, w, bias, y, g, act)
     if _use_tc(g):
         ws, n = _tc_ws(x, g)
         _lib.check(_L().ladder_conv2d_fprop_tc(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(_f32(y)), *g.args(), ACT[act],
-                                               _p(ws), n, _stream()), 'conv2d_fprop_tc')
+                                               int(out_d2s), _p(ws), n, _stream()), 'conv2d_fprop_tc')
         return y
     ws, n = _conv_ws(x, g)
     _lib.check(_L().ladder_conv2d_fprop(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(_f32(y)), *g.args(), ACT[act],
-                                        _p(ws), n, _stream()), 'conv2d_fprop')
+                                        int(out_d2s), _p(ws), n, _stream()), 'conv2d_fprop')
     return y
 
 
-def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False):
+def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False, out_s2d=0):
+    """dx = conv^T(dy, w) [* act'(act_out)]; out_s2d = r writes dx at the position of the depth_to_space INPUT."""
     if _use_tc(g):
         ws, n = _tc_ws(dy, g)
         _lib.check(_L().ladder_conv2d_dgrad_tc(_p(_f32(dy)), _p(_f32(w)), _p(act_out), _p(_f32(dx)), *g.args(), ACT[act],
-                                               int(accumulate), _p(ws), n, _stream()), 'conv2d_dgrad_tc')
+                                               int(accumulate), int(out_s2d), _p(ws), n, _stream()), 'conv2d_dgrad_tc')
         return dx
     _lib.check(_L().ladder_conv2d_dgrad(_p(_f32(dy)), _p(_f32(w)), _p(act_out), _p(_f32(dx)), *g.args(), ACT[act],
-                                        int(accumulate), _stream()), 'conv2d_dgrad')
+                                        int(accumulate), int(out_s2d), _stream()), 'conv2d_dgrad')
     return dx
 
 
 def conv2d_wgrad(x, dy, dw, dbias, g):
+    if MATH_MODE == 'bf16' and _is_tap_gemm(g) and g.Cin % 64 == 0:
+        return _tap_gemm_wgrad_tc(x, dy, dw, dbias, g)
     if _use_tc(g) and g.Cin % 64 == 0:
         ws, n = _tc_ws(x, g)
         _lib.check(_L().ladder_conv2d_wgrad_tc(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dw)), *g.args(), _p(ws), n, _stream()),

@@ -127,3 +127,38 @@ def test_clip_adam_matches_oracle(ops):
         ops.clip_adam(pd, dev(g), m, v, lr, step)
     assert int(step.item()) == 5
     np.testing.assert_allclose(pd.cpu().numpy(), params['w'], rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'bf16'])
+def test_fused_depth_to_space_epilogues(mode):
+    """fprop writing straight into depth_to_space layout, and dgrad scattering back through it (+ act')."""
+    from ladder_latent_data_distribution_modelling_b200 import ops
+    ops.set_math_mode(mode)
+    tol = 2e-5 if mode == 'fp32' else 1.5e-2
+    rng = np.random.default_rng(0)
+    try:
+        for (B, H, Cin, Cout, r) in [(3, 4, 64, 256, 2), (2, 8, 64, 64, 2), (2, 1, 16, 1024, 4), (2, 4, 32, 36, 3)]:
+            x = rng.normal(size=(B, H, H, Cin)); w = rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin)
+            b = rng.normal(size=(Cout,))
+            X, Wv, Bv = T.Var(x), T.Var(w), T.Var(b)
+            y = T.leaky_relu(T.conv2d(X, Wv, Bv, stride=1, padding='same'))
+            y2 = T.depth_to_space(y, r)
+            g = ops.ConvGeom(B, H, H, Cin, 3, 3, Cout, 1, 'same')
+            yd = torch.empty(B, H, H, Cout, device='cuda')
+            ops.conv2d_fprop(dev(x), dev(w), dev(b), yd, g, 'leaky_relu', out_d2s=r)
+            close(yd.view(y2.shape), y2.v, tol)
+            # consumer conv on the d2s output; its dgrad goes straight back to the producer's layout with act'
+            C2 = Cout // (r * r)
+            w2 = rng.normal(size=(3, 3, C2, 40)) / np.sqrt(9 * C2)
+            W2 = T.Var(w2)
+            z = T.conv2d(y2, W2, None, stride=1, padding='same')
+            up = rng.normal(size=z.shape)
+            T.backward(z, seed=up)
+            g2 = ops.ConvGeom(B, H * r, H * r, C2, 3, 3, 40, 1, 'same')
+            y_d2s = dev(y2.v)
+            dprod = torch.empty(B, H, H, Cout, device='cuda')
+            ops.conv2d_dgrad(dev(up), dev(w2), dprod, g2, act_out=y_d2s, act='leaky_relu', out_s2d=r)
+            want = y.g * np.where(y.v > 0, 1.0, 0.2)            # gradient w.r.t. the producer's pre-activation
+            close(dprod, want, tol * 3)
+    finally:
+        ops.set_math_mode('fp32')
