@@ -290,31 +290,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
     int lkb = 0, skb = 0;
     decode_tile<MODE>(a, blockIdx.x, total, pixels, L);
     S = L;
-    // Affine fast path (64-aligned channels; FPROP any stride, DGRAD stride 1): the source offset of (row, tap, c)
-    // is rbase[row] + tapoff(tap) + c with a per-row validity mask per tap row / column, so a k-block costs one
-    // add + one predicate per 16-byte load instead of re-deriving (b, y, x) -> offset every time.
-    const bool affine = fast && (MODE == FPROP || (MODE == DGRAD && a.stride == 1));
-    long long rbase[8];
-    unsigned rvy[8], rvx[8];
-    auto pixel_affine = [&](long long p, long long lim, long long& base, unsigned& vy, unsigned& vx) {
-      base = 0; vy = 0; vx = 0;
+    // Fast path (64-aligned channels, any stride, FPROP and DGRAD): per tile every thread keeps, for its 8 rows, the
+    // batch base offset and the (y, x) origin of the patch; a k-block (= one tap, 64 channels) then costs a handful of
+    // integer ops + one predicate per 16-byte load instead of re-deriving (b, y, x) -> offset per element.
+    const bool affine = fast;
+    long long rbase[8];              // batch offset of the gathered tensor, -1 for rows past the end
+    int rvy[8], rvx[8];              // FPROP: y*s - pad_t, x*s - pad_l;  DGRAD: y + pad_t, x + pad_l
+    auto pixel_affine = [&](long long p, long long lim, long long& base, int& oy, int& ox) {
+      base = -1; oy = 0; ox = 0;
       if (p >= lim) return;
       const unsigned pu = (unsigned)p;
       const int x = (int)(pu % (unsigned)gw);
       const unsigned r = pu / (unsigned)gw;
       const int y = (int)(r % (unsigned)gh), b = (int)(r / (unsigned)gh);
-      if (MODE == DGRAD) {            // ny = y + pad_t - kh, nx = x + pad_l - kw  (stride 1)
-        base = (((long long)b * a.OH + y + a.pad_t) * a.OW + x + a.pad_l) * a.Cout;
-        for (int k = 0; k < a.KH; ++k) { const int ny = y + a.pad_t - k; vy |= (unsigned)(ny >= 0 && ny < a.OH) << k; }
-        for (int k = 0; k < a.KW; ++k) { const int nx = x + a.pad_l - k; vx |= (unsigned)(nx >= 0 && nx < a.OW) << k; }
-      } else {                        // iy = y*s - pad_t + kh, ix = x*s - pad_l + kw
-        base = (((long long)b * a.H + y * a.stride - a.pad_t) * a.W + x * a.stride - a.pad_l) * a.Cin;
-        for (int k = 0; k < a.KH; ++k) { const int iy = y * a.stride - a.pad_t + k; vy |= (unsigned)(iy >= 0 && iy < a.H) << k; }
-        for (int k = 0; k < a.KW; ++k) { const int ix = x * a.stride - a.pad_l + k; vx |= (unsigned)(ix >= 0 && ix < a.W) << k; }
+      if (MODE == DGRAD) {
+        base = (long long)b * a.OH * a.OW * a.Cout;
+        oy = y + a.pad_t; ox = x + a.pad_l;
+      } else {
+        base = (long long)b * a.H * a.W * a.Cin;
+        oy = y * a.stride - a.pad_t; ox = x * a.stride - a.pad_l;
       }
     };
-    auto tap_delta = [&](int kh, int kw) -> long long {
-      return MODE == DGRAD ? -((long long)kh * a.OW + kw) * a.Cout : ((long long)kh * a.W + kw) * a.Cin;
+    // element offset of tap (kh, kw) for a row prepared by pixel_affine, or -1 (padding / between strides)
+    auto tap_off = [&](long long base, int oy, int ox, int kh, int kw) -> long long {
+      if (base < 0) return -1;
+      if (MODE == DGRAD) {
+        int ny = oy - kh, nx = ox - kw;
+        if (ny < 0 || nx < 0) return -1;
+        if (a.stride == 2) {
+          if ((ny | nx) & 1) return -1;
+          ny >>= 1; nx >>= 1;
+        } else if (a.stride > 2) {
+          if (ny % a.stride || nx % a.stride) return -1;
+          ny /= a.stride; nx /= a.stride;
+        }
+        if (ny >= a.OH || nx >= a.OW) return -1;
+        return base + ((long long)ny * a.OW + nx) * a.Cout;
+      } else {
+        const int iy = oy + kh, ix = ox + kw;
+        if (iy < 0 || ix < 0 || iy >= a.H || ix >= a.W) return -1;
+        return base + ((long long)iy * a.W + ix) * a.Cin;
+      }
     };
     auto row_coords = [&]() {
       if (MODE == WGRAD || !L.valid || !affine) return;
@@ -332,10 +348,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
           // K order on the fast path: 64-channel chunk major, tap minor -- the KH*KW consecutive k-blocks of one
           // chunk re-read the same [pixels x 64 channels] slab shifted by one pixel, so all but the first hit L1
           const int taps = a.KH * a.KW, tap = lkb % taps, c0 = (lkb / taps) * BK, kh = tap / a.KW, kw = tap % a.KW;
-          const float* srck = a.src + tap_delta(kh, kw) + c0 + 4 * f4;
+          const float* srck = a.src + c0 + 4 * f4;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if ((rvy[i] >> kh) & (rvx[i] >> kw) & 1u) v[i] = __ldg(reinterpret_cast<const float4*>(srck + rbase[i]));
+          for (int i = 0; i < 8; ++i) {
+            const long long off = tap_off(rbase[i], rvy[i], rvx[i], kh, kw);
+            if (off >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(srck + off));
+          }
         } else {
           // general gather (narrow / ragged channel counts, strided dgrad): 4 patch entries per lane, element-wise
 #pragma unroll
@@ -370,15 +388,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = j * 16 + warp * 2 + rsel;
-          long long base; unsigned vy, vx;
-          pixel_affine(L.k_lo + (long long)lkb * BK + k, lim, base, vy, vx);
+          long long base; int oy, ox;
+          pixel_affine(L.k_lo + (long long)lkb * BK + k, lim, base, oy, ox);
 #pragma unroll
           for (int mb = 0; mb < 2; ++mb) {
             const long long kd0 = (long long)L.m_tile * BM + mb * 64;
             if (kd0 < patch) {
-              const int tap = (int)(kd0 / C), c0 = (int)(kd0 % C), kh = tap / a.KW, kw = tap % a.KW;
-              if ((vy >> kh) & (vx >> kw) & 1u)
-                v[mb * 4 + j] = __ldg(reinterpret_cast<const float4*>(a.src + base + tap_delta(kh, kw) + c0 + 4 * f4));
+              const int tap = (int)(kd0 / C), c0 = (int)(kd0 % C);
+              const long long off = tap_off(base, oy, ox, tap / a.KW, tap % a.KW);
+              if (off >= 0) v[mb * 4 + j] = __ldg(reinterpret_cast<const float4*>(a.src + off + c0 + 4 * f4));
             }
           }
         }
