@@ -138,6 +138,32 @@ int ladder_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, in
                            int Cout, int stride, int pad_t, int pad_l, int OH, int OW, void* workspace,
                            size_t workspace_bytes, cudaStream_t stream);
 
+/* Second-generation tensor-core path: activations / gradients stored in HBM as bf16 NHWC, BOTH GEMM operands
+ * staged by TMA (the activation tile of each filter tap is one cp.async.bulk.tensor.4d box whose out-of-bounds
+ * zero fill implements the TF padding).  Stride-1 layers with 64-aligned channels of the gathered tensor and a
+ * pixel grid that cuts into 128-pixel (wgrad: 64-pixel) boxes -- ladder_conv2d_tma_supported(mode 0 fprop /
+ * 1 dgrad / 2 wgrad) says which; every other geometry stays on the *_tc / fp32 entry points above.
+ * x_bf16 / dy_bf16: bf16 NHWC, 16-byte aligned.  y / dx are fp32 or bf16 (y_bf16 / dx_bf16 flag), act_out likewise.
+ * Same fused epilogues and geometry arguments as the *_tc calls; `workspace` holds the bf16 weight repack
+ * (ladder_conv2d_tma_workspace_bytes).  wgrad_tma overwrites dw (fp32); bias gradient = ladder_colsum_bf16(dy). */
+int ladder_conv2d_tma_supported(int mode, int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int OH,
+                                int OW);
+size_t ladder_conv2d_tma_workspace_bytes(int Cin, int KH, int KW, int Cout);
+int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bias /*nullable*/, void* y, int y_bf16,
+                            int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l,
+                            int OH, int OW, int act, int out_d2s, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream);
+int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w, const void* act_out /*nullable*/, int act_out_bf16,
+                            void* dx, int dx_bf16, int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride,
+                            int pad_t, int pad_l, int OH, int OW, int act, int accumulate, int out_s2d,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, int B, int H, int W, int Cin, int KH,
+                            int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream);
+/* dtype plumbing for the bf16-resident activations */
+int ladder_f32_to_bf16(const float* x, void* y_bf16, long long n, cudaStream_t stream);
+int ladder_bf16_to_f32(const void* x_bf16, float* y, long long n, cudaStream_t stream);
+int ladder_colsum_bf16(const void* g_bf16, long long rows, int cols, float* out, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Layout ops.  replaces tf.pad(..., "SYMMETRIC") codes/models.py:48-50,200-202 and
  * tf.nn.depth_to_space (NHWC, DCR order) codes/models.py:113-141,271-308.                  */

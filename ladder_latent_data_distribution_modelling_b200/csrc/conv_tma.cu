@@ -1,0 +1,670 @@
+// K1/K2, second generation: stride-1 conv2d / dense as implicit GEMM with BOTH operands fed by TMA.
+//
+// conv_tc.cu gathers fp32 activations through registers (8 producer warps, ~10 B/clk/SM) -- that gather, not the
+// tensor pipe, bounds it.  Here activations and gradients live in HBM as bf16 NHWC and the A operand of every
+// k-block (one filter tap x 64 channels of a 128-pixel tile) is ONE 4-D tiled tensor-map copy
+//     cp.async.bulk.tensor.4d  box {64 ch, bw, bh, bb}  at  {c0, x0 + dx(tap), y0 + dy(tap), b0}
+// whose out-of-bounds zero fill IS the TF zero padding and whose SWIZZLE_128B mode writes exactly the K-major
+// (fprop / dgrad) or MN-major (wgrad) canonical UMMA layout.  No im2col matrix, no staging through registers.
+//
+//   warp 0     TMA producer (one elected lane): tensor-map copy of A, bulk copy of the pre-swizzled weight tile
+//              image (fprop/dgrad) or tensor-map copies of the dy tile (wgrad); full/empty mbarrier ring
+//   warp 1     MMA issuer: tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators double-buffered in TMEM
+//   warps 2-5  epilogue: tcgen05.ld -> smem transpose -> coalesced stores, fused bias+activation (fprop),
+//              producer-activation derivative / accumulate / space_to_depth (dgrad), split-K red.add (wgrad);
+//              output fp32 or bf16
+//   persistent grid = min(#tiles, #SMs)
+#include "common.cuh"
+#include "ladder_sm100.h"
+#include "tc_ptx.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdlib>
+#include <cstring>
+
+namespace ladder {
+namespace tma {
+using namespace ladder::tc;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int NTHREADS = 192;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int EPI_BYTES = 4 * 32 * 36 * 4;
+constexpr int BIAS_BYTES = 256 * 4;
+__host__ __device__ constexpr int stages_for(int bn) {
+  // 227 KB - alignment slack - barriers - epilogue staging, divided by the stage size
+  return (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES) / (A_STAGE_BYTES + bn * BK * 2) > 8
+             ? 8
+             : (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES) / (A_STAGE_BYTES + bn * BK * 2);
+}
+
+enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
+
+struct Args {
+  const __nv_bfloat16* wt;   // FPROP/DGRAD: packed weight tile images [n_tile][kb]
+  const float* bias;
+  const void* aux;           // DGRAD: saved output of the layer that produced x (activation derivative), fp32 or bf16
+  void* out;                 // y / dx (fp32 or bf16), dw (fp32)
+  int GW, GH, B;             // pixel grid of the GEMM rows (FPROP: y, DGRAD: dx) or of the reduction (WGRAD: y)
+  int C;                     // channels of the TMA-gathered tensor
+  int KH, KW;
+  int off_y, off_x, sign;    // tap (kh, kw) of grid pixel (y, x) reads source pixel (y + off_y + sign*kh, x + off_x + sign*kw)
+  int Ng;                    // GEMM N: Cout (FPROP, WGRAD) or Cin (DGRAD)
+  int act, accumulate, out_bf16, aux_bf16;
+  int nkb;                   // FPROP/DGRAD: k-blocks per tile = taps * C/64
+  int kb_per_split;          // WGRAD: 64-pixel k-blocks per split
+  long long total_kb;        // WGRAD: 64-pixel k-blocks overall
+  int m_valid;               // WGRAD: rows of dw that exist (= KH*KW*C)
+  int m_tiles, n_tiles, splits;
+  int perm_r;                // fused depth_to_space (FPROP) / space_to_depth (DGRAD) store, 0 = off
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+struct Tile {
+  long long t;
+  int m_tile, n_tile, nkb;
+  long long k_lo;            // WGRAD: first 64-pixel k-block of the slice
+  bool valid;
+};
+
+template <int MODE>
+__device__ __forceinline__ void decode_tile(const Args& a, long long t, long long total, Tile& c) {
+  c.t = t;
+  c.valid = t < total;
+  if (!c.valid) { c.nkb = 0; return; }
+  c.n_tile = (int)(t % a.n_tiles);
+  const long long r = t / a.n_tiles;
+  if (MODE == WGRAD) {
+    c.m_tile = (int)(r % a.m_tiles);
+    const long long split = r / a.m_tiles;
+    c.k_lo = split * a.kb_per_split;
+    const long long k_hi = min(a.total_kb, c.k_lo + a.kb_per_split);
+    c.nkb = (int)(k_hi - c.k_lo);
+  } else {
+    c.m_tile = (int)r;
+    c.k_lo = 0;
+    c.nkb = a.nkb;
+  }
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t h) { return __uint_as_float(h << 16); }
+
+// Ragged / scalar tail of the epilogue (N not a multiple of 4, depth_to_space with C' % 4 != 0): kept out of line so the
+// hot store loop stays small.
+template <int MODE, bool OUT16>
+__device__ __noinline__ void slow_store(const Args& a, float4 q, long long m, int col, long long o, float slope, bool is_tanh) {
+  float* outf = reinterpret_cast<float*>(a.out);
+  __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(a.out);
+  const float e4[4] = {q.x, q.y, q.z, q.w};
+  const int Ng = a.Ng;
+  for (int t = 0; t < 4; ++t) {
+    if (col + t >= Ng) break;
+    float e = e4[t];
+    long long oo = o + t;
+    if (MODE == FPROP && a.perm_r > 0) oo = d2s_dest(m, col + t, a.GH, a.GW, Ng, a.perm_r);
+    if (MODE == DGRAD) {
+      if (a.aux != nullptr) {
+        const long long ai = m * Ng + col + t;
+        const float ax = a.aux_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.aux)[ai])
+                                    : reinterpret_cast<const float*>(a.aux)[ai];
+        e *= is_tanh ? 1.f - ax * ax : (ax > 0.f ? 1.f : slope);
+      }
+      if (a.accumulate) e += OUT16 ? __bfloat162float(outh[oo]) : outf[oo];
+    }
+    if (MODE == WGRAD) atomicAdd(outf + oo, e);
+    else if (OUT16) outh[oo] = __float2bfloat16_rn(e);
+    else outf[oo] = e;
+  }
+}
+
+template <int MODE, int BN, bool OUT16>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Args a) {
+  constexpr int STAGES = stages_for(BN);
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + STAGES * A_STAGE_BYTES;
+  const uint32_t bars = sB + STAGES * B_STAGE_BYTES;            // full[S], empty[S], tfull[2], tempty[2], slot
+  const uint32_t bar_full = bars, bar_empty = bars + STAGES * 8, bar_tfull = bars + 2 * STAGES * 8,
+                 bar_tempty = bars + (2 * STAGES + 2) * 8;
+  const uint32_t slot = bars + (2 * STAGES + 4) * 8;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (slot - base));
+  const uint32_t stage_off = bars + 256 - base;                 // epilogue staging (4 x 32 x 36 floats)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long pixels = (long long)a.B * a.GH * a.GW;
+  const long long Mg = MODE == WGRAD ? (long long)a.m_valid : pixels;
+  const int Ng = a.Ng;
+  const long long total = (long long)a.m_tiles * a.n_tiles * a.splits;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + i * 8, 1);
+      mbar_init(bar_tempty + i * 8, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+      if (MODE == WGRAD) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+      const int taps = a.KH * a.KW;
+      Tile T;
+      decode_tile<MODE>(a, blockIdx.x, total, T);
+      unsigned it = 0;
+      while (T.valid) {
+        if (MODE != WGRAD) {
+          const unsigned m0 = (unsigned)T.m_tile * BM;
+          const int x0 = (int)(m0 % (unsigned)a.GW);
+          const unsigned r = m0 / (unsigned)a.GW;
+          const int y0 = (int)(r % (unsigned)a.GH), b0 = (int)(r / (unsigned)a.GH);
+          int tap = 0, c0 = 0;
+          for (int kb = 0; kb < T.nkb; ++kb, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
+            const int kh = tap / a.KW, kw = tap - kh * a.KW;
+            mbar_arrive_expect_tx(bar_full + s * 8, A_STAGE_BYTES + B_STAGE_BYTES);
+            tma_load_4d(sA + s * A_STAGE_BYTES, &mapA, c0, x0 + a.off_x + a.sign * kw, y0 + a.off_y + a.sign * kh, b0,
+                        bar_full + s * 8);
+            tma_bulk_g2s(sB + s * B_STAGE_BYTES,
+                         reinterpret_cast<const uint8_t*>(a.wt) + ((size_t)T.n_tile * T.nkb + kb) * B_STAGE_BYTES,
+                         B_STAGE_BYTES, bar_full + s * 8);
+            if (++tap == taps) { tap = 0; c0 += BK; }      // K order: 64-channel chunk major, tap minor
+          }
+        } else {
+          // rows of dw: patch entries (tap, ci); a 128-row tile = two 64-channel blocks (possibly of different taps)
+          int oy[2], ox[2], cc[2];
+          bool on[2];
+#pragma unroll
+          for (int mb = 0; mb < 2; ++mb) {
+            const int kd0 = T.m_tile * BM + mb * 64;
+            on[mb] = kd0 < a.m_valid;
+            const int tp = kd0 / a.C;
+            cc[mb] = kd0 - tp * a.C;
+            const int kh = tp / a.KW, kw = tp - kh * a.KW;
+            oy[mb] = a.off_y + a.sign * kh;
+            ox[mb] = a.off_x + a.sign * kw;
+          }
+          const uint32_t bytes = (uint32_t)((on[0] ? 8192 : 0) + (on[1] ? 8192 : 0) + B_STAGE_BYTES);
+          for (int kb = 0; kb < T.nkb; ++kb, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
+            const unsigned p0 = (unsigned)(T.k_lo + kb) * BK;
+            const int x0 = (int)(p0 % (unsigned)a.GW);
+            const unsigned r = p0 / (unsigned)a.GW;
+            const int y0 = (int)(r % (unsigned)a.GH), b0 = (int)(r / (unsigned)a.GH);
+            mbar_arrive_expect_tx(bar_full + s * 8, bytes);
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+              if (on[mb])
+                tma_load_4d(sA + s * A_STAGE_BYTES + mb * 8192, &mapA, cc[mb], x0 + ox[mb], y0 + oy[mb], b0, bar_full + s * 8);
+#pragma unroll
+            for (int nb = 0; nb < BN / 64; ++nb)
+              tma_load_4d(sB + s * B_STAGE_BYTES + nb * 8192, &mapB, T.n_tile * BN + nb * 64, x0, y0, b0, bar_full + s * 8);
+          }
+        }
+        decode_tile<MODE>(a, T.t + gridDim.x, total, T);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, MODE == WGRAD);
+      Tile T;
+      decode_tile<MODE>(a, blockIdx.x, total, T);
+      unsigned it = 0, j = 0;
+      while (T.valid) {
+        const uint32_t acc = j & 1;
+        mbar_wait(bar_tempty + acc * 8, ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < T.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t tA = sA + s * A_STAGE_BYTES, tB = sB + s * B_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            if (MODE == WGRAD)
+              umma_bf16(tmem_d, make_desc_mn(tA + k * 2048, 8192), make_desc_mn(tB + k * 2048, 8192), idesc, (kb | k) != 0);
+            else
+              umma_bf16(tmem_d, make_desc(tA + k * 32), make_desc(tB + k * 32), idesc, (kb | k) != 0);
+          }
+          umma_commit(bar_empty + s * 8);
+        }
+        umma_commit(bar_tfull + acc * 8);
+        ++j;
+        decode_tile<MODE>(a, T.t + gridDim.x, total, T);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue
+    // tcgen05.ld hands every thread one accumulator ROW.  FPROP applies bias + activation right there (the bias tile
+    // sits in shared memory), then each warp transposes its 32x32 chunk through a private padded smem tile so that 8
+    // lanes cover 128 contiguous bytes of one output row.  The store loop is kept small on purpose (slope-form
+    // activations, ragged / permuted-scalar cases in a __noinline__ slow path): the fully unrolled first version of
+    // this epilogue was instruction-fetch bound (ncu: stall_no_inst on every store-side instruction).
+    const int quad = warp & 3;                     // tcgen05.ld: warp w may touch TMEM lanes 32*(w%4)..+31
+    float* stage = reinterpret_cast<float*>(smem + stage_off) + quad * (32 * 36);
+    float* sbias = reinterpret_cast<float*>(smem + stage_off + EPI_BYTES);
+    const int etid = tid - 64;                     // 0..127 among the epilogue warps
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    const float slope = a.act == ACT_LEAKY ? 0.2f : (a.act == ACT_RELU ? 0.f : 1.f);
+    const bool is_tanh = a.act == ACT_TANH;
+    float* outf = reinterpret_cast<float*>(a.out);
+    __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(a.out);
+    const float* auxf = reinterpret_cast<const float*>(a.aux);
+    const __nv_bfloat16* auxh = reinterpret_cast<const __nv_bfloat16*>(a.aux);
+    Tile T;
+    decode_tile<MODE>(a, blockIdx.x, total, T);
+    unsigned j = 0;
+    int bias_tile = -1;
+    while (T.valid) {
+      const uint32_t acc = j & 1;
+      const int n0 = T.n_tile * BN;
+      if (MODE == FPROP && bias_tile != T.n_tile) {          // (re)load the bias tile; uniform across the 4 warps
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = etid; i < BN; i += 128) sbias[i] = (a.bias != nullptr && n0 + i < Ng) ? __ldg(a.bias + n0 + i) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bias_tile = T.n_tile;
+      }
+      mbar_wait(bar_tfull + acc * 8, (j >> 1) & 1);
+      tc_fence_after();
+      const long long mrow0 = (long long)T.m_tile * BM + quad * 32;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c0, v);
+        const int nb = n0 + c0;
+        if (nb >= Ng) continue;                    // warp-uniform
+        if (MODE == FPROP) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float u = v[i] + sbias[c0 + i];
+            v[i] = u > 0.f ? u : u * slope;
+          }
+          if (is_tanh) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        __syncwarp();
+        const int col = nb + c4;
+        bool vec_ok = (Ng & 3) == 0 && col + 4 <= Ng;
+        long long coloff = col;
+        if (MODE == FPROP && a.perm_r > 0) {
+          const int r = a.perm_r, Cp = Ng / (r * r), ij = col / Cp, c = col % Cp;
+          coloff = ((long long)(ij / r) * a.GW * r + ij % r) * Cp + c;
+          vec_ok = vec_ok && (Cp & 3) == 0;
+        }
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + sub;
+          const long long m = mrow0 + r;
+          const float4 q = *reinterpret_cast<const float4*>(stage + r * 36 + c4);
+          if (m >= Mg || col >= Ng) continue;
+          long long o = m * Ng;
+          if (a.perm_r > 0) {
+            if (MODE == FPROP) o = d2s_dest(m, 0, a.GH, a.GW, Ng, a.perm_r);
+            if (MODE == DGRAD) o = s2d_dest(m, 0, a.GH, a.GW, Ng, a.perm_r);
+          }
+          o += coloff;
+          if (!vec_ok) {
+            slow_store<MODE, OUT16>(a, q, m, col, o, slope, is_tanh);
+            continue;
+          }
+          float e[4] = {q.x, q.y, q.z, q.w};
+          if (MODE == DGRAD) {
+            if (a.aux != nullptr) {
+              float ax[4];
+              const long long ai = m * Ng + col;
+              if (a.aux_bf16) {
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(auxh + ai));
+                ax[0] = bf16_bits_to_float(u.x & 0xffffu); ax[1] = bf16_bits_to_float(u.x >> 16);
+                ax[2] = bf16_bits_to_float(u.y & 0xffffu); ax[3] = bf16_bits_to_float(u.y >> 16);
+              } else {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(auxf + ai));
+                ax[0] = f.x; ax[1] = f.y; ax[2] = f.z; ax[3] = f.w;
+              }
+#pragma unroll
+              for (int t = 0; t < 4; ++t) e[t] *= is_tanh ? 1.f - ax[t] * ax[t] : (ax[t] > 0.f ? 1.f : slope);
+            }
+            if (a.accumulate) {
+              if (OUT16) {
+                const uint2 u = *reinterpret_cast<const uint2*>(outh + o);
+                e[0] += bf16_bits_to_float(u.x & 0xffffu); e[1] += bf16_bits_to_float(u.x >> 16);
+                e[2] += bf16_bits_to_float(u.y & 0xffffu); e[3] += bf16_bits_to_float(u.y >> 16);
+              } else {
+                const float4 f = *reinterpret_cast<const float4*>(outf + o);
+                e[0] += f.x; e[1] += f.y; e[2] += f.z; e[3] += f.w;
+              }
+            }
+          }
+          if (MODE == WGRAD) {
+            atomicAdd(reinterpret_cast<float4*>(outf + o), make_float4(e[0], e[1], e[2], e[3]));   // red.global.add.v4.f32
+          } else if (OUT16) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(e[0], e[1]), p1 = __floats2bfloat162_rn(e[2], e[3]);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&p0);
+            u.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(outh + o) = u;
+          } else {
+            *reinterpret_cast<float4*>(outf + o) = make_float4(e[0], e[1], e[2], e[3]);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + acc * 8);
+      ++j;
+      decode_tile<MODE>(a, T.t + gridDim.x, total, T);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Box {64 channels, bw, bh, bb} covering `px` consecutive pixels of the row-major [B, GH, GW] grid; false if the grid
+// cannot be cut into such boxes (then the register-gather kernel of conv_tc.cu takes the layer).
+static bool pixel_box(int GW, int GH, int B, int px, int& bw, int& bh, int& bb) {
+  bw = bh = bb = 1;
+  if (GW >= px) {
+    if (GW % px) return false;
+    bw = px;
+    return true;
+  }
+  if (px % GW) return false;
+  bw = GW;
+  const int rem = px / GW;
+  if (GH >= rem) {
+    if (GH % rem) return false;
+    bh = rem;
+    return true;
+  }
+  if (rem % GH) return false;
+  bh = GH;
+  bb = rem / GH;
+  return bb <= 256 && B >= bb;
+}
+
+// bf16 NHWC tensor [B, SH, SW, C] as a 4-D tensor map {C, SW, SH, B}, SWIZZLE_128B, zero fill outside
+static int make_map(CUtensorMap* map, const void* ptr, int B, int SH, int SW, int C, int bw, int bh, int bb) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(LADDER_ERR_CUDA, "conv2d_tma: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)SW, (cuuint64_t)SH, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)SW * C * 2, (cuuint64_t)SH * SW * C * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LADDER_ERR_CUDA, "conv2d_tma: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return LADDER_OK;
+}
+
+template <int MODE>
+static int launch(const CUtensorMap& mA, const CUtensorMap& mB, Args& a, long long Mg, int bn, cudaStream_t st) {
+  a.m_tiles = (int)ceil_div64(Mg, BM);
+  a.n_tiles = ceil_div(a.Ng, bn);
+  const long long total = (long long)a.m_tiles * a.n_tiles * a.splits;
+  const int sms = num_sms();
+  const unsigned grid = (unsigned)(total < sms ? total : sms);
+  auto go = [&](auto kern, int BNv) {
+    const size_t smem = (size_t)stages_for(BNv) * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256 + EPI_BYTES + BIAS_BYTES;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, NTHREADS, smem, st>>>(mA, mB, a);
+  };
+  if (a.out_bf16) {
+    if constexpr (MODE != WGRAD) {
+      switch (bn) {
+        case 32: go(tma_kernel<MODE, 32, true>, 32); break;
+        case 64: go(tma_kernel<MODE, 64, true>, 64); break;
+        case 128: go(tma_kernel<MODE, 128, true>, 128); break;
+        default: go(tma_kernel<MODE, 256, true>, 256); break;
+      }
+    }
+  } else {
+    switch (bn) {
+      case 32: if constexpr (MODE != WGRAD) { go(tma_kernel<MODE, 32, false>, 32); } break;
+      case 64: go(tma_kernel<MODE, 64, false>, 64); break;
+      case 128: go(tma_kernel<MODE, 128, false>, 128); break;
+      default: go(tma_kernel<MODE, 256, false>, 256); break;
+    }
+  }
+  return check_launch("tcgen05 TMA conv kernel");
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long n8 = n / 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(x) + 2 * i), v1 = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+    const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    reinterpret_cast<uint4*>(y)[i] = pack8(f);
+  }
+  for (long long i = n8 * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = __float2bfloat16_rn(x[i]);
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = __bfloat162float(x[i]);
+}
+
+// column sums of a bf16 [rows, cols] matrix (bias gradient of a layer whose dy is stored in bf16)
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ g, long long rows, int cols, float* __restrict__ out) {
+  // block = 256 threads = 8 row-lanes x 32 column-lanes; grid.x = column groups of 32, grid.y = row slices
+  __shared__ float part[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) s += __bfloat162float(g[r * cols + c]);
+  part[rl][cl] = s;
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][cl];
+    atomicAdd(out + c, t);
+  }
+}
+
+}  // namespace tma
+}  // namespace ladder
+
+using namespace ladder;
+using namespace ladder::tma;
+
+static bool geometry_ok(int B, int GH, int GW, int px) {
+  int bw, bh, bb;
+  return pixel_box(GW, GH, B, px, bw, bh, bb);
+}
+
+extern "C" {
+
+/* mode 0 fprop, 1 dgrad, 2 wgrad: 1 iff the TMA-fed kernel takes this geometry (stride 1, 64-aligned channels of the
+ * gathered tensor, pixel grid divisible into 128- (64- for wgrad) pixel boxes) */
+int ladder_conv2d_tma_supported(int mode, int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int OH, int OW) {
+  if (stride != 1 || B <= 0) return 0;
+  if ((long long)B * H * W >= (1LL << 31) / 64 * 64 || (long long)B * OH * OW >= (1LL << 31) / 64 * 64) return 0;
+  (void)KH; (void)KW;
+  switch (mode) {
+    case 0: return Cin % 64 == 0 && geometry_ok(B, OH, OW, 128);
+    case 1: return Cout % 64 == 0 && geometry_ok(B, H, W, 128);
+    case 2: return Cin % 64 == 0 && Cout % 64 == 0 && geometry_ok(B, OH, OW, 64);
+    default: return 0;
+  }
+}
+
+size_t ladder_conv2d_tma_workspace_bytes(int Cin, int KH, int KW, int Cout) {
+  const size_t f = tc::pack_bytes(Cout, KH * KW * Cin), d = tc::pack_bytes(Cin, KH * KW * Cout);
+  return (f > d ? f : d) + 256;
+}
+
+int ladder_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream) {
+  if (n <= 0) return LADDER_OK;
+  LADDER_REQUIRE(x && y, "f32_to_bf16: null pointer");
+  LADDER_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "f32_to_bf16: pointers must be 16-byte aligned");
+  long long blocks = ceil_div64(ceil_div64(n, 8), 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y), n);
+  return check_launch("f32_to_bf16");
+}
+
+int ladder_bf16_to_f32(const void* x, float* y, long long n, cudaStream_t stream) {
+  if (n <= 0) return LADDER_OK;
+  LADDER_REQUIRE(x && y, "bf16_to_f32: null pointer");
+  long long blocks = ceil_div64(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bf16_to_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), y, n);
+  return check_launch("bf16_to_f32");
+}
+
+int ladder_colsum_bf16(const void* g, long long rows, int cols, float* out, cudaStream_t stream) {
+  LADDER_REQUIRE(g && out && rows > 0 && cols > 0, "colsum_bf16: bad arguments");
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), stream);
+  if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "colsum_bf16 memset: %s", cudaGetErrorString(e));
+  const int gx = ceil_div(cols, 32);
+  long long gy = ceil_div64(rows, 8 * 16);
+  const long long cap = (148 * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  colsum_bf16_kernel<<<dim3(gx, (unsigned)gy), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(g), rows, cols, out);
+  return check_launch("colsum_bf16");
+}
+
+int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bias, void* y, int y_bf16, int B, int H, int W,
+                            int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
+                            int out_d2s, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  LADDER_REQUIRE(x_bf16 && w && y && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, "conv2d_fprop_tma: bad arguments");
+  LADDER_REQUIRE(ladder_conv2d_tma_supported(0, B, H, W, Cin, KH, KW, Cout, stride, OH, OW),
+                 "conv2d_fprop_tma: unsupported geometry (see ladder_conv2d_tma_supported)");
+  LADDER_REQUIRE(out_d2s == 0 || (out_d2s > 0 && Cout % (out_d2s * out_d2s) == 0),
+                 "conv2d_fprop_tma: depth_to_space(%d) output needs Cout %% r^2 == 0", out_d2s);
+  LADDER_REQUIRE(((uintptr_t)x_bf16 & 15) == 0, "conv2d_fprop_tma: x must be 16-byte aligned");
+  int rc = tc::pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, stream);
+  if (rc) return rc;
+  int bw, bh, bb;
+  pixel_box(OW, OH, B, BM, bw, bh, bb);
+  CUtensorMap mA;
+  rc = make_map(&mA, x_bf16, B, H, W, Cin, bw, bh, bb);
+  if (rc) return rc;
+  Args a;
+  memset(&a, 0, sizeof(a));
+  a.wt = static_cast<const __nv_bfloat16*>(workspace);
+  a.bias = bias; a.out = y; a.out_bf16 = y_bf16;
+  a.GW = OW; a.GH = OH; a.B = B; a.C = Cin; a.KH = KH; a.KW = KW;
+  a.off_y = -pad_t; a.off_x = -pad_l; a.sign = 1;
+  a.Ng = Cout; a.act = act; a.nkb = KH * KW * (Cin / BK); a.splits = 1; a.perm_r = out_d2s;
+  return launch<FPROP>(mA, mA, a, (long long)B * OH * OW, tc::pick_bn(Cout), stream);
+}
+
+int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w, const void* act_out, int act_out_bf16, void* dx, int dx_bf16,
+                            int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH,
+                            int OW, int act, int accumulate, int out_s2d, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream) {
+  LADDER_REQUIRE(dy_bf16 && w && dx && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, "conv2d_dgrad_tma: bad arguments");
+  LADDER_REQUIRE(ladder_conv2d_tma_supported(1, B, H, W, Cin, KH, KW, Cout, stride, OH, OW),
+                 "conv2d_dgrad_tma: unsupported geometry (see ladder_conv2d_tma_supported)");
+  LADDER_REQUIRE(out_s2d == 0 || (out_s2d > 0 && H % out_s2d == 0 && W % out_s2d == 0),
+                 "conv2d_dgrad_tma: space_to_depth(%d) output needs H, W divisible by r", out_s2d);
+  LADDER_REQUIRE(((uintptr_t)dy_bf16 & 15) == 0, "conv2d_dgrad_tma: dy must be 16-byte aligned");
+  int rc = tc::pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, stream);
+  if (rc) return rc;
+  int bw, bh, bb;
+  pixel_box(W, H, B, BM, bw, bh, bb);
+  CUtensorMap mA;
+  rc = make_map(&mA, dy_bf16, B, OH, OW, Cout, bw, bh, bb);
+  if (rc) return rc;
+  Args a;
+  memset(&a, 0, sizeof(a));
+  a.wt = static_cast<const __nv_bfloat16*>(workspace);
+  a.aux = act_out; a.aux_bf16 = act_out_bf16; a.out = dx; a.out_bf16 = dx_bf16;
+  a.GW = W; a.GH = H; a.B = B; a.C = Cout; a.KH = KH; a.KW = KW;
+  a.off_y = pad_t; a.off_x = pad_l; a.sign = -1;       // dx(y, x) += dy(y + pad_t - kh, x + pad_l - kw) . w(kh, kw)
+  a.Ng = Cin; a.act = act; a.accumulate = accumulate; a.nkb = KH * KW * (Cout / BK); a.splits = 1; a.perm_r = out_s2d;
+  return launch<DGRAD>(mA, mA, a, (long long)B * H * W, tc::pick_bn(Cin), stream);
+}
+
+/* dw (fp32, HWIO) is overwritten; the bias gradient is ladder_colsum_bf16(dy). */
+int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, int B, int H, int W, int Cin, int KH, int KW,
+                            int Cout, int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream) {
+  LADDER_REQUIRE(x_bf16 && dy_bf16 && dw && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, "conv2d_wgrad_tma: bad arguments");
+  LADDER_REQUIRE(ladder_conv2d_tma_supported(2, B, H, W, Cin, KH, KW, Cout, stride, OH, OW),
+                 "conv2d_wgrad_tma: unsupported geometry (see ladder_conv2d_tma_supported)");
+  LADDER_REQUIRE((((uintptr_t)x_bf16 | (uintptr_t)dy_bf16) & 15) == 0, "conv2d_wgrad_tma: operands must be 16-byte aligned");
+  const int patch = KH * KW * Cin;
+  cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)patch * Cout * sizeof(float), stream);
+  if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "conv2d_wgrad_tma memset: %s", cudaGetErrorString(e));
+  int bw, bh, bb;
+  pixel_box(OW, OH, B, BK, bw, bh, bb);
+  CUtensorMap mA, mB;
+  int rc = make_map(&mA, x_bf16, B, H, W, Cin, bw, bh, bb);
+  if (rc) return rc;
+  rc = make_map(&mB, dy_bf16, B, OH, OW, Cout, bw, bh, bb);
+  if (rc) return rc;
+  int bn = tc::pick_bn(Cout);
+  if (bn < 64) bn = 64;
+  // pixel boxes of 64: the last one may hang over the batch axis (zero filled on both operands)
+  const long long box_px = (long long)bw * bh * bb;            // == 64
+  const long long total_kb = bb > 1 ? ceil_div64(B, bb) : (long long)B * OH * OW / box_px;
+  const long long tiles = ceil_div64(patch, BM) * ceil_div(Cout, bn);
+  long long splits = (2LL * num_sms()) / tiles;                // <= 2 full waves of the persistent grid
+  const long long max_splits = ceil_div64(total_kb, 4);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const long long per = ceil_div64(total_kb, splits);
+  Args a;
+  memset(&a, 0, sizeof(a));
+  a.out = dw;
+  a.GW = OW; a.GH = OH; a.B = B; a.C = Cin; a.KH = KH; a.KW = KW;
+  a.off_y = -pad_t; a.off_x = -pad_l; a.sign = 1;
+  a.Ng = Cout; a.kb_per_split = (int)per; a.total_kb = total_kb; a.m_valid = patch;
+  a.splits = (int)ceil_div64(total_kb, per);
+  return launch<WGRAD>(mA, mB, a, patch, bn, stream);
+}
+
+}  // extern "C"

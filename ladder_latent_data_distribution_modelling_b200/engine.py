@@ -77,33 +77,57 @@ def glorot_uniform_(t, shape, gen):
 
 # ------------------------------------------------------------------------------ layers
 class Conv:
-    """conv2d (or dense) + bias + activation with preallocated output and gradients."""
+    """conv2d (or dense) + bias + activation with preallocated output and gradients.
 
-    def __init__(self, group, wname, geom, act, device):
+    Layers the TMA-fed tensor-core kernel takes (ops.tma_supported) read bf16 operands: an fp32 input is
+    converted once per forward into `x16` (reused by wgrad), an fp32 upstream gradient once per backward
+    (shared by wgrad and dgrad).  `out_dtype=torch.bfloat16` makes the layer write its activation in bf16
+    (only valid when every consumer of `y` reads bf16)."""
+
+    def __init__(self, group, wname, geom, act, device, out_dtype=torch.float32):
         self.group, self.geom, self.act = group, geom, act
         self.w = group.p(wname + '/kernel')
         self.b = group.p(wname + '/bias')
         self.dw = group.g(wname + '/kernel')
         self.db = group.g(wname + '/bias')
         g = geom
-        self.y = torch.empty(g.B, g.OH, g.OW, g.Cout, device=device)
+        self.tma = [ops.tma_supported(g, m) for m in (ops.FPROP, ops.DGRAD, ops.WGRAD)]
+        if out_dtype != torch.float32 and not self.tma[0]:
+            raise RuntimeError('engine: bf16 activations need the TMA path for %s' % wname)
+        self.y = torch.empty(g.B, g.OH, g.OW, g.Cout, device=device, dtype=out_dtype)
         self.x = None
+        self.x16 = None
 
     def forward(self, x, d2s=0):
         """d2s = r: the output is written directly in depth_to_space(r) layout (self.y must then be viewed as
         [B, OH*r, OW*r, Cout/r^2] by the caller)."""
-        self.x = x
+        self.x = self.xw = x                 # xw: the copy wgrad reads (bf16 on the TMA path, else as given)
+        if x.dtype == torch.float32 and self.tma[0]:
+            if self.x16 is None or self.x16.shape != x.shape:
+                self.x16 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+            x = ops.to_bf16(x, self.x16)
+            if self.tma[2]:
+                self.xw = x
         return ops.conv2d_fprop(x, self.w, self.b, self.y, self.geom, self.act, out_d2s=d2s)
 
     def backward(self, dpre, dx=None, producer=None, wgrad=True, accumulate=False, s2d=0):
         """dpre: d loss / d pre-activation of this layer.  producer = (act_out, act) of the layer
         that produced x, whose activation derivative is fused into dx.  s2d = r: x was the depth_to_space(r)
         of the producer's output, so dx is scattered back to the producer's layout in the epilogue."""
+        g = self.geom
+        dy = dpre
+        if dpre.dtype == torch.float32 and ((wgrad and self.tma[2]) or (dx is not None and self.tma[1])):
+            dy = ops.to_bf16(dpre, tag='dy16')          # one conversion shared by wgrad and dgrad
         if wgrad:
-            ops.conv2d_wgrad(self.x, dpre, self.dw, self.db, self.geom)
+            if self.tma[2]:
+                ops.conv2d_wgrad(self.xw, dy, self.dw, None, g)
+                ops.colsum(dpre, g.B * g.OH * g.OW, g.Cout, self.db)
+            else:
+                ops.conv2d_wgrad(self.xw, dpre, self.dw, self.db, g)
         if dx is not None:
             ao, act = producer if producer is not None else (None, None)
-            ops.conv2d_dgrad(dpre, self.w, dx, self.geom, act_out=ao, act=act, accumulate=accumulate, out_s2d=s2d)
+            ops.conv2d_dgrad(dy if self.tma[1] else dpre, self.w, dx, g, act_out=ao, act=act, accumulate=accumulate,
+                             out_s2d=s2d)
         return dx
 
 

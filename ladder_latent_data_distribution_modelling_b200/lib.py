@@ -41,6 +41,14 @@ SIGNATURES = {
     'ladder_conv2d_dgrad_tc': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 15 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_wgrad_tc_supported': (C.c_int, [C.c_int, C.c_int]),
     'ladder_conv2d_wgrad_tc': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [ptr, C.c_size_t, stream_t]),
+    'ladder_conv2d_tma_supported': (C.c_int, [C.c_int] * 11),
+    'ladder_conv2d_tma_workspace_bytes': (C.c_size_t, [C.c_int] * 4),
+    'ladder_conv2d_fprop_tma': (C.c_int, [ptr, ptr, ptr, ptr, C.c_int] + [C.c_int] * 14 + [ptr, C.c_size_t, stream_t]),
+    'ladder_conv2d_dgrad_tma': (C.c_int, [ptr, ptr, ptr, C.c_int, ptr, C.c_int] + [C.c_int] * 15 + [ptr, C.c_size_t, stream_t]),
+    'ladder_conv2d_wgrad_tma': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [stream_t]),
+    'ladder_f32_to_bf16': (C.c_int, [ptr, ptr, C.c_longlong, stream_t]),
+    'ladder_bf16_to_f32': (C.c_int, [ptr, ptr, C.c_longlong, stream_t]),
+    'ladder_colsum_bf16': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, stream_t]),
     # layout / elementwise
     'ladder_sym_pad': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),
     'ladder_depth_to_space': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),

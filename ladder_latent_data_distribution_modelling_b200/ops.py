@@ -16,6 +16,7 @@ ACT = {None: 0, 'none': 0, 'leaky_relu': 1, 'relu': 2, 'tanh': 3}
 
 _checked_devices = set()
 _workspaces = {}
+_retired = []
 
 
 def _L():
@@ -40,11 +41,26 @@ def _f32(t, name='tensor'):
     return t
 
 
+def _act_t(t, name='tensor'):
+    """Activation / gradient tensor: contiguous fp32 or bf16 on an sm_100 device."""
+    if t.dtype == torch.float32:
+        return _f32(t, name)
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()):
+        raise RuntimeError('%s must be a contiguous fp32 or bf16 CUDA tensor' % name)
+    return t
+
+
+def _is16(t):
+    return int(t is not None and t.dtype == torch.bfloat16)
+
+
 def _workspace(device, nbytes, tag):
     """Zero-initialised, grow-only scratch buffer per (device, tag)."""
     key = (str(device), tag)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _retired.append(ws)      # captured CUDA graphs may still reference the smaller buffer: never free it
         ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
@@ -295,10 +311,78 @@ def _tc_ws(x, g):
     return ws, ws.numel()
 
 
+# TMA-fed tcgen05 kernels on bf16-resident activations (csrc/conv_tma.cu); LADDER_TMA=0 keeps the register-gather path
+TMA = os.environ.get('LADDER_TMA', '1') != '0'
+_tma_ok = {}
+FPROP, DGRAD, WGRAD = 0, 1, 2
+
+
+def tma_supported(g, mode):
+    """True if GEMM `mode` (FPROP / DGRAD / WGRAD) of geometry g runs on the TMA-fed kernel."""
+    if not (TMA and MATH_MODE == 'bf16') or not _use_tc(g):
+        return False
+    key = (mode,) + g.args()
+    r = _tma_ok.get(key)
+    if r is None:
+        r = bool(_L().ladder_conv2d_tma_supported(mode, g.B, g.H, g.W, g.Cin, g.KH, g.KW, g.Cout, g.stride, g.OH, g.OW))
+        _tma_ok[key] = r
+    return r
+
+
+def to_bf16(x, out=None, tag='cvt16'):
+    """fp32 -> bf16 copy (into `out`, or a per-tag scratch buffer that the next call with that tag overwrites)."""
+    _f32(x, 'x')
+    n = x.numel()
+    if out is None:
+        out = _workspace(x.device, max(2 * n, 16), tag).view(torch.bfloat16)[:n].view(x.shape)
+    _lib.check(_L().ladder_f32_to_bf16(_p(x), _p(out), n, _stream()), 'f32_to_bf16')
+    return out
+
+
+def to_f32(x, out=None, tag='cvt32'):
+    n = x.numel()
+    if out is None:
+        out = _workspace(x.device, max(4 * n, 16), tag).view(torch.float32)[:n].view(x.shape)
+    _lib.check(_L().ladder_bf16_to_f32(_p(x), _p(_f32(out)), n, _stream()), 'bf16_to_f32')
+    return out
+
+
+def _as16(x, tag):
+    return x if x.dtype == torch.bfloat16 else to_bf16(x, tag=tag)
+
+
+def _as32(x, tag):
+    return x if x is None or x.dtype == torch.float32 else to_f32(x, tag=tag)
+
+
+def _tma_ws(x, g):
+    n = _L().ladder_conv2d_tma_workspace_bytes(g.Cin, g.KH, g.KW, g.Cout)
+    ws = _workspace(x.device, n, 'conv_tc')
+    return ws, ws.numel()
+
+
+def colsum(dy, rows, cols, out):
+    if dy.dtype == torch.bfloat16:
+        _lib.check(_L().ladder_colsum_bf16(_p(dy), rows, cols, _p(out), _stream()), 'colsum_bf16')
+    else:
+        _lib.check(_L().ladder_colsum(_p(dy), rows, cols, _p(out), _stream()), 'colsum')
+    return out
+
+
 def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0):
-    """y = act(conv(x, w) + bias); out_d2s = r writes y directly in depth_to_space(r) layout."""
+    """y = act(conv(x, w) + bias); out_d2s = r writes y directly in depth_to_space(r) layout.
+    x and y may each be fp32 or bf16 when the layer runs on the TMA-fed kernel (tma_supported(g, FPROP))."""
+    _act_t(x, 'x'), _act_t(y, 'y')
     if MATH_MODE == 'bf16' and _is_tap_gemm(g) and g.Cin % 64 == 0 and not out_d2s:
         return _tap_gemm_fprop_tc(x, w, bias, y, g, act)
+    if tma_supported(g, FPROP):
+        ws, n = _tma_ws(x, g)
+        _lib.check(_L().ladder_conv2d_fprop_tma(_p(_as16(x, 'x16')), _p(_f32(w)), _p(bias), _p(y), _is16(y), *g.args(),
+                                                ACT[act], int(out_d2s), _p(ws), n, _stream()), 'conv2d_fprop_tma')
+        return y
+    x = _as32(x, 'x32')
+    if y.dtype != torch.float32:
+        raise RuntimeError('conv2d_fprop: bf16 output needs the TMA path (geometry %r)' % (g.args(),))
     if _use_tc(g):
         ws, n = _tc_ws(x, g)
         _lib.check(_L().ladder_conv2d_fprop_tc(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(_f32(y)), *g.args(), ACT[act],
@@ -312,6 +396,16 @@ def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0):
 
 def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False, out_s2d=0):
     """dx = conv^T(dy, w) [* act'(act_out)]; out_s2d = r writes dx at the position of the depth_to_space INPUT."""
+    _act_t(dy, 'dy'), _act_t(dx, 'dx')
+    if tma_supported(g, DGRAD):
+        ws, n = _tma_ws(dy, g)
+        _lib.check(_L().ladder_conv2d_dgrad_tma(_p(_as16(dy, 'dy16')), _p(_f32(w)), _p(act_out), _is16(act_out), _p(dx),
+                                                _is16(dx), *g.args(), ACT[act], int(accumulate), int(out_s2d), _p(ws), n,
+                                                _stream()), 'conv2d_dgrad_tma')
+        return dx
+    dy, act_out = _as32(dy, 'dy32'), _as32(act_out, 'ao32')
+    if dx.dtype != torch.float32:
+        raise RuntimeError('conv2d_dgrad: bf16 output needs the TMA path (geometry %r)' % (g.args(),))
     if _use_tc(g):
         ws, n = _tc_ws(dy, g)
         _lib.check(_L().ladder_conv2d_dgrad_tc(_p(_f32(dy)), _p(_f32(w)), _p(act_out), _p(_f32(dx)), *g.args(), ACT[act],
@@ -323,8 +417,17 @@ def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False, out_s2d
 
 
 def conv2d_wgrad(x, dy, dw, dbias, g):
+    _act_t(x, 'x'), _act_t(dy, 'dy')
     if MATH_MODE == 'bf16' and _is_tap_gemm(g) and g.Cin % 64 == 0:
         return _tap_gemm_wgrad_tc(x, dy, dw, dbias, g)
+    if tma_supported(g, WGRAD):
+        dy16 = _as16(dy, 'dy16')
+        _lib.check(_L().ladder_conv2d_wgrad_tma(_p(_as16(x, 'x16')), _p(dy16), _p(_f32(dw)), *g.args(), _stream()),
+                   'conv2d_wgrad_tma')
+        if dbias is not None:
+            colsum(dy if dy.dtype == torch.float32 else dy16, g.B * g.OH * g.OW, g.Cout, dbias)
+        return dw
+    x, dy = _as32(x, 'x32'), _as32(dy, 'dy32')
     if _use_tc(g) and g.Cin % 64 == 0:
         ws, n = _tc_ws(x, g)
         _lib.check(_L().ladder_conv2d_wgrad_tc(_p(_f32(x)), _p(_f32(dy)), _p(_f32(dw)), *g.args(), _p(ws), n, _stream()),

@@ -43,8 +43,17 @@ def main():
                          ('dgrad', lambda: ops.conv2d_dgrad(dy, w, dx, g)),
                          ('wgrad', lambda: ops.conv2d_wgrad(x, dy, dw, None, g))):
             ms = time_ms(fn)
-            out.append({'layer': name, 'op': what, 'ms': ms, 'tflops': flops / ms / 1e9})
-    print(json.dumps(out))
+            out.append({'layer': name, 'op': what, 'io': 'fp32', 'ms': ms, 'tflops': flops / ms / 1e9})
+        if mode == 'bf16' and ops.tma_supported(g, ops.FPROP):
+            # bf16-resident tensors: no conversion launches, only the weight repack + the TMA-fed kernel
+            x16, y16, dy16, dx16 = (t.to(torch.bfloat16) for t in (x, y, dy, dx))
+            for what, fn in (('fprop', lambda: ops.conv2d_fprop(x16, w, b, y16, g, 'leaky_relu')),
+                             ('dgrad', lambda: ops.conv2d_dgrad(dy16, w, dx16, g)),
+                             ('wgrad', lambda: ops.conv2d_wgrad(x16, dy16, dw, None, g))):
+                ms = time_ms(fn)
+                out.append({'layer': name, 'op': what, 'io': 'bf16', 'ms': ms, 'tflops': flops / ms / 1e9})
+    for r in out:
+        print(json.dumps(r))
 
 
 if __name__ == '__main__':

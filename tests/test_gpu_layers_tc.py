@@ -113,3 +113,123 @@ def test_tc_repeatability_stress(ops):
     ops.conv2d_wgrad(x, dy, dwr, None, g)
     for a, r in ((y0, yr), (dx0, dxr), (dw0, dwr)):
         assert (a - r).abs().max().item() < TOL * r.abs().max().item()
+
+
+# ---------------------------------------------------------------------------- TMA-fed kernels (csrc/conv_tma.cu)
+# (B, H, W, Cin, k, Cout, padding, act): stride-1 geometries whose three GEMMs all run on the TMA path
+TMA_CASES = [
+    (8, 16, 16, 64, 3, 256, 'same', 'leaky_relu'),     # fashion decoder conv2d_3: box 16 x 8 x 1
+    (2, 4, 128, 64, 3, 64, 'same', None),              # W = 128: one image row per tile
+    (64, 2, 2, 128, 3, 128, 'same', 'leaky_relu'),     # CelebA 2x2 maps: box 2 x 2 x 32 spans images
+    (130, 2, 2, 64, 3, 64, 'same', None),              # ragged batch: last box hangs over B (zero fill + row mask)
+    (32, 4, 4, 128, 3, 128, 'valid', 'leaky_relu'),    # VALID 3x3: 4x4 -> 2x2
+    (4, 8, 8, 64, 5, 192, 'same', 'relu'),             # 5x5 taps, Cout = 192 (wgrad N tile with an OOB channel block)
+    (300, 1, 1, 512, 1, 512, 'valid', 'leaky_relu'),   # dense
+]
+
+
+@pytest.mark.parametrize('case', TMA_CASES)
+@pytest.mark.parametrize('io16', [False, True])
+def test_tma_conv_fprop_dgrad_wgrad(ops, case, io16):
+    """TMA-fed tcgen05 kernels vs the float64 oracle evaluated on the SAME bf16-rounded operands when the
+    tensors are bf16-resident (io16), so the only difference left is fp32 accumulation order + output rounding."""
+    B, H, W, Cin, k, Cout, padding, act = case
+    g = ops.ConvGeom(B, H, W, Cin, k, k, Cout, 1, padding)
+    assert all(ops.tma_supported(g, m) for m in (ops.FPROP, ops.DGRAD, ops.WGRAD)), 'case must exercise the TMA path'
+    rng = np.random.default_rng(abs(hash(case)) % 2**32)
+    bf = lambda a: torch.tensor(a, dtype=torch.float32).to(torch.bfloat16).to(torch.float32).numpy().astype(np.float64)  # noqa: E731
+    x = rng.normal(size=(B, H, W, Cin)); w = rng.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)
+    b = rng.normal(size=(Cout,))
+    if io16:
+        x = bf(x)
+    X, Wv, Bv = T.Var(x), T.Var(w), T.Var(b)
+    pre = T.conv2d(X, Wv, Bv, stride=1, padding=padding)
+    actf = {None: lambda v: v, 'leaky_relu': T.leaky_relu, 'relu': T.relu}[act]
+    y = actf(pre)
+    up = rng.normal(size=y.shape)
+    T.backward(y, seed=up)
+    dt = torch.bfloat16 if io16 else torch.float32
+    xd, wd, bd = dev(x).to(dt), dev(w), dev(b)
+    yd = torch.full((B, g.OH, g.OW, Cout), 5.0, device='cuda', dtype=dt)
+    ops.conv2d_fprop(xd, wd, bd, yd, g, act)
+    close(yd.float(), y.v)
+    dy = bf(pre.g) if io16 else pre.g
+    # gradients of the linear maps for THIS dy (the oracle's are linear in dy, so recompute with the rounded one)
+    X2, W2 = T.Var(x), T.Var(w)
+    T.backward(T.conv2d(X2, W2, None, stride=1, padding=padding), seed=dy)
+    dyd = dev(dy).to(dt)
+    dwd = torch.full_like(wd, 7.0); dbd = torch.full_like(bd, 7.0)
+    ops.conv2d_wgrad(xd, dyd, dwd, dbd, g)
+    close(dwd, W2.g)
+    close(dbd, dy.sum(axis=(0, 1, 2)), 2e-3 if io16 else 1e-4)
+    dxd = torch.full((B, H, W, Cin), 3.0, device='cuda', dtype=dt)
+    ops.conv2d_dgrad(dyd, wd, dxd, g)
+    close(dxd.float(), X2.g)
+    prod = dev(rng.normal(size=x.shape)).to(dt); base = dev(rng.normal(size=x.shape))
+    out = base.clone()
+    ops.conv2d_dgrad(dyd, wd, out, g, act_out=prod, act='leaky_relu', accumulate=True)
+    close(out, base.cpu().numpy() + X2.g * np.where(prod.float().cpu().numpy() > 0, 1.0, 0.2))
+
+
+@pytest.mark.parametrize('io16', [False, True])
+def test_tma_fused_depth_to_space(ops, io16):
+    """fprop writing depth_to_space layout and dgrad scattering back through it, on the TMA path, fp32 and bf16 I/O."""
+    rng = np.random.default_rng(5)
+    dt = torch.bfloat16 if io16 else torch.float32
+    for (B, H, Cin, Cout, r) in [(8, 4, 64, 256, 2), (32, 2, 64, 1024, 4)]:
+        x = rng.normal(size=(B, H, H, Cin)); w = rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin)
+        b = rng.normal(size=(Cout,))
+        X, Wv, Bv = T.Var(x), T.Var(w), T.Var(b)
+        y = T.leaky_relu(T.conv2d(X, Wv, Bv, stride=1, padding='same'))
+        y2 = T.depth_to_space(y, r)
+        g = ops.ConvGeom(B, H, H, Cin, 3, 3, Cout, 1, 'same')
+        assert ops.tma_supported(g, ops.FPROP)
+        yd = torch.empty(B, H, H, Cout, device='cuda', dtype=dt)
+        ops.conv2d_fprop(dev(x), dev(w), dev(b), yd, g, 'leaky_relu', out_d2s=r)
+        close(yd.float().view(y2.shape), y2.v, 2e-2)
+        C2 = Cout // (r * r)
+        w2 = rng.normal(size=(3, 3, C2, 64)) / np.sqrt(9 * C2)
+        W2 = T.Var(w2)
+        z = T.conv2d(y2, W2, None, stride=1, padding='same')
+        up = rng.normal(size=z.shape)
+        T.backward(z, seed=up)
+        g2 = ops.ConvGeom(B, H * r, H * r, C2, 3, 3, 64, 1, 'same')
+        assert ops.tma_supported(g2, ops.DGRAD)
+        dprod = torch.empty(B, H, H, Cout, device='cuda', dtype=dt)
+        ops.conv2d_dgrad(dev(up), dev(w2), dprod, g2, act_out=dev(y2.v).to(dt), act='leaky_relu', out_s2d=r)
+        want = y.g * np.where(y.v > 0, 1.0, 0.2)
+        close(dprod.float(), want, 4.5e-2)
+
+
+def test_tma_repeatability_and_register_gather_agreement(ops):
+    """Race detector for the TMA pipeline (full/empty ring, TMEM double buffering, split-K atomics): 20 repeats must
+    reproduce the first result bit-for-bit (fprop / dgrad); and the TMA kernels must agree with the register-gather
+    tcgen05 kernels of conv_tc.cu (same bf16 operand rounding, fp32 accumulation) to accumulation-order noise."""
+    B, H = 256, 256
+    g = ops.ConvGeom(B, 16, 16, H // 4, 3, 3, H, 1, 'same')
+    gen = torch.Generator(device='cuda'); gen.manual_seed(1)
+    x = torch.randn(B, 16, 16, H // 4, device='cuda', generator=gen)
+    w = torch.randn(3, 3, H // 4, H, device='cuda', generator=gen) * 0.05
+    b = torch.randn(H, device='cuda', generator=gen)
+    dy = torch.randn(B, 16, 16, H, device='cuda', generator=gen)
+    outs = {}
+    for tma in (True, False):
+        ops.TMA = tma
+        try:
+            y0 = torch.empty(B, 16, 16, H, device='cuda'); dx0 = torch.empty_like(x); dw0 = torch.empty_like(w)
+            ops.conv2d_fprop(x, w, b, y0, g, 'leaky_relu')
+            ops.conv2d_dgrad(dy, w, dx0, g)
+            ops.conv2d_wgrad(x, dy, dw0, None, g)
+            if tma:
+                y = torch.empty_like(y0); dx = torch.empty_like(dx0); dw = torch.empty_like(dw0)
+                for _ in range(20):
+                    ops.conv2d_fprop(x, w, b, y, g, 'leaky_relu')
+                    ops.conv2d_dgrad(dy, w, dx, g)
+                    ops.conv2d_wgrad(x, dy, dw, None, g)
+                    assert torch.equal(y, y0) and torch.equal(dx, dx0)
+                    assert (dw - dw0).abs().max().item() <= 1e-4 * dw0.abs().max().item()
+            outs[tma] = (y0, dx0, dw0)
+        finally:
+            ops.TMA = True
+    for a, r in zip(outs[True], outs[False]):
+        assert (a - r).abs().max().item() < 1e-4 * r.abs().max().item()
