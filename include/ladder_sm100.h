@@ -159,6 +159,17 @@ int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w, const void* act
                             void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, int B, int H, int W, int Cin, int KH,
                             int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream);
+/* Thin-output (Cout <= 8) KxK stride-1 conv (the decoders' last layers, codes/models.py:143-148, 310-315, 581-587) as
+ * bandwidth-bound element-wise passes: dgrad with fused producer-activation derivative / space_to_depth scatter and
+ * fp32 or bf16 output; and the bf16 [B*H*W, ld] shifted copy DYS[p, tap] = dy[p - tap] that feeds the TMA wgrad. */
+int ladder_tap_dgrad(const float* dy, const float* w, const void* act_out /*nullable*/, int act_out_bf16, void* dx,
+                     int dx_bf16, int B, int H, int W, int C, int Co /* <= 8 */, int KH, int KW, int pad_t, int pad_l, int OH,
+                     int OW, int act, int out_s2d, cudaStream_t stream);
+/* dw[c, co] = sum_p x[p, c] dy[p, co] for a 1x1 conv with <= 8 outputs; x fp32 or bf16, dw (HWIO) overwritten */
+int ladder_thin_wgrad_1x1(const void* x, int x_bf16, const float* dy, float* dw, long long P, int C, int Co,
+                          cudaStream_t stream);
+int ladder_tap_scatter_bf16(const float* dy, void* dys_bf16, int ld, int B, int H, int W, int KH, int KW, int pad_t,
+                            int pad_l, int OH, int OW, cudaStream_t stream);
 /* dtype plumbing for the bf16-resident activations */
 int ladder_f32_to_bf16(const float* x, void* y_bf16, long long n, cudaStream_t stream);
 int ladder_bf16_to_f32(const void* x_bf16, float* y, long long n, cudaStream_t stream);

@@ -49,7 +49,8 @@ struct Args {
   int GW, GH, B;             // pixel grid of the GEMM rows (FPROP: y, DGRAD: dx) or of the reduction (WGRAD: y)
   int C;                     // channels of the TMA-gathered tensor
   int KH, KW;
-  int off_y, off_x, sign;    // tap (kh, kw) of grid pixel (y, x) reads source pixel (y + off_y + sign*kh, x + off_x + sign*kw)
+  int off_y, off_x, sign;    // tap (kh, kw) of grid pixel (y, x) reads source pixel (y*stride + off_y + sign*kh, x*stride + off_x + sign*kw)
+  int stride;                // FPROP/WGRAD: conv stride (the tensor map traverses the source with this element stride)
   int Ng;                    // GEMM N: Cout (FPROP, WGRAD) or Cin (DGRAD)
   int act, accumulate, out_bf16, aux_bf16;
   int nkb;                   // FPROP/DGRAD: k-blocks per tile = taps * C/64
@@ -185,7 +186,7 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
             mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
             const int kh = tap / a.KW, kw = tap - kh * a.KW;
             mbar_arrive_expect_tx(bar_full + s * 8, A_STAGE_BYTES + B_STAGE_BYTES);
-            tma_load_4d(sA + s * A_STAGE_BYTES, &mapA, c0, x0 + a.off_x + a.sign * kw, y0 + a.off_y + a.sign * kh, b0,
+            tma_load_4d(sA + s * A_STAGE_BYTES, &mapA, c0, x0 * a.stride + a.off_x + a.sign * kw, y0 * a.stride + a.off_y + a.sign * kh, b0,
                         bar_full + s * 8);
             tma_bulk_g2s(sB + s * B_STAGE_BYTES,
                          reinterpret_cast<const uint8_t*>(a.wt) + ((size_t)T.n_tile * T.nkb + kb) * B_STAGE_BYTES,
@@ -218,7 +219,7 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb)
               if (on[mb])
-                tma_load_4d(sA + s * A_STAGE_BYTES + mb * 8192, &mapA, cc[mb], x0 + ox[mb], y0 + oy[mb], b0, bar_full + s * 8);
+                tma_load_4d(sA + s * A_STAGE_BYTES + mb * 8192, &mapA, cc[mb], x0 * a.stride + ox[mb], y0 * a.stride + oy[mb], b0, bar_full + s * 8);
 #pragma unroll
             for (int nb = 0; nb < BN / 64; ++nb)
               tma_load_4d(sB + s * B_STAGE_BYTES + nb * 8192, &mapB, T.n_tile * BN + nb * 64, x0, y0, b0, bar_full + s * 8);
@@ -431,13 +432,14 @@ static bool pixel_box(int GW, int GH, int B, int px, int& bw, int& bh, int& bb) 
 }
 
 // bf16 NHWC tensor [B, SH, SW, C] as a 4-D tensor map {C, SW, SH, B}, SWIZZLE_128B, zero fill outside
-static int make_map(CUtensorMap* map, const void* ptr, int B, int SH, int SW, int C, int bw, int bh, int bb) {
+static int make_map(CUtensorMap* map, const void* ptr, int B, int SH, int SW, int C, int bw, int bh, int bb, int es = 1) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(LADDER_ERR_CUDA, "conv2d_tma: cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)SW, (cuuint64_t)SH, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)SW * C * 2, (cuuint64_t)SH * SW * C * 2};
-  const cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  // element stride es > 1 (strided conv): the box spans bw*es x bh*es source pixels and TMA keeps every es-th one
+  const cuuint32_t box[4] = {64, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), (cuuint32_t)bb};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -525,16 +527,18 @@ static bool geometry_ok(int B, int GH, int GW, int px) {
 
 extern "C" {
 
-/* mode 0 fprop, 1 dgrad, 2 wgrad: 1 iff the TMA-fed kernel takes this geometry (stride 1, 64-aligned channels of the
- * gathered tensor, pixel grid divisible into 128- (64- for wgrad) pixel boxes) */
+/* mode 0 fprop, 1 dgrad, 2 wgrad: 1 iff the TMA-fed kernel takes this geometry (64-aligned channels of the gathered
+ * tensor, pixel grid divisible into 128- (64- for wgrad) pixel boxes; strided fprop / wgrad use the tensor map's element
+ * stride, strided dgrad is not taken) */
 int ladder_conv2d_tma_supported(int mode, int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int OH, int OW) {
-  if (stride != 1 || B <= 0) return 0;
+  if (stride < 1 || stride > 8 || B <= 0) return 0;
   if ((long long)B * H * W >= (1LL << 31) / 64 * 64 || (long long)B * OH * OW >= (1LL << 31) / 64 * 64) return 0;
   (void)KH; (void)KW;
+  int bw, bh, bb;
   switch (mode) {
-    case 0: return Cin % 64 == 0 && geometry_ok(B, OH, OW, 128);
-    case 1: return Cout % 64 == 0 && geometry_ok(B, H, W, 128);
-    case 2: return Cin % 64 == 0 && Cout % 64 == 0 && geometry_ok(B, OH, OW, 64);
+    case 0: return Cin % 64 == 0 && pixel_box(OW, OH, B, 128, bw, bh, bb) && bw * stride <= 256 && bh * stride <= 256;
+    case 1: return stride == 1 && Cout % 64 == 0 && geometry_ok(B, H, W, 128);
+    case 2: return Cin % 64 == 0 && Cout % 64 == 0 && pixel_box(OW, OH, B, 64, bw, bh, bb) && bw * stride <= 256 && bh * stride <= 256;
     default: return 0;
   }
 }
@@ -590,10 +594,11 @@ int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bia
   int bw, bh, bb;
   pixel_box(OW, OH, B, BM, bw, bh, bb);
   CUtensorMap mA;
-  rc = make_map(&mA, x_bf16, B, H, W, Cin, bw, bh, bb);
+  rc = make_map(&mA, x_bf16, B, H, W, Cin, bw, bh, bb, stride);
   if (rc) return rc;
   Args a;
   memset(&a, 0, sizeof(a));
+  a.stride = stride;
   a.wt = static_cast<const __nv_bfloat16*>(workspace);
   a.bias = bias; a.out = y; a.out_bf16 = y_bf16;
   a.GW = OW; a.GH = OH; a.B = B; a.C = Cin; a.KH = KH; a.KW = KW;
@@ -622,6 +627,7 @@ int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w, const void* act
   Args a;
   memset(&a, 0, sizeof(a));
   a.wt = static_cast<const __nv_bfloat16*>(workspace);
+  a.stride = 1;
   a.aux = act_out; a.aux_bf16 = act_out_bf16; a.out = dx; a.out_bf16 = dx_bf16;
   a.GW = W; a.GH = H; a.B = B; a.C = Cout; a.KH = KH; a.KW = KW;
   a.off_y = pad_t; a.off_x = pad_l; a.sign = -1;       // dx(y, x) += dy(y + pad_t - kh, x + pad_l - kw) . w(kh, kw)
@@ -642,7 +648,7 @@ int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, 
   int bw, bh, bb;
   pixel_box(OW, OH, B, BK, bw, bh, bb);
   CUtensorMap mA, mB;
-  int rc = make_map(&mA, x_bf16, B, H, W, Cin, bw, bh, bb);
+  int rc = make_map(&mA, x_bf16, B, H, W, Cin, bw, bh, bb, stride);
   if (rc) return rc;
   rc = make_map(&mB, dy_bf16, B, OH, OW, Cout, bw, bh, bb);
   if (rc) return rc;
@@ -659,7 +665,7 @@ int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, 
   const long long per = ceil_div64(total_kb, splits);
   Args a;
   memset(&a, 0, sizeof(a));
-  a.out = dw;
+  a.out = dw; a.stride = stride;
   a.GW = OW; a.GH = OH; a.B = B; a.C = Cin; a.KH = KH; a.KW = KW;
   a.off_y = -pad_t; a.off_x = -pad_l; a.sign = 1;
   a.Ng = Cout; a.kb_per_split = (int)per; a.total_kb = total_kb; a.m_valid = patch;

@@ -1,0 +1,227 @@
+// Thin (single-output-channel) KxK conv helpers for the bf16-resident decoder tail of the MNIST models
+// (codes/models.py:143-148, 310-315: conv2d 5x5 VALID -> 1 channel).  These layers carry ~3 % of the MACs but, run
+// as generic GEMMs, cost a disproportionate share of the step; they are bandwidth-bound element-wise passes.
+//
+//   ladder_tap_dgrad        dx[b,y,x,c] = act'(aux) * sum_{tap,co} dy[b, y+pad_t-kh, x+pad_l-kw, co] * w[tap, c, co]   (Co <= 8;
+//                           also CelebA's 1x1 conv to 3 channels, models.py:581-587)
+//                           (stride 1), fused producer-activation derivative, optional space_to_depth scatter,
+//                           output fp32 or bf16 -- replaces the fp32 SIMT implicit-GEMM dgrad (K = taps only)
+//   ladder_tap_scatter_bf16 DYS[p, tap] = dy[p - tap] written as bf16 with a 64-wide leading dimension, so that the
+//                           weight gradient dw[tap, c] = sum_p DYS[p, tap] x[p, c] runs on the TMA-fed wgrad kernel
+#include "common.cuh"
+#include "ladder_sm100.h"
+#include <cuda_bf16.h>
+
+namespace ladder {
+
+struct TapArgs {
+  const float* dy;           // [B, OH, OW, Co] (Co <= 8 output channels)
+  const float* w;            // [KH*KW, C, Co] (HWIO)
+  const void* aux;           // saved producer output indexed like dx rows (fp32 or bf16) or null
+  void* dx;                  // [B, H, W, C] or its space_to_depth position
+  int B, H, W, C, Co, KH, KW, pad_t, pad_l, OH, OW;
+  int act, aux_bf16, out_bf16, s2d;
+};
+
+// one thread = one pixel x 8 channels; the KH*KW*C weights sit in shared memory
+__global__ void __launch_bounds__(256) tap_dgrad_kernel(TapArgs a) {
+  extern __shared__ float sw[];
+  const int T = a.KH * a.KW;
+  // smem layout [tap][co][c] so that one thread's 8 channels are contiguous
+  for (int i = threadIdx.x; i < T * a.C * a.Co; i += blockDim.x) {
+    const int co = i % a.Co, c = (i / a.Co) % a.C, tap = i / (a.Co * a.C);
+    sw[(tap * a.Co + co) * a.C + c] = a.w[i];
+  }
+  __syncthreads();
+  const int c8 = a.C / 8;
+  const long long total = (long long)a.B * a.H * a.W * c8;
+  const float slope = a.act == ACT_LEAKY ? 0.2f : (a.act == ACT_RELU ? 0.f : 1.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % c8) * 8;
+    const long long m = i / c8;
+    const int x = (int)(m % a.W);
+    const long long r = m / a.W;
+    const int y = (int)(r % a.H);
+    const long long b = r / a.H;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int kh = 0; kh < a.KH; ++kh) {
+      const int ny = y + a.pad_t - kh;
+      if (ny < 0 || ny >= a.OH) continue;
+      for (int kw = 0; kw < a.KW; ++kw) {
+        const int nx = x + a.pad_l - kw;
+        if (nx < 0 || nx >= a.OW) continue;
+        const float* gp = a.dy + ((b * a.OH + ny) * a.OW + nx) * a.Co;
+        const float* wp = sw + (kh * a.KW + kw) * a.Co * a.C + c0;
+        for (int co = 0; co < a.Co; ++co) {
+          const float g = __ldg(gp + co);
+          const float4 w0 = *reinterpret_cast<const float4*>(wp + co * a.C);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + co * a.C + 4);
+          acc[0] += g * w0.x; acc[1] += g * w0.y; acc[2] += g * w0.z; acc[3] += g * w0.w;
+          acc[4] += g * w1.x; acc[5] += g * w1.y; acc[6] += g * w1.z; acc[7] += g * w1.w;
+        }
+      }
+    }
+    if (a.aux != nullptr) {
+      float ax[8];
+      if (a.aux_bf16) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.aux) + m * a.C + c0));
+        const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { ax[2 * t] = __uint_as_float(q[t] << 16); ax[2 * t + 1] = __uint_as_float(q[t] & 0xffff0000u); }
+      } else {
+        const float* p = reinterpret_cast<const float*>(a.aux) + m * a.C + c0;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(p)), v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+        ax[0] = v0.x; ax[1] = v0.y; ax[2] = v0.z; ax[3] = v0.w; ax[4] = v1.x; ax[5] = v1.y; ax[6] = v1.z; ax[7] = v1.w;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] *= a.act == ACT_TANH ? 1.f - ax[t] * ax[t] : (ax[t] > 0.f ? 1.f : slope);
+    }
+    const long long o = a.s2d > 0 ? s2d_dest(m, c0, a.H, a.W, a.C, a.s2d) : m * a.C + c0;
+    if (a.out_bf16) {
+      uint4 u;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[4], acc[5]), p3 = __floats2bfloat162_rn(acc[6], acc[7]);
+      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dx) + o) = u;
+    } else {
+      float* p = reinterpret_cast<float*>(a.dx) + o;
+      *reinterpret_cast<float4*>(p) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
+// DYS[p, tap] (bf16, leading dimension ld, zero padded): one thread = one input pixel x 8 taps
+__global__ void __launch_bounds__(256) tap_scatter_bf16_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dys,
+                                                               int ld, int B, int H, int W, int KH, int KW, int pad_t,
+                                                               int pad_l, int OH, int OW) {
+  const int T = KH * KW, l8 = ld / 8;
+  const long long total = (long long)B * H * W * l8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t0 = (int)(i % l8) * 8;
+    const long long m = i / l8;
+    const int x = (int)(m % W);
+    const long long r = m / W;
+    const int y = (int)(r % H);
+    const long long b = r / H;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int tap = t0 + j;
+      v[j] = 0.f;
+      if (tap < T) {
+        const int ny = y + pad_t - tap / KW, nx = x + pad_l - tap % KW;
+        if (ny >= 0 && nx >= 0 && ny < OH && nx < OW) v[j] = __ldg(dy + (b * OH + ny) * OW + nx);
+      }
+    }
+    uint4 u;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(dys + m * ld + t0) = u;
+  }
+}
+
+
+// dw[c, co] = sum_p x[p, c] dy[p, co] for a 1x1 conv with Co <= 8 outputs (CelebA decoder/conv2d_8): one thread = 8 channels
+// x a strided set of pixels; block-level smem reduction, then one red.global.add per (c, co) per block.
+template <bool X16>
+__global__ void __launch_bounds__(256) thin_wgrad_1x1_kernel(const void* __restrict__ xv, const float* __restrict__ dy,
+                                                             float* __restrict__ dw, long long P, int C, int Co, long long per) {
+  extern __shared__ float red[];                  // [lanes][C*Co]
+  const int c8 = C / 8, lanes = blockDim.x / c8;
+  const int cg = threadIdx.x % c8, pl = threadIdx.x / c8;
+  const long long lo = (long long)blockIdx.x * per, hi = min(P, lo + per);
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  if (pl < lanes) {
+    for (long long p = lo + pl; p < hi; p += lanes) {
+      float xs[8];
+      if (X16) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(xv) + p * C + cg * 8));
+        const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { xs[2 * t] = __uint_as_float(q[t] << 16); xs[2 * t + 1] = __uint_as_float(q[t] & 0xffff0000u); }
+      } else {
+        const float* xp = reinterpret_cast<const float*>(xv) + p * C + cg * 8;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(xp)), v1 = __ldg(reinterpret_cast<const float4*>(xp + 4));
+        xs[0] = v0.x; xs[1] = v0.y; xs[2] = v0.z; xs[3] = v0.w; xs[4] = v1.x; xs[5] = v1.y; xs[6] = v1.z; xs[7] = v1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < Co) {
+          const float g = __ldg(dy + p * Co + j);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i][j] = fmaf(xs[i], g, acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < Co) red[(size_t)pl * C * Co + (cg * 8 + i) * Co + j] = acc[i][j];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < C * Co; e += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[(size_t)l * C * Co + e];
+    atomicAdd(dw + e, s);
+  }
+}
+
+}  // namespace ladder
+
+using namespace ladder;
+
+extern "C" {
+
+int ladder_tap_dgrad(const float* dy, const float* w, const void* act_out, int act_out_bf16, void* dx, int dx_bf16, int B,
+                     int H, int W, int C, int Co, int KH, int KW, int pad_t, int pad_l, int OH, int OW, int act, int out_s2d,
+                     cudaStream_t stream) {
+  LADDER_REQUIRE(Co >= 1 && Co <= 8, "tap_dgrad: 1..8 output channels (got %d)", Co);
+  LADDER_REQUIRE(dy && w && dx && B > 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && OH > 0 && OW > 0, "tap_dgrad: bad arguments");
+  LADDER_REQUIRE(C % 8 == 0, "tap_dgrad: channel count must be a multiple of 8 (got %d)", C);
+  LADDER_REQUIRE(out_s2d == 0 || (H % out_s2d == 0 && W % out_s2d == 0), "tap_dgrad: space_to_depth(%d) needs H, W divisible by r", out_s2d);
+  const size_t smem = (size_t)KH * KW * C * Co * sizeof(float);
+  LADDER_REQUIRE(smem <= 48 * 1024, "tap_dgrad: KH*KW*C*Co = %d weights do not fit in 48 KB of shared memory", KH * KW * C * Co);
+  TapArgs a{dy, w, act_out, dx, B, H, W, C, Co, KH, KW, pad_t, pad_l, OH, OW, act, act_out_bf16, dx_bf16, out_s2d};
+  long long blocks = ceil_div64((long long)B * H * W * (C / 8), 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tap_dgrad_kernel<<<(unsigned)blocks, 256, smem, stream>>>(a);
+  return check_launch("tap_dgrad");
+}
+
+int ladder_tap_scatter_bf16(const float* dy, void* dys_bf16, int ld, int B, int H, int W, int KH, int KW, int pad_t, int pad_l,
+                            int OH, int OW, cudaStream_t stream) {
+  LADDER_REQUIRE(dy && dys_bf16 && ld >= KH * KW && ld % 8 == 0 && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0,
+                 "tap_scatter_bf16: bad arguments");
+  long long blocks = ceil_div64((long long)B * H * W * (ld / 8), 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tap_scatter_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dy, static_cast<__nv_bfloat16*>(dys_bf16), ld, B, H, W, KH, KW,
+                                                                pad_t, pad_l, OH, OW);
+  return check_launch("tap_scatter_bf16");
+}
+
+int ladder_thin_wgrad_1x1(const void* x, int x_bf16, const float* dy, float* dw, long long P, int C, int Co, cudaStream_t stream) {
+  LADDER_REQUIRE(x && dy && dw && P > 0 && C > 0 && Co >= 1 && Co <= 8, "thin_wgrad_1x1: bad arguments");
+  LADDER_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "thin_wgrad_1x1: C/8 must divide 256 (got C = %d)", C);
+  cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)C * Co * sizeof(float), stream);
+  if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "thin_wgrad_1x1 memset: %s", cudaGetErrorString(e));
+  const int lanes = 256 / (C / 8);
+  const size_t smem = (size_t)lanes * C * Co * sizeof(float);
+  LADDER_REQUIRE(smem <= 48 * 1024, "thin_wgrad_1x1: reduction buffer %zu B exceeds 48 KB", smem);
+  long long blocks = 148 * 4;
+  long long per = ceil_div64(P, blocks);
+  if (per < lanes) per = lanes;
+  blocks = ceil_div64(P, per);
+  if (x_bf16) thin_wgrad_1x1_kernel<true><<<(unsigned)blocks, 256, smem, stream>>>(x, dy, dw, P, C, Co, per);
+  else thin_wgrad_1x1_kernel<false><<<(unsigned)blocks, 256, smem, stream>>>(x, dy, dw, P, C, Co, per);
+  return check_launch("thin_wgrad_1x1");
+}
+
+}  // extern "C"

@@ -138,10 +138,10 @@ class Buffers:
         self.device = device
         self.t = {}
 
-    def get(self, name, *shape):
+    def get(self, name, *shape, dtype=torch.float32):
         t = self.t.get(name)
-        if t is None or tuple(t.shape) != tuple(shape):
-            t = torch.empty(*shape, device=self.device)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(*shape, device=self.device, dtype=dtype)
             self.t[name] = t
         return t
 
@@ -190,13 +190,17 @@ class MnistOuterVAE:
             last = (16, H, 2, 'decoder/conv2d_4', H // 4)
         # decoder chain: every layer writes its activation straight in depth_to_space layout (fused epilogue), which
         # is the input of the next conv; stage = (hw_in, c_in, r, conv) with conv consuming [B, hw*r, hw*r, c_in/r^2]
+        # bf16-resident activations: a conv writes its output in bf16 when it runs on the TMA-fed kernel and its consumer
+        # (the next conv) reads bf16 -- the activation then never exists in fp32 and no conversion pass is launched.
         self.dec = []
-        for hw, cin, r, name, kk, cout in stages:
-            conv = Conv(group, name, G(B, hw * r, hw * r, cin // (r * r), kk, kk, cout, 1, 'same'), LEAKY, device)
-            self.dec.append((hw, cin, r, conv))
+        geoms = [G(B, hw * r, hw * r, cin // (r * r), kk, kk, cout, 1, 'same') for hw, cin, r, name, kk, cout in stages]
         hw, cin, r, name, cl = last
-        conv = Conv(group, name, G(B, hw * r, hw * r, cl, 5, 5, 1, 1, 'valid'), 'relu', device)
-        self.dec.append((hw, cin, r, conv))
+        geoms.append(G(B, hw * r, hw * r, cl, 5, 5, 1, 1, 'valid'))
+        for i, (hw, cin, r, name, kk, cout) in enumerate(stages):
+            dt = torch.bfloat16 if ops.tma_supported(geoms[i], ops.FPROP) and ops.reads_bf16(geoms[i + 1]) else torch.float32
+            self.dec.append((hw, cin, r, Conv(group, name, geoms[i], LEAKY, device, out_dtype=dt)))
+        hw, cin, r, name, cl = last
+        self.dec.append((hw, cin, r, Conv(group, name, geoms[-1], 'relu', device)))
         self.flat, self.feat, self.C = flat, feat, C
         self.mean = self.head_mean.y.view(B, C)
         self.std = self.head_std.y.view(B, C)              # becomes relu(.)+floor in place
@@ -237,7 +241,9 @@ class MnistOuterVAE:
         for i in range(len(self.dec) - 1, -1, -1):
             hw, cin, r, conv = self.dec[i]
             prod = self.dec[i - 1][3] if i > 0 else self.dec_dense
-            dp = self.buf.get('dp%d' % i, B, hw, hw, cin)              # producer layout
+            # producer layout; bf16 when this layer's dgrad can write it and the producer's backward reads it on the TMA path
+            dt = torch.bfloat16 if ops.dgrad_writes_bf16(conv.geom) and (prod.tma[1] or prod.tma[2]) else torch.float32
+            dp = self.buf.get('dp%d' % i, B, hw, hw, cin, dtype=dt)
             conv.backward(dpre, dx=dp, producer=(prod.y, prod.act), wgrad=wgrad, s2d=r)
             dpre = dp
         self.dec_dense.backward(dpre.view(B, 1, 1, -1), dx=dz.view(B, 1, 1, self.C), wgrad=wgrad)

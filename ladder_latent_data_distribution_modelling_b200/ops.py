@@ -284,14 +284,27 @@ def _tap_gemm_fprop_tc(x, w, bias, y, g, act):
 
 
 def _tap_gemm_wgrad_tc(x, dy, dw, dbias, g):
-    """dw[tap, c] = sum_p DYS[p, tap] x[p, c]: shifted copy of dy, then a dense wgrad with x as the (64-aligned) input."""
-    P, ld, T = g.B * g.H * g.W, _tap_ld(g), g.KH * g.KW
-    dys = _workspace(x.device, P * ld * 4, 'tap_z').view(torch.float32)[:P * ld].view(P, 1, 1, ld)
-    _lib.check(_L().ladder_tap_scatter(_p(_f32(dy)), _p(dys), ld, g.B, g.H, g.W, g.KH, g.KW, g.stride, g.pad_t, g.pad_l,
-                                       g.OH, g.OW, _stream()), 'tap_scatter')
-    dwt = _workspace(x.device, g.Cin * ld * 4, 'tap_w').view(torch.float32)[:g.Cin * ld].view(1, 1, g.Cin, ld)
-    conv2d_wgrad(x.view(P, 1, 1, g.Cin), dys, dwt, None, ConvGeom.dense(P, g.Cin, ld))
-    dw.view(T, g.Cin).copy_(dwt.view(g.Cin, ld)[:, :T].t())
+    """dw[tap, c] = sum_p DYS[p, tap] x[p, c]: shifted copy of dy, then a dense wgrad with x as the (64-aligned) input.
+    With the TMA path DYS is written directly as bf16 with a 64-wide leading dimension and the GEMM is TMA-fed."""
+    P, T = g.B * g.H * g.W, g.KH * g.KW
+    gd = ConvGeom.dense(P, g.Cin, 64)
+    if g.stride == 1 and T <= 64 and TMA and _L().ladder_conv2d_tma_supported(WGRAD, P, 1, 1, g.Cin, 1, 1, 64, 1, 1, 1):
+        dys = _workspace(x.device, P * 64 * 2, 'tap_z').view(torch.bfloat16)[:P * 64].view(P, 1, 1, 64)
+        _lib.check(_L().ladder_tap_scatter_bf16(_p(_f32(dy)), _p(dys), 64, g.B, g.H, g.W, g.KH, g.KW, g.pad_t, g.pad_l,
+                                                g.OH, g.OW, _stream()), 'tap_scatter_bf16')
+        dwt = _workspace(x.device, g.Cin * 64 * 4, 'tap_w').view(torch.float32)[:g.Cin * 64].view(1, 1, g.Cin, 64)
+        _lib.check(_L().ladder_conv2d_wgrad_tma(_p(_as16(x, 'x16')), _p(dys), _p(dwt), *gd.args(), _stream()),
+                   'conv2d_wgrad_tma')
+        dw.view(T, g.Cin).copy_(dwt.view(g.Cin, 64)[:, :T].t())
+    else:
+        ld = _tap_ld(g)
+        x = _as32(x, 'x32')
+        dys = _workspace(x.device, P * ld * 4, 'tap_z').view(torch.float32)[:P * ld].view(P, 1, 1, ld)
+        _lib.check(_L().ladder_tap_scatter(_p(_f32(dy)), _p(dys), ld, g.B, g.H, g.W, g.KH, g.KW, g.stride, g.pad_t, g.pad_l,
+                                           g.OH, g.OW, _stream()), 'tap_scatter')
+        dwt = _workspace(x.device, g.Cin * ld * 4, 'tap_w').view(torch.float32)[:g.Cin * ld].view(1, 1, g.Cin, ld)
+        conv2d_wgrad(x.view(P, 1, 1, g.Cin), dys, dwt, None, ConvGeom.dense(P, g.Cin, ld))
+        dw.view(T, g.Cin).copy_(dwt.view(g.Cin, ld)[:, :T].t())
     if dbias is not None:
         _lib.check(_L().ladder_colsum(_p(dy), g.B * g.OH * g.OW, 1, _p(dbias), _stream()), 'colsum')
     return dw
@@ -327,6 +340,24 @@ def tma_supported(g, mode):
         r = bool(_L().ladder_conv2d_tma_supported(mode, g.B, g.H, g.W, g.Cin, g.KH, g.KW, g.Cout, g.stride, g.OH, g.OW))
         _tma_ok[key] = r
     return r
+
+
+def thin_dgrad(g):
+    """Layers with <= 8 output channels: dgrad is a bandwidth-bound element-wise pass (csrc/thin_ops.cu) that can write
+    fp32 or bf16."""
+    return (MATH_MODE == 'bf16' and TMA and g.Cout <= 8 and g.stride == 1 and g.Cin % 8 == 0
+            and g.KH * g.KW * g.Cin * g.Cout * 4 <= 48 * 1024)
+
+
+def reads_bf16(g):
+    """True if every GEMM of layer g that reads its INPUT activation takes bf16 without a conversion pass."""
+    if MATH_MODE == 'bf16' and TMA and _is_tap_gemm(g) and g.Cin % 64 == 0 and g.stride == 1:
+        return True                       # tap-GEMM: dense TMA GEMMs over the input pixels
+    return tma_supported(g, FPROP) and (tma_supported(g, WGRAD) or g.Cout <= 8)
+
+
+def dgrad_writes_bf16(g):
+    return thin_dgrad(g) or tma_supported(g, DGRAD)
 
 
 def to_bf16(x, out=None, tag='cvt16'):
@@ -397,6 +428,11 @@ def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0):
 def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False, out_s2d=0):
     """dx = conv^T(dy, w) [* act'(act_out)]; out_s2d = r writes dx at the position of the depth_to_space INPUT."""
     _act_t(dy, 'dy'), _act_t(dx, 'dx')
+    if thin_dgrad(g) and not accumulate and dy.dtype == torch.float32:
+        _lib.check(_L().ladder_tap_dgrad(_p(dy), _p(_f32(w)), _p(act_out), _is16(act_out), _p(dx), _is16(dx), g.B, g.H, g.W,
+                                         g.Cin, g.Cout, g.KH, g.KW, g.pad_t, g.pad_l, g.OH, g.OW, ACT[act], int(out_s2d),
+                                         _stream()), 'tap_dgrad')
+        return dx
     if tma_supported(g, DGRAD):
         ws, n = _tma_ws(dy, g)
         _lib.check(_L().ladder_conv2d_dgrad_tma(_p(_as16(dy, 'dy16')), _p(_f32(w)), _p(act_out), _is16(act_out), _p(dx),
@@ -420,6 +456,13 @@ def conv2d_wgrad(x, dy, dw, dbias, g):
     _act_t(x, 'x'), _act_t(dy, 'dy')
     if MATH_MODE == 'bf16' and _is_tap_gemm(g) and g.Cin % 64 == 0:
         return _tap_gemm_wgrad_tc(x, dy, dw, dbias, g)
+    if (MATH_MODE == 'bf16' and TMA and g.KH == 1 and g.KW == 1 and g.stride == 1 and g.Cout <= 8 and g.Cin % 8 == 0
+            and 256 % (g.Cin // 8) == 0 and dy.dtype == torch.float32 and g.Cin * g.Cout * 4 * (256 // (g.Cin // 8)) <= 48 * 1024):
+        _lib.check(_L().ladder_thin_wgrad_1x1(_p(x), _is16(x), _p(dy), _p(_f32(dw)), g.B * g.H * g.W, g.Cin, g.Cout, _stream()),
+                   'thin_wgrad_1x1')
+        if dbias is not None:
+            colsum(dy, g.B * g.OH * g.OW, g.Cout, dbias)
+        return dw
     if tma_supported(g, WGRAD):
         dy16 = _as16(dy, 'dy16')
         _lib.check(_L().ladder_conv2d_wgrad_tma(_p(_as16(x, 'x16')), _p(dy16), _p(_f32(dw)), *g.args(), _stream()),

@@ -233,3 +233,33 @@ def test_tma_repeatability_and_register_gather_agreement(ops):
             ops.TMA = True
     for a, r in zip(outs[True], outs[False]):
         assert (a - r).abs().max().item() < 1e-4 * r.abs().max().item()
+
+
+# ---------------------------------------------------------------------------- thin-output layers (csrc/thin_ops.cu)
+@pytest.mark.parametrize('case', [(4, 32, 32, 64, 5, 1, 'valid'),      # fashion decoder/conv2d_4
+                                  (2, 16, 16, 128, 1, 3, 'same'),      # CelebA decoder/conv2d_8 (1x1 -> RGB)
+                                  (3, 8, 8, 16, 3, 2, 'same')])
+@pytest.mark.parametrize('io16', [False, True])
+def test_thin_output_conv_backward(ops, case, io16):
+    """Cout <= 8: dgrad (fused act', fp32 / bf16 output) and the 1x1 / tap-GEMM wgrad against the float64 oracle."""
+    B, H, W, Cin, k, Cout, padding = case
+    g = ops.ConvGeom(B, H, W, Cin, k, k, Cout, 1, padding)
+    assert ops.thin_dgrad(g)
+    rng = np.random.default_rng(11)
+    bf = lambda a: torch.tensor(a, dtype=torch.float32).to(torch.bfloat16).to(torch.float32).numpy().astype(np.float64)  # noqa: E731
+    x = rng.normal(size=(B, H, W, Cin)); w = rng.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)
+    if io16:
+        x = bf(x)
+    X, Wv = T.Var(x), T.Var(w)
+    z = T.conv2d(X, Wv, None, stride=1, padding=padding)
+    dy = rng.normal(size=z.shape)
+    T.backward(z, seed=dy)
+    dt = torch.bfloat16 if io16 else torch.float32
+    xd, wd, dyd = dev(x).to(dt), dev(w), dev(dy)
+    dxd = torch.full((B, H, W, Cin), 3.0, device='cuda', dtype=dt)
+    ops.conv2d_dgrad(dyd, wd, dxd, g, act_out=xd, act='leaky_relu')
+    close(dxd.float(), X.g * np.where(x > 0, 1.0, 0.2), 1e-2 if io16 else 1e-5)
+    dwd = torch.full_like(wd, 7.0); dbd = torch.full((Cout,), 7.0, device='cuda')
+    ops.conv2d_wgrad(xd, dyd, dwd, dbd, g)
+    close(dwd, Wv.g, TOL if k > 1 else 1e-4)
+    close(dbd, dy.sum(axis=(0, 1, 2)), 1e-4)
