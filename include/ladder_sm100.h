@@ -214,6 +214,13 @@ int ladder_resize_bilinear_fwd(const float* x, float* y, int B, int H, int W, in
                                cudaStream_t stream);
 int ladder_resize_bilinear_bwd(const float* dy, float* dx, int B, int H, int W, int C, int OH, int OW,
                                cudaStream_t stream);
+/* fp32 / bf16 on either side (C % 8 == 0 for bf16); bwd optionally fuses the activation derivative of the layer whose
+ * OUTPUT was resized (act_out indexed like dx), replacing a separate ladder_act_bwd pass */
+int ladder_resize_bilinear_fwd_ex(const void* x, int x_bf16, void* y, int y_bf16, int B, int H, int W, int C, int OH,
+                                  int OW, cudaStream_t stream);
+int ladder_resize_bilinear_bwd_ex(const void* dy, int dy_bf16, void* dx, int dx_bf16, const void* act_out /*nullable*/,
+                                  int act_out_bf16, int act, int B, int H, int W, int C, int OH, int OW,
+                                  cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * The `scalars` buffer: LADDER_SCALARS_LEN floats on the device.  [0,16) are running sums the

@@ -11,6 +11,7 @@
 //  * tf.image.resize_images (TF1 legacy bilinear: src = dst*in/out, no half-pixel centres).
 #include "common.cuh"
 #include "ladder_sm100.h"
+#include <cuda_bf16.h>
 
 namespace ladder {
 
@@ -249,6 +250,108 @@ __global__ void resize_bwd_kernel(const float* __restrict__ dy, float* __restric
   }
 }
 
+// ---- 8-channel vector forms (C % 8 == 0), fp32 or bf16 on either side: the bf16-resident decoder reads / writes half the bytes
+template <bool IS16>
+__device__ __forceinline__ void ld8(const void* p, long long off, float (&v)[8]) {
+  if (IS16) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + off));
+    const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { v[2 * t] = __uint_as_float(q[t] << 16); v[2 * t + 1] = __uint_as_float(q[t] & 0xffff0000u); }
+  } else {
+    const float* f = reinterpret_cast<const float*>(p) + off;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(f)), b = __ldg(reinterpret_cast<const float4*>(f + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+template <bool IS16>
+__device__ __forceinline__ void st8(void* p, long long off, const float (&v)[8]) {
+  if (IS16) {
+    uint4 u;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + off) = u;
+  } else {
+    float* f = reinterpret_cast<float*>(p) + off;
+    *reinterpret_cast<float4*>(f) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(f + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+template <bool IN16, bool OUT16>
+__global__ void __launch_bounds__(256) resize_fwd8_kernel(const void* __restrict__ x, void* __restrict__ y, int B, int H, int W,
+                                                          int C, int OH, int OW) {
+  const float sy = (float)H / OH, sx = (float)W / OW;
+  const int c8 = C / 8;
+  const long long n = (long long)B * OH * OW * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % c8) * 8;
+    long long r = i / c8;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const long long b = r / OH;
+    int y0, y1, x0, x1;
+    float fy, fx;
+    lerp_taps(oy, sy, H, y0, y1, fy);
+    lerp_taps(ox, sx, W, x0, x1, fx);
+    const long long base = b * H * W * C + c0;
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    ld8<IN16>(x, base + ((long long)y0 * W + x0) * C, v00);
+    ld8<IN16>(x, base + ((long long)y0 * W + x1) * C, v01);
+    ld8<IN16>(x, base + ((long long)y1 * W + x0) * C, v10);
+    ld8<IN16>(x, base + ((long long)y1 * W + x1) * C, v11);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float top = v00[t] + (v01[t] - v00[t]) * fx, bot = v10[t] + (v11[t] - v10[t]) * fx;
+      o[t] = top + (bot - top) * fy;
+    }
+    st8<OUT16>(y, (i / c8) * C + c0, o);
+  }
+}
+
+// gather-form transpose, optionally fused with the activation derivative of the layer whose output was resized
+template <bool IN16, bool OUT16, bool AUX16>
+__global__ void __launch_bounds__(256) resize_bwd8_kernel(const void* __restrict__ dy, void* __restrict__ dx,
+                                                          const void* __restrict__ aux, int act, int B, int H, int W, int C,
+                                                          int OH, int OW) {
+  const float sy = (float)H / OH, sx = (float)W / OW;
+  const int c8 = C / 8;
+  const long long n = (long long)B * H * W * c8;
+  const float slope = act == ACT_LEAKY ? 0.2f : (act == ACT_RELU ? 0.f : 1.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % c8) * 8;
+    long long r = i / c8;
+    const int ix = (int)(r % W); r /= W;
+    const int iy = (int)(r % H);
+    const long long b = r / H;
+    const int oy_lo = max(0, (int)ceilf((iy - 1) / sy)), oy_hi = min(OH - 1, (int)ceilf((iy + 1) / sy) - 1);
+    const int ox_lo = max(0, (int)ceilf((ix - 1) / sx)), ox_hi = min(OW - 1, (int)ceilf((ix + 1) / sx) - 1);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const float wy = tap_weight(oy, iy, sy, H);
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        const float wx = tap_weight(ox, ix, sx, W);
+        if (wx == 0.f) continue;
+        float g[8];
+        ld8<IN16>(dy, ((b * OH + oy) * OW + ox) * C + c0, g);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = fmaf(wy * wx, g[t], acc[t]);
+      }
+    }
+    const long long o = (i / c8) * C + c0;
+    if (aux != nullptr) {
+      float ax[8];
+      ld8<AUX16>(aux, o, ax);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] *= act == ACT_TANH ? 1.f - ax[t] * ax[t] : (ax[t] > 0.f ? 1.f : slope);
+    }
+    st8<OUT16>(dx, o, acc);
+  }
+}
+
 static unsigned ew_blocks(long long n) {
   long long b = ceil_div64(n, 256);
   const long long cap = 148LL * 16;
@@ -330,16 +433,55 @@ int ladder_instnorm_style_bwd(const float* dout, const float* y, const float* x,
   return check_launch("instnorm bwd apply");
 }
 
-int ladder_resize_bilinear_fwd(const float* x, float* y, int B, int H, int W, int C, int OH, int OW, cudaStream_t stream) {
+int ladder_resize_bilinear_fwd_ex(const void* x, int x_bf16, void* y, int y_bf16, int B, int H, int W, int C, int OH, int OW,
+                                  cudaStream_t stream) {
   LADDER_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, "resize_bilinear_fwd: bad arguments");
-  resize_fwd_kernel<<<ew_blocks((long long)B * OH * OW * C), 256, 0, stream>>>(x, y, B, H, W, C, OH, OW);
+  if (C % 8 == 0) {
+    const unsigned blocks = ew_blocks((long long)B * OH * OW * (C / 8));
+    if (x_bf16 && y_bf16) resize_fwd8_kernel<true, true><<<blocks, 256, 0, stream>>>(x, y, B, H, W, C, OH, OW);
+    else if (x_bf16) resize_fwd8_kernel<true, false><<<blocks, 256, 0, stream>>>(x, y, B, H, W, C, OH, OW);
+    else if (y_bf16) resize_fwd8_kernel<false, true><<<blocks, 256, 0, stream>>>(x, y, B, H, W, C, OH, OW);
+    else resize_fwd8_kernel<false, false><<<blocks, 256, 0, stream>>>(x, y, B, H, W, C, OH, OW);
+    return check_launch("resize_bilinear_fwd");
+  }
+  LADDER_REQUIRE(!x_bf16 && !y_bf16, "resize_bilinear_fwd: bf16 tensors need C %% 8 == 0 (got %d)", C);
+  resize_fwd_kernel<<<ew_blocks((long long)B * OH * OW * C), 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(y),
+                                                                                B, H, W, C, OH, OW);
   return check_launch("resize_bilinear_fwd");
 }
 
-int ladder_resize_bilinear_bwd(const float* dy, float* dx, int B, int H, int W, int C, int OH, int OW, cudaStream_t stream) {
+int ladder_resize_bilinear_fwd(const float* x, float* y, int B, int H, int W, int C, int OH, int OW, cudaStream_t stream) {
+  return ladder_resize_bilinear_fwd_ex(x, 0, y, 0, B, H, W, C, OH, OW, stream);
+}
+
+int ladder_resize_bilinear_bwd_ex(const void* dy, int dy_bf16, void* dx, int dx_bf16, const void* act_out, int act_out_bf16,
+                                  int act, int B, int H, int W, int C, int OH, int OW, cudaStream_t stream) {
   LADDER_REQUIRE(dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && OH > 0 && OW > 0, "resize_bilinear_bwd: bad arguments");
-  resize_bwd_kernel<<<ew_blocks((long long)B * H * W * C), 256, 0, stream>>>(dy, dx, B, H, W, C, OH, OW);
+  if (C % 8 == 0) {
+    const unsigned blocks = ew_blocks((long long)B * H * W * (C / 8));
+#define LADDER_RB(I, O, A) resize_bwd8_kernel<I, O, A><<<blocks, 256, 0, stream>>>(dy, dx, act_out, act, B, H, W, C, OH, OW)
+    const int key = (dy_bf16 ? 4 : 0) | (dx_bf16 ? 2 : 0) | (act_out_bf16 ? 1 : 0);
+    switch (key) {
+      case 0: LADDER_RB(false, false, false); break;
+      case 1: LADDER_RB(false, false, true); break;
+      case 2: LADDER_RB(false, true, false); break;
+      case 3: LADDER_RB(false, true, true); break;
+      case 4: LADDER_RB(true, false, false); break;
+      case 5: LADDER_RB(true, false, true); break;
+      case 6: LADDER_RB(true, true, false); break;
+      default: LADDER_RB(true, true, true); break;
+    }
+#undef LADDER_RB
+    return check_launch("resize_bilinear_bwd");
+  }
+  LADDER_REQUIRE(!dy_bf16 && !dx_bf16 && act_out == nullptr, "resize_bilinear_bwd: bf16 / fused act' need C %% 8 == 0 (got %d)", C);
+  resize_bwd_kernel<<<ew_blocks((long long)B * H * W * C), 256, 0, stream>>>(static_cast<const float*>(dy), static_cast<float*>(dx),
+                                                                              B, H, W, C, OH, OW);
   return check_launch("resize_bilinear_bwd");
+}
+
+int ladder_resize_bilinear_bwd(const float* dy, float* dx, int B, int H, int W, int C, int OH, int OW, cudaStream_t stream) {
+  return ladder_resize_bilinear_bwd_ex(dy, 0, dx, 0, nullptr, 0, 0, B, H, W, C, OH, OW, stream);
 }
 
 }  // extern "C"

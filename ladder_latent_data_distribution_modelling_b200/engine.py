@@ -364,16 +364,25 @@ class CelebAOuterVAE:
         self.conv0 = Conv(group, 'decoder/conv2d', G(B, 1, 1, H, 1, 1, H, 1, 'same'), None, device)
         self.sb1 = StyleBlock(group, 1, 0, G(B, 2, 2, H, 3, 3, H, 1, 'same'), B, H, device)
         self.sb2 = StyleBlock(group, 2, 1, G(B, 2, 2, H, 3, 3, H, 1, 'same'), B, H, device)
-        self.conv3 = Conv(group, 'decoder/conv2d_3', G(B, 8, 8, H, 3, 3, H, 1, 'same'), LEAKY, device)
+        bf = torch.bfloat16
+        g3, g5 = G(B, 8, 8, H, 3, 3, H, 1, 'same'), G(B, 32, 32, H // 2, 3, 3, H // 2, 1, 'same')
+        g7, g8 = G(B, 128, 128, H // 4, 3, 3, H // 4, 1, 'same'), G(B, 128, 128, H // 4, 1, 1, ch, 1, 'same')
+        # bf16-resident activations: conv outputs that only feed a resize / the next conv / an activation derivative
+        # are written in bf16 by the TMA-fed kernel; the resized maps (inputs of the big convs) exist only in bf16
+        o16 = lambda g: bf if ops.tma_supported(g, ops.FPROP) else torch.float32           # noqa: E731
+        self.conv3 = Conv(group, 'decoder/conv2d_3', g3, LEAKY, device, out_dtype=o16(g3))
         self.sb4 = StyleBlock(group, 4, 2, G(B, 16, 16, H, 3, 3, H // 2, 1, 'same'), B, H, device)
-        self.conv5 = Conv(group, 'decoder/conv2d_5', G(B, 32, 32, H // 2, 3, 3, H // 2, 1, 'same'), LEAKY, device)
+        self.conv5 = Conv(group, 'decoder/conv2d_5', g5, LEAKY, device, out_dtype=o16(g5))
         self.sb6 = StyleBlock(group, 6, 3, G(B, 64, 64, H // 2, 3, 3, H // 4, 1, 'same'), B, H, device)
-        self.conv7 = Conv(group, 'decoder/conv2d_7', G(B, 128, 128, H // 4, 3, 3, H // 4, 1, 'same'), LEAKY, device)
-        self.conv8 = Conv(group, 'decoder/conv2d_8', G(B, 128, 128, H // 4, 1, 1, ch, 1, 'same'), None, device)
+        self.conv7 = Conv(group, 'decoder/conv2d_7', g7, LEAKY, device,
+                          out_dtype=bf if ops.tma_supported(g7, ops.FPROP) and ops.reads_bf16(g8) else torch.float32)
+        self.conv8 = Conv(group, 'decoder/conv2d_8', g8, None, device)
         self.decoded = self.conv8.y
-        E = lambda *shape: torch.empty(*shape, device=device)           # noqa: E731
-        self.r0, self.r2, self.r3 = E(B, 2, 2, H), E(B, 8, 8, H), E(B, 16, 16, H)
-        self.r4, self.r5, self.r6 = E(B, 32, 32, H // 2), E(B, 64, 64, H // 2), E(B, 128, 128, H // 4)
+        E = lambda conv, *shape: torch.empty(*shape, device=device,                        # noqa: E731
+                                             dtype=bf if ops.reads_bf16(conv.geom) else torch.float32)
+        self.r0, self.r2, self.r3 = E(self.sb1.conv, B, 2, 2, H), E(self.conv3, B, 8, 8, H), E(self.sb4.conv, B, 16, 16, H)
+        self.r4, self.r5 = E(self.conv5, B, 32, 32, H // 2), E(self.sb6.conv, B, 64, 64, H // 2)
+        self.r6 = E(self.conv7, B, 128, 128, H // 4)
 
     def encode(self, x, eps_z, stats_z):
         B = self.B
@@ -409,33 +418,38 @@ class CelebAOuterVAE:
         g = self.buf.get
         dl_out = self.mapping[-1].y
         d_dl = g('d_dl', B, 1, 1, H)                      # pre-activation gradient of the last mapping layer
-        d7 = g('d7', *self.conv7.y.shape)
-        self.conv8.backward(dpre_last, dx=d7, producer=(self.conv7.y, LEAKY), wgrad=wgrad)
-        dr6 = g('dr6', *self.r6.shape)
-        self.conv7.backward(d7, dx=dr6, wgrad=wgrad)
+        bf = torch.bfloat16
+        # gradient dtypes: bf16 wherever the producing kernel can write it and the consumer reads it (TMA GEMMs, resize)
+        gdt = lambda conv: bf if conv.tma[1] else torch.float32                              # noqa: E731
+        c7 = self.conv7
+        d7 = g('d7', *c7.y.shape, dtype=bf if ops.dgrad_writes_bf16(self.conv8.geom) and (c7.tma[1] or c7.tma[2])
+               else torch.float32)
+        self.conv8.backward(dpre_last, dx=d7, producer=(c7.y, LEAKY), wgrad=wgrad)
+        dr6 = g('dr6', *self.r6.shape, dtype=gdt(c7))
+        c7.backward(d7, dx=dr6, wgrad=wgrad)
         da6 = g('da6', *self.sb6.y.shape)
         ops.resize_bilinear_bwd(dr6, da6)
-        dr5 = g('dr5', *self.r5.shape)
+        dr5 = g('dr5', *self.r5.shape, dtype=gdt(self.sb6.conv))
         self.sb6.backward(da6, dr5, d_dl, dl_out, first=True)
-        da5 = g('da5', *self.conv5.y.shape)
-        ops.resize_bilinear_bwd(dr5, da5)
-        ops.act_bwd(da5, self.conv5.y, LEAKY)
-        dr4 = g('dr4', *self.r4.shape)
-        self.conv5.backward(da5, dx=dr4, wgrad=wgrad)
+        c5 = self.conv5
+        da5 = g('da5', *c5.y.shape, dtype=bf if (c5.tma[1] or c5.tma[2]) else torch.float32)
+        ops.resize_bilinear_bwd(dr5, da5, act_out=c5.y, act=LEAKY)       # resize^T fused with conv5's leaky derivative
+        dr4 = g('dr4', *self.r4.shape, dtype=gdt(c5))
+        c5.backward(da5, dx=dr4, wgrad=wgrad)
         da4 = g('da4', *self.sb4.y.shape)
         ops.resize_bilinear_bwd(dr4, da4)
-        dr3 = g('dr3', *self.r3.shape)
+        dr3 = g('dr3', *self.r3.shape, dtype=gdt(self.sb4.conv))
         self.sb4.backward(da4, dr3, d_dl, dl_out, first=False)
-        da3 = g('da3', *self.conv3.y.shape)
-        ops.resize_bilinear_bwd(dr3, da3)
-        ops.act_bwd(da3, self.conv3.y, LEAKY)
-        dr2 = g('dr2', *self.r2.shape)
-        self.conv3.backward(da3, dx=dr2, wgrad=wgrad)
+        c3 = self.conv3
+        da3 = g('da3', *c3.y.shape, dtype=bf if (c3.tma[1] or c3.tma[2]) else torch.float32)
+        ops.resize_bilinear_bwd(dr3, da3, act_out=c3.y, act=LEAKY)
+        dr2 = g('dr2', *self.r2.shape, dtype=gdt(c3))
+        c3.backward(da3, dx=dr2, wgrad=wgrad)
         da2 = g('da2', *self.sb2.y.shape)
         ops.resize_bilinear_bwd(dr2, da2)
         da1 = g('da1', *self.sb1.y.shape)
         self.sb2.backward(da2, da1, d_dl, dl_out, first=False)
-        dr0 = g('dr0', *self.r0.shape)
+        dr0 = g('dr0', *self.r0.shape, dtype=gdt(self.sb1.conv))
         self.sb1.backward(da1, dr0, d_dl, dl_out, first=False)
         dh0 = g('dh0', B, 1, 1, H)
         ops.resize_bilinear_bwd(dr0, dh0)

@@ -67,6 +67,8 @@ SIGNATURES = {
     'ladder_instnorm_style_bwd': (C.c_int, [ptr] * 7 + [C.c_int, C.c_int, C.c_int, C.c_int, stream_t]),
     'ladder_resize_bilinear_fwd': (C.c_int, [ptr, ptr] + [C.c_int] * 6 + [stream_t]),
     'ladder_resize_bilinear_bwd': (C.c_int, [ptr, ptr] + [C.c_int] * 6 + [stream_t]),
+    'ladder_resize_bilinear_fwd_ex': (C.c_int, [ptr, C.c_int, ptr, C.c_int] + [C.c_int] * 6 + [stream_t]),
+    'ladder_resize_bilinear_bwd_ex': (C.c_int, [ptr, C.c_int, ptr, C.c_int, ptr, C.c_int, C.c_int] + [C.c_int] * 6 + [stream_t]),
     # ELBO pieces
     'ladder_gauss_head_fwd': (C.c_int, [ptr, ptr, ptr, ptr, C.c_longlong, C.c_float, ptr, stream_t]),
     'ladder_gauss_head_bwd': (C.c_int, [ptr] * 8 + [C.c_longlong, C.c_float, C.c_float, C.c_float, stream_t]),

@@ -621,14 +621,17 @@ def instnorm_style_bwd(dout, y, x, stats, style, dstyle, dx, act='leaky_relu'):
 
 
 def resize_bilinear_fwd(x, y):
+    """x, y: fp32 or bf16 NHWC."""
     B, H, W, Cc = x.shape
-    _lib.check(_L().ladder_resize_bilinear_fwd(_p(_f32(x)), _p(_f32(y)), B, H, W, Cc, y.shape[1], y.shape[2], _stream()),
-               'resize_bilinear_fwd')
+    _lib.check(_L().ladder_resize_bilinear_fwd_ex(_p(_act_t(x)), _is16(x), _p(_act_t(y)), _is16(y), B, H, W, Cc, y.shape[1],
+                                                  y.shape[2], _stream()), 'resize_bilinear_fwd')
     return y
 
 
-def resize_bilinear_bwd(dy, dx):
+def resize_bilinear_bwd(dy, dx, act_out=None, act=None):
+    """dx = resize^T(dy) [* act'(act_out)]; tensors fp32 or bf16."""
     B, H, W, Cc = dx.shape
-    _lib.check(_L().ladder_resize_bilinear_bwd(_p(_f32(dy)), _p(_f32(dx)), B, H, W, Cc, dy.shape[1], dy.shape[2],
-                                               _stream()), 'resize_bilinear_bwd')
+    _lib.check(_L().ladder_resize_bilinear_bwd_ex(_p(_act_t(dy)), _is16(dy), _p(_act_t(dx)), _is16(dx), _p(act_out),
+                                                  _is16(act_out), ACT[act], B, H, W, Cc, dy.shape[1], dy.shape[2], _stream()),
+               'resize_bilinear_bwd')
     return dx

@@ -116,15 +116,19 @@ def test_tc_repeatability_stress(ops):
 
 
 # ---------------------------------------------------------------------------- TMA-fed kernels (csrc/conv_tma.cu)
-# (B, H, W, Cin, k, Cout, padding, act): stride-1 geometries whose three GEMMs all run on the TMA path
+# (B, H, W, Cin, k, Cout, stride, padding, act): geometries whose GEMMs run on the TMA path (strided: fprop + wgrad)
 TMA_CASES = [
-    (8, 16, 16, 64, 3, 256, 'same', 'leaky_relu'),     # fashion decoder conv2d_3: box 16 x 8 x 1
-    (2, 4, 128, 64, 3, 64, 'same', None),              # W = 128: one image row per tile
-    (64, 2, 2, 128, 3, 128, 'same', 'leaky_relu'),     # CelebA 2x2 maps: box 2 x 2 x 32 spans images
-    (130, 2, 2, 64, 3, 64, 'same', None),              # ragged batch: last box hangs over B (zero fill + row mask)
-    (32, 4, 4, 128, 3, 128, 'valid', 'leaky_relu'),    # VALID 3x3: 4x4 -> 2x2
-    (4, 8, 8, 64, 5, 192, 'same', 'relu'),             # 5x5 taps, Cout = 192 (wgrad N tile with an OOB channel block)
-    (300, 1, 1, 512, 1, 512, 'valid', 'leaky_relu'),   # dense
+    (8, 16, 16, 64, 3, 256, 1, 'same', 'leaky_relu'),     # fashion decoder conv2d_3: box 16 x 8 x 1
+    (2, 4, 128, 64, 3, 64, 1, 'same', None),              # W = 128: one image row per tile
+    (64, 2, 2, 128, 3, 128, 1, 'same', 'leaky_relu'),     # CelebA 2x2 maps: box 2 x 2 x 32 spans images
+    (130, 2, 2, 64, 3, 64, 1, 'same', None),              # ragged batch: last box hangs over B (zero fill + row mask)
+    (32, 4, 4, 128, 3, 128, 1, 'valid', 'leaky_relu'),    # VALID 3x3: 4x4 -> 2x2
+    (4, 8, 8, 64, 5, 192, 1, 'same', 'relu'),             # 5x5 taps, Cout = 192 (wgrad N tile with an OOB channel block)
+    (300, 1, 1, 512, 1, 512, 1, 'valid', 'leaky_relu'),   # dense
+    (8, 16, 16, 64, 3, 128, 2, 'same', 'leaky_relu'),     # stride 2, even input: TF SAME pads (0, 1); element-stride box
+    (16, 8, 8, 128, 3, 64, 2, 'same', None),              # stride 2 on 8x8 -> 4x4: box 4 x 4 x 8
+    (8, 15, 15, 64, 3, 64, 2, 'valid', None),             # stride 2 VALID, odd input -> 7x7?  (not box-divisible: skipped)
+    (2, 32, 32, 64, 5, 64, 2, 'same', 'relu'),            # stride 2, 5x5 taps, pads (1, 2)
 ]
 
 
@@ -133,9 +137,12 @@ TMA_CASES = [
 def test_tma_conv_fprop_dgrad_wgrad(ops, case, io16):
     """TMA-fed tcgen05 kernels vs the float64 oracle evaluated on the SAME bf16-rounded operands when the
     tensors are bf16-resident (io16), so the only difference left is fp32 accumulation order + output rounding."""
-    B, H, W, Cin, k, Cout, padding, act = case
-    g = ops.ConvGeom(B, H, W, Cin, k, k, Cout, 1, padding)
-    assert all(ops.tma_supported(g, m) for m in (ops.FPROP, ops.DGRAD, ops.WGRAD)), 'case must exercise the TMA path'
+    B, H, W, Cin, k, Cout, stride, padding, act = case
+    g = ops.ConvGeom(B, H, W, Cin, k, k, Cout, stride, padding)
+    modes = (ops.FPROP, ops.DGRAD, ops.WGRAD) if stride == 1 else (ops.FPROP, ops.WGRAD)
+    if not all(ops.tma_supported(g, m) for m in modes):
+        assert stride > 1 and g.OW == 7, 'case must exercise the TMA path'
+        pytest.skip('pixel grid does not cut into TMA boxes: stays on the register-gather kernel')
     rng = np.random.default_rng(abs(hash(case)) % 2**32)
     bf = lambda a: torch.tensor(a, dtype=torch.float32).to(torch.bfloat16).to(torch.float32).numpy().astype(np.float64)  # noqa: E731
     x = rng.normal(size=(B, H, W, Cin)); w = rng.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)
@@ -143,7 +150,7 @@ def test_tma_conv_fprop_dgrad_wgrad(ops, case, io16):
     if io16:
         x = bf(x)
     X, Wv, Bv = T.Var(x), T.Var(w), T.Var(b)
-    pre = T.conv2d(X, Wv, Bv, stride=1, padding=padding)
+    pre = T.conv2d(X, Wv, Bv, stride=stride, padding=padding)
     actf = {None: lambda v: v, 'leaky_relu': T.leaky_relu, 'relu': T.relu}[act]
     y = actf(pre)
     up = rng.normal(size=y.shape)
@@ -156,19 +163,20 @@ def test_tma_conv_fprop_dgrad_wgrad(ops, case, io16):
     dy = bf(pre.g) if io16 else pre.g
     # gradients of the linear maps for THIS dy (the oracle's are linear in dy, so recompute with the rounded one)
     X2, W2 = T.Var(x), T.Var(w)
-    T.backward(T.conv2d(X2, W2, None, stride=1, padding=padding), seed=dy)
+    T.backward(T.conv2d(X2, W2, None, stride=stride, padding=padding), seed=dy)
     dyd = dev(dy).to(dt)
     dwd = torch.full_like(wd, 7.0); dbd = torch.full_like(bd, 7.0)
     ops.conv2d_wgrad(xd, dyd, dwd, dbd, g)
     close(dwd, W2.g)
     close(dbd, dy.sum(axis=(0, 1, 2)), 2e-3 if io16 else 1e-4)
-    dxd = torch.full((B, H, W, Cin), 3.0, device='cuda', dtype=dt)
+    dxd = torch.full((B, H, W, Cin), 3.0, device='cuda', dtype=dt if stride == 1 else torch.float32)
     ops.conv2d_dgrad(dyd, wd, dxd, g)
     close(dxd.float(), X2.g)
-    prod = dev(rng.normal(size=x.shape)).to(dt); base = dev(rng.normal(size=x.shape))
-    out = base.clone()
-    ops.conv2d_dgrad(dyd, wd, out, g, act_out=prod, act='leaky_relu', accumulate=True)
-    close(out, base.cpu().numpy() + X2.g * np.where(prod.float().cpu().numpy() > 0, 1.0, 0.2))
+    if stride == 1:
+        prod = dev(rng.normal(size=x.shape)).to(dt); base = dev(rng.normal(size=x.shape))
+        out = base.clone()
+        ops.conv2d_dgrad(dyd, wd, out, g, act_out=prod, act='leaky_relu', accumulate=True)
+        close(out, base.cpu().numpy() + X2.g * np.where(prod.float().cpu().numpy() > 0, 1.0, 0.2))
 
 
 @pytest.mark.parametrize('io16', [False, True])
@@ -263,3 +271,36 @@ def test_thin_output_conv_backward(ops, case, io16):
     ops.conv2d_wgrad(xd, dyd, dwd, dbd, g)
     close(dwd, Wv.g, TOL if k > 1 else 1e-4)
     close(dbd, dy.sum(axis=(0, 1, 2)), 1e-4)
+
+
+def test_resize_dtype_variants_and_fused_activation_grad(ops):
+    """bf16 / mixed-dtype bilinear resize (forward, transpose, transpose fused with leaky') against the fp32 kernels,
+    which tests/test_gpu_celeba.py pins to the oracle."""
+    gen = torch.Generator(device='cuda'); gen.manual_seed(3)
+    B, H, C, OH = 3, 8, 64, 16
+    x = torch.randn(B, H, H, C, device='cuda', generator=gen)
+    y32 = torch.empty(B, OH, OH, C, device='cuda')
+    ops.resize_bilinear_fwd(x, y32)
+    for xin in (x, x.bfloat16()):
+        for ydt in (torch.float32, torch.bfloat16):
+            y = torch.empty(B, OH, OH, C, device='cuda', dtype=ydt)
+            ops.resize_bilinear_fwd(xin, y)
+            ref = y32 if xin.dtype == torch.float32 else ops.resize_bilinear_fwd(xin.float(), torch.empty_like(y32))
+            assert (y.float() - ref).abs().max().item() <= (2e-2 if ydt == torch.bfloat16 else 1e-6) * ref.abs().max().item()
+    dy = torch.randn(B, OH, OH, C, device='cuda', generator=gen)
+    aout = torch.randn(B, H, H, C, device='cuda', generator=gen)
+    dx32 = torch.empty_like(x)
+    ops.resize_bilinear_bwd(dy, dx32)
+    fused_ref = dx32 * torch.where(aout > 0, 1.0, 0.2)
+    for dyin in (dy, dy.bfloat16()):
+        ref = dx32 if dyin.dtype == torch.float32 else ops.resize_bilinear_bwd(dyin.float(), torch.empty_like(dx32))
+        for dxdt in (torch.float32, torch.bfloat16):
+            tol = (2e-2 if dxdt == torch.bfloat16 else 1e-6) * ref.abs().max().item()
+            dx = torch.empty(B, H, H, C, device='cuda', dtype=dxdt)
+            ops.resize_bilinear_bwd(dyin, dx)
+            assert (dx.float() - ref).abs().max().item() <= tol
+            for a in (aout, aout.bfloat16()):
+                ops.resize_bilinear_bwd(dyin, dx, act_out=a, act='leaky_relu')
+                want = ref * torch.where(a.float() > 0, 1.0, 0.2)
+                assert (dx.float() - want).abs().max().item() <= tol
+    assert (fused_ref - dx32 * torch.where(aout > 0, 1.0, 0.2)).abs().max().item() == 0.0
