@@ -149,11 +149,22 @@ int ladder_conv2d_wgrad_tc(const float* x, const float* dy, float* dw, int B, in
 int ladder_conv2d_tma_supported(int mode, int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int OH,
                                 int OW);
 size_t ladder_conv2d_tma_workspace_bytes(int Cin, int KH, int KW, int Cout);
-int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bias /*nullable*/, void* y, int y_bf16,
+/* Pre-packed weights: passing w == NULL to fprop_tma / dgrad_tma makes them read `workspace` as an already packed
+ * image (ladder_conv2d_tma_pack with bn = ladder_conv2d_tma_bn of the same geometry, or one
+ * ladder_pack_weights_multi launch per optimiser step for a whole parameter group). */
+int ladder_conv2d_tma_bn(int mode, int B, int H, int W, int Cin, int Cout, int OH, int OW);
+size_t ladder_conv2d_tma_pack_bytes(int mode, int KH, int KW, int Cin, int Cout, int bn);
+int ladder_conv2d_tma_pack(const float* w, void* image, size_t image_bytes, int mode, int KH, int KW, int Cin, int Cout,
+                           int bn, cudaStream_t stream);
+/* desc_dev: n records {int64 w_off (floats from params), int64 img_off (bf16 from images), int64 first (prefix sum of
+ * image elements), int32 mode, taps, Cin, Cout, bn, pad}; total = sum of image elements */
+int ladder_pack_weights_multi(const float* params, void* images, const void* desc_dev, int n, long long total,
+                              cudaStream_t stream);
+int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w /*NULL: prepacked*/, const float* bias /*nullable*/, void* y, int y_bf16,
                             int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l,
                             int OH, int OW, int act, int out_d2s, void* workspace, size_t workspace_bytes,
                             cudaStream_t stream);
-int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w, const void* act_out /*nullable*/, int act_out_bf16,
+int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w /*NULL: prepacked*/, const void* act_out /*nullable*/, int act_out_bf16,
                             void* dx, int dx_bf16, int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride,
                             int pad_t, int pad_l, int OH, int OW, int act, int accumulate, int out_s2d,
                             void* workspace, size_t workspace_bytes, cudaStream_t stream);

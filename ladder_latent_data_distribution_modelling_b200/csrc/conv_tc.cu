@@ -611,8 +611,8 @@ using namespace ladder;
 using namespace ladder::tc;
 
 namespace ladder { namespace tc {
-size_t pack_bytes(int N, int K) {
-  const int bn = pick_bn(N);
+size_t pack_bytes(int N, int K, int bn) {
+  if (bn <= 0) bn = pick_bn(N);
   return (size_t)ceil_div(N, bn) * ceil_div(K, BK) * bn * BK * 2;
 }
 } }
@@ -623,24 +623,77 @@ static size_t pack_dy_bytes(long long P, int Cout) {
 }
 
 namespace ladder { namespace tc {
-int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, cudaStream_t st) {
+int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, cudaStream_t st, int bn) {
   const int N = mode == FPROP ? Cout : Cin, K = taps * (mode == FPROP ? Cin : Cout);
-  const size_t need = pack_bytes(N, K);
+  if (bn <= 0) bn = pick_bn(N);
+  const size_t need = pack_bytes(N, K, bn);
   if (ws == nullptr || ws_bytes < need) return fail(LADDER_ERR_WORKSPACE, "conv2d_tc: workspace %zu < %zu bytes", ws_bytes, need);
   if ((uintptr_t)ws & 127) return fail(LADDER_ERR_ARG, "conv2d_tc: workspace must be 128-byte aligned");
-  const int bn = pick_bn(N), num_kb = ceil_div(K, BK), n_tiles = ceil_div(N, bn);
+  const int num_kb = ceil_div(K, BK), n_tiles = ceil_div(N, bn);
   long long blocks = ceil_div64((long long)n_tiles * num_kb * bn * BK, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(ws), mode, taps, Cin, Cout, bn, num_kb, n_tiles);
   return check_launch("conv2d_tc weight pack");
 }
+
+// Every weight image of one optimiser group in ONE launch (run right after the group's Adam step, so the forward /
+// backward GEMMs never repack): desc[i] = {w offset (floats), image offset (bf16), mode, taps, Cin, Cout, bn, first
+// element of the flattened work list}; element e of entry i is the same (tile, row, k) the single-layer kernel writes.
+struct PackDesc { long long w_off, img_off, first; int mode, taps, Cin, Cout, bn, pad; };
+__global__ void pack_multi_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ images,
+                                  const PackDesc* __restrict__ desc, int n, long long total) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {                       // last entry with first <= e
+      const int mid = (lo + hi + 1) >> 1;
+      if (desc[mid].first <= e) lo = mid; else hi = mid - 1;
+    }
+    const PackDesc d = desc[lo];
+    const long long i = e - d.first;
+    const int N = d.mode == FPROP ? d.Cout : d.Cin, Cg = d.mode == FPROP ? d.Cin : d.Cout, K = d.taps * Cg;
+    const int num_kb = ceil_div(K, BK);
+    const int kk = (int)(i % BK);
+    long long r = i / BK;
+    const int rr = (int)(r % d.bn); r /= d.bn;
+    const int kb = (int)(r % num_kb);
+    const int nt = (int)(r / num_kb);
+    const int nn = nt * d.bn + rr;
+    int k = kb * BK + kk;
+    if (Cg % BK == 0) {
+      const int tap = kb % d.taps, c = (kb / d.taps) * BK + kk;
+      k = tap * Cg + c;
+    }
+    float v = 0.f;
+    if (nn < N && k < K) {
+      const float* w = params + d.w_off;
+      if (d.mode == FPROP) v = w[(long long)k * d.Cout + nn];
+      else {
+        const int tap = k / d.Cout, co = k % d.Cout;
+        v = w[((long long)tap * d.Cin + nn) * d.Cout + co];
+      }
+    }
+    const long long tile = (long long)nt * num_kb + kb;
+    images[d.img_off + tile * d.bn * BK + rr * BK + ((((kk >> 3) ^ (rr & 7))) << 3) + (kk & 7)] = __float2bfloat16_rn(v);
+  }
+}
 } }
 
 extern "C" {
 
+/* desc_dev: n records of 6 x int64 {w_off, img_off, first, mode | taps << 32, Cin | Cout << 32, bn} -- see PackDesc */
+int ladder_pack_weights_multi(const float* params, void* images, const void* desc_dev, int n, long long total,
+                              cudaStream_t stream) {
+  LADDER_REQUIRE(params && images && desc_dev && n > 0 && total > 0, "pack_weights_multi: bad arguments");
+  long long blocks = ceil_div64(total, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_multi_kernel<<<(unsigned)blocks, 256, 0, stream>>>(params, static_cast<__nv_bfloat16*>(images),
+                                                          static_cast<const PackDesc*>(desc_dev), n, total);
+  return check_launch("pack_weights_multi");
+}
+
 size_t ladder_conv2d_tc_workspace_bytes(int B, int H, int W, int Cin, int KH, int KW, int Cout) {
   const int OHmax = H, OWmax = W;                       // OH*OW <= H*W for every geometry the library accepts
-  const size_t f = pack_bytes(Cout, KH * KW * Cin), d = pack_bytes(Cin, KH * KW * Cout);
+  const size_t f = pack_bytes(Cout, KH * KW * Cin, 0), d = pack_bytes(Cin, KH * KW * Cout, 0);
   const size_t g = Cin % BK == 0 ? pack_dy_bytes((long long)B * OHmax * OWmax, Cout) : 0;
   size_t m = f > d ? f : d;
   if (g > m) m = g;
@@ -658,7 +711,7 @@ int ladder_conv2d_fprop_tc(const float* x, const float* w, const float* bias, fl
   LADDER_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
                  "conv2d_fprop_tc: bad arguments");
   LADDER_REQUIRE((long long)B * OH * OW < (1LL << 31) && (long long)B * H * W < (1LL << 31), "conv2d_fprop_tc: too many pixels");
-  int rc = pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, stream);
+  int rc = pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, stream, 0);
   if (rc) return rc;
   TcArgs a{x, nullptr, static_cast<const __nv_bfloat16*>(workspace), bias, nullptr, y, B, H, W, Cin, KH, KW, Cout, stride,
            pad_t, pad_l, OH, OW, act, 0, 0, round_up(KH * KW * Cin, BK), 0, 0, 0, 0, out_d2s};
@@ -673,7 +726,7 @@ int ladder_conv2d_dgrad_tc(const float* dy, const float* w, const float* act_out
   LADDER_REQUIRE(dy && w && dx && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && OH > 0 && OW > 0,
                  "conv2d_dgrad_tc: bad arguments");
   LADDER_REQUIRE((long long)B * OH * OW < (1LL << 31) && (long long)B * H * W < (1LL << 31), "conv2d_dgrad_tc: too many pixels");
-  int rc = pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, stream);
+  int rc = pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, stream, 0);
   if (rc) return rc;
   TcArgs a{dy, nullptr, static_cast<const __nv_bfloat16*>(workspace), nullptr, act_out, dx, B, H, W, Cin, KH, KW, Cout, stride,
            pad_t, pad_l, OH, OW, act, accumulate, 0, round_up(KH * KW * Cout, BK), 0, 0, 0, 0, out_s2d};

@@ -428,7 +428,8 @@ static bool pixel_box(int GW, int GH, int B, int px, int& bw, int& bh, int& bb) 
   if (rem % GH) return false;
   bh = GH;
   bb = rem / GH;
-  return bb <= 256 && B >= bb;
+  (void)B;                 // a box taller than the batch is legal: rows past B are zero filled and masked
+  return bb <= 256;
 }
 
 // bf16 NHWC tensor [B, SH, SW, C] as a 4-D tensor map {C, SW, SH, B}, SWIZZLE_128B, zero fill outside
@@ -520,6 +521,17 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ g, long lon
 using namespace ladder;
 using namespace ladder::tma;
 
+// N tile: as wide as the GEMM allows, narrowed while the launch would fill less than half of the SMs (small-batch
+// dense layers: M = batch rows give a single M tile, so the CTA count comes from N tiles alone)
+static int choose_bn(int mode, long long Mg, int Ng) {
+  int bn = tc::pick_bn(Ng);
+  const int floor_bn = mode == WGRAD ? 64 : 32;
+  if (mode == WGRAD && bn < 64) bn = 64;
+  const long long m_tiles = ceil_div64(Mg, BM);
+  while (bn > floor_bn && m_tiles * ceil_div(Ng, bn) * 2 <= num_sms()) bn >>= 1;
+  return bn;
+}
+
 static bool geometry_ok(int B, int GH, int GW, int px) {
   int bw, bh, bb;
   return pixel_box(GW, GH, B, px, bw, bh, bb);
@@ -544,8 +556,32 @@ int ladder_conv2d_tma_supported(int mode, int B, int H, int W, int Cin, int KH, 
 }
 
 size_t ladder_conv2d_tma_workspace_bytes(int Cin, int KH, int KW, int Cout) {
-  const size_t f = tc::pack_bytes(Cout, KH * KW * Cin), d = tc::pack_bytes(Cin, KH * KW * Cout);
-  return (f > d ? f : d) + 256;
+  size_t m = 0;
+  for (int bn = 32; bn <= 256; bn <<= 1) {        // any N tile the launcher may pick
+    const size_t f = tc::pack_bytes(Cout, KH * KW * Cin, bn), d = tc::pack_bytes(Cin, KH * KW * Cout, bn);
+    if (f > m) m = f;
+    if (d > m) m = d;
+  }
+  return m + 256;
+}
+
+/* N tile width the TMA launcher uses for GEMM `mode` of this geometry (the packed weight image depends on it) */
+int ladder_conv2d_tma_bn(int mode, int B, int H, int W, int Cin, int Cout, int OH, int OW) {
+  switch (mode) {
+    case 0: return choose_bn(FPROP, (long long)B * OH * OW, Cout);
+    case 1: return choose_bn(DGRAD, (long long)B * H * W, Cin);
+    default: return 0;
+  }
+}
+
+/* bf16 tile image of one layer's weights for mode 0 (fprop) / 1 (dgrad) with N tile bn, as the TMA kernels stage it */
+size_t ladder_conv2d_tma_pack_bytes(int mode, int KH, int KW, int Cin, int Cout, int bn) {
+  return mode == 0 ? tc::pack_bytes(Cout, KH * KW * Cin, bn) : tc::pack_bytes(Cin, KH * KW * Cout, bn);
+}
+int ladder_conv2d_tma_pack(const float* w, void* image, size_t image_bytes, int mode, int KH, int KW, int Cin, int Cout, int bn,
+                           cudaStream_t stream) {
+  LADDER_REQUIRE(w && image && (mode == 0 || mode == 1) && bn >= 32, "conv2d_tma_pack: bad arguments");
+  return tc::pack(w, image, image_bytes, mode, KH * KW, Cin, Cout, stream, bn);
 }
 
 int ladder_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t stream) {
@@ -583,13 +619,17 @@ int ladder_colsum_bf16(const void* g, long long rows, int cols, float* out, cuda
 int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bias, void* y, int y_bf16, int B, int H, int W,
                             int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
                             int out_d2s, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  LADDER_REQUIRE(x_bf16 && w && y && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, "conv2d_fprop_tma: bad arguments");
+  LADDER_REQUIRE(x_bf16 && y && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, "conv2d_fprop_tma: bad arguments");
   LADDER_REQUIRE(ladder_conv2d_tma_supported(0, B, H, W, Cin, KH, KW, Cout, stride, OH, OW),
                  "conv2d_fprop_tma: unsupported geometry (see ladder_conv2d_tma_supported)");
   LADDER_REQUIRE(out_d2s == 0 || (out_d2s > 0 && Cout % (out_d2s * out_d2s) == 0),
                  "conv2d_fprop_tma: depth_to_space(%d) output needs Cout %% r^2 == 0", out_d2s);
   LADDER_REQUIRE(((uintptr_t)x_bf16 & 15) == 0, "conv2d_fprop_tma: x must be 16-byte aligned");
-  int rc = tc::pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, stream);
+  const int bn = choose_bn(FPROP, (long long)B * OH * OW, Cout);
+  int rc = LADDER_OK;
+  if (w != nullptr) rc = tc::pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, stream, bn);
+  else if (workspace == nullptr || workspace_bytes < tc::pack_bytes(Cout, KH * KW * Cin, bn))
+    rc = fail(LADDER_ERR_WORKSPACE, "conv2d_fprop_tma: packed weight image too small");
   if (rc) return rc;
   int bw, bh, bb;
   pixel_box(OW, OH, B, BM, bw, bh, bb);
@@ -604,20 +644,24 @@ int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bia
   a.GW = OW; a.GH = OH; a.B = B; a.C = Cin; a.KH = KH; a.KW = KW;
   a.off_y = -pad_t; a.off_x = -pad_l; a.sign = 1;
   a.Ng = Cout; a.act = act; a.nkb = KH * KW * (Cin / BK); a.splits = 1; a.perm_r = out_d2s;
-  return launch<FPROP>(mA, mA, a, (long long)B * OH * OW, tc::pick_bn(Cout), stream);
+  return launch<FPROP>(mA, mA, a, (long long)B * OH * OW, bn, stream);
 }
 
 int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w, const void* act_out, int act_out_bf16, void* dx, int dx_bf16,
                             int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH,
                             int OW, int act, int accumulate, int out_s2d, void* workspace, size_t workspace_bytes,
                             cudaStream_t stream) {
-  LADDER_REQUIRE(dy_bf16 && w && dx && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, "conv2d_dgrad_tma: bad arguments");
+  LADDER_REQUIRE(dy_bf16 && dx && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, "conv2d_dgrad_tma: bad arguments");
   LADDER_REQUIRE(ladder_conv2d_tma_supported(1, B, H, W, Cin, KH, KW, Cout, stride, OH, OW),
                  "conv2d_dgrad_tma: unsupported geometry (see ladder_conv2d_tma_supported)");
   LADDER_REQUIRE(out_s2d == 0 || (out_s2d > 0 && H % out_s2d == 0 && W % out_s2d == 0),
                  "conv2d_dgrad_tma: space_to_depth(%d) output needs H, W divisible by r", out_s2d);
   LADDER_REQUIRE(((uintptr_t)dy_bf16 & 15) == 0, "conv2d_dgrad_tma: dy must be 16-byte aligned");
-  int rc = tc::pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, stream);
+  const int bn = choose_bn(DGRAD, (long long)B * H * W, Cin);
+  int rc = LADDER_OK;
+  if (w != nullptr) rc = tc::pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, stream, bn);
+  else if (workspace == nullptr || workspace_bytes < tc::pack_bytes(Cin, KH * KW * Cout, bn))
+    rc = fail(LADDER_ERR_WORKSPACE, "conv2d_dgrad_tma: packed weight image too small");
   if (rc) return rc;
   int bw, bh, bb;
   pixel_box(W, H, B, BM, bw, bh, bb);
@@ -632,7 +676,7 @@ int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w, const void* act
   a.GW = W; a.GH = H; a.B = B; a.C = Cout; a.KH = KH; a.KW = KW;
   a.off_y = pad_t; a.off_x = pad_l; a.sign = -1;       // dx(y, x) += dy(y + pad_t - kh, x + pad_l - kw) . w(kh, kw)
   a.Ng = Cin; a.act = act; a.accumulate = accumulate; a.nkb = KH * KW * (Cout / BK); a.splits = 1; a.perm_r = out_s2d;
-  return launch<DGRAD>(mA, mA, a, (long long)B * H * W, tc::pick_bn(Cin), stream);
+  return launch<DGRAD>(mA, mA, a, (long long)B * H * W, bn, stream);
 }
 
 /* dw (fp32, HWIO) is overwritten; the bias gradient is ladder_colsum_bf16(dy). */
@@ -652,8 +696,7 @@ int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, 
   if (rc) return rc;
   rc = make_map(&mB, dy_bf16, B, OH, OW, Cout, bw, bh, bb);
   if (rc) return rc;
-  int bn = tc::pick_bn(Cout);
-  if (bn < 64) bn = 64;
+  const int bn = choose_bn(WGRAD, patch, Cout);
   // pixel boxes of 64: the last one may hang over the batch axis (zero filled on both operands)
   const long long box_px = (long long)bw * bh * bb;            // == 64
   const long long total_kb = bb > 1 ? ceil_div64(B, bb) : (long long)B * OH * OW / box_px;

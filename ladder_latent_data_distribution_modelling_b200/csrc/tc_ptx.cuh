@@ -104,9 +104,9 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // host helpers defined in conv_tc.cu, shared with conv_tma.cu
 int pick_bn(int Ng);
 int round_up(int x, int m);
-size_t pack_bytes(int N, int K);
+size_t pack_bytes(int N, int K, int bn);   // bn <= 0: pick_bn(N)
 // fp32 HWIO weights -> bf16 SWIZZLE_128B tile images [n_tile][kb] (mode 0: fprop, 1: dgrad), one launch
-int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, cudaStream_t st);
+int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, cudaStream_t st, int bn);
 
 }  // namespace tc
 }  // namespace ladder

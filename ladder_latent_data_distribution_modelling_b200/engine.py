@@ -43,6 +43,7 @@ class ParamGroup:
         self.m = torch.zeros(self.numel, device=device)
         self.v = torch.zeros(self.numel, device=device)
         self.lr = torch.zeros(1, device=device)
+        self.convs = []            # Conv layers whose weights live in this group (filled by Conv.__init__)
         self.step = torch.zeros(1, dtype=torch.int32, device=device)
 
     def view(self, buf, pname):
@@ -57,6 +58,33 @@ class ParamGroup:
 
     def names(self):
         return [n for n, _ in self.specs]
+
+    # -- pre-packed bf16 weight images of the TMA-fed GEMMs: one launch per sub-step instead of one per conv call
+    def plan_packs(self):
+        rec = np.dtype([('w_off', '<i8'), ('img_off', '<i8'), ('first', '<i8'), ('mode', '<i4'), ('taps', '<i4'),
+                        ('Cin', '<i4'), ('Cout', '<i4'), ('bn', '<i4'), ('pad', '<i4')])
+        rows, total, slots = [], 0, []
+        for conv in self.convs:
+            g = conv.geom
+            for mode in (ops.FPROP, ops.DGRAD):
+                if not conv.tma[mode]:
+                    continue
+                bn, n_el = ops.tma_pack_plan(g, mode)
+                rows.append((self.offsets[conv.wname + '/kernel'][0], total, total, mode, g.KH * g.KW, g.Cin, g.Cout, bn, 0))
+                slots.append((conv, mode, total, n_el))
+                total += n_el
+        self.n_packs, self.pack_total = len(rows), total
+        if not rows:
+            return
+        dev = self.param.device
+        self.images = torch.empty(total, dtype=torch.bfloat16, device=dev)
+        self.pack_desc = torch.from_numpy(np.array(rows, dtype=rec).view(np.uint8).copy()).to(dev)
+        for conv, mode, off, n_el in slots:
+            conv.wimg[mode] = self.images[off:off + n_el]
+
+    def repack(self):
+        if getattr(self, 'n_packs', 0):
+            ops.pack_weights_multi(self.param, self.images, self.pack_desc, self.n_packs, self.pack_total)
 
     def apply_adam(self, grad=None):
         """ClipIfNotNone + Adam (base.py:464,502) with this group's own step counter."""
@@ -85,7 +113,9 @@ class Conv:
     (only valid when every consumer of `y` reads bf16)."""
 
     def __init__(self, group, wname, geom, act, device, out_dtype=torch.float32):
-        self.group, self.geom, self.act = group, geom, act
+        self.group, self.geom, self.act, self.wname = group, geom, act, wname
+        group.convs.append(self)
+        self.wimg = {ops.FPROP: None, ops.DGRAD: None}     # pre-packed weight images (ParamGroup.plan_packs)
         self.w = group.p(wname + '/kernel')
         self.b = group.p(wname + '/bias')
         self.dw = group.g(wname + '/kernel')
@@ -108,7 +138,7 @@ class Conv:
             x = ops.to_bf16(x, self.x16)
             if self.tma[2]:
                 self.xw = x
-        return ops.conv2d_fprop(x, self.w, self.b, self.y, self.geom, self.act, out_d2s=d2s)
+        return ops.conv2d_fprop(x, self.w, self.b, self.y, self.geom, self.act, out_d2s=d2s, wimg=self.wimg[ops.FPROP])
 
     def backward(self, dpre, dx=None, producer=None, wgrad=True, accumulate=False, s2d=0):
         """dpre: d loss / d pre-activation of this layer.  producer = (act_out, act) of the layer
@@ -127,7 +157,7 @@ class Conv:
         if dx is not None:
             ao, act = producer if producer is not None else (None, None)
             ops.conv2d_dgrad(dy if self.tma[1] else dpre, self.w, dx, g, act_out=ao, act=act, accumulate=accumulate,
-                             out_s2d=s2d)
+                             out_s2d=s2d, wimg=self.wimg[ops.DGRAD])
         return dx
 
 
@@ -670,6 +700,8 @@ class LadderEngine:
         else:
             self.outer = MnistOuterVAE(config, self.ae, B, dev)
         self.pvae = PriorVAE(config, self.prior_g, B, dev) if self.has_prior else None
+        for grp in self.groups.values():
+            grp.plan_packs()
         self.scalars = torch.zeros(ops.SCALARS_LEN, device=dev)
         self.eps_z = torch.zeros(B, self.C, device=dev)
         self.dz = torch.zeros(B, self.C, device=dev)
@@ -770,6 +802,10 @@ class LadderEngine:
         """One forward pass; fills self.scalars with the ELBO terms of the GLOBAL batch."""
         s = self.scalars
         s[:16].zero_()
+        # bf16 weight images of every TMA-fed GEMM, refreshed from the fp32 master weights once per sub-step
+        self.ae.repack()
+        if self.has_prior and prior:
+            self.prior_g.repack()
         z = self.outer.encode(x, self.eps_z, s[0:3])
         if dec:
             xhat = self.outer.decode(z)

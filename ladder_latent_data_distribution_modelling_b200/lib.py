@@ -43,6 +43,10 @@ SIGNATURES = {
     'ladder_conv2d_wgrad_tc': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_tma_supported': (C.c_int, [C.c_int] * 11),
     'ladder_conv2d_tma_workspace_bytes': (C.c_size_t, [C.c_int] * 4),
+    'ladder_conv2d_tma_bn': (C.c_int, [C.c_int] * 8),
+    'ladder_conv2d_tma_pack_bytes': (C.c_size_t, [C.c_int] * 6),
+    'ladder_conv2d_tma_pack': (C.c_int, [ptr, ptr, C.c_size_t] + [C.c_int] * 6 + [stream_t]),
+    'ladder_pack_weights_multi': (C.c_int, [ptr, ptr, ptr, C.c_int, C.c_longlong, stream_t]),
     'ladder_conv2d_fprop_tma': (C.c_int, [ptr, ptr, ptr, ptr, C.c_int] + [C.c_int] * 14 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_dgrad_tma': (C.c_int, [ptr, ptr, ptr, C.c_int, ptr, C.c_int] + [C.c_int] * 15 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_wgrad_tma': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [stream_t]),

@@ -400,15 +400,30 @@ def colsum(dy, rows, cols, out):
     return out
 
 
-def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0):
+def tma_pack_plan(g, mode):
+    """(bn, image elements) of the pre-packed bf16 weight image GEMM `mode` (FPROP / DGRAD) of geometry g reads."""
+    bn = _L().ladder_conv2d_tma_bn(mode, g.B, g.H, g.W, g.Cin, g.Cout, g.OH, g.OW)
+    return bn, _L().ladder_conv2d_tma_pack_bytes(mode, g.KH, g.KW, g.Cin, g.Cout, bn) // 2
+
+
+def pack_weights_multi(params, images, desc, n, total):
+    _lib.check(_L().ladder_pack_weights_multi(_p(_f32(params)), _p(images), _p(desc), n, total, _stream()),
+               'pack_weights_multi')
+
+
+def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0, wimg=None):
     """y = act(conv(x, w) + bias); out_d2s = r writes y directly in depth_to_space(r) layout.
-    x and y may each be fp32 or bf16 when the layer runs on the TMA-fed kernel (tma_supported(g, FPROP))."""
+    x and y may each be fp32 or bf16 when the layer runs on the TMA-fed kernel (tma_supported(g, FPROP));
+    wimg: pre-packed bf16 weight image of that kernel (tma_pack_plan) -- skips the per-call repack of w."""
     _act_t(x, 'x'), _act_t(y, 'y')
     if MATH_MODE == 'bf16' and _is_tap_gemm(g) and g.Cin % 64 == 0 and not out_d2s:
         return _tap_gemm_fprop_tc(x, w, bias, y, g, act)
     if tma_supported(g, FPROP):
-        ws, n = _tma_ws(x, g)
-        _lib.check(_L().ladder_conv2d_fprop_tma(_p(_as16(x, 'x16')), _p(_f32(w)), _p(bias), _p(y), _is16(y), *g.args(),
+        if wimg is not None:
+            ws, n, wp = wimg, wimg.numel() * 2, None
+        else:
+            (ws, n), wp = _tma_ws(x, g), _f32(w)
+        _lib.check(_L().ladder_conv2d_fprop_tma(_p(_as16(x, 'x16')), _p(wp), _p(bias), _p(y), _is16(y), *g.args(),
                                                 ACT[act], int(out_d2s), _p(ws), n, _stream()), 'conv2d_fprop_tma')
         return y
     x = _as32(x, 'x32')
@@ -425,7 +440,7 @@ def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0):
     return y
 
 
-def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False, out_s2d=0):
+def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False, out_s2d=0, wimg=None):
     """dx = conv^T(dy, w) [* act'(act_out)]; out_s2d = r writes dx at the position of the depth_to_space INPUT."""
     _act_t(dy, 'dy'), _act_t(dx, 'dx')
     if thin_dgrad(g) and not accumulate and dy.dtype == torch.float32:
@@ -434,8 +449,11 @@ def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False, out_s2d
                                          _stream()), 'tap_dgrad')
         return dx
     if tma_supported(g, DGRAD):
-        ws, n = _tma_ws(dy, g)
-        _lib.check(_L().ladder_conv2d_dgrad_tma(_p(_as16(dy, 'dy16')), _p(_f32(w)), _p(act_out), _is16(act_out), _p(dx),
+        if wimg is not None:
+            ws, n, wp = wimg, wimg.numel() * 2, None
+        else:
+            (ws, n), wp = _tma_ws(dy, g), _f32(w)
+        _lib.check(_L().ladder_conv2d_dgrad_tma(_p(_as16(dy, 'dy16')), _p(wp), _p(act_out), _is16(act_out), _p(dx),
                                                 _is16(dx), *g.args(), ACT[act], int(accumulate), int(out_s2d), _p(ws), n,
                                                 _stream()), 'conv2d_dgrad_tma')
         return dx

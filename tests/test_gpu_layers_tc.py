@@ -125,6 +125,8 @@ TMA_CASES = [
     (32, 4, 4, 128, 3, 128, 1, 'valid', 'leaky_relu'),    # VALID 3x3: 4x4 -> 2x2
     (4, 8, 8, 64, 5, 192, 1, 'same', 'relu'),             # 5x5 taps, Cout = 192 (wgrad N tile with an OOB channel block)
     (300, 1, 1, 512, 1, 512, 1, 'valid', 'leaky_relu'),   # dense
+    (64, 1, 1, 512, 1, 512, 1, 'valid', 'leaky_relu'),    # dense, batch < box: 128-row box on a 64-row tensor, narrow N tiles
+    (3, 2, 2, 64, 3, 128, 1, 'same', None),               # 12 pixels in one 128-pixel box
     (8, 16, 16, 64, 3, 128, 2, 'same', 'leaky_relu'),     # stride 2, even input: TF SAME pads (0, 1); element-stride box
     (16, 8, 8, 128, 3, 64, 2, 'same', None),              # stride 2 on 8x8 -> 4x4: box 4 x 4 x 8
     (8, 15, 15, 64, 3, 64, 2, 'valid', None),             # stride 2 VALID, odd input -> 7x7?  (not box-divisible: skipped)
