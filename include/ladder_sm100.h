@@ -157,7 +157,8 @@ size_t ladder_conv2d_tma_pack_bytes(int mode, int KH, int KW, int Cin, int Cout,
 int ladder_conv2d_tma_pack(const float* w, void* image, size_t image_bytes, int mode, int KH, int KW, int Cin, int Cout,
                            int bn, cudaStream_t stream);
 /* desc_dev: n records {int64 w_off (floats from params), int64 img_off (bf16 from images), int64 first (prefix sum of
- * image elements), int32 mode, taps, Cin, Cout, bn, pad}; total = sum of image elements */
+ * work units), int32 mode, taps, Cin, Cout, bn, pad}; one work unit = a [min(bn,64) rows x 64 k] block of an image;
+ * total = number of units over all entries */
 int ladder_pack_weights_multi(const float* params, void* images, const void* desc_dev, int n, long long total,
                               cudaStream_t stream);
 int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w /*NULL: prepacked*/, const float* bias /*nullable*/, void* y, int y_bf16,
@@ -174,7 +175,7 @@ int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, 
  * bandwidth-bound element-wise passes: dgrad with fused producer-activation derivative / space_to_depth scatter and
  * fp32 or bf16 output; and the bf16 [B*H*W, ld] shifted copy DYS[p, tap] = dy[p - tap] that feeds the TMA wgrad. */
 int ladder_tap_dgrad(const float* dy, const float* w, const void* act_out /*nullable*/, int act_out_bf16, void* dx,
-                     int dx_bf16, int B, int H, int W, int C, int Co /* <= 8 */, int KH, int KW, int pad_t, int pad_l, int OH,
+                     int dx_bf16, int B, int H, int W, int C, int Co /* <= 32 */, int KH, int KW, int pad_t, int pad_l, int OH,
                      int OW, int act, int out_s2d, cudaStream_t stream);
 /* dw[c, co] = sum_p x[p, c] dy[p, co] for a 1x1 conv with <= 8 outputs; x fp32 or bf16, dw (HWIO) overwritten */
 int ladder_thin_wgrad_1x1(const void* x, int x_bf16, const float* dy, float* dw, long long P, int C, int Co,

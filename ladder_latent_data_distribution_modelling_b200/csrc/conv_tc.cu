@@ -518,7 +518,7 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // stored as consecutive [BN x 64] tiles (tile index = n_tile * num_kb + kb), each already in the SWIZZLE_128B
 // shared-memory image (row rr at rr*128, 16-byte chunk j at ((j ^ (rr & 7)) << 4)), so one bulk TMA copy stages it.
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img, int mode, int taps, int Cin,
-                                    int Cout, int bn, int num_kb, int n_tiles) {
+                                    int Cout, int bn, int num_kb, int n_tiles, TapMap tm) {
   const int N = mode == FPROP ? Cout : Cin;
   const int Cg = mode == FPROP ? Cin : Cout;        // channels of the gathered (A) tensor
   const int K = taps * Cg;
@@ -539,7 +539,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     if (n < N && k < K) {
       if (mode == FPROP) v = w[(long long)k * Cout + n];
       else {
-        const int tap = k / Cout, co = k % Cout;
+        int tap = k / Cout;
+        const int co = k % Cout;
+        if (tm.nkw > 0) tap = (tm.kh0 + tm.s * (tap / tm.nkw)) * tm.KW + tm.kw0 + tm.s * (tap % tm.nkw);   // tap subset of one parity class
         v = w[((long long)tap * Cin + n) * Cout + co];
       }
     }
@@ -623,7 +625,7 @@ static size_t pack_dy_bytes(long long P, int Cout) {
 }
 
 namespace ladder { namespace tc {
-int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, cudaStream_t st, int bn) {
+int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, cudaStream_t st, int bn, TapMap tm) {
   const int N = mode == FPROP ? Cout : Cin, K = taps * (mode == FPROP ? Cin : Cout);
   if (bn <= 0) bn = pick_bn(N);
   const size_t need = pack_bytes(N, K, bn);
@@ -632,59 +634,75 @@ int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin,
   const int num_kb = ceil_div(K, BK), n_tiles = ceil_div(N, bn);
   long long blocks = ceil_div64((long long)n_tiles * num_kb * bn * BK, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(ws), mode, taps, Cin, Cout, bn, num_kb, n_tiles);
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(ws), mode, taps, Cin, Cout, bn, num_kb, n_tiles, tm);
   return check_launch("conv2d_tc weight pack");
 }
 
-// Every weight image of one optimiser group in ONE launch (run right after the group's Adam step, so the forward /
-// backward GEMMs never repack): desc[i] = {w offset (floats), image offset (bf16), mode, taps, Cin, Cout, bn, first
-// element of the flattened work list}; element e of entry i is the same (tile, row, k) the single-layer kernel writes.
+// Every weight image of one optimiser group in ONE launch (run at the start of each sub-step, so the forward / backward
+// GEMMs never repack).  Work unit = one [min(bn,64) rows x 64 k] block of one image, transposed through shared memory
+// so that both the fp32 weight reads (HWIO: contiguous along Cout) and the bf16 image writes (16-byte swizzled chunks)
+// are coalesced.  desc[i].first = number of units before entry i.
 struct PackDesc { long long w_off, img_off, first; int mode, taps, Cin, Cout, bn, pad; };
-__global__ void pack_multi_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ images,
-                                  const PackDesc* __restrict__ desc, int n, long long total) {
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) pack_multi_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ images,
+                                                         const PackDesc* __restrict__ desc, int n, long long total_units) {
+  __shared__ float tile[64][65];                   // [kk][row]
+  const int tid = threadIdx.x;
+  for (long long u = blockIdx.x; u < total_units; u += gridDim.x) {
     int lo = 0, hi = n - 1;
-    while (lo < hi) {                       // last entry with first <= e
+    while (lo < hi) {                              // last entry with first <= u
       const int mid = (lo + hi + 1) >> 1;
-      if (desc[mid].first <= e) lo = mid; else hi = mid - 1;
+      if (desc[mid].first <= u) lo = mid; else hi = mid - 1;
     }
     const PackDesc d = desc[lo];
-    const long long i = e - d.first;
+    const long long i = u - d.first;
     const int N = d.mode == FPROP ? d.Cout : d.Cin, Cg = d.mode == FPROP ? d.Cin : d.Cout, K = d.taps * Cg;
-    const int num_kb = ceil_div(K, BK);
-    const int kk = (int)(i % BK);
-    long long r = i / BK;
-    const int rr = (int)(r % d.bn); r /= d.bn;
-    const int kb = (int)(r % num_kb);
-    const int nt = (int)(r / num_kb);
-    const int nn = nt * d.bn + rr;
-    int k = kb * BK + kk;
-    if (Cg % BK == 0) {
-      const int tap = kb % d.taps, c = (kb / d.taps) * BK + kk;
-      k = tap * Cg + c;
-    }
-    float v = 0.f;
-    if (nn < N && k < K) {
-      const float* w = params + d.w_off;
-      if (d.mode == FPROP) v = w[(long long)k * d.Cout + nn];
-      else {
-        const int tap = k / d.Cout, co = k % d.Cout;
-        v = w[((long long)tap * d.Cin + nn) * d.Cout + co];
+    const int num_kb = ceil_div(K, BK), sr = d.bn < 64 ? d.bn : 64, subs = d.bn / sr;
+    const int sb = (int)(i % subs);
+    const long long r = i / subs;
+    const int kb = (int)(r % num_kb), nt = (int)(r / num_kb);
+    const int n0 = nt * d.bn + sb * sr;
+    const bool chunked = Cg % BK == 0;             // channel-chunk-major K order of the TMA / affine producers
+    const int ktap = kb % d.taps, kc0 = (kb / d.taps) * BK;
+    const float* w = params + d.w_off;
+    if (d.mode == FPROP) {                         // w[k][n]: lanes along n
+      const int nn = tid & 63;
+      for (int kk = tid >> 6; kk < BK; kk += 4) {
+        const int k = chunked ? ktap * Cg + kc0 + kk : kb * BK + kk;
+        float v = 0.f;
+        if (nn < sr && n0 + nn < N && k < K) v = __ldg(w + (long long)k * d.Cout + n0 + nn);
+        tile[kk][nn] = v;
+      }
+    } else {                                       // w[tap][n][co]: lanes along k = (tap, co)
+      const int kk = tid & 63;
+      const int k = chunked ? ktap * Cg + kc0 + kk : kb * BK + kk;
+      const int tap = k / d.Cout, co = k - tap * d.Cout;
+      for (int nn = tid >> 6; nn < sr; nn += 4) {
+        float v = 0.f;
+        if (n0 + nn < N && k < K) v = __ldg(w + ((long long)tap * d.Cin + n0 + nn) * d.Cout + co);
+        tile[kk][nn] = v;
       }
     }
-    const long long tile = (long long)nt * num_kb + kb;
-    images[d.img_off + tile * d.bn * BK + rr * BK + ((((kk >> 3) ^ (rr & 7))) << 3) + (kk & 7)] = __float2bfloat16_rn(v);
+    __syncthreads();
+    __nv_bfloat16* img = images + d.img_off + ((long long)nt * num_kb + kb) * d.bn * BK;
+    for (int c = tid; c < sr * 8; c += 256) {      // 16-byte chunks: row rr, chunk ch
+      const int rr = c >> 3, ch = c & 7, row = sb * sr + rr;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = tile[ch * 8 + j][rr];
+      *reinterpret_cast<uint4*>(img + row * BK + ((ch ^ (row & 7)) << 3)) = pack8(f);
+    }
+    __syncthreads();
   }
 }
 } }
 
 extern "C" {
 
-/* desc_dev: n records of 6 x int64 {w_off, img_off, first, mode | taps << 32, Cin | Cout << 32, bn} -- see PackDesc */
+/* desc_dev: n PackDesc records; total = number of [min(bn,64) x 64] work units over all entries */
 int ladder_pack_weights_multi(const float* params, void* images, const void* desc_dev, int n, long long total,
                               cudaStream_t stream) {
   LADDER_REQUIRE(params && images && desc_dev && n > 0 && total > 0, "pack_weights_multi: bad arguments");
-  long long blocks = ceil_div64(total, 256);
+  long long blocks = total;                        // units
   if (blocks > 148 * 8) blocks = 148 * 8;
   pack_multi_kernel<<<(unsigned)blocks, 256, 0, stream>>>(params, static_cast<__nv_bfloat16*>(images),
                                                           static_cast<const PackDesc*>(desc_dev), n, total);

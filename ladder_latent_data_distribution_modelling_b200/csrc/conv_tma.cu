@@ -59,6 +59,8 @@ struct Args {
   int m_valid;               // WGRAD: rows of dw that exist (= KH*KW*C)
   int m_tiles, n_tiles, splits;
   int perm_r;                // fused depth_to_space (FPROP) / space_to_depth (DGRAD) store, 0 = off
+  int os, opy, opx, OHf, OWf; // DGRAD of a strided conv, one output-parity class: row (b, i, j) of the [B, GH, GW] grid is
+                             // dx pixel (b, i*os + opy, j*os + opx) of the full [B, OHf, OWf] map (os = 0/1: off)
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -99,7 +101,8 @@ __device__ __forceinline__ float bf16_bits_to_float(uint32_t h) { return __uint_
 // Ragged / scalar tail of the epilogue (N not a multiple of 4, depth_to_space with C' % 4 != 0): kept out of line so the
 // hot store loop stays small.
 template <int MODE, bool OUT16>
-__device__ __noinline__ void slow_store(const Args& a, float4 q, long long m, int col, long long o, float slope, bool is_tanh) {
+__device__ __noinline__ void slow_store(const Args& a, float4 q, long long m, int col, long long o, long long arow, float slope,
+                                        bool is_tanh) {
   float* outf = reinterpret_cast<float*>(a.out);
   __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(a.out);
   const float e4[4] = {q.x, q.y, q.z, q.w};
@@ -111,7 +114,7 @@ __device__ __noinline__ void slow_store(const Args& a, float4 q, long long m, in
     if (MODE == FPROP && a.perm_r > 0) oo = d2s_dest(m, col + t, a.GH, a.GW, Ng, a.perm_r);
     if (MODE == DGRAD) {
       if (a.aux != nullptr) {
-        const long long ai = m * Ng + col + t;
+        const long long ai = arow + col + t;
         const float ax = a.aux_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.aux)[ai])
                                     : reinterpret_cast<const float*>(a.aux)[ai];
         e *= is_tanh ? 1.f - ax * ax : (ax > 0.f ? 1.f : slope);
@@ -330,21 +333,28 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           const long long m = mrow0 + r;
           const float4 q = *reinterpret_cast<const float4*>(stage + r * 36 + c4);
           if (m >= Mg || col >= Ng) continue;
-          long long o = m * Ng;
+          long long o = m * Ng, arow = m * Ng;           // output row / row of the saved activation (aux)
+          if (MODE == DGRAD && a.os > 1) {               // parity class of a strided dgrad: scatter into the full map
+            const unsigned mu = (unsigned)m;
+            const int jx = (int)(mu % (unsigned)a.GW);
+            const unsigned rq = mu / (unsigned)a.GW;
+            const int iy = (int)(rq % (unsigned)a.GH), bb = (int)(rq / (unsigned)a.GH);
+            o = arow = (((long long)bb * a.OHf + iy * a.os + a.opy) * a.OWf + jx * a.os + a.opx) * Ng;
+          }
           if (a.perm_r > 0) {
             if (MODE == FPROP) o = d2s_dest(m, 0, a.GH, a.GW, Ng, a.perm_r);
             if (MODE == DGRAD) o = s2d_dest(m, 0, a.GH, a.GW, Ng, a.perm_r);
           }
           o += coloff;
           if (!vec_ok) {
-            slow_store<MODE, OUT16>(a, q, m, col, o, slope, is_tanh);
+            slow_store<MODE, OUT16>(a, q, m, col, o, arow, slope, is_tanh);
             continue;
           }
           float e[4] = {q.x, q.y, q.z, q.w};
           if (MODE == DGRAD) {
             if (a.aux != nullptr) {
               float ax[4];
-              const long long ai = m * Ng + col;
+              const long long ai = arow + col;
               if (a.aux_bf16) {
                 const uint2 u = __ldg(reinterpret_cast<const uint2*>(auxh + ai));
                 ax[0] = bf16_bits_to_float(u.x & 0xffffu); ax[1] = bf16_bits_to_float(u.x >> 16);
@@ -412,6 +422,10 @@ static EncodeTiledFn encode_fn() {
 // cannot be cut into such boxes (then the register-gather kernel of conv_tc.cu takes the layer).
 static bool pixel_box(int GW, int GH, int B, int px, int& bw, int& bh, int& bb) {
   bw = bh = bb = 1;
+  if (GH == 1 && B == 1) {   // one row of pixels (dense layers, see dense_as_row): a ragged last box is zero filled
+    bw = px;
+    return true;
+  }
   if (GW >= px) {
     if (GW % px) return false;
     bw = px;
@@ -430,6 +444,16 @@ static bool pixel_box(int GW, int GH, int B, int px, int& bw, int& bh, int& bb) 
   bb = rem / GH;
   (void)B;                 // a box taller than the batch is legal: rows past B are zero filled and masked
   return bb <= 256;
+}
+
+// Dense layers ([B,1,1,C] "images") are presented to TMA as ONE image row of B pixels: boxes {64, px, 1, 1} walk the
+// fastest pixel axis.  (Boxes {64, 1, 1, px} over the batch axis fetch one 128-byte row per outermost index and ran ~5x
+// slower: 1.1 TB/s on the 1M-row tap-GEMM of the fashion decoder.)
+static void dense_as_row(int& B, int& H, int& W, int KH, int KW, int& OH, int& OW) {
+  if (H == 1 && W == 1 && OH == 1 && OW == 1 && KH == 1 && KW == 1) {
+    W = OW = B;
+    B = 1;
+  }
 }
 
 // bf16 NHWC tensor [B, SH, SW, C] as a 4-D tensor map {C, SW, SH, B}, SWIZZLE_128B, zero fill outside
@@ -523,10 +547,11 @@ using namespace ladder::tma;
 
 // N tile: as wide as the GEMM allows, narrowed while the launch would fill less than half of the SMs (small-batch
 // dense layers: M = batch rows give a single M tile, so the CTA count comes from N tiles alone)
-static int choose_bn(int mode, long long Mg, int Ng) {
+static int choose_bn(int mode, long long Mg, int Ng, long long wgrad_kb = 0) {
   int bn = tc::pick_bn(Ng);
   const int floor_bn = mode == WGRAD ? 64 : 32;
   if (mode == WGRAD && bn < 64) bn = 64;
+  if (mode == WGRAD && wgrad_kb > 4) return bn;      // long pixel reductions get their CTAs from split-K instead
   const long long m_tiles = ceil_div64(Mg, BM);
   while (bn > floor_bn && m_tiles * ceil_div(Ng, bn) * 2 <= num_sms()) bn >>= 1;
   return bn;
@@ -541,15 +566,19 @@ extern "C" {
 
 /* mode 0 fprop, 1 dgrad, 2 wgrad: 1 iff the TMA-fed kernel takes this geometry (64-aligned channels of the gathered
  * tensor, pixel grid divisible into 128- (64- for wgrad) pixel boxes; strided fprop / wgrad use the tensor map's element
- * stride, strided dgrad is not taken) */
+ * stride, strided dgrad runs one stride-1 GEMM per output-parity class -- no zero-insertion, no wasted MACs) */
 int ladder_conv2d_tma_supported(int mode, int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int OH, int OW) {
   if (stride < 1 || stride > 8 || B <= 0) return 0;
+  dense_as_row(B, H, W, KH, KW, OH, OW);
   if ((long long)B * H * W >= (1LL << 31) / 64 * 64 || (long long)B * OH * OW >= (1LL << 31) / 64 * 64) return 0;
-  (void)KH; (void)KW;
   int bw, bh, bb;
   switch (mode) {
     case 0: return Cin % 64 == 0 && pixel_box(OW, OH, B, 128, bw, bh, bb) && bw * stride <= 256 && bh * stride <= 256;
-    case 1: return stride == 1 && Cout % 64 == 0 && geometry_ok(B, H, W, 128);
+    case 1:
+      if (Cout % 64 != 0) return 0;
+      if (stride == 1) return geometry_ok(B, H, W, 128);
+      // strided: one stride-1 GEMM per output-parity class over the [B, H/s, W/s] grid (every class needs >= 1 tap)
+      return H % stride == 0 && W % stride == 0 && KH >= stride && KW >= stride && geometry_ok(B, H / stride, W / stride, 128);
     case 2: return Cin % 64 == 0 && Cout % 64 == 0 && pixel_box(OW, OH, B, 64, bw, bh, bb) && bw * stride <= 256 && bh * stride <= 256;
     default: return 0;
   }
@@ -562,7 +591,7 @@ size_t ladder_conv2d_tma_workspace_bytes(int Cin, int KH, int KW, int Cout) {
     if (f > m) m = f;
     if (d > m) m = d;
   }
-  return m + 256;
+  return m + 256 + 64 * 1024;    // + alignment slack of the per-class images of a strided dgrad
 }
 
 /* N tile width the TMA launcher uses for GEMM `mode` of this geometry (the packed weight image depends on it) */
@@ -625,6 +654,7 @@ int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bia
   LADDER_REQUIRE(out_d2s == 0 || (out_d2s > 0 && Cout % (out_d2s * out_d2s) == 0),
                  "conv2d_fprop_tma: depth_to_space(%d) output needs Cout %% r^2 == 0", out_d2s);
   LADDER_REQUIRE(((uintptr_t)x_bf16 & 15) == 0, "conv2d_fprop_tma: x must be 16-byte aligned");
+  dense_as_row(B, H, W, KH, KW, OH, OW);
   const int bn = choose_bn(FPROP, (long long)B * OH * OW, Cout);
   int rc = LADDER_OK;
   if (w != nullptr) rc = tc::pack(w, workspace, workspace_bytes, FPROP, KH * KW, Cin, Cout, stream, bn);
@@ -657,6 +687,44 @@ int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w, const void* act
   LADDER_REQUIRE(out_s2d == 0 || (out_s2d > 0 && H % out_s2d == 0 && W % out_s2d == 0),
                  "conv2d_dgrad_tma: space_to_depth(%d) output needs H, W divisible by r", out_s2d);
   LADDER_REQUIRE(((uintptr_t)dy_bf16 & 15) == 0, "conv2d_dgrad_tma: dy must be 16-byte aligned");
+  if (stride > 1) {
+    // dx(s*i + py, s*j + px) = sum over taps kh = kh0 + s*a, kw = kw0 + s*b (kh0 = (py + pad_t) % s, ...) of
+    // dy(i + (py + pad_t - kh0)/s - a, j + (px + pad_l - kw0)/s - b) . w(kh, kw): a stride-1 correlation per class
+    LADDER_REQUIRE(w != nullptr, "conv2d_dgrad_tma: strided dgrad packs its per-class weight images itself (w required)");
+    LADDER_REQUIRE(out_s2d == 0, "conv2d_dgrad_tma: space_to_depth output is not available for strided layers");
+    const int GH = H / stride, GW = W / stride;
+    const int bn = choose_bn(DGRAD, (long long)B * GH * GW, Cin);
+    int bw, bh, bb;
+    pixel_box(GW, GH, B, BM, bw, bh, bb);
+    CUtensorMap mA;
+    int rc = make_map(&mA, dy_bf16, B, OH, OW, Cout, bw, bh, bb);
+    if (rc) return rc;
+    size_t ws_off = 0;
+    for (int py = 0; py < stride; ++py)
+      for (int px = 0; px < stride; ++px) {
+        const int kh0 = (py + pad_t) % stride, kw0 = (px + pad_l) % stride;
+        const int nkh = (KH - kh0 + stride - 1) / stride, nkw = (KW - kw0 + stride - 1) / stride;
+        const size_t bytes = tc::pack_bytes(Cin, nkh * nkw * Cout, bn);
+        LADDER_REQUIRE(workspace != nullptr && ws_off + bytes <= workspace_bytes, "conv2d_dgrad_tma: workspace too small");
+        uint8_t* img = static_cast<uint8_t*>(workspace) + ws_off;
+        rc = tc::pack(w, img, bytes, DGRAD, nkh * nkw, Cin, Cout, stream, bn, tc::TapMap{KW, kh0, kw0, nkw, stride});
+        if (rc) return rc;
+        ws_off += (bytes + 1023) / 1024 * 1024;
+        Args a;
+        memset(&a, 0, sizeof(a));
+        a.stride = 1;
+        a.wt = reinterpret_cast<const __nv_bfloat16*>(img);
+        a.aux = act_out; a.aux_bf16 = act_out_bf16; a.out = dx; a.out_bf16 = dx_bf16;
+        a.GW = GW; a.GH = GH; a.B = B; a.C = Cout; a.KH = nkh; a.KW = nkw;
+        a.off_y = (py + pad_t - kh0) / stride; a.off_x = (px + pad_l - kw0) / stride; a.sign = -1;
+        a.Ng = Cin; a.act = act; a.accumulate = accumulate; a.nkb = nkh * nkw * (Cout / BK); a.splits = 1;
+        a.os = stride; a.opy = py; a.opx = px; a.OHf = H; a.OWf = W;
+        rc = launch<DGRAD>(mA, mA, a, (long long)B * GH * GW, bn, stream);
+        if (rc) return rc;
+      }
+    return LADDER_OK;
+  }
+  dense_as_row(B, H, W, KH, KW, OH, OW);
   const int bn = choose_bn(DGRAD, (long long)B * H * W, Cin);
   int rc = LADDER_OK;
   if (w != nullptr) rc = tc::pack(w, workspace, workspace_bytes, DGRAD, KH * KW, Cin, Cout, stream, bn);
@@ -689,6 +757,7 @@ int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, 
   const int patch = KH * KW * Cin;
   cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)patch * Cout * sizeof(float), stream);
   if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "conv2d_wgrad_tma memset: %s", cudaGetErrorString(e));
+  dense_as_row(B, H, W, KH, KW, OH, OW);
   int bw, bh, bb;
   pixel_box(OW, OH, B, BK, bw, bh, bb);
   CUtensorMap mA, mB;
@@ -696,10 +765,10 @@ int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, 
   if (rc) return rc;
   rc = make_map(&mB, dy_bf16, B, OH, OW, Cout, bw, bh, bb);
   if (rc) return rc;
-  const int bn = choose_bn(WGRAD, patch, Cout);
   // pixel boxes of 64: the last one may hang over the batch axis (zero filled on both operands)
   const long long box_px = (long long)bw * bh * bb;            // == 64
-  const long long total_kb = bb > 1 ? ceil_div64(B, bb) : (long long)B * OH * OW / box_px;
+  const long long total_kb = bb > 1 ? ceil_div64(B, bb) : ceil_div64((long long)B * OH * OW, box_px);
+  const int bn = choose_bn(WGRAD, patch, Cout, total_kb);
   const long long tiles = ceil_div64(patch, BM) * ceil_div(Cout, bn);
   long long splits = (2LL * num_sms()) / tiles;                // <= 2 full waves of the persistent grid
   const long long max_splits = ceil_div64(total_kb, 4);

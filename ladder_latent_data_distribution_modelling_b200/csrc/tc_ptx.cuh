@@ -101,12 +101,17 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
+// Tap subset of one output-parity class of a strided dgrad: class tap t = (a, b) of an [nkh x nkw] grid is filter tap
+// (kh0 + s*a, kw0 + s*b) of the KH x KW filter.  nkw == 0: identity (all taps).
+struct TapMap { int KW, kh0, kw0, nkw, s; };
+
 // host helpers defined in conv_tc.cu, shared with conv_tma.cu
 int pick_bn(int Ng);
 int round_up(int x, int m);
 size_t pack_bytes(int N, int K, int bn);   // bn <= 0: pick_bn(N)
 // fp32 HWIO weights -> bf16 SWIZZLE_128B tile images [n_tile][kb] (mode 0: fprop, 1: dgrad), one launch
-int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, cudaStream_t st, int bn);
+int pack(const float* w, void* ws, size_t ws_bytes, int mode, int taps, int Cin, int Cout, cudaStream_t st, int bn,
+         TapMap tm = TapMap{0, 0, 0, 0, 1});
 
 }  // namespace tc
 }  // namespace ladder

@@ -15,7 +15,7 @@
 namespace ladder {
 
 struct TapArgs {
-  const float* dy;           // [B, OH, OW, Co] (Co <= 8 output channels)
+  const float* dy;           // [B, OH, OW, Co] (Co <= 32 output channels)
   const float* w;            // [KH*KW, C, Co] (HWIO)
   const void* aux;           // saved producer output indexed like dx rows (fp32 or bf16) or null
   void* dx;                  // [B, H, W, C] or its space_to_depth position
@@ -183,7 +183,7 @@ extern "C" {
 int ladder_tap_dgrad(const float* dy, const float* w, const void* act_out, int act_out_bf16, void* dx, int dx_bf16, int B,
                      int H, int W, int C, int Co, int KH, int KW, int pad_t, int pad_l, int OH, int OW, int act, int out_s2d,
                      cudaStream_t stream) {
-  LADDER_REQUIRE(Co >= 1 && Co <= 8, "tap_dgrad: 1..8 output channels (got %d)", Co);
+  LADDER_REQUIRE(Co >= 1 && Co <= 32, "tap_dgrad: 1..32 output channels (got %d)", Co);
   LADDER_REQUIRE(dy && w && dx && B > 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && OH > 0 && OW > 0, "tap_dgrad: bad arguments");
   LADDER_REQUIRE(C % 8 == 0, "tap_dgrad: channel count must be a multiple of 8 (got %d)", C);
   LADDER_REQUIRE(out_s2d == 0 || (H % out_s2d == 0 && W % out_s2d == 0), "tap_dgrad: space_to_depth(%d) needs H, W divisible by r", out_s2d);

@@ -63,17 +63,18 @@ class ParamGroup:
     def plan_packs(self):
         rec = np.dtype([('w_off', '<i8'), ('img_off', '<i8'), ('first', '<i8'), ('mode', '<i4'), ('taps', '<i4'),
                         ('Cin', '<i4'), ('Cout', '<i4'), ('bn', '<i4'), ('pad', '<i4')])
-        rows, total, slots = [], 0, []
+        rows, total, units, slots = [], 0, 0, []
         for conv in self.convs:
             g = conv.geom
             for mode in (ops.FPROP, ops.DGRAD):
-                if not conv.tma[mode]:
+                if not conv.tma[mode] or (mode == ops.DGRAD and g.stride > 1):   # strided dgrad packs per parity class
                     continue
                 bn, n_el = ops.tma_pack_plan(g, mode)
-                rows.append((self.offsets[conv.wname + '/kernel'][0], total, total, mode, g.KH * g.KW, g.Cin, g.Cout, bn, 0))
+                rows.append((self.offsets[conv.wname + '/kernel'][0], total, units, mode, g.KH * g.KW, g.Cin, g.Cout, bn, 0))
                 slots.append((conv, mode, total, n_el))
                 total += n_el
-        self.n_packs, self.pack_total = len(rows), total
+                units += n_el // (min(bn, 64) * 64)          # work units of the multi-pack kernel
+        self.n_packs, self.pack_total = len(rows), units
         if not rows:
             return
         dev = self.param.device

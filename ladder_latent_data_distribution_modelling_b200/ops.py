@@ -343,9 +343,9 @@ def tma_supported(g, mode):
 
 
 def thin_dgrad(g):
-    """Layers with <= 8 output channels: dgrad is a bandwidth-bound element-wise pass (csrc/thin_ops.cu) that can write
+    """Layers with <= 32 output channels (K = taps * Cout is too short for a 64-wide k-block): dgrad is a bandwidth-bound element-wise pass (csrc/thin_ops.cu) that can write
     fp32 or bf16."""
-    return (MATH_MODE == 'bf16' and TMA and g.Cout <= 8 and g.stride == 1 and g.Cin % 8 == 0
+    return (MATH_MODE == 'bf16' and TMA and g.Cout <= 32 and g.stride == 1 and g.Cin % 8 == 0
             and g.KH * g.KW * g.Cin * g.Cout * 4 <= 48 * 1024)
 
 
@@ -404,6 +404,15 @@ def tma_pack_plan(g, mode):
     """(bn, image elements) of the pre-packed bf16 weight image GEMM `mode` (FPROP / DGRAD) of geometry g reads."""
     bn = _L().ladder_conv2d_tma_bn(mode, g.B, g.H, g.W, g.Cin, g.Cout, g.OH, g.OW)
     return bn, _L().ladder_conv2d_tma_pack_bytes(mode, g.KH, g.KW, g.Cin, g.Cout, bn) // 2
+
+
+def tma_pack(w, g, mode):
+    """bf16 weight image of one layer (single-layer pack launch); the reference the multi-tensor pack is tested against."""
+    bn, n_el = tma_pack_plan(g, mode)
+    img = torch.empty(n_el, dtype=torch.bfloat16, device=w.device)
+    _lib.check(_L().ladder_conv2d_tma_pack(_p(_f32(w)), _p(img), n_el * 2, mode, g.KH, g.KW, g.Cin, g.Cout, bn, _stream()),
+               'conv2d_tma_pack')
+    return img
 
 
 def pack_weights_multi(params, images, desc, n, total):

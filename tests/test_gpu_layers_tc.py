@@ -306,3 +306,26 @@ def test_resize_dtype_variants_and_fused_activation_grad(ops):
                 want = ref * torch.where(a.float() > 0, 1.0, 0.2)
                 assert (dx.float() - want).abs().max().item() <= tol
     assert (fused_ref - dx32 * torch.where(aout > 0, 1.0, 0.2)).abs().max().item() == 0.0
+
+
+def test_multi_tensor_weight_pack_matches_single_layer_pack(ops):
+    """One pack launch per parameter group (smem-transposed, coalesced) must reproduce the per-layer images bit for bit."""
+    from ladder_latent_data_distribution_modelling_b200 import engine
+    G = ops.ConvGeom
+    geoms = {'a': G(8, 16, 16, 64, 3, 3, 256, 1, 'same'), 'b': G(64, 1, 1, 512, 1, 1, 512, 1, 'valid'),
+             'c': G(16, 8, 8, 128, 3, 3, 64, 2, 'same'), 'd': G(4, 8, 8, 64, 5, 5, 192, 1, 'same'),
+             'e': G(256, 1, 1, 512, 1, 1, 2, 1, 'valid'), 'f': G(2, 16, 16, 128, 1, 1, 3, 1, 'same')}
+    specs = []
+    for n, g in geoms.items():
+        specs += [(n + '/kernel', (g.KH, g.KW, g.Cin, g.Cout)), (n + '/bias', (g.Cout,))]
+    grp = engine.ParamGroup('t', specs, 'cuda')
+    grp.param.normal_()
+    convs = {n: engine.Conv(grp, n, g, None, 'cuda') for n, g in geoms.items()}
+    grp.plan_packs()
+    assert grp.n_packs >= 8
+    grp.images.fill_(7.0)
+    grp.repack()
+    for n, c in convs.items():
+        for mode in (ops.FPROP, ops.DGRAD):
+            if c.tma[mode] and c.wimg[mode] is not None:       # strided dgrad packs per parity class at call time
+                assert torch.equal(c.wimg[mode], ops.tma_pack(c.w, c.geom, mode)), (n, mode)
