@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 METRIC = 'train imgs/sec (ELBO fwd+bwd, 4 sub-steps per image batch)'
 
 
+# dram bytes (read+write) per launch of the roofline kernel from the committed `ncu --set full` capture (profiles/)
+TRAFFIC = {}
+
 WORKLOAD = 'mnist_fashion'       # set from --workload; the default is BASELINE.json configs[1]
 
 
@@ -219,11 +222,18 @@ def run_ours(args):
         sampler.start()
     launches0 = ops.launch_count() + eng.replayed_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profile = os.environ.get('LADDER_BENCH_PROFILE') == '1'     # ncu --profile-from-start off: timed region only
+    if profile:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         iteration(pool[i % n_pool])
     e1.record()
     barrier()
+    if profile:
+        torch.cuda.profiler.stop()
+        print('profiled %d iterations (no bench line under a profiler)' % args.steps, file=sys.stderr)
+        return
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count() + eng.replayed_launches - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -290,31 +300,40 @@ def run_ours(args):
         dom_name, hw, ci, co = {'mnist_fashion': ('decoder/conv2d_3', 16, H // 4, H), 'mnist_digit': ('decoder/conv2d', 4, H, H),
                                 'celeba': ('decoder/conv2d_7', 128, H // 4, H // 4)}[WORKLOAD]
         g = ops.ConvGeom(B, hw, hw, ci, 3, 3, co, 1, 'same')
-        xk = torch.randn(B, hw, hw, ci, device=dev)
+        tma = args.dtype == 'bf16' and ops.tma_supported(g, ops.FPROP)
+        adt = torch.bfloat16 if tma else torch.float32     # the step keeps this layer's activations bf16-resident
+        xk = torch.randn(B, hw, hw, ci, device=dev).to(adt)
         wk = torch.randn(3, 3, ci, co, device=dev) * 0.05
         bk = torch.zeros(co, device=dev)
-        yk = torch.empty(B, hw, hw, co, device=dev)
+        yk = torch.empty(B, hw, hw, co, device=dev, dtype=adt)
+        wimg = ops.tma_pack(wk, g, ops.FPROP) if tma else None   # the step packs all weights once per sub-step
         for _ in range(3):
-            ops.conv2d_fprop(xk, wk, bk, yk, g, 'leaky_relu')
+            ops.conv2d_fprop(xk, wk, bk, yk, g, 'leaky_relu', wimg=wimg)
         torch.cuda.synchronize()
-        reps = 10
+        reps = 20
         e0.record()
         for _ in range(reps):
-            ops.conv2d_fprop(xk, wk, bk, yk, g, 'leaky_relu')
+            ops.conv2d_fprop(xk, wk, bk, yk, g, 'leaky_relu', wimg=wimg)
         e1.record()
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / reps
         flops = 2.0 * B * hw * hw * co * 9 * ci
         ach = flops / (k_ms * 1e-3) / 1e12
-        ops.set_math_mode(args.dtype)
-        kname = 'tc_kernel<FPROP,256> (tcgen05)' if args.dtype == 'bf16' else 'igemm_kernel<FPROP> (fp32 SIMT)'
+        esz = 2 if tma else 4
+        alg_bytes = esz * B * hw * hw * (ci + co) + 2 * 9 * ci * co
+        kname = ('tma_kernel<FPROP> (TMA im2col + tcgen05, bf16 in/out)' if tma else
+                 'tc_kernel<FPROP> (tcgen05, fp32 activations)' if args.dtype == 'bf16' else 'igemm_kernel<FPROP> (fp32 SIMT)')
         roofline = {'kernel': kname + ' %s [B,%d,%d,%d]->%d 3x3' % (dom_name, hw, hw, ci, co),
                     'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                    'frac': ach / peaks['bf16_tflops'], 'traffic': None, 'peak_source': peaks['source'] + ' bf16 burst',
-                    'ms_per_launch': k_ms, 'algorithmic_flops_per_launch': flops,
-                    'timed': 'CUDA events around 10 back-to-back ladder_conv2d_fprop calls (bf16: includes the 147 k-element weight repack launch)',
-                    'note': 'fp32 activations in HBM, converted to bf16 while staged to shared memory; fp32 accumulation in TMEM'
-                    if args.dtype == 'bf16' else 'fp32 SIMT kernel; denominator is the bf16 tensor peak'}
+                    'frac': ach / peaks['bf16_tflops'], 'traffic': TRAFFIC.get((WORKLOAD, args.dtype, B)),
+                    'peak_source': peaks['source'] + ' bf16 burst (kernel timed alone)',
+                    'ms_per_launch': k_ms, 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': alg_bytes,
+                    'hbm_floor_ms': alg_bytes / (peaks['hbm_gbs'] * 1e9) * 1e3,
+                    'tensor_floor_ms': flops / (peaks['bf16_tflops'] * 1e12) * 1e3,
+                    'timed': 'CUDA events on the launch stream around %d back-to-back launches; input + output = %d MB '
+                             '(%s the 126 MB L2)' % (reps, alg_bytes >> 20, 'exceeds' if alg_bytes > 126 << 20 else 'FITS in'),
+                    'note': 'bf16 activations and pre-packed bf16 weights in HBM, fp32 accumulation in TMEM'
+                    if tma else 'denominator is the bf16 tensor peak'}
         # ---- hyper-prior micro-benchmark (second half of the metric): 65 536 x 65 536 pairs, D = 2
         rng = np.random.default_rng(1234)
         N = 65536
