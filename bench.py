@@ -162,6 +162,61 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def celeba_leg(args, dev, rank, world, group):
+    """Same 4-sub-step iteration on codes/celeba_config.json (128x128x3 conv VAE + prior VAE + hyper-prior), synthetic
+    batches of --celeba-batch images per GPU resident in HBM; max over ranks of the CUDA-event time."""
+    import torch
+    import torch.distributed as dist
+    from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
+    with open(os.path.join(ROOT, 'codes', 'celeba_config.json')) as f:
+        cfg = json.load(f)
+    B = args.celeba_batch
+    cfg.update(batch_size=B, seed=1234, compute_dtype=args.dtype)
+    if args.no_graphs:
+        cfg['cuda_graphs'] = False
+    eng = LadderEngine(cfg, B, dev, seed=4321 + rank, dist_group=group)
+    if world > 1:
+        for g in eng.groups.values():
+            dist.broadcast(g.param, 0)
+    gm = synthetic_mixture(cfg['n_mixtures'], cfg['representation_size'])
+    eng.set_feeds(prior_mean=gm[0], prior_cov=gm[1], prior_weight=gm[2], use_standard_gaussian_prior=False, use_mask=False)
+    eng.set_lrs(cfg['learning_rate_ae'], cfg['learning_rate_sigma'], cfg['learning_rate_prior'],
+                cfg['learning_rate_inner_sigma'])
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7 + rank)
+    pool = [torch.rand(B, 128, 128, 3, device=dev, generator=gen) for _ in range(4)]
+    steps = args.celeba_steps
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for i in range(3):
+        for name in ('ae', 'sigma', 'prior', 'inner_sigma'):
+            eng.run_step(name, pool[i % 4])
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        for name in ('ae', 'sigma', 'prior', 'inner_sigma'):
+            eng.run_step(name, pool[i % 4])
+    e1.record()
+    sync()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    fl = 3 * 10.04e9          # SURVEY 8d: algorithmic fwd+bwd flop per image (one fused pass; the 4-sub-step protocol runs more)
+    v = B * world * steps / (ms * 1e-3)
+    out = {'workload': 'codes/celeba_config.json @ batch %d per GPU (128x128x3, H=512, C=256), all 4 sub-steps' % B,
+           'value': v, 'unit': 'imgs/s', 'ms_per_step': ms / steps, 'steps': steps, 'warmup': 3, 'global_batch': B * world,
+           'algorithmic_tflops': v * fl / 1e12 / world, 'loss_ae': eng.fetch(['loss_ae'])['loss_ae']}
+    eng.release_graphs()
+    del eng, pool
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -290,6 +345,14 @@ def run_ours(args):
     e2e_ms = float(t.item())
     e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
 
+    # ---- secondary workload: CelebA-shape (128x128x3) training step, BASELINE.json configs[3] per-GPU batch
+    celeba = None
+    if WORKLOAD != 'celeba' and args.celeba_batch > 0:
+        del model, trainer
+        eng.release_graphs()
+        torch.cuda.empty_cache()
+        celeba = celeba_leg(args, dev, rank, world, group)
+
     line = None
     if rank == 0:
         peaks = measured_peaks()
@@ -373,7 +436,7 @@ def run_ours(args):
                         'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps,
                         'api': '*Trainer_joint_training.train_step_ae + train_step_prior on pinned host batches'},
                 'roofline': roofline, 'cpu_baseline': {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
-                'hyper_prior': hyper, 'loss_prior_last': loss_check, 'loss_ae_last_e2e': last}
+                'hyper_prior': hyper, 'celeba_shape': celeba, 'loss_prior_last': loss_check, 'loss_ae_last_e2e': last}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -391,6 +454,8 @@ def main():
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of CUDA-graph replay')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'], help='GEMM math: bf16 tcgen05 or fp32 SIMT')
     ap.add_argument('--cpu-sample', type=int, default=32, help='batch of the bounded CPU-baseline sample')
+    ap.add_argument('--celeba-batch', type=int, default=64, help='per-GPU batch of the secondary CelebA-shape leg (0 = skip)')
+    ap.add_argument('--celeba-steps', type=int, default=10)
     ap.add_argument('--workload', default='mnist_fashion', choices=['mnist_fashion', 'mnist_digit', 'celeba'],
                     help='config file under codes/ (default: BASELINE.json configs[1])')
     args = ap.parse_args()

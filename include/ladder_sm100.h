@@ -79,6 +79,19 @@ size_t ladder_mixture_tc_workspace_bytes(long long N, int K);
 int ladder_mixture_logprob_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
                               float iso_scale, float ref_log2, float* logp, void* workspace,
                               size_t workspace_bytes, cudaStream_t stream);
+/* VampPrior mixture (codes/base.py:215-254): K diagonal Gaussians with equal weights whose means / stds are device
+ * tensors produced by the shared encoder from the trainable pseudo-inputs.
+ *  - ladder_mixture_pack_diag_device packs the mode-1 table and its log2 frame ON THE DEVICE (no host round trip, graph
+ *    capturable); ladder_mixture_logprob_devref evaluates log p / d log p / d t against such a table;
+ *  - ladder_mixture_diag_param_grad: dmean[K,D] = coef * sum_n r_nk (t_n - mu_k) / sd_k^2,
+ *    dstd[K,D] = coef * sum_n r_nk ((t_n - mu_k)^2 / sd_k^3 - 1 / sd_k), r_nk = exp(e_nk - logp_n)  (outputs overwritten). */
+int ladder_mixture_pack_diag_device(const float* mean_dev, const float* std_dev, int K, int D, float* table_dev,
+                                    float* ref_log2_dev, cudaStream_t stream);
+int ladder_mixture_logprob_devref(const float* t, long long N, int D, const float* table, int K, int mode,
+                                  const float* ref_log2_dev, float* logp, float* grad_t, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream);
+int ladder_mixture_diag_param_grad(const float* t, long long N, int D, const float* mean_dev, const float* std_dev, int K,
+                                   const float* logp, float coef, float* dmean, float* dstd, cudaStream_t stream);
 /* (max, sum-exp) combine of P shard partials laid out [P,N] (+ [P,N,D] gradients). */
 int ladder_mixture_combine(const float* m_parts, const float* s_parts, const float* g_parts, int P,
                            long long N, int D, float* logp, float* grad_t, cudaStream_t stream);
@@ -191,6 +204,9 @@ int ladder_colsum_bf16(const void* g_bf16, long long rows, int cols, float* out,
  * Layout ops.  replaces tf.pad(..., "SYMMETRIC") codes/models.py:48-50,200-202 and
  * tf.nn.depth_to_space (NHWC, DCR order) codes/models.py:113-141,271-308.                  */
 int ladder_sym_pad(const float* x, float* y, int B, int H, int W, int C, int pad, cudaStream_t stream);
+/* gradient of the symmetric pad w.r.t. its input (the VampPrior pseudo-inputs are trained through the encoder's
+ * tf.pad, codes/base.py:224-229 + codes/models.py:48-50): dy [B,H+2p,W+2p,C] -> dx [B,H,W,C]; needs 2*pad <= H, W  */
+int ladder_sym_pad_bwd(const float* dy, float* dx, int B, int H, int W, int C, int pad, cudaStream_t stream);
 int ladder_depth_to_space(const float* x, float* y, int B, int H, int W, int C, int r, cudaStream_t stream);
 /* gradient of depth_to_space fused with the producer's activation derivative:
  * out[b,h,w,ch] = g[d2s position of ch] * act'(act_out[b,h,w,ch]);  (H,W,C) are the PRE-d2s dims */
@@ -307,7 +323,8 @@ int ladder_code_recon_bwd(const float* z, const float* zhat, const float* code_s
                           int dz_accumulate, long long n, cudaStream_t stream);
 /* define_loss scalar assembly (codes/base.py:257-413) + sigma (codes/models.py:152-159) +
  * inner_sigma clamp (codes/base.py:204-212).  prior_kind: 0 standard_gaussian, 1 ours,
- * 2 hierarchical.  R_entropy is R except the hierarchical branch's hard-coded 2 (base.py:345). */
+ * 2 hierarchical, 3 mixture over the MC samples of q(z|x) in z-space ("GMM" base.py:323-329 and
+ * "vampPrior" base.py:362-370; inner_sigma_var may be null).  R_entropy is R except the hierarchical branch's hard-coded 2 (base.py:345). */
 int ladder_elbo_scalars(float* scalars, const float* sigma_var, const float* inner_sigma_var, int B, int C, int R,
                         int R_entropy, int D_in, int N_mc, int sigma_takes_max, int clip_inner_sigma,
                         float inner_sigma_lb, float inner_sigma_ub, int prior_kind, int use_standard_gaussian,

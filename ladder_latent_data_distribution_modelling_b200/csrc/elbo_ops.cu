@@ -64,6 +64,31 @@ __global__ void sym_pad_kernel(const float* __restrict__ x, float* __restrict__ 
   }
 }
 
+// gradient of the symmetric pad (gather form): source pixel (h, w) collects its own image in the padded map plus the
+// mirror images -h-1 (h < p), 2H-1-h (h >= H-p), and likewise along w -- up to 4 padded positions, no atomics
+__global__ void sym_pad_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int B, int H, int W, int C, int p) {
+  const int HP = H + 2 * p, WP = W + 2 * p;
+  const long long n = (long long)B * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    int hs[3], ws[3], nh = 0, nw = 0;
+    hs[nh++] = h + p;
+    if (h < p) hs[nh++] = p - 1 - h;                   // padded row -h-1
+    if (h >= H - p) hs[nh++] = 2 * H - 1 - h + p;      // padded row 2H-1-h
+    ws[nw++] = w + p;
+    if (w < p) ws[nw++] = p - 1 - w;
+    if (w >= W - p) ws[nw++] = 2 * W - 1 - w + p;
+    float a = 0.f;
+    for (int ih = 0; ih < nh; ++ih)
+      for (int iw = 0; iw < nw; ++iw) a += dy[(((long long)b * HP + hs[ih]) * WP + ws[iw]) * C + c];
+    dx[i] = a;
+  }
+}
+
 // depth_to_space, NHWC "DCR": out[b, h*r+i, w*r+j, c] = in[b, h, w, (i*r+j)*Co + c]
 __global__ void d2s_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C, int r) {
   const int Co = C / (r * r);
@@ -263,7 +288,11 @@ __global__ void elbo_scalars_kernel(float* s, const float* sigma_var, const floa
   s[LADDER_O_RECON_LL] = recon_ll;
   s[LADDER_O_SIGMA_REG] = sigma_reg;
   float ce_prior = ce_sg;
-  if (c.prior_kind != 0) {
+  if (c.prior_kind == 3) {
+    // prior "GMM" (base.py:323-329) and "vampPrior" (base.py:362-370): mean log-density of the L MC samples of q(z|x)
+    // under a mixture in z-space; vampPrior switches back to the standard normal while use_standard_gaussian_prior
+    if (!c.use_sg) ce_prior = s[LADDER_S_MIX_LOGP] / (float)c.N_mc;
+  } else if (c.prior_kind != 0) {
     const float iv = fabsf(*inner_sigma_var);
     float isig = iv;
     bool pass = true;
@@ -342,6 +371,14 @@ int ladder_sym_pad(const float* x, float* y, int B, int H, int W, int C, int pad
   const long long n = (long long)B * (H + 2 * pad) * (W + 2 * pad) * C;
   LAUNCH_EW(sym_pad_kernel, n, x, y, B, H, W, C, pad);
   return check_launch("sym_pad");
+}
+
+int ladder_sym_pad_bwd(const float* dy, float* dx, int B, int H, int W, int C, int pad, cudaStream_t stream) {
+  LADDER_REQUIRE(dy && dx && B > 0 && H > 0 && W > 0 && C > 0 && pad >= 0 && 2 * pad <= H && 2 * pad <= W,
+                 "sym_pad_bwd: bad arguments");
+  const long long n = (long long)B * H * W * C;
+  LAUNCH_EW(sym_pad_bwd_kernel, n, dy, dx, B, H, W, C, pad);
+  return check_launch("sym_pad_bwd");
 }
 
 int ladder_depth_to_space(const float* x, float* y, int B, int H, int W, int C, int r, cudaStream_t stream) {
@@ -438,7 +475,7 @@ int ladder_elbo_scalars(float* scalars, const float* sigma_var, const float* inn
                         int R_entropy, int D_in, int N_mc, int sigma_takes_max, int clip_inner_sigma, float inner_sigma_lb,
                         float inner_sigma_ub, int prior_kind, int use_standard_gaussian, cudaStream_t stream) {
   LADDER_REQUIRE(scalars && sigma_var && B > 0 && C > 0 && D_in > 0, "elbo_scalars: bad arguments");
-  LADDER_REQUIRE(prior_kind == 0 || inner_sigma_var != nullptr, "elbo_scalars: inner_sigma missing");
+  LADDER_REQUIRE(prior_kind == 0 || prior_kind == 3 || inner_sigma_var != nullptr, "elbo_scalars: inner_sigma missing");
   ElboCfg c{B, C, R, R_entropy, D_in, N_mc, sigma_takes_max, clip_inner_sigma, inner_sigma_lb, inner_sigma_ub, prior_kind,
             use_standard_gaussian};
   elbo_scalars_kernel<<<1, 32, 0, stream>>>(scalars, sigma_var, inner_sigma_var, c);

@@ -71,7 +71,7 @@ __device__ __forceinline__ float ex2(float x) {
 template <int D, int MODE, int R, bool GRAD>
 __device__ __forceinline__ void accumulate_component(const float* __restrict__ c, const float (&t)[R][D],
                                                      float (&S)[R], float (&G)[R][GRAD ? D : 1]) {
-  if constexpr (D <= 8) {
+  if constexpr (D <= 8 || MODE == 2) {       // full covariance keeps y in registers up to D = 16 (R = 1 there)
     float y[R][D];
     float e[R];
     if constexpr (MODE == 0) {
@@ -131,7 +131,6 @@ __device__ __forceinline__ void accumulate_component(const float* __restrict__ c
     }
   } else {
     // wide-D path (iso / diag only): sweep dims in float4 groups, recompute y for the gradient
-    static_assert(MODE != 2 || D <= 8, "full covariance is register-path only for D <= 8");
     const float4* c4 = reinterpret_cast<const float4*>(c);
     float e[R];
     const float ck = MODE == 0 ? c[D] : c[2 * D];
@@ -228,6 +227,7 @@ struct MixArgs {
   int k_per_split;       // components per grid.y slice (multiple of kc)
   float iso_scale;       // a' for MODE 0 (queries are pre-scaled in-kernel)
   float ref_log2;        // M
+  const float* ref_dev;  // null, or M on the device (tables packed by ladder_mixture_pack_diag_device)
 };
 
 template <int D, int MODE, int R, bool GRAD>
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(MIX_THREADS) mix_kernel(MixArgs a) {
   for (int r = 0; r < R; ++r) {
     const long long n = row0 + (long long)r * MIX_THREADS + tid;
     if (n >= a.N) continue;
-    float frame = a.ref_log2;
+    float frame = a.ref_dev != nullptr ? __ldg(a.ref_dev) : a.ref_log2;
     float s = S[r];
     float g[GD];
 #pragma unroll
@@ -445,8 +445,8 @@ template <int D, bool GRAD>
 static int mix_dispatch_mode(int mode, const MixArgs& a, const MixPlan& p, cudaStream_t st) {
   if (mode == 0) return mix_launch<D, 0, GRAD>(a, p, st);
   if (mode == 1) return mix_launch<D, 1, GRAD>(a, p, st);
-  if constexpr (D <= 4) return mix_launch<D, 2, GRAD>(a, p, st);
-  return fail(LADDER_ERR_ARG, "full-covariance mixture supports D <= 4 (got %d)", D);
+  if constexpr (D <= 16) return mix_launch<D, 2, GRAD>(a, p, st);
+  return fail(LADDER_ERR_ARG, "full-covariance mixture supports D <= 16 (got %d)", D);
 }
 
 template <bool GRAD>
@@ -462,6 +462,119 @@ static int mix_dispatch(int D, int mode, const MixArgs& a, const MixPlan& p, cud
     case 64: return mix_dispatch_mode<64, GRAD>(mode, a, p, st);
     default: return fail(LADDER_ERR_ARG, "mixture: unsupported latent dim %d (1,2,3,4,8,16,32,64)", D);
   }
+}
+
+
+// ---------------------------------------------------------------- VampPrior support (codes/base.py:215-254)
+// The VampPrior mixture's means / stds are NETWORK OUTPUTS (shared encoder applied to the K pseudo-inputs), so its
+// table is packed on the device every step, the frame M lives on the device, and the loss needs d/d mean, d/d std.
+__global__ void mix_pack_diag_dev_kernel(const float* __restrict__ mean, const float* __restrict__ sd, int K, int D,
+                                         float* __restrict__ table, float* __restrict__ ref_log2) {
+  // one block; equal weights 1/K (tf.constant(1 / n_mixtures), base.py:241)
+  extern __shared__ float c2s[];                       // [K]
+  __shared__ float s_max;
+  const int stride = mix_stride(D, 1);
+  const float LOG2E = 1.4426950408889634f, HALF_LOG_2PI = 0.9189385332046727f;
+  const float sc = sqrtf(0.5f * LOG2E);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float* row = table + (size_t)k * stride;
+    float logdet = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float sdv = sd[(size_t)k * D + d], a = sc / sdv;
+      logdet -= logf(sdv);
+      row[d] = a;
+      row[D + d] = -a * mean[(size_t)k * D + d];
+    }
+    for (int i = 2 * D + 1; i < stride; ++i) row[i] = 0.f;
+    c2s[k] = (-logf((float)K) - D * HALF_LOG_2PI + logdet) * LOG2E;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) m = fmaxf(m, c2s[k]);
+    s_max = m;
+    *ref_log2 = m;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) table[(size_t)k * stride + 2 * D] = c2s[k] - s_max;
+}
+
+// dmean[k,d] += coef * sum_n r_nk (t_nd - mu_kd) / sd_kd^2
+// dstd [k,d] += coef * sum_n r_nk ((t_nd - mu_kd)^2 / sd_kd^3 - 1 / sd_kd),   r_nk = exp(e_nk - logp_n)
+// grid = (K, query slices); one component per block, queries strided over the threads, block reduce + one atomic per
+// (k, d, slice).
+constexpr int PG_THREADS = 256;
+template <int D>
+__global__ void __launch_bounds__(PG_THREADS) mix_diag_param_grad_kernel(const float* __restrict__ t, long long N,
+                                                                          const float* __restrict__ mean,
+                                                                          const float* __restrict__ sd, int K,
+                                                                          const float* __restrict__ logp, float coef,
+                                                                          long long rows_per_block,
+                                                                          float* __restrict__ dmean, float* __restrict__ dstd) {
+  const int k = blockIdx.x;
+  __shared__ float red[PG_THREADS / 32][2 * D];
+  float mu[D], isd[D];
+  float ck = -logf((float)K) - D * 0.9189385332046727f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    mu[d] = __ldg(mean + (size_t)k * D + d);
+    const float s = __ldg(sd + (size_t)k * D + d);
+    isd[d] = 1.f / s;
+    ck -= logf(s);
+  }
+  float gm[D], gs[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) gm[d] = gs[d] = 0.f;
+  const long long n0 = (long long)blockIdx.y * rows_per_block;
+  const long long n1 = min(N, n0 + rows_per_block);
+  for (long long n = n0 + threadIdx.x; n < n1; n += PG_THREADS) {
+    float u[D];
+    float q = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      u[d] = (__ldg(t + n * D + d) - mu[d]) * isd[d];
+      q = fmaf(u[d], u[d], q);
+    }
+    const float r = __expf(ck - 0.5f * q - __ldg(logp + n));
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      gm[d] = fmaf(r, u[d], gm[d]);                    // r * (t - mu) / sd          (one more 1/sd below)
+      gs[d] = fmaf(r, fmaf(u[d], u[d], -1.f), gs[d]);  // r * ((t - mu)^2 / sd^2 - 1) (one more 1/sd below)
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    float a = gm[d], b = gs[d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { red[warp][d] = a; red[warp][D + d] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * D) {
+    float a = 0.f;
+    for (int w = 0; w < PG_THREADS / 32; ++w) a += red[w][threadIdx.x];
+    const int d = threadIdx.x < D ? threadIdx.x : threadIdx.x - D;
+    const float v = coef * a * (1.f / __ldg(sd + (size_t)k * D + d));
+    atomicAdd((threadIdx.x < D ? dmean : dstd) + (size_t)k * D + d, v);
+  }
+}
+
+template <int D>
+static int param_grad_launch(const float* t, long long N, const float* mean, const float* sd, int K, const float* logp,
+                             float coef, float* dmean, float* dstd, cudaStream_t st) {
+  const int sms = num_sms();
+  long long slices = ceil_div64(4LL * sms, K);                       // ~4 blocks per SM overall
+  const long long max_slices = ceil_div64(N, PG_THREADS);
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  const long long rows = ceil_div64(N, slices);
+  dim3 grid((unsigned)K, (unsigned)ceil_div64(N, rows));
+  mix_diag_param_grad_kernel<D><<<grid, PG_THREADS, 0, st>>>(t, N, mean, sd, K, logp, coef, rows, dmean, dstd);
+  return check_launch("mixture diag param-grad kernel");
 }
 
 // (m, s[, g]) combine across P shards -> logp (and normalised gradient)
@@ -499,7 +612,7 @@ int ladder_mixture_table_stride(int D, int mode) {
 int ladder_mixture_pack_full(const double* mean, const double* cov, const double* weight, int K, int D,
                              float* table, float* ref_log2) {
   LADDER_REQUIRE(mean && cov && weight && table && ref_log2, "mixture_pack_full: null pointer");
-  LADDER_REQUIRE(K >= 1 && D >= 1 && D <= 8, "mixture_pack_full: need K >= 1, 1 <= D <= 8");
+  LADDER_REQUIRE(K >= 1 && D >= 1 && D <= 16, "mixture_pack_full: need K >= 1, 1 <= D <= 16");
   const int stride = mix_stride(D, 2), TRI = D * (D + 1) / 2;
   const double LOG2E = 1.4426950408889634, HALF_LOG_2PI = 0.9189385332046727;
   const double sc = std::sqrt(0.5 * LOG2E);
@@ -597,9 +710,9 @@ size_t ladder_mixture_workspace_bytes(long long N, int K, int D, int mode, int w
   return mix_plan(N, K, D, mode, with_grad != 0).ws_bytes;
 }
 
-int ladder_mixture_logprob(const float* t, long long N, int D, const float* table, int K, int mode,
-                           float iso_scale, float ref_log2, float* logp, float* grad_t, float* m_out,
-                           float* s_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+static int mixture_logprob_impl(const float* t, long long N, int D, const float* table, int K, int mode,
+                                float iso_scale, float ref_log2, const float* ref_dev, float* logp, float* grad_t,
+                                float* m_out, float* s_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   LADDER_REQUIRE(N >= 0 && K >= 1, "mixture_logprob: need N >= 0, K >= 1 (N=%lld K=%d)", N, K);
   LADDER_REQUIRE(mode >= 0 && mode <= 2, "mixture_logprob: mode must be 0 (iso), 1 (diag) or 2 (full)");
   LADDER_REQUIRE((m_out == nullptr) == (s_out == nullptr), "mixture_logprob: m_out and s_out go together");
@@ -617,8 +730,53 @@ int ladder_mixture_logprob(const float* t, long long N, int D, const float* tabl
   size_t off = 256 + (size_t)p.row_tiles * sizeof(unsigned);
   off = (off + 255) / 256 * 256;
   a.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + off);
-  a.N = N; a.K = K; a.kc = p.kc; a.k_per_split = p.k_per_split; a.iso_scale = iso_scale; a.ref_log2 = ref_log2;
+  a.N = N; a.K = K; a.kc = p.kc; a.k_per_split = p.k_per_split; a.iso_scale = iso_scale; a.ref_log2 = ref_log2; a.ref_dev = ref_dev;
   return grad ? mix_dispatch<true>(D, mode, a, p, stream) : mix_dispatch<false>(D, mode, a, p, stream);
+}
+
+int ladder_mixture_logprob(const float* t, long long N, int D, const float* table, int K, int mode,
+                           float iso_scale, float ref_log2, float* logp, float* grad_t, float* m_out,
+                           float* s_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return mixture_logprob_impl(t, N, D, table, K, mode, iso_scale, ref_log2, nullptr, logp, grad_t, m_out, s_out, workspace,
+                              workspace_bytes, stream);
+}
+
+int ladder_mixture_logprob_devref(const float* t, long long N, int D, const float* table, int K, int mode,
+                                  const float* ref_log2_dev, float* logp, float* grad_t, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream) {
+  LADDER_REQUIRE(ref_log2_dev != nullptr && mode == 1, "mixture_logprob_devref: diagonal tables packed on the device only");
+  return mixture_logprob_impl(t, N, D, table, K, mode, 1.f, 0.f, ref_log2_dev, logp, grad_t, nullptr, nullptr, workspace,
+                              workspace_bytes, stream);
+}
+
+int ladder_mixture_pack_diag_device(const float* mean_dev, const float* std_dev, int K, int D, float* table_dev,
+                                    float* ref_log2_dev, cudaStream_t stream) {
+  LADDER_REQUIRE(mean_dev && std_dev && table_dev && ref_log2_dev, "mixture_pack_diag_device: null pointer");
+  LADDER_REQUIRE(K >= 1 && K <= 8192 && D >= 1, "mixture_pack_diag_device: need 1 <= K <= 8192, D >= 1");
+  mix_pack_diag_dev_kernel<<<1, 256, (size_t)K * sizeof(float), stream>>>(mean_dev, std_dev, K, D, table_dev, ref_log2_dev);
+  return check_launch("mixture pack (device)");
+}
+
+int ladder_mixture_diag_param_grad(const float* t, long long N, int D, const float* mean_dev, const float* std_dev, int K,
+                                   const float* logp, float coef, float* dmean, float* dstd, cudaStream_t stream) {
+  LADDER_REQUIRE(N >= 0 && K >= 1, "mixture_diag_param_grad: bad sizes");
+  LADDER_REQUIRE(mean_dev && std_dev && dmean && dstd, "mixture_diag_param_grad: null pointer");
+  if (cudaMemsetAsync(dmean, 0, (size_t)K * D * sizeof(float), stream) != cudaSuccess ||
+      cudaMemsetAsync(dstd, 0, (size_t)K * D * sizeof(float), stream) != cudaSuccess)
+    return fail(LADDER_ERR_CUDA, "mixture_diag_param_grad: memset failed");
+  if (N == 0) return LADDER_OK;
+  LADDER_REQUIRE(t && logp, "mixture_diag_param_grad: null input");
+  switch (D) {
+    case 1: return param_grad_launch<1>(t, N, mean_dev, std_dev, K, logp, coef, dmean, dstd, stream);
+    case 2: return param_grad_launch<2>(t, N, mean_dev, std_dev, K, logp, coef, dmean, dstd, stream);
+    case 3: return param_grad_launch<3>(t, N, mean_dev, std_dev, K, logp, coef, dmean, dstd, stream);
+    case 4: return param_grad_launch<4>(t, N, mean_dev, std_dev, K, logp, coef, dmean, dstd, stream);
+    case 8: return param_grad_launch<8>(t, N, mean_dev, std_dev, K, logp, coef, dmean, dstd, stream);
+    case 16: return param_grad_launch<16>(t, N, mean_dev, std_dev, K, logp, coef, dmean, dstd, stream);
+    case 32: return param_grad_launch<32>(t, N, mean_dev, std_dev, K, logp, coef, dmean, dstd, stream);
+    case 64: return param_grad_launch<64>(t, N, mean_dev, std_dev, K, logp, coef, dmean, dstd, stream);
+    default: return fail(LADDER_ERR_ARG, "mixture_diag_param_grad: unsupported latent dim %d (1,2,3,4,8,16,32,64)", D);
+  }
 }
 
 int ladder_mixture_combine(const float* m_parts, const float* s_parts, const float* g_parts, int P,

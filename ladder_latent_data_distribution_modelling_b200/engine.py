@@ -12,6 +12,7 @@ dgrad fuses the activation derivative of the layer that PRODUCED its input, and 
 depth_to_space gradient kernel does the same across the permutation.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -280,13 +281,14 @@ class MnistOuterVAE:
         self.dec_dense.backward(dpre.view(B, 1, 1, -1), dx=dz.view(B, 1, 1, self.C), wgrad=wgrad)
         return dz
 
-    def encode_backward(self, dz, c_entropy, c_sg):
-        """dz: d loss / d code_sample (already summed over its consumers)."""
+    def encode_backward(self, dz, c_entropy, c_sg, dmean_add=None, dstd_add=None):
+        """dz: d loss / d code_sample (already summed over its consumers); dmean_add / dstd_add: extra gradient on
+        code_mean / code_std_dev (the MC-sample terms of the GMM prior branch)."""
         B, C = self.B, self.C
         floor = float(self.cfg['latent_variance_precision'])
         dmean = self.buf.get('dmean', B, C)
         dstd = self.buf.get('dstd', B, C)
-        ops.gauss_head_bwd(dz, self.mean, self.std, self.eps_z, None, None, dmean, dstd, floor, c_entropy, c_sg)
+        ops.gauss_head_bwd(dz, self.mean, self.std, self.eps_z, dmean_add, dstd_add, dmean, dstd, floor, c_entropy, c_sg)
         dfeat = self.buf.get('dfeat', B, 1, 1, self.feat)
         prod = (self.enc_dense.y, LEAKY)
         self.head_mean.backward(dmean.view(B, 1, 1, C), dx=dfeat, producer=prod)
@@ -496,11 +498,11 @@ class CelebAOuterVAE:
         self.dec_dense.backward(d_enc, dx=dz.view(B, 1, 1, self.C), wgrad=wgrad)
         return dz
 
-    def encode_backward(self, dz, c_entropy, c_sg):
+    def encode_backward(self, dz, c_entropy, c_sg, dmean_add=None, dstd_add=None):
         B, C = self.B, self.C
         floor = float(self.cfg['latent_variance_precision'])
         dmean, dstd = self.buf.get('dmean', B, C), self.buf.get('dstd', B, C)
-        ops.gauss_head_bwd(dz, self.mean, self.std, self.eps_z, None, None, dmean, dstd, floor, c_entropy, c_sg)
+        ops.gauss_head_bwd(dz, self.mean, self.std, self.eps_z, dmean_add, dstd_add, dmean, dstd, floor, c_entropy, c_sg)
         dflat = self.buf.get('dflat', B, 1, 1, self.flat)
         self.head_mean.backward(dmean.view(B, 1, 1, C), dx=dflat)
         self.head_std.backward(dstd.view(B, 1, 1, C), dx=dflat, accumulate=True)
@@ -583,7 +585,7 @@ class PriorVAE:
 
 
 # ------------------------------------------------------------------------------ the sub-step engine
-PRIOR_KIND = {'standard_gaussian': 0, 'ours': 1, 'hierarchical': 2}
+PRIOR_KIND = {'standard_gaussian': 0, 'ours': 1, 'hierarchical': 2, 'GMM': 3}
 
 
 def vae_param_specs(config):
@@ -718,10 +720,20 @@ class LadderEngine:
             self.dmu_add = torch.empty(B, self.R, device=dev)
             self.dsd_add = torch.empty(B, self.R, device=dev)
             self.mixture = None
+        if self.prior == 'GMM':
+            # prior "GMM" (base.py:323-329): L samples of q(z|x) scored under a full-covariance mixture in z-space (D = C)
+            self.eps_mc = torch.zeros(self.L, B, self.C, device=dev)
+            self.t_mc = torch.empty(self.L * B, self.C, device=dev)
+            self.g_mc = torch.empty(self.L * B, self.C, device=dev)
+            self.logp_mc = torch.empty(self.L * B, device=dev)
+            self.dmu_add = torch.empty(B, self.C, device=dev)
+            self.dsd_add = torch.empty(B, self.C, device=dev)
+            self.mixture = None
         self.use_sg = self.prior == 'standard_gaussian'
         self.use_mask = False
-        # CUDA graphs: on by default on one GPU (optional config key `cuda_graphs`)
-        self.use_graphs = bool(config.get('cuda_graphs', self.world == 1))
+        # CUDA graphs: on by default (optional config key `cuda_graphs`); data-parallel runs capture the NCCL all-reduces
+        # of torch.distributed inside the sub-step graph (LADDER_DP_GRAPHS=0 launches data-parallel sub-steps eagerly)
+        self.use_graphs = bool(config.get('cuda_graphs', self.world == 1 or os.environ.get('LADDER_DP_GRAPHS', '1') != '0'))
         self._graphs, self._static_x, self._feed_version = {}, None, 0
         self._graph_launches, self.replayed_launches = {}, 0     # kernels of libladder_sm100 replayed through graphs
 
@@ -785,7 +797,7 @@ class LadderEngine:
             self.eps_z.normal_(generator=self.gen)
         if t and self.has_prior:
             self.eps_t.normal_(generator=self.gen)
-        if mc and self.prior == 'ours':
+        if mc and self.prior in ('ours', 'GMM'):
             self.eps_mc.normal_(generator=self.gen)
 
     def set_noise(self, eps_z=None, eps_t=None, eps_mc=None):
@@ -823,6 +835,15 @@ class LadderEngine:
                 ops.mixture_logprob(self.t_mc, self.mixture, want_grad=True,
                                     out={'logp': self.logp_mc, 'grad': self.g_mc})
                 ops.sum_into(self.logp_mc, s[11:12])
+        elif self.prior == 'GMM':
+            kind = PRIOR_KIND['GMM']
+            if mix:
+                if self.mixture is None:
+                    raise RuntimeError('engine: mixture feeds (prior_mean/prior_cov/prior_weight) were never set')
+                ops.mc_sample(self.outer.mean, self.outer.std, self.eps_mc, self.t_mc)
+                ops.mixture_logprob(self.t_mc, self.mixture, want_grad=True,
+                                    out={'logp': self.logp_mc, 'grad': self.g_mc})
+                ops.sum_into(self.logp_mc, s[11:12])
         self._allreduce(s[:12])            # batch-global sums (sigma, means) across data-parallel ranks
         cfg = self.cfg
         takes_max = cfg['exp_name'] == 'celeba' or int(cfg['TRAIN_sigma']) == 1
@@ -853,7 +874,12 @@ class LadderEngine:
         if self.has_prior and not self.use_sg:
             self._prior_backward(self.dz, wgrad=False)
         Bg = self.B_global
-        self.outer.encode_backward(self.dz, -1.0 / Bg, (1.0 / Bg) if self.use_sg else 0.0)
+        if self.prior == 'GMM':
+            # d(-mean log p)/d(code_mean, code_std_dev) through the L reparameterised samples
+            ops.mc_reduce(self.g_mc, self.eps_mc, -1.0 / (self.L * Bg), self.dmu_add, self.dsd_add)
+            self.outer.encode_backward(self.dz, -1.0 / Bg, 0.0, self.dmu_add, self.dsd_add)
+        else:
+            self.outer.encode_backward(self.dz, -1.0 / Bg, (1.0 / Bg) if self.use_sg else 0.0)
         self._allreduce(self.ae.grad)
         if apply:
             self.ae.apply_adam()
@@ -910,7 +936,8 @@ class LadderEngine:
             n0 = ops.launch_count()
             if hasattr(g, 'register_generator_state'):
                 g.register_generator_state(self.gen)
-            with torch.cuda.graph(g):
+            # thread_local: the NCCL watchdog thread of torch.distributed may touch CUDA while this thread captures
+            with torch.cuda.graph(g, capture_error_mode='thread_local' if self.world > 1 else 'global'):
                 self.draw_noise(**self._STEP_NOISE[name])
                 fn(self._static_x)
             self._graphs = {k: v for k, v in self._graphs.items() if k[1] == self._feed_version}
@@ -920,6 +947,10 @@ class LadderEngine:
             self._static_x.copy_(x)
         g.replay()
         self.replayed_launches += self._graph_launches[key]
+
+    def release_graphs(self):
+        """Drop the captured sub-step graphs (and their private memory pools)."""
+        self._graphs, self._graph_launches = {}, {}
 
     def fetch(self, names):
         """Device->host read of named ELBO terms (reference attribute names)."""

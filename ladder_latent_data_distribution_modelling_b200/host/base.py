@@ -252,6 +252,20 @@ class BaseTrain_joint(BaseTrain):
             feed['use_standard_gaussian_prior'] = self.cur_epoch <= cfg['sg_pretraining']
         elif cfg['prior'] == 'standard_gaussian':
             pass
+        elif cfg['prior'] == 'GMM':
+            C = cfg['code_size']
+            if self.cur_epoch == 1:                                     # base.py:912-923: K copies of N(0, I) in z-space
+                if getattr(self, '_dummy_fed', None) != 'dummy':
+                    feed.update(prior_mean=np.zeros((K, C)), prior_cov=np.tile(np.eye(C)[None], (K, 1, 1)),
+                                prior_weight=np.ones(K) / K)
+                    self._dummy_fed = 'dummy'
+            else:
+                gm = self.model.GM_prior_training
+                stamp = ('fit', id(gm.means_))
+                if getattr(self, '_dummy_fed', None) != stamp:          # base.py:924-933: fitted covariances + 0.01 I
+                    feed.update(prior_mean=gm.means_, prior_cov=gm.covariances_ + 0.01 * np.eye(C)[None],
+                                prior_weight=gm.weights_)
+                    self._dummy_fed = stamp
         else:
             raise NotImplementedError("prior=%r feeds are not built yet" % cfg['prior'])
         return feed

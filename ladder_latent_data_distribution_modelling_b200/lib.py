@@ -28,6 +28,11 @@ SIGNATURES = {
     'ladder_mixture_workspace_bytes': (C.c_size_t, [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]),
     'ladder_mixture_logprob': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, C.c_int, C.c_int, C.c_float, C.c_float,
                                          ptr, ptr, ptr, ptr, ptr, C.c_size_t, stream_t]),
+    'ladder_mixture_pack_diag_device': (C.c_int, [ptr, ptr, C.c_int, C.c_int, ptr, ptr, stream_t]),
+    'ladder_mixture_logprob_devref': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, C.c_int, C.c_int, ptr, ptr, ptr, ptr,
+                                                C.c_size_t, stream_t]),
+    'ladder_mixture_diag_param_grad': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, ptr, C.c_int, ptr, C.c_float, ptr, ptr,
+                                                 stream_t]),
     # conv / dense
     'ladder_conv2d_workspace_bytes': (C.c_size_t, [C.c_int] * 7),
     'ladder_conv2d_fprop': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 14 + [ptr, C.c_size_t, stream_t]),
@@ -58,6 +63,7 @@ SIGNATURES = {
     'ladder_colsum_bf16': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, stream_t]),
     # layout / elementwise
     'ladder_sym_pad': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),
+    'ladder_sym_pad_bwd': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),
     'ladder_depth_to_space': (C.c_int, [ptr, ptr] + [C.c_int] * 5 + [stream_t]),
     'ladder_space_to_depth_actgrad': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 6 + [stream_t]),
     'ladder_act_bwd': (C.c_int, [ptr, ptr, C.c_longlong, C.c_int, stream_t]),

@@ -73,6 +73,7 @@ class MixtureTable:
     def __init__(self, table, K, D, mode, iso_scale, ref_log2, tc_image=None):
         self.table, self.K, self.D, self.mode = table, K, D, mode
         self.iso_scale, self.ref_log2 = iso_scale, ref_log2
+        self.ref_dev = None               # device-resident frame (tables packed by mixture_pack_diag_device)
         self.tc_image = tc_image          # tensor-core operand image (isotropic, D in {32, 64}); forward only
 
     def shard(self, rank, world):
@@ -127,6 +128,28 @@ def mixture_pack_diag(mean, std, weight=None, device='cuda'):
     return MixtureTable(torch.from_numpy(table).to(device), K, D, mode, iso.value, ref.value, tc_image)
 
 
+def mixture_pack_diag_device(mean, std, tab=None):
+    """Pack a diagonal equal-weight mixture whose mean / std [K,D] are DEVICE tensors (VampPrior: outputs of the shared
+    encoder on the pseudo-inputs, base.py:226-254) without leaving the device; `tab` is reused when given."""
+    _f32(mean, 'mean'), _f32(std, 'std')
+    K, D = mean.shape
+    if tab is None:
+        stride = _L().ladder_mixture_table_stride(D, 1)
+        tab = MixtureTable(torch.zeros(K, stride, device=mean.device), K, D, 1, 1.0, 0.0)
+        tab.ref_dev = torch.zeros(1, device=mean.device)
+    _lib.check(_L().ladder_mixture_pack_diag_device(_p(mean), _p(std), K, D, _p(tab.table), _p(tab.ref_dev), _stream()),
+               'mixture_pack_diag_device')
+    return tab
+
+
+def mixture_diag_param_grad(t, mean, std, logp, coef, dmean, dstd):
+    """d(coef * sum_n log p(t_n)) / d(mean, std) of the diagonal equal-weight mixture (overwrites dmean, dstd)."""
+    N, D = t.shape
+    _lib.check(_L().ladder_mixture_diag_param_grad(_p(_f32(t)), N, D, _p(_f32(mean)), _p(_f32(std)), mean.shape[0],
+                                                   _p(_f32(logp)), float(coef), _p(_f32(dmean)), _p(_f32(dstd)), _stream()),
+               'mixture_diag_param_grad')
+
+
 MIXTURE_TC = True      # use the tcgen05 kernel for isotropic D in {32, 64} forward evaluations
 
 
@@ -166,6 +189,13 @@ def mixture_logprob(t, tab, want_grad=False, partial=False, out=None, exact=Fals
         logp = out.get('logp') if 'logp' in out else torch.empty(N, device=dev, dtype=torch.float32)
     nbytes = _L().ladder_mixture_workspace_bytes(N, tab.K, D, tab.mode, int(want_grad))
     ws = _workspace(dev, nbytes, 'mixture')
+    if getattr(tab, 'ref_dev', None) is not None:          # frame lives on the device (mixture_pack_diag_device)
+        if partial:
+            raise RuntimeError('mixture_logprob: device-packed tables do not support shard partials')
+        _lib.check(_L().ladder_mixture_logprob_devref(_p(t), N, D, _p(tab.table), tab.K, tab.mode, _p(tab.ref_dev),
+                                                      _p(logp), _p(grad), _p(ws), ws.numel(), _stream()),
+                   'mixture_logprob_devref')
+        return (logp, grad) if want_grad else logp
     _lib.check(_L().ladder_mixture_logprob(_p(t), N, D, _p(tab.table), tab.K, tab.mode, tab.iso_scale, tab.ref_log2,
                                            _p(logp), _p(grad), _p(m), _p(s), _p(ws), ws.numel(), _stream()),
                'mixture_logprob')
@@ -515,6 +545,11 @@ def conv2d_wgrad(x, dy, dw, dbias, g):
 def sym_pad(x, y, B, H, W, Cc, pad):
     _lib.check(_L().ladder_sym_pad(_p(_f32(x)), _p(_f32(y)), B, H, W, Cc, pad, _stream()), 'sym_pad')
     return y
+
+
+def sym_pad_bwd(dy, dx, B, H, W, Cc, pad):
+    _lib.check(_L().ladder_sym_pad_bwd(_p(_f32(dy)), _p(_f32(dx)), B, H, W, Cc, pad, _stream()), 'sym_pad_bwd')
+    return dx
 
 
 def depth_to_space(x, y, B, H, W, Cc, r):

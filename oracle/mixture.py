@@ -111,3 +111,28 @@ def mixture_logprob_var(samples, mean, cov, weight):
     lp = lp.astype(samples.v.dtype).reshape(shp[:-1])
     g = g.astype(samples.v.dtype).reshape(shp)
     return Var(lp, (samples,), lambda up: (up[..., None] * g,))
+
+
+def diag_mixture_logprob_var(samples, mean, std):
+    """Tape op: the VampPrior mixture `psedeu_prior.log_prob(samples)` (base.py:241-254): K diagonal Gaussians
+    N(mean_k, diag(std_k^2)) with equal weights 1/K.  Unlike the fed GMM, `mean` [K,D] and `std` [K,D] are network
+    outputs (the shared encoder applied to the pseudo-inputs), so the gradient flows to samples, mean AND std."""
+    shp = samples.shape
+    t = samples.v.reshape(-1, shp[-1]).astype(np.float64)
+    mu, sd = mean.v.astype(np.float64), std.v.astype(np.float64)
+    K, D = mu.shape
+    diff = t[:, None, :] - mu[None]                                     # [N,K,D]
+    e = -np.log(K) - 0.5 * D * LOG_2PI - np.log(sd).sum(axis=1)[None] - 0.5 * np.square(diff / sd[None]).sum(axis=2)
+    lp = logsumexp(e, axis=1)
+    r = np.exp(e - lp[:, None])                                         # responsibilities [N,K]
+    dt = diff / np.square(sd)[None]                                     # -d e / d t = d e / d mu
+
+    def back(up):
+        u = up.reshape(-1).astype(np.float64)
+        w = u[:, None] * r                                              # [N,K]
+        g_t = -(w[:, :, None] * dt).sum(axis=1)
+        g_mu = (w[:, :, None] * dt).sum(axis=0)
+        g_sd = (w[:, :, None] * (np.square(diff) / sd[None] ** 3 - 1.0 / sd[None])).sum(axis=0)
+        dt_ = samples.v.dtype
+        return g_t.astype(dt_).reshape(shp), g_mu.astype(dt_), g_sd.astype(dt_)
+    return Var(lp.astype(samples.v.dtype).reshape(shp[:-1]), (samples, mean, std), back)

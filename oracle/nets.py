@@ -12,7 +12,7 @@ eps_mc [L,B,R or C]).  PARITY UNPINNED (see oracle/__init__.py).
 import numpy as np
 
 from . import tape as T
-from .mixture import mixture_logprob_var
+from .mixture import diag_mixture_logprob_var, mixture_logprob_var
 
 TWO_PI = 2.0 * np.pi
 
@@ -231,6 +231,12 @@ def define_loss(config, x, o, feeds, noise):
         samples = o['code_mean'] + o['code_std_dev'] * noise['eps_mc']
         lp = mixture_logprob_var(samples, feeds['prior_mean'], feeds['prior_cov'], feeds['prior_weight'])
         o['crossEntropy_prior'] = T.reduce_mean(lp)
+    elif prior == 'vampPrior':
+        # base.py:362-370: L samples of q(z|x) under the pseudo-input mixture; tf.cond picks the N(0, I) term in pretraining
+        samples = o['code_mean'] + o['code_std_dev'] * noise['eps_mc']
+        lp = diag_mixture_logprob_var(samples, o['code_mean_prior'], o['code_std_dev_prior'])
+        o['vampPrior_crossEntropy'] = T.reduce_mean(lp)
+        o['crossEntropy_prior'] = o['crossEntropy_prior_sg'] if use_sg else o['vampPrior_crossEntropy']
     else:
         raise NotImplementedError(prior)
 
@@ -246,6 +252,8 @@ def define_loss(config, x, o, feeds, noise):
     o['loss_ae'] = o['negative_elbo']
     if prior in ('ours', 'hierarchical'):
         o['loss_prior'] = -o['elbo_prior']
+    elif prior == 'vampPrior':
+        o['loss_prior'] = o['negative_elbo']                                   # base.py:407-408
     return o
 
 
@@ -257,6 +265,10 @@ def build(config, params, x, noise, feeds, dtype=np.float64, code_input=None):
     o = outer_vae(config, P, xv, nz['eps_z'], code_input=code_input)
     if config['prior'] in ('ours', 'hierarchical'):
         o.update(inner_vae(config, P, o['code_sample'], nz['eps_t']))
+    elif config['prior'] == 'vampPrior':
+        # define_vampPrior (base.py:215-254): the SHARED encoder + heads applied to the K trainable pseudo-inputs
+        feat = ENCODERS[config['exp_name']](config, P, P['prior/Variable'])
+        o['code_mean_prior'], o['code_std_dev_prior'] = gaussian_head(config, P, feat)
     define_loss(config, xv, o, feeds, nz)
     return P, o
 

@@ -89,7 +89,11 @@ def vae_param_specs(config):
 
 
 def prior_param_specs(config):
-    """[(name, shape)] for scope prior (+ 'inner_sigma/Variable'), base.py:141-205."""
+    """[(name, shape)] for scope prior (+ 'inner_sigma/Variable'), base.py:141-205; prior == 'vampPrior': the one
+    pseudo-input variable of define_vampPrior (base.py:224-225)."""
+    if config.get('prior') == 'vampPrior':
+        return [('prior/Variable', (int(config['n_mixtures']), int(config['dim_input_x']), int(config['dim_input_y']),
+                                    int(config['dim_input_channel'])))]
     C = int(config['code_size'])
     R = int(config['representation_size'])
     Hi = int(config['num_hidden_units_inner_VAE'])
@@ -127,6 +131,8 @@ def glorot_init(specs, config, seed, dtype=np.float64):
             v = np.asarray(config['sigma'], dtype=dtype)
         elif name == 'inner_sigma/Variable':
             v = np.asarray(config['inner_sigma'], dtype=dtype)
+        elif name == 'prior/Variable':                       # tf.random.normal pseudo-inputs (base.py:224)
+            v = rng.normal(size=shape).astype(dtype)
         elif name.endswith('/kernel'):
             if len(shape) == 4:
                 rf = shape[0] * shape[1]

@@ -33,6 +33,8 @@ def compute_feeds(config, cur_epoch, gm=None):
         f['use_mask'] = cur_epoch >= int(config['use_mask_start'])
     elif prior == 'hierarchical':
         f['use_standard_gaussian_prior'] = cur_epoch <= int(config['sg_pretraining'])
+    elif prior == 'vampPrior':
+        f['use_standard_gaussian_prior'] = cur_epoch <= int(config['sg_pretraining'])    # base.py:934-941
     elif prior == 'GMM':
         C = int(config['code_size'])
         if cur_epoch == 1:
@@ -84,6 +86,9 @@ class OracleTrainer:
             self.names_inner_sigma = ['inner_sigma/Variable']
             self.opt_prior = AdamGroup(self.names_prior, self.params)
             self.opt_inner_sigma = AdamGroup(self.names_inner_sigma, self.params)
+        elif config['prior'] == 'vampPrior':
+            self.names_prior = ['prior/Variable']                    # prior_vars_ae = the pseudo-inputs (base.py:424-429)
+            self.opt_prior = AdamGroup(self.names_prior, self.params)
 
     def run(self, x, noise, feeds):
         return nets.build(self.config, self.params, x, noise, feeds, dtype=self.dtype)
@@ -111,7 +116,7 @@ class OracleTrainer:
         self.opt_prior.apply(self.params, g, lr)
         keys = ('elbo_prior', 'code_l1_reconstruction_error', 'code_reconstruction_likelihood',
                 'entropy_t', 'crossEntropy_representation', 'inner_sigma')
-        return {k: float(o[k].v) for k in keys}, g
+        return {k: float(o[k].v) for k in keys if k in o}, g
 
     def train_step_inner_sigma(self, x, noise, feeds, lr):
         """base.py:636-639"""
@@ -130,9 +135,9 @@ class OracleTrainer:
             out['ae'], _ = self.train_step_ae(x, noises[0], feeds, lr_ae)
             if int(cfg['TRAIN_sigma']) == 1:
                 out['sigma'], _ = self.train_step_sigma(x, noises[1], feeds, lr_sigma)
-        if cur_epoch > int(cfg['sg_pretraining']) - 1 and cfg['prior'] in ('ours', 'hierarchical') \
+        if cur_epoch > int(cfg['sg_pretraining']) - 1 and cfg['prior'] in ('ours', 'hierarchical', 'vampPrior') \
                 and int(cfg['TRAIN_prior']) == 1:
             out['prior'], _ = self.train_step_prior(x, noises[2], feeds, lr_prior)
-            if int(cfg['TRAIN_inner_sigma']) == 1:
+            if cfg['prior'] != 'vampPrior' and int(cfg['TRAIN_inner_sigma']) == 1:
                 out['inner_sigma'], _ = self.train_step_inner_sigma(x, noises[3], feeds, lr_is)
         return out

@@ -36,8 +36,9 @@ def make_case(exp, B, seed, prior='ours', epoch=None, **over):
                    eps_mc=rng.normal(size=(L, B, R)).astype(np.float32)) for _ in range(4)]
     if epoch is None:
         epoch = cfg['sg_pretraining'] + 1
-    a = rng.normal(size=(K, R, R))
-    gm = (rng.normal(size=(K, R)), a @ a.transpose(0, 2, 1) * 0.3 + 0.05 * np.eye(R), rng.uniform(0.05, 1, size=K))
+    Dm = C if prior == 'GMM' else R           # the "GMM" branch fits its mixture in z-space
+    a = rng.normal(size=(K, Dm, Dm))
+    gm = (rng.normal(size=(K, Dm)), a @ a.transpose(0, 2, 1) * 0.3 * 2 / Dm + 0.05 * np.eye(Dm), rng.uniform(0.05, 1, size=K))
     feeds = steps.compute_feeds(cfg, epoch, gm)
     return cfg, P, x, noises, feeds, epoch
 
@@ -153,6 +154,26 @@ def test_other_prior_branches(prior):
     if prior == 'hierarchical':
         eng.step_prior(torch.tensor(x, device='cuda'), apply=False)
         grad_check(eng, eng.prior_g, nets.grads_of(o['loss_prior'], Pv, eng.prior_g.names()))
+
+
+@pytest.mark.parametrize('exp,epoch', [('mnist_digit', 1), ('mnist_digit', 3), ('mnist_fashion', 3)])
+def test_gmm_prior_branch(exp, epoch):
+    """prior = "GMM" (base.py:323-329): L samples of q(z|x) under a full-covariance mixture in z-space (D = code_size
+    8 / 16), gradient through the reparameterised samples into the encoder heads; epoch 1 feeds the N(0, I) dummies,
+    later epochs the fitted mixture + 0.01 I (base.py:912-933)."""
+    B = 5
+    cfg, P, x, noises, feeds, _ = make_case(exp, B, 17, prior='GMM', epoch=epoch)
+    C, L = cfg['code_size'], cfg['n_MC_samples']
+    rng = np.random.default_rng(99)
+    nz = dict(noises[0], eps_mc=rng.normal(size=(L, B, C)).astype(np.float32))
+    eng = make_engine(cfg, P, feeds, B)
+    eng.set_noise(**{k: v for k, v in nz.items() if k != 'eps_t'})
+    eng.step_ae(torch.tensor(x, device='cuda'), apply=False)
+    Pv, o = nets.build(cfg, P, x, nz, feeds)
+    got = eng.fetch(SCALARS_AE)
+    for k in SCALARS_AE:
+        assert rel(got[k], float(o[k].v)) < 5e-5, (k, got[k], float(o[k].v))
+    grad_check(eng, eng.ae, nets.grads_of(o['loss_ae'], Pv, eng.ae.names()))
 
 
 @pytest.mark.parametrize('exp', ['mnist_digit', 'mnist_fashion'])

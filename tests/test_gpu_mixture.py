@@ -69,7 +69,7 @@ def test_diag_iso_all_dims(ops, D, mode):
 
 def test_full_cov_other_dims(ops):
     rng = np.random.default_rng(0)
-    for D in (1, 3, 4):
+    for D in (1, 3, 4, 8, 16):        # 8 / 16: the z-space mixture of the "GMM" prior branch (D = code_size)
         K, N = 13, 500
         m = rng.normal(size=(K, D)); a = rng.normal(size=(K, D, D))
         cov = a @ a.transpose(0, 2, 1) + 0.2 * np.eye(D)
