@@ -61,8 +61,9 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+    """nvidia-smi clocks / throttle reasons (the profiling recipe's query, one row every 20 ms, time-stamped) recorded for
+    the whole run; `summary(windows)` keeps the rows whose timestamp falls DURING the timed regions."""
+    Q = ('timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
@@ -76,32 +77,43 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
-        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.proc is None:
-            return out
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        self.proc = None
+
+    def summary(self, windows):
+        """windows: [(t0, t1)] host wall-clock bounds (time.time()) of the timed regions."""
+        import datetime
+        self.stop()
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0,
+               'windows': 'rows of `nvidia-smi -lms 20` time-stamped inside the %d timed region(s)' % len(windows)}
         sm, reasons = [], set()
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(',')]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    out['sm_max_mhz'] = float(f[2])
+                    ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                    mhz, mx = float(f[2]), float(f[3])
                 except ValueError:
                     continue
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if not any(t0 <= ts <= t1 for t0, t1 in windows):
+                    continue
+                sm.append(mhz)
+                out['sm_max_mhz'] = mx
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[6:10]):
                     if v.lower().startswith('active'):
                         reasons.add(name)
             os.unlink(self.path)
@@ -269,12 +281,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        iteration(pool[i % n_pool])
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        iteration(pool[i % n_pool])
+    barrier()
+    windows = []
+    w0 = time.time()
     launches0 = ops.launch_count() + eng.replayed_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     profile = os.environ.get('LADDER_BENCH_PROFILE') == '1'     # ncu --profile-from-start off: timed region only
@@ -287,11 +301,13 @@ def run_ours(args):
     barrier()
     if profile:
         torch.cuda.profiler.stop()
+        if rank == 0:
+            sampler.stop()
         print('profiled %d iterations (no bench line under a profiler)' % args.steps, file=sys.stderr)
         return
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count() + eng.replayed_launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    windows.append((w0, time.time()))
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -334,6 +350,7 @@ def run_ours(args):
         e2e_iteration(host_pool[i % n_pool])
     trainer._pending = []
     barrier()
+    w0 = time.time()
     e0.record()
     for i in range(args.steps):
         last = e2e_iteration(host_pool[i % n_pool])
@@ -344,6 +361,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
+    windows.append((w0, time.time()))               # second sampling window: the end-to-end timed region
+    clocks = sampler.summary(windows) if rank == 0 else None
 
     # ---- secondary workload: CelebA-shape (128x128x3) training step, BASELINE.json configs[3] per-GPU batch
     celeba = None

@@ -189,7 +189,20 @@ int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, 
  * fp32 or bf16 output; and the bf16 [B*H*W, ld] shifted copy DYS[p, tap] = dy[p - tap] that feeds the TMA wgrad. */
 int ladder_tap_dgrad(const float* dy, const float* w, const void* act_out /*nullable*/, int act_out_bf16, void* dx,
                      int dx_bf16, int B, int H, int W, int C, int Co /* <= 32 */, int KH, int KW, int pad_t, int pad_l, int OH,
-                     int OW, int act, int out_s2d, cudaStream_t stream);
+                     int OW, int act, int out_s2d, int accumulate /* dx += */, cudaStream_t stream);
+/* Short-reduction layers (KH*KW*Cin <= 32, Cout % 8 == 0, Cout <= 1024): the first encoder conv on the 1- / 3-channel image
+ * (codes/models.py:52-56, 203-207, 398-404) and dense layers fed by a latent (decoder/dense, codes/base.py:174-176).
+ * fp32 element-wise passes instead of GEMMs padded to a 64-wide k-block: fprop (bias + activation fused, y fp32 or bf16)
+ * and wgrad (dw, dbias overwritten; dbias nullable).  ladder_thin_n_dgrad: dx[M,N] (+)= dy[M,K] . w[N,K]^T for a dense
+ * layer with N = Cin <= 16 (gradient w.r.t. a latent code). */
+int ladder_thin_k_supported(int KH, int KW, int Cin, int Cout);
+int ladder_thin_k_fprop(const float* x, const float* w, const float* bias /*nullable*/, void* y, int y_bf16, int B, int H,
+                        int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
+                        cudaStream_t stream);
+int ladder_thin_k_wgrad(const float* x, const float* dy, float* dw, float* dbias /*nullable*/, int B, int H, int W, int Cin,
+                        int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream);
+int ladder_thin_n_dgrad(const float* dy, const float* w, float* dx, long long M, int N, int K, int accumulate,
+                        cudaStream_t stream);
 /* dw[c, co] = sum_p x[p, c] dy[p, co] for a 1x1 conv with <= 8 outputs; x fp32 or bf16, dw (HWIO) overwritten */
 int ladder_thin_wgrad_1x1(const void* x, int x_bf16, const float* dy, float* dw, long long P, int C, int Co,
                           cudaStream_t stream);

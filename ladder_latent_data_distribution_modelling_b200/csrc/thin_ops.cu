@@ -20,7 +20,7 @@ struct TapArgs {
   const void* aux;           // saved producer output indexed like dx rows (fp32 or bf16) or null
   void* dx;                  // [B, H, W, C] or its space_to_depth position
   int B, H, W, C, Co, KH, KW, pad_t, pad_l, OH, OW;
-  int act, aux_bf16, out_bf16, s2d;
+  int act, aux_bf16, out_bf16, s2d, accumulate;
 };
 
 // one thread = one pixel x 8 channels; the KH*KW*C weights sit in shared memory
@@ -77,6 +77,18 @@ __global__ void __launch_bounds__(256) tap_dgrad_kernel(TapArgs a) {
       for (int t = 0; t < 8; ++t) acc[t] *= a.act == ACT_TANH ? 1.f - ax[t] * ax[t] : (ax[t] > 0.f ? 1.f : slope);
     }
     const long long o = a.s2d > 0 ? s2d_dest(m, c0, a.H, a.W, a.C, a.s2d) : m * a.C + c0;
+    if (a.accumulate) {                                    // dx += ... (a second consumer of the same activation)
+      if (a.out_bf16) {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.dx) + o);
+        const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { acc[2 * t] += __uint_as_float(q[t] << 16); acc[2 * t + 1] += __uint_as_float(q[t] & 0xffff0000u); }
+      } else {
+        const float* p = reinterpret_cast<const float*>(a.dx) + o;
+        const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
+        acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w; acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+      }
+    }
     if (a.out_bf16) {
       uint4 u;
       __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
@@ -174,6 +186,174 @@ __global__ void __launch_bounds__(256) thin_wgrad_1x1_kernel(const void* __restr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Short-reduction layers (K = KH*KW*Cin <= 32): the first encoder conv on the 1- or 3-channel image (models.py:52-56,
+// 203-207, 398-404) and the dense layers fed by a latent (decoder/dense on z, prior decoder on t, prior encoder on z).
+// As GEMMs they pad K to a 64-wide k-block and run at a few percent of any roofline; they are bandwidth-bound
+// element-wise passes: fp32 math on fp32 inputs, output fp32 or bf16.
+struct ThinK {
+  const float* x;            // [B, H, W, Cin] fp32
+  const float* w;            // [KH*KW*Cin, Cout] (HWIO)
+  const float* bias;         // [Cout] or null
+  void* y;                   // [B, OH, OW, Cout] fp32 or bf16
+  int B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, act, out_bf16;
+};
+
+// one thread = one output pixel x 8 output channels; weights / bias through the read-only cache
+__global__ void __launch_bounds__(256) thin_k_fprop_kernel(ThinK a) {
+  const int n8 = a.Cout / 8;
+  const long long total = (long long)a.B * a.OH * a.OW * n8;
+  const float slope = a.act == ACT_LEAKY ? 0.2f : (a.act == ACT_RELU ? 0.f : 1.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n0 = (int)(i % n8) * 8;
+    const long long m = i / n8;
+    const int ox = (int)(m % a.OW);
+    const long long r = m / a.OW;
+    const int oy = (int)(r % a.OH);
+    const long long b = r / a.OH;
+    float acc[8];
+    if (a.bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + n0)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + 4));
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+    }
+    for (int kh = 0; kh < a.KH; ++kh) {
+      const int iy = oy * a.stride - a.pad_t + kh;
+      if (iy < 0 || iy >= a.H) continue;
+      for (int kw = 0; kw < a.KW; ++kw) {
+        const int ix = ox * a.stride - a.pad_l + kw;
+        if (ix < 0 || ix >= a.W) continue;
+        const float* xp = a.x + ((b * a.H + iy) * a.W + ix) * a.Cin;
+        const float* wp = a.w + (size_t)(kh * a.KW + kw) * a.Cin * a.Cout + n0;
+        for (int c = 0; c < a.Cin; ++c) {
+          const float xv = __ldg(xp + c);
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + (size_t)c * a.Cout));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + (size_t)c * a.Cout + 4));
+          acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+          acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]); acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = a.act == ACT_TANH ? tanhf(acc[t]) : (acc[t] > 0.f ? acc[t] : acc[t] * slope);
+    const long long o = m * a.Cout + n0;
+    if (a.out_bf16) {
+      uint4 u;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[4], acc[5]), p3 = __floats2bfloat162_rn(acc[6], acc[7]);
+      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + o) = u;
+    } else {
+      float* p = reinterpret_cast<float*>(a.y) + o;
+      *reinterpret_cast<float4*>(p) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(p + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
+// dw[k, n] = sum_p patch(p)[k] dy[p, n], db[n] = sum_p dy[p, n] for K <= KMAX.  Thread = 4 output channels x a strided set of
+// pixels of this block's pixel range; accumulators in registers; per-k block reduction through a small smem tile, then one
+// red.global.add per (k, n) per block.  dw / db must be zero on entry (the host wrapper clears them).
+template <int KMAX>
+__global__ void __launch_bounds__(256) thin_k_wgrad_kernel(ThinK a, const float* __restrict__ dy, float* __restrict__ dw,
+                                                           float* __restrict__ db, long long per) {
+  extern __shared__ float red[];                    // [lanes][Cout]
+  const int n4 = a.Cout / 4, lanes = blockDim.x / n4;
+  const int ng = threadIdx.x % n4, pl = threadIdx.x / n4;
+  const long long P = (long long)a.B * a.OH * a.OW;
+  const long long lo = (long long)blockIdx.x * per, hi = min(P, lo + per);
+  const int K = a.KH * a.KW * a.Cin;
+  __shared__ int koff[KMAX];                        // (kh << 16) | (kw << 8) | c of patch entry k: no division in the pixel loop
+  for (int k = threadIdx.x; k < KMAX; k += blockDim.x) {
+    const int c = k % a.Cin, tap = k / a.Cin;
+    koff[k] = k < K ? ((tap / a.KW) << 16) | ((tap % a.KW) << 8) | c : 0;
+  }
+  __syncthreads();
+  float acc[KMAX][4];
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+  if (pl < lanes) {
+    for (long long p = lo + pl; p < hi; p += lanes) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dy + p * a.Cout + ng * 4));
+      accb[0] += g.x; accb[1] += g.y; accb[2] += g.z; accb[3] += g.w;
+      const int ox = (int)(p % a.OW);
+      const long long r = p / a.OW;
+      const int oy = (int)(r % a.OH);
+      const long long b = r / a.OH;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          const int ko = koff[k];
+          const int c = ko & 0xff, iy = oy * a.stride - a.pad_t + (ko >> 16), ix = ox * a.stride - a.pad_l + ((ko >> 8) & 0xff);
+          float xv = 0.f;
+          if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) xv = __ldg(a.x + ((b * a.H + iy) * a.W + ix) * a.Cin + c);
+          acc[k][0] = fmaf(xv, g.x, acc[k][0]); acc[k][1] = fmaf(xv, g.y, acc[k][1]);
+          acc[k][2] = fmaf(xv, g.z, acc[k][2]); acc[k][3] = fmaf(xv, g.w, acc[k][3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k <= KMAX; ++k) {                 // k == KMAX: the bias row
+    if (k < K || k == KMAX) {
+      if (pl < lanes) {
+        float4 v = k == KMAX ? make_float4(accb[0], accb[1], accb[2], accb[3])
+                             : make_float4(acc[k < KMAX ? k : 0][0], acc[k < KMAX ? k : 0][1], acc[k < KMAX ? k : 0][2], acc[k < KMAX ? k : 0][3]);
+        *reinterpret_cast<float4*>(red + (size_t)pl * a.Cout + ng * 4) = v;
+      }
+      __syncthreads();
+      for (int n = threadIdx.x; n < a.Cout; n += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[(size_t)l * a.Cout + n];
+        if (k == KMAX) { if (db != nullptr) atomicAdd(db + n, s); }
+        else atomicAdd(dw + (size_t)k * a.Cout + n, s);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// dx[m, n] (+)= sum_k dy[m, k] w[n, k] for a dense layer with N = Cin <= 16 inputs (gradient w.r.t. a latent): one warp per
+// row, lanes stride over k (coalesced dy and w rows), warp-shuffle reduction of the N partial dot products.
+__global__ void __launch_bounds__(256) thin_n_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                           float* __restrict__ dx, long long M, int N, int K, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long m = warp; m < M; m += nwarps) {
+    float acc[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+    const float* g = dy + m * K;
+    for (int k = lane; k < K; k += 32) {
+      const float gv = __ldg(g + k);
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        if (n < N) acc[n] = fmaf(gv, __ldg(w + (size_t)n * K + k), acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      if (n < N) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+      }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int n = 0; n < 16; ++n)
+      if (n == lane) mine = acc[n];
+    if (lane < N) {
+      float* o = dx + m * N + lane;
+      *o = accumulate ? *o + mine : mine;
+    }
+  }
+}
+
 }  // namespace ladder
 
 using namespace ladder;
@@ -182,18 +362,70 @@ extern "C" {
 
 int ladder_tap_dgrad(const float* dy, const float* w, const void* act_out, int act_out_bf16, void* dx, int dx_bf16, int B,
                      int H, int W, int C, int Co, int KH, int KW, int pad_t, int pad_l, int OH, int OW, int act, int out_s2d,
-                     cudaStream_t stream) {
+                     int accumulate, cudaStream_t stream) {
   LADDER_REQUIRE(Co >= 1 && Co <= 32, "tap_dgrad: 1..32 output channels (got %d)", Co);
   LADDER_REQUIRE(dy && w && dx && B > 0 && H > 0 && W > 0 && C > 0 && KH > 0 && KW > 0 && OH > 0 && OW > 0, "tap_dgrad: bad arguments");
   LADDER_REQUIRE(C % 8 == 0, "tap_dgrad: channel count must be a multiple of 8 (got %d)", C);
   LADDER_REQUIRE(out_s2d == 0 || (H % out_s2d == 0 && W % out_s2d == 0), "tap_dgrad: space_to_depth(%d) needs H, W divisible by r", out_s2d);
   const size_t smem = (size_t)KH * KW * C * Co * sizeof(float);
   LADDER_REQUIRE(smem <= 48 * 1024, "tap_dgrad: KH*KW*C*Co = %d weights do not fit in 48 KB of shared memory", KH * KW * C * Co);
-  TapArgs a{dy, w, act_out, dx, B, H, W, C, Co, KH, KW, pad_t, pad_l, OH, OW, act, act_out_bf16, dx_bf16, out_s2d};
+  TapArgs a{dy, w, act_out, dx, B, H, W, C, Co, KH, KW, pad_t, pad_l, OH, OW, act, act_out_bf16, dx_bf16, out_s2d, accumulate};
   long long blocks = ceil_div64((long long)B * H * W * (C / 8), 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   tap_dgrad_kernel<<<(unsigned)blocks, 256, smem, stream>>>(a);
   return check_launch("tap_dgrad");
+}
+
+int ladder_thin_k_supported(int KH, int KW, int Cin, int Cout) {
+  return KH * KW * Cin <= 32 && Cout % 8 == 0 && Cout / 4 <= 256;
+}
+
+int ladder_thin_k_fprop(const float* x, const float* w, const float* bias, void* y, int y_bf16, int B, int H, int W, int Cin,
+                        int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act, cudaStream_t stream) {
+  LADDER_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && stride >= 1, "thin_k_fprop: bad arguments");
+  LADDER_REQUIRE(ladder_thin_k_supported(KH, KW, Cin, Cout), "thin_k_fprop: needs KH*KW*Cin <= 32 and Cout %% 8 == 0");
+  LADDER_REQUIRE(((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0 && (bias == nullptr || ((uintptr_t)bias & 15) == 0),
+                 "thin_k_fprop: w, bias and y must be 16-byte aligned");
+  ThinK a{x, w, bias, y, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, act, y_bf16};
+  long long blocks = ceil_div64((long long)B * OH * OW * (Cout / 8), 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  thin_k_fprop_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+  return check_launch("thin_k_fprop");
+}
+
+int ladder_thin_k_wgrad(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cin, int KH, int KW,
+                        int Cout, int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream) {
+  LADDER_REQUIRE(x && dy && dw && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && stride >= 1, "thin_k_wgrad: bad arguments");
+  LADDER_REQUIRE(ladder_thin_k_supported(KH, KW, Cin, Cout), "thin_k_wgrad: needs KH*KW*Cin <= 32 and Cout %% 8 == 0");
+  LADDER_REQUIRE(((uintptr_t)dy & 15) == 0, "thin_k_wgrad: dy must be 16-byte aligned");
+  const int K = KH * KW * Cin;
+  cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)K * Cout * sizeof(float), stream);
+  if (e == cudaSuccess && dbias != nullptr) e = cudaMemsetAsync(dbias, 0, (size_t)Cout * sizeof(float), stream);
+  if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "thin_k_wgrad memset: %s", cudaGetErrorString(e));
+  ThinK a{x, nullptr, nullptr, nullptr, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, 0, 0};
+  const int n4 = Cout / 4;
+  const int threads = n4 >= 256 ? n4 : 256 / n4 * n4;            // whole pixel lanes only
+  const int lanes = threads / n4;
+  const long long P = (long long)B * OH * OW;
+  long long blocks = 148 * 2;
+  long long per = ceil_div64(P, blocks);
+  if (per < 4LL * lanes) per = 4LL * lanes;
+  blocks = ceil_div64(P, per);
+  const size_t smem = (size_t)lanes * Cout * sizeof(float);
+  if (K <= 2) thin_k_wgrad_kernel<2><<<(unsigned)blocks, threads, smem, stream>>>(a, dy, dw, dbias, per);
+  else if (K <= 9) thin_k_wgrad_kernel<9><<<(unsigned)blocks, threads, smem, stream>>>(a, dy, dw, dbias, per);
+  else if (K <= 16) thin_k_wgrad_kernel<16><<<(unsigned)blocks, threads, smem, stream>>>(a, dy, dw, dbias, per);
+  else thin_k_wgrad_kernel<32><<<(unsigned)blocks, threads, smem, stream>>>(a, dy, dw, dbias, per);
+  return check_launch("thin_k_wgrad");
+}
+
+int ladder_thin_n_dgrad(const float* dy, const float* w, float* dx, long long M, int N, int K, int accumulate,
+                        cudaStream_t stream) {
+  LADDER_REQUIRE(dy && w && dx && M > 0 && N >= 1 && N <= 16 && K >= 1, "thin_n_dgrad: need 1 <= N <= 16 (got %d)", N);
+  long long blocks = ceil_div64(M, 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  thin_n_dgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dy, w, dx, M, N, K, accumulate);
+  return check_launch("thin_n_dgrad");
 }
 
 int ladder_tap_scatter_bf16(const float* dy, void* dys_bf16, int ld, int B, int H, int W, int KH, int KW, int pad_t, int pad_l,

@@ -94,6 +94,19 @@ class ParamGroup:
         ops.clip_adam(self.param, self.grad if grad is None else grad, self.m, self.v, self.lr, self.step)
 
 
+class SharedGroup(ParamGroup):
+    """A second instance of layers over the SAME parameters (tf.variable_scope(reuse=True), base.py:228-238): reads
+    the master group's flat parameter buffer, accumulates weight gradients into a buffer of its own (added to the
+    master gradient by the engine), and owns the weight images its own layer geometries need."""
+
+    def __init__(self, master):
+        self.name = master.name + '/shared'
+        self.specs, self.offsets, self.numel = master.specs, master.offsets, master.numel
+        self.param = master.param
+        self.grad = torch.zeros_like(master.grad)
+        self.convs = []
+
+
 def glorot_uniform_(t, shape, gen):
     """tf xavier_initializer / glorot_uniform: U(-l, l), l = sqrt(6 / (fan_in + fan_out))."""
     if len(shape) == 4:
@@ -150,16 +163,19 @@ class Conv:
         dy = dpre
         if dpre.dtype == torch.float32 and ((wgrad and self.tma[2]) or (dx is not None and self.tma[1])):
             dy = ops.to_bf16(dpre, tag='dy16')          # one conversion shared by wgrad and dgrad
+        dys = None
+        if wgrad and dx is not None and dpre.dtype == torch.float32 and ops.TAP_DGRAD_TC and ops.tap_gemm_dgrad_ok(g):
+            dys = ops.tap_dys(dpre, g)      # single-output-channel conv: one shifted copy of dy feeds wgrad and dgrad
         if wgrad:
             if self.tma[2]:
                 ops.conv2d_wgrad(self.xw, dy, self.dw, None, g)
                 ops.colsum(dpre, g.B * g.OH * g.OW, g.Cout, self.db)
             else:
-                ops.conv2d_wgrad(self.xw, dpre, self.dw, self.db, g)
+                ops.conv2d_wgrad(self.xw, dpre, self.dw, self.db, g, dys=dys)
         if dx is not None:
             ao, act = producer if producer is not None else (None, None)
             ops.conv2d_dgrad(dy if self.tma[1] else dpre, self.w, dx, g, act_out=ao, act=act, accumulate=accumulate,
-                             out_s2d=s2d, wimg=self.wimg[ops.DGRAD])
+                             out_s2d=s2d, wimg=self.wimg[ops.DGRAD], dys=dys)
         return dx
 
 
@@ -184,7 +200,7 @@ class MnistOuterVAE:
     (codes/models.py:199-315) for a fixed batch size."""
     last_act = 'relu'
 
-    def __init__(self, config, group, B, device):
+    def __init__(self, config, group, B, device, encoder_only=False):
         self.cfg, self.group, self.B, self.dev = config, group, B, device
         exp = config['exp_name']
         H = int(config['num_hidden_units'])
@@ -209,6 +225,13 @@ class MnistOuterVAE:
         self.enc_dense = Conv(group, 'encoder/dense', G.dense(B, flat, feat), LEAKY, device)
         self.head_mean = Conv(group, 'encoder/code_mean', G.dense(B, feat, C), None, device)
         self.head_std = Conv(group, 'encoder/code_std_dev', G.dense(B, feat, C), None, device)
+        self.flat, self.feat, self.C = flat, feat, C
+        self.mean = self.head_mean.y.view(B, C)
+        self.std = self.head_std.y.view(B, C)              # becomes relu(.)+floor in place
+        self.z = torch.empty(B, C, device=device)
+        self.dec, self.decoded = [], None
+        if encoder_only:                                   # VampPrior pseudo-input path (base.py:228-238)
+            return
         # decoder: dense -> [d2s -> conv]* -> d2s -> conv5x5 valid relu
         if exp == 'mnist_digit':
             self.dec_dense = Conv(group, 'decoder/dense', G.dense(B, C, 16 * H), LEAKY, device)
@@ -233,10 +256,6 @@ class MnistOuterVAE:
             self.dec.append((hw, cin, r, Conv(group, name, geoms[i], LEAKY, device, out_dtype=dt)))
         hw, cin, r, name, cl = last
         self.dec.append((hw, cin, r, Conv(group, name, geoms[-1], 'relu', device)))
-        self.flat, self.feat, self.C = flat, feat, C
-        self.mean = self.head_mean.y.view(B, C)
-        self.std = self.head_std.y.view(B, C)              # becomes relu(.)+floor in place
-        self.z = torch.empty(B, C, device=device)
         self.decoded = self.dec[-1][3].y
 
     # -- forward
@@ -281,9 +300,10 @@ class MnistOuterVAE:
         self.dec_dense.backward(dpre.view(B, 1, 1, -1), dx=dz.view(B, 1, 1, self.C), wgrad=wgrad)
         return dz
 
-    def encode_backward(self, dz, c_entropy, c_sg, dmean_add=None, dstd_add=None):
+    def encode_backward(self, dz, c_entropy, c_sg, dmean_add=None, dstd_add=None, wgrad=True, dx_image=None):
         """dz: d loss / d code_sample (already summed over its consumers); dmean_add / dstd_add: extra gradient on
-        code_mean / code_std_dev (the MC-sample terms of the GMM prior branch)."""
+        code_mean / code_std_dev (the MC-sample terms of the GMM / VampPrior branches); dx_image [B,28,28,1]: also
+        return the gradient w.r.t. the input image (VampPrior pseudo-inputs), through the symmetric pad."""
         B, C = self.B, self.C
         floor = float(self.cfg['latent_variance_precision'])
         dmean = self.buf.get('dmean', B, C)
@@ -291,18 +311,23 @@ class MnistOuterVAE:
         ops.gauss_head_bwd(dz, self.mean, self.std, self.eps_z, dmean_add, dstd_add, dmean, dstd, floor, c_entropy, c_sg)
         dfeat = self.buf.get('dfeat', B, 1, 1, self.feat)
         prod = (self.enc_dense.y, LEAKY)
-        self.head_mean.backward(dmean.view(B, 1, 1, C), dx=dfeat, producer=prod)
-        self.head_std.backward(dstd.view(B, 1, 1, C), dx=dfeat, producer=prod, accumulate=True)
+        self.head_mean.backward(dmean.view(B, 1, 1, C), dx=dfeat, producer=prod, wgrad=wgrad)
+        self.head_std.backward(dstd.view(B, 1, 1, C), dx=dfeat, producer=prod, accumulate=True, wgrad=wgrad)
         last = self.enc_convs[-1]
         dflat = self.buf.get('dflat', B, 1, 1, self.flat)
-        self.enc_dense.backward(dfeat, dx=dflat, producer=(last.y.view(B, 1, 1, self.flat), LEAKY))
+        self.enc_dense.backward(dfeat, dx=dflat, producer=(last.y.view(B, 1, 1, self.flat), LEAKY), wgrad=wgrad)
         dpre = dflat.view(*last.y.shape)
         for i in range(len(self.enc_convs) - 1, 0, -1):
             c, prev = self.enc_convs[i], self.enc_convs[i - 1]
             dx = self.buf.get('de%d' % i, *prev.y.shape)
-            c.backward(dpre, dx=dx, producer=(prev.y, LEAKY))
+            c.backward(dpre, dx=dx, producer=(prev.y, LEAKY), wgrad=wgrad)
             dpre = dx
-        self.enc_convs[0].backward(dpre, dx=None)            # no gradient w.r.t. the image
+        if dx_image is None:
+            self.enc_convs[0].backward(dpre, dx=None, wgrad=wgrad)            # no gradient w.r.t. the image
+        else:
+            dxpad = self.buf.get('dxpad', *self.xpad.shape)
+            self.enc_convs[0].backward(dpre, dx=dxpad, wgrad=wgrad)
+            ops.sym_pad_bwd(dxpad, dx_image, B, 28, 28, 1, 2)
 
 
 # ------------------------------------------------------------------------------ outer VAE (CelebA)
@@ -585,7 +610,7 @@ class PriorVAE:
 
 
 # ------------------------------------------------------------------------------ the sub-step engine
-PRIOR_KIND = {'standard_gaussian': 0, 'ours': 1, 'hierarchical': 2, 'GMM': 3}
+PRIOR_KIND = {'standard_gaussian': 0, 'ours': 1, 'hierarchical': 2, 'GMM': 3, 'vampPrior': 3}
 
 
 def vae_param_specs(config):
@@ -695,6 +720,14 @@ class LadderEngine:
             self.prior_g = ParamGroup('prior', prior_param_specs(config), dev)
             self.inner_sigma = ParamGroup('inner_sigma', [('inner_sigma/Variable', ())], dev)
             self.groups.update(prior=self.prior_g, inner_sigma=self.inner_sigma)
+        if self.prior == 'vampPrior':
+            if config['exp_name'] == 'celeba':
+                raise NotImplementedError('prior=vampPrior is built for the MNIST models (28x28x1 pseudo-inputs) only')
+            # the K trainable pseudo-inputs, the only variable of scope `prior` (base.py:224-225, 424-429)
+            self.prior_g = ParamGroup('prior', [('prior/Variable', (self.K, int(config['dim_input_x']),
+                                                                    int(config['dim_input_y']),
+                                                                    int(config['dim_input_channel'])))], dev)
+            self.groups['prior'] = self.prior_g
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(seed)
         self.init_params()
@@ -703,7 +736,12 @@ class LadderEngine:
         else:
             self.outer = MnistOuterVAE(config, self.ae, B, dev)
         self.pvae = PriorVAE(config, self.prior_g, B, dev) if self.has_prior else None
-        for grp in self.groups.values():
+        self.shared = None
+        if self.prior == 'vampPrior':
+            # define_vampPrior (base.py:215-254): the shared encoder + heads on the K pseudo-inputs
+            self.shared = SharedGroup(self.ae)
+            self.pseudo = MnistOuterVAE(config, self.shared, self.K, dev, encoder_only=True)
+        for grp in list(self.groups.values()) + ([self.shared] if self.shared is not None else []):
             grp.plan_packs()
         self.scalars = torch.zeros(ops.SCALARS_LEN, device=dev)
         self.eps_z = torch.zeros(B, self.C, device=dev)
@@ -720,7 +758,15 @@ class LadderEngine:
             self.dmu_add = torch.empty(B, self.R, device=dev)
             self.dsd_add = torch.empty(B, self.R, device=dev)
             self.mixture = None
-        if self.prior == 'GMM':
+        if self.prior == 'vampPrior':
+            K, C = self.K, self.C
+            self.pseudo_eps = torch.zeros(K, C, device=dev)          # the pseudo path uses the heads, not a sample
+            self.pseudo_stats = torch.zeros(3, device=dev)
+            self.pseudo_dz = torch.zeros(K, C, device=dev)
+            self.dmean_p = torch.empty(K, C, device=dev)
+            self.dstd_p = torch.empty(K, C, device=dev)
+            self.vamp_tab = None
+        if self.prior in ('GMM', 'vampPrior'):
             # prior "GMM" (base.py:323-329): L samples of q(z|x) scored under a full-covariance mixture in z-space (D = C)
             self.eps_mc = torch.zeros(self.L, B, self.C, device=dev)
             self.t_mc = torch.empty(self.L * B, self.C, device=dev)
@@ -746,6 +792,8 @@ class LadderEngine:
                     t.fill_(float(self.cfg['sigma']))
                 elif name == 'inner_sigma/Variable':
                     t.fill_(float(self.cfg['inner_sigma']))
+                elif name == 'prior/Variable':                      # tf.random.normal pseudo-inputs (base.py:224)
+                    t.normal_(generator=self.gen)
                 elif name.endswith('/kernel'):
                     glorot_uniform_(t, shape, self.gen)
                 elif name.endswith('/gamma'):
@@ -797,7 +845,7 @@ class LadderEngine:
             self.eps_z.normal_(generator=self.gen)
         if t and self.has_prior:
             self.eps_t.normal_(generator=self.gen)
-        if mc and self.prior in ('ours', 'GMM'):
+        if mc and self.prior in ('ours', 'GMM', 'vampPrior'):
             self.eps_mc.normal_(generator=self.gen)
 
     def set_noise(self, eps_z=None, eps_t=None, eps_mc=None):
@@ -844,6 +892,16 @@ class LadderEngine:
                 ops.mixture_logprob(self.t_mc, self.mixture, want_grad=True,
                                     out={'logp': self.logp_mc, 'grad': self.g_mc})
                 ops.sum_into(self.logp_mc, s[11:12])
+        elif self.prior == 'vampPrior':
+            kind = PRIOR_KIND['vampPrior']
+            if mix and not self.use_sg:                  # tf.cond(use_standard_gaussian_prior): branch not taken
+                self.shared.repack()
+                self.pseudo.encode(self.prior_g.p('prior/Variable'), self.pseudo_eps, self.pseudo_stats)
+                self.vamp_tab = ops.mixture_pack_diag_device(self.pseudo.mean, self.pseudo.std, self.vamp_tab)
+                ops.mc_sample(self.outer.mean, self.outer.std, self.eps_mc, self.t_mc)
+                ops.mixture_logprob(self.t_mc, self.vamp_tab, want_grad=True,
+                                    out={'logp': self.logp_mc, 'grad': self.g_mc})
+                ops.sum_into(self.logp_mc, s[11:12])
         self._allreduce(s[:12])            # batch-global sums (sigma, means) across data-parallel ranks
         cfg = self.cfg
         takes_max = cfg['exp_name'] == 'celeba' or int(cfg['TRAIN_sigma']) == 1
@@ -874,7 +932,16 @@ class LadderEngine:
         if self.has_prior and not self.use_sg:
             self._prior_backward(self.dz, wgrad=False)
         Bg = self.B_global
-        if self.prior == 'GMM':
+        if self.prior == 'vampPrior' and not self.use_sg:
+            coef = -1.0 / (self.L * Bg)
+            ops.mc_reduce(self.g_mc, self.eps_mc, coef, self.dmu_add, self.dsd_add)
+            # the shared encoder also receives the gradient that reaches it through the pseudo-input mixture
+            ops.mixture_diag_param_grad(self.t_mc, self.pseudo.mean, self.pseudo.std, self.logp_mc, coef, self.dmean_p,
+                                        self.dstd_p)
+            self.pseudo.encode_backward(self.pseudo_dz, 0.0, 0.0, self.dmean_p, self.dstd_p)
+            self.outer.encode_backward(self.dz, -1.0 / Bg, 0.0, self.dmu_add, self.dsd_add)
+            ops.axpy(self.ae.grad, self.shared.grad, 1.0)
+        elif self.prior == 'GMM':
             # d(-mean log p)/d(code_mean, code_std_dev) through the L reparameterised samples
             ops.mc_reduce(self.g_mc, self.eps_mc, -1.0 / (self.L * Bg), self.dmu_add, self.dsd_add)
             self.outer.encode_backward(self.dz, -1.0 / Bg, 0.0, self.dmu_add, self.dsd_add)
@@ -892,6 +959,20 @@ class LadderEngine:
 
     def step_prior(self, x, apply=True):
         """train_step_prior: d(-elbo_prior) / d scope 'prior' only (base.py:479)."""
+        if self.prior == 'vampPrior':
+            # loss_prior = -elbo (base.py:407-408); only its mixture term depends on the pseudo-inputs
+            self.forward(x, dec=True, prior=True, mix=True)
+            pg = self.prior_g.g('prior/Variable')
+            if self.use_sg:
+                pg.zero_()
+            else:
+                ops.mixture_diag_param_grad(self.t_mc, self.pseudo.mean, self.pseudo.std, self.logp_mc,
+                                            -1.0 / (self.L * self.B_global), self.dmean_p, self.dstd_p)
+                self.pseudo.encode_backward(self.pseudo_dz, 0.0, 0.0, self.dmean_p, self.dstd_p, wgrad=False, dx_image=pg)
+            self._allreduce(self.prior_g.grad)
+            if apply:
+                self.prior_g.apply_adam()
+            return
         self.forward(x, dec=False, prior=True, mix=True)
         self._prior_backward(None, wgrad=True)
         self._allreduce(self.prior_g.grad)

@@ -73,6 +73,12 @@ class BaseTrain:
                 self.elbo_train.append(g('elbo'))
             elif kind == 'train_sigma':
                 self.sigma_train.append(g('sigma'))
+            elif kind == 'train_prior_vamp':                      # base.py:629-634
+                self.train_loss_prior.append(g('loss_ae'))        # loss_prior = -elbo for the VampPrior (base.py:407)
+                self.vampPrior_crossEntropy_prior_train.append(g('crossEntropy_prior'))
+            elif kind == 'val_prior_vamp':                        # base.py:673-677
+                self.val_loss_prior.append(g('loss_ae'))
+                self.vampPrior_crossEntropy_prior_val.append(g('crossEntropy_prior'))
             elif kind == 'train_prior':
                 self.code_recons_error_train.append(g('code_l1_reconstruction_error'))
                 self.code_recons_likelihood_train.append(g('code_reconstruction_likelihood'))
@@ -125,7 +131,7 @@ class BaseTrain:
         x = self._apply_feeds(batch_data, "prior")
         eng.set_lrs(lr_prior=self.config['learning_rate_prior'] * (1.01 ** (self.cur_epoch - 1)))
         eng.run_step('prior', x)
-        self._snapshot('train_prior')
+        self._snapshot('train_prior_vamp' if self.config['prior'] == 'vampPrior' else 'train_prior')
         if self.config['prior'] in ("ours", "hierarchical") and self.config['TRAIN_inner_sigma'] == 1:
             eng.set_lrs(lr_inner_sigma=self.config['learning_rate_inner_sigma'] * (1.01 ** (self.cur_epoch - 1)))
             eng.run_step('inner_sigma', x)
@@ -137,6 +143,10 @@ class BaseTrain:
         if model_to_train == "VAE":
             eng.forward(x, dec=True, prior=True, mix=True)
             self._snapshot('val_ae')
+            return eng.scalars[ops.O['loss_ae']].clone()
+        if self.config['prior'] == 'vampPrior':
+            eng.forward(x, dec=True, prior=True, mix=True)
+            self._snapshot('val_prior_vamp')
             return eng.scalars[ops.O['loss_ae']].clone()
         eng.forward(x, dec=False, prior=True, mix=True)
         self._snapshot('val_prior')
@@ -252,6 +262,8 @@ class BaseTrain_joint(BaseTrain):
             feed['use_standard_gaussian_prior'] = self.cur_epoch <= cfg['sg_pretraining']
         elif cfg['prior'] == 'standard_gaussian':
             pass
+        elif cfg['prior'] == 'vampPrior':                               # base.py:934-941
+            feed['use_standard_gaussian_prior'] = self.cur_epoch <= cfg['sg_pretraining']
         elif cfg['prior'] == 'GMM':
             C = cfg['code_size']
             if self.cur_epoch == 1:                                     # base.py:912-923: K copies of N(0, I) in z-space

@@ -134,8 +134,8 @@ class BaseModel:
         if model == "VAE" or (model == "joint" and self.config['TRAIN_VAE'] == 1):
             self._save(self.saver_path_ae, [e.ae, e.sigma])
             print("Outer VAE model saved.")
-        if e.has_prior and (model == "prior" or (model == "joint" and self.config['TRAIN_prior'] == 1)):
-            self._save(self.saver_path_prior, [e.prior_g, e.inner_sigma])
+        if 'prior' in e.groups and (model == "prior" or (model == "joint" and self.config['TRAIN_prior'] == 1)):
+            self._save(self.saver_path_prior, [e.prior_g] + ([e.inner_sigma] if e.has_prior else []))
             print("Prior model saved.")
 
     def load(self, sess, model):

@@ -313,15 +313,48 @@ def _tap_gemm_fprop_tc(x, w, bias, y, g, act):
     return y
 
 
-def _tap_gemm_wgrad_tc(x, dy, dw, dbias, g):
+def tap_dys(dy, g):
+    """DYS[p, tap] = dy[p - tap] over the INPUT pixels p of a single-output-channel KxK conv, bf16 with a 64-wide leading
+    dimension (zero padded): the shared operand of that layer's weight gradient (DYS^T . x) and data gradient (DYS . w)."""
+    P = g.B * g.H * g.W
+    dys = _workspace(dy.device, P * 64 * 2, 'tap_z').view(torch.bfloat16)[:P * 64].view(P, 1, 1, 64)
+    _lib.check(_L().ladder_tap_scatter_bf16(_p(_f32(dy)), _p(dys), 64, g.B, g.H, g.W, g.KH, g.KW, g.pad_t, g.pad_l,
+                                            g.OH, g.OW, _stream()), 'tap_scatter_bf16')
+    return dys
+
+
+def _tap_dgrad_geom(g):
+    return ConvGeom(g.B, g.H, g.W, g.Cin, 1, 1, 64, 1, 'valid')
+
+
+def tap_gemm_dgrad_ok(g):
+    """True if the data gradient of the single-output-channel conv g runs as DYS . w on the TMA-fed dgrad kernel."""
+    return (MATH_MODE == 'bf16' and TMA and _is_tap_gemm(g) and g.stride == 1 and g.KH * g.KW <= 64 and g.Cin % 64 == 0
+            and tma_supported(_tap_dgrad_geom(g), DGRAD))
+
+
+def _tap_gemm_dgrad_tc(dy, w, dx, g, act_out, act, accumulate, out_s2d, dys=None):
+    """dx[p, c] = act'(.) * sum_tap DYS[p, tap] w[tap, c]: the 1x1 "dgrad" of a [Cin -> 64 taps] layer over the input pixel grid,
+    with the fused producer-activation derivative / space_to_depth store / bf16 output of the TMA-fed dgrad kernel."""
+    T = g.KH * g.KW
+    if dys is None:
+        dys = tap_dys(dy, g)
+    wt = _workspace(dy.device, g.Cin * 64 * 4, 'tap_wt').view(torch.float32)[:g.Cin * 64].view(g.Cin, 64)
+    wt.zero_()
+    wt[:, :T].copy_(w.view(T, g.Cin).t())
+    return conv2d_dgrad(dys.view(g.B, g.H, g.W, 64), wt.view(1, 1, g.Cin, 64), dx, _tap_dgrad_geom(g), act_out=act_out, act=act,
+                        accumulate=accumulate, out_s2d=out_s2d)
+
+
+def _tap_gemm_wgrad_tc(x, dy, dw, dbias, g, dys=None):
     """dw[tap, c] = sum_p DYS[p, tap] x[p, c]: shifted copy of dy, then a dense wgrad with x as the (64-aligned) input.
     With the TMA path DYS is written directly as bf16 with a 64-wide leading dimension and the GEMM is TMA-fed."""
     P, T = g.B * g.H * g.W, g.KH * g.KW
     gd = ConvGeom.dense(P, g.Cin, 64)
     if g.stride == 1 and T <= 64 and TMA and _L().ladder_conv2d_tma_supported(WGRAD, P, 1, 1, g.Cin, 1, 1, 64, 1, 1, 1):
-        dys = _workspace(x.device, P * 64 * 2, 'tap_z').view(torch.bfloat16)[:P * 64].view(P, 1, 1, 64)
-        _lib.check(_L().ladder_tap_scatter_bf16(_p(_f32(dy)), _p(dys), 64, g.B, g.H, g.W, g.KH, g.KW, g.pad_t, g.pad_l,
-                                                g.OH, g.OW, _stream()), 'tap_scatter_bf16')
+        if dys is None:
+            dys = tap_dys(dy, g)
+        dys = dys.view(P, 1, 1, 64)
         dwt = _workspace(x.device, g.Cin * 64 * 4, 'tap_w').view(torch.float32)[:g.Cin * 64].view(1, 1, g.Cin, 64)
         _lib.check(_L().ladder_conv2d_wgrad_tma(_p(_as16(x, 'x16')), _p(dys), _p(dwt), *gd.args(), _stream()),
                    'conv2d_wgrad_tma')
@@ -354,6 +387,8 @@ def _tc_ws(x, g):
     return ws, ws.numel()
 
 
+# data gradient of single-output-channel KxK convs as DYS . w on the tensor cores (LADDER_TAP_DGRAD_TC=0: element-wise kernel)
+TAP_DGRAD_TC = os.environ.get('LADDER_TAP_DGRAD_TC', '1') != '0'
 # TMA-fed tcgen05 kernels on bf16-resident activations (csrc/conv_tma.cu); LADDER_TMA=0 keeps the register-gather path
 TMA = os.environ.get('LADDER_TMA', '1') != '0'
 _tma_ok = {}
@@ -377,6 +412,18 @@ def thin_dgrad(g):
     fp32 or bf16."""
     return (MATH_MODE == 'bf16' and TMA and g.Cout <= 32 and g.stride == 1 and g.Cin % 8 == 0
             and g.KH * g.KW * g.Cin * g.Cout * 4 <= 48 * 1024)
+
+
+def thin_k(g):
+    """Short-reduction layers (K = KH*KW*Cin <= 32: first conv on the image, dense layers on a latent): fp32 element-wise
+    fprop / wgrad passes (csrc/thin_ops.cu) instead of GEMMs padded to a 64-wide k-block."""
+    return (MATH_MODE == 'bf16' and TMA and g.KH * g.KW * g.Cin <= 32 and not _is_tap_gemm(g)
+            and bool(_L().ladder_thin_k_supported(g.KH, g.KW, g.Cin, g.Cout)))
+
+
+def thin_n(g):
+    """Dense layers with <= 16 inputs: the gradient w.r.t. the latent is a warp-per-row dot-product pass."""
+    return MATH_MODE == 'bf16' and TMA and g.KH == 1 and g.KW == 1 and g.stride == 1 and g.Cin <= 16
 
 
 def reads_bf16(g):
@@ -457,6 +504,10 @@ def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0, wimg=None):
     _act_t(x, 'x'), _act_t(y, 'y')
     if MATH_MODE == 'bf16' and _is_tap_gemm(g) and g.Cin % 64 == 0 and not out_d2s:
         return _tap_gemm_fprop_tc(x, w, bias, y, g, act)
+    if thin_k(g) and x.dtype == torch.float32 and not out_d2s:
+        _lib.check(_L().ladder_thin_k_fprop(_p(x), _p(_f32(w)), _p(bias), _p(y), _is16(y), *g.args(), ACT[act], _stream()),
+                   'thin_k_fprop')
+        return y
     if tma_supported(g, FPROP):
         if wimg is not None:
             ws, n, wp = wimg, wimg.numel() * 2, None
@@ -479,13 +530,20 @@ def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0, wimg=None):
     return y
 
 
-def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False, out_s2d=0, wimg=None):
-    """dx = conv^T(dy, w) [* act'(act_out)]; out_s2d = r writes dx at the position of the depth_to_space INPUT."""
+def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False, out_s2d=0, wimg=None, dys=None):
+    """dx = conv^T(dy, w) [* act'(act_out)]; out_s2d = r writes dx at the position of the depth_to_space INPUT.
+    dys: the tap_dys(dy, g) of a single-output-channel layer when the caller already made it for the weight gradient."""
     _act_t(dy, 'dy'), _act_t(dx, 'dx')
-    if thin_dgrad(g) and not accumulate and dy.dtype == torch.float32:
+    if TAP_DGRAD_TC and dy.dtype == torch.float32 and tap_gemm_dgrad_ok(g):
+        return _tap_gemm_dgrad_tc(dy, w, dx, g, act_out, act, accumulate, out_s2d, dys)
+    if thin_dgrad(g) and dy.dtype == torch.float32:
         _lib.check(_L().ladder_tap_dgrad(_p(dy), _p(_f32(w)), _p(act_out), _is16(act_out), _p(dx), _is16(dx), g.B, g.H, g.W,
                                          g.Cin, g.Cout, g.KH, g.KW, g.pad_t, g.pad_l, g.OH, g.OW, ACT[act], int(out_s2d),
-                                         _stream()), 'tap_dgrad')
+                                         int(accumulate), _stream()), 'tap_dgrad')
+        return dx
+    if (thin_n(g) and dy.dtype == torch.float32 and dx.dtype == torch.float32 and act_out is None and not out_s2d):
+        _lib.check(_L().ladder_thin_n_dgrad(_p(dy), _p(_f32(w)), _p(dx), g.B * g.H * g.W, g.Cin, g.Cout, int(accumulate),
+                                            _stream()), 'thin_n_dgrad')
         return dx
     if tma_supported(g, DGRAD):
         if wimg is not None:
@@ -509,16 +567,19 @@ def conv2d_dgrad(dy, w, dx, g, act_out=None, act=None, accumulate=False, out_s2d
     return dx
 
 
-def conv2d_wgrad(x, dy, dw, dbias, g):
+def conv2d_wgrad(x, dy, dw, dbias, g, dys=None):
     _act_t(x, 'x'), _act_t(dy, 'dy')
     if MATH_MODE == 'bf16' and _is_tap_gemm(g) and g.Cin % 64 == 0:
-        return _tap_gemm_wgrad_tc(x, dy, dw, dbias, g)
+        return _tap_gemm_wgrad_tc(x, dy, dw, dbias, g, dys)
     if (MATH_MODE == 'bf16' and TMA and g.KH == 1 and g.KW == 1 and g.stride == 1 and g.Cout <= 8 and g.Cin % 8 == 0
             and 256 % (g.Cin // 8) == 0 and dy.dtype == torch.float32 and g.Cin * g.Cout * 4 * (256 // (g.Cin // 8)) <= 48 * 1024):
         _lib.check(_L().ladder_thin_wgrad_1x1(_p(x), _is16(x), _p(dy), _p(_f32(dw)), g.B * g.H * g.W, g.Cin, g.Cout, _stream()),
                    'thin_wgrad_1x1')
         if dbias is not None:
             colsum(dy, g.B * g.OH * g.OW, g.Cout, dbias)
+        return dw
+    if thin_k(g) and x.dtype == torch.float32 and dy.dtype == torch.float32:
+        _lib.check(_L().ladder_thin_k_wgrad(_p(x), _p(dy), _p(_f32(dw)), _p(dbias), *g.args(), _stream()), 'thin_k_wgrad')
         return dw
     if tma_supported(g, WGRAD):
         dy16 = _as16(dy, 'dy16')

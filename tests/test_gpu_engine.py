@@ -23,7 +23,8 @@ def make_case(exp, B, seed, prior='ours', epoch=None, **over):
     over.setdefault('compute_dtype', 'fp32')
     cfg = load_config(exp, batch_size=B, n_MC_samples=10, prior=prior, **over)
     rng = np.random.default_rng(seed)
-    spec = oparams.vae_param_specs(cfg) + (oparams.prior_param_specs(cfg) if prior in ('ours', 'hierarchical') else [])
+    spec = oparams.vae_param_specs(cfg) + (oparams.prior_param_specs(cfg)
+                                           if prior in ('ours', 'hierarchical', 'vampPrior') else [])
     P = oparams.glorot_init(spec, cfg, seed + 1, dtype=np.float32)
     for k in P:
         if k.endswith('/bias'):
@@ -174,6 +175,40 @@ def test_gmm_prior_branch(exp, epoch):
     for k in SCALARS_AE:
         assert rel(got[k], float(o[k].v)) < 5e-5, (k, got[k], float(o[k].v))
     grad_check(eng, eng.ae, nets.grads_of(o['loss_ae'], Pv, eng.ae.names()))
+
+
+@pytest.mark.parametrize('exp', ['mnist_digit', 'mnist_fashion'])
+@pytest.mark.parametrize('pretrain', [False, True])
+def test_vamp_prior_branch(exp, pretrain):
+    """prior = "vampPrior" (base.py:215-254, 362-370, 407-408): K pseudo-inputs through the SHARED encoder give a diagonal
+    equal-weight mixture in z-space; loss_ae's gradient reaches the encoder through q(z|x), its L samples AND the
+    pseudo-input path; loss_prior = -elbo trains the pseudo-inputs (through the encoder and the symmetric pad)."""
+    B = 5
+    cfg, P, x, noises, feeds, epoch = make_case(exp, B, 23, prior='vampPrior', epoch=1 if pretrain else None, n_mixtures=7)
+    C, L = cfg['code_size'], cfg['n_MC_samples']
+    rng = np.random.default_rng(5)
+    P['encoder/code_std_dev/bias'] = P['encoder/code_std_dev/bias'] + np.float32(0.5)     # stds away from the 1e-3 floor
+    P['prior/Variable'] = (0.5 + 0.5 * P['prior/Variable']).astype(np.float32)
+    nz = dict(eps_z=noises[0]['eps_z'], eps_mc=rng.normal(size=(L, B, C)).astype(np.float32))
+    assert feeds['use_standard_gaussian_prior'] == pretrain
+    eng = make_engine(cfg, P, feeds, B)
+    eng.set_noise(**nz)
+    xd = torch.tensor(x, device='cuda')
+    eng.step_ae(xd, apply=False)
+    Pv, o = nets.build(cfg, P, x, nz, feeds)
+    got = eng.fetch(SCALARS_AE)
+    for k in SCALARS_AE:
+        assert rel(got[k], float(o[k].v)) < 5e-5, (k, got[k], float(o[k].v))
+    grad_check(eng, eng.ae, nets.grads_of(o['loss_ae'], Pv, eng.ae.names()))
+    eng.step_prior(xd, apply=False)
+    g = nets.grads_of(o['loss_prior'], Pv, ['prior/Variable'])['prior/Variable']
+    gg = eng.prior_g.g('prior/Variable').cpu().numpy()
+    if pretrain:
+        assert np.abs(g).max() == 0 and np.abs(gg).max() == 0
+    else:
+        assert np.abs(gg - g).max() <= 1e-3 * np.abs(g).max(), (np.abs(gg - g).max(), np.abs(g).max())
+    got = eng.fetch(['loss_ae', 'crossEntropy_prior'])
+    assert rel(got['loss_ae'], float(o['loss_prior'].v)) < 5e-5
 
 
 @pytest.mark.parametrize('exp', ['mnist_digit', 'mnist_fashion'])

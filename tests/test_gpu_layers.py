@@ -113,6 +113,21 @@ def test_sym_pad(ops):
     assert np.array_equal(y.cpu().numpy(), np.pad(x, ((0, 0), (2, 2), (2, 2), (0, 0)), mode='symmetric').astype(np.float32))
 
 
+@pytest.mark.parametrize('shape,pad', [((3, 28, 28, 1), 2), ((2, 6, 5, 3), 1), ((2, 4, 4, 2), 2)])
+def test_sym_pad_bwd(ops, shape, pad):
+    """Gradient of the symmetric pad (needed to train the VampPrior pseudo-inputs): mirror images fold back."""
+    from oracle import tape as T
+    rng = np.random.default_rng(1)
+    B, H, W, C = shape
+    X = T.Var(rng.normal(size=shape))
+    y = T.sym_pad(X, pad)
+    up = rng.normal(size=y.shape)
+    T.backward(y, seed=up)
+    dx = torch.empty(*shape, device='cuda')
+    ops.sym_pad_bwd(dev(up), dx, B, H, W, C, pad)
+    close(dx, X.g, 1e-6)
+
+
 def test_clip_adam_matches_oracle(ops):
     from oracle.adam import AdamGroup
     rng = np.random.default_rng(0)

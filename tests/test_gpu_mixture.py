@@ -183,3 +183,31 @@ def test_tensor_core_path_far_queries_rescued(ops):
     ref = OM.mixture_logprob(t.astype(np.float64), mu, A, c)
     assert torch.isfinite(lp).all()
     np.testing.assert_allclose(lp.cpu().numpy(), ref, rtol=2e-5)
+
+
+@pytest.mark.parametrize('D', [2, 8, 16])
+def test_vamp_prior_device_pack_and_param_grads(ops, D):
+    """VampPrior mixture (base.py:241-254): table packed on the device from device mean/std, log p and d/dt through
+    the device frame, and d/d mean, d/d std of coef * sum_n log p(t_n) against the float64 oracle."""
+    from oracle import tape as T
+    rng = np.random.default_rng(D)
+    K, N = 11, 700
+    mean = rng.normal(size=(K, D)); std = rng.uniform(0.3, 1.5, size=(K, D))
+    t = rng.normal(size=(N, D)) * 1.5
+    tv, mv, sv = T.Var(t), T.Var(mean), T.Var(std)
+    lp = OM.diag_mixture_logprob_var(tv, mv, sv)
+    coef = -1.0 / N
+    T.backward(T.reduce_sum(lp) * coef)
+    md, sd, td = _dev(mean.astype(np.float32)), _dev(std.astype(np.float32)), _dev(t.astype(np.float32))
+    tab = ops.mixture_pack_diag_device(md, sd)
+    logp, g = ops.mixture_logprob(td, tab, want_grad=True)
+    np.testing.assert_allclose(logp.cpu().numpy(), lp.v, rtol=2e-5, atol=2e-4)
+    np.testing.assert_allclose(g.cpu().numpy() * coef, tv.g, rtol=2e-3, atol=2e-3 / N)
+    host = ops.mixture_pack_diag(mean, std, None, 'cuda')           # same table as the host (double) packer
+    np.testing.assert_allclose(tab.table.cpu().numpy(), host.table.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    dm, ds = torch.full((K, D), 7.0, device='cuda'), torch.full((K, D), 7.0, device='cuda')
+    ops.mixture_diag_param_grad(td, md, sd, logp, coef, dm, ds)
+    np.testing.assert_allclose(dm.cpu().numpy(), mv.g, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(ds.cpu().numpy(), sv.g, rtol=1e-3, atol=1e-5)
+    tab2 = ops.mixture_pack_diag_device(md * 0 + 1, sd, tab)         # repack in place reuses the table
+    assert tab2 is tab

@@ -98,3 +98,72 @@ def test_adam_matches_closed_form():
     m = 0.1 * gc; v = 0.05 * gc * gc
     lr_t = 0.1 * np.sqrt(1 - 0.95) / (1 - 0.9)
     np.testing.assert_allclose(p['w'], np.array([1.0, -2.0]) - lr_t * m / (np.sqrt(v) + 1e-8), rtol=1e-14)
+
+
+@pytest.mark.parametrize('prior', ['vampPrior', 'GMM'])
+@pytest.mark.parametrize('exp', ['mnist_digit', 'mnist_fashion'])
+def test_z_space_mixture_branches_fd(exp, prior):
+    """prior = "vampPrior" (base.py:215-254, 362-370: pseudo-inputs through the shared encoder, gradient to encoder,
+    heads AND pseudo-inputs) and "GMM" (base.py:323-329: fed full-covariance mixture in z-space): tape gradient of
+    loss_ae == central finite differences."""
+    cfg = dict(small(exp), prior=prior)
+    rng = np.random.default_rng(3)
+    spec = params.vae_param_specs(cfg) + (params.prior_param_specs(cfg) if prior == 'vampPrior' else [])
+    P = params.glorot_init(spec, cfg, 4)
+    for k in P:
+        if k.endswith('/bias'):
+            P[k] = rng.normal(size=P[k].shape) * 0.1
+    P['encoder/code_std_dev/bias'] = P['encoder/code_std_dev/bias'] + 0.5
+    B, C, L, K = 2, cfg['code_size'], cfg['n_MC_samples'], cfg['n_mixtures']
+    x = rng.uniform(size=(B, 28, 28, 1))
+    nz = dict(eps_z=rng.normal(size=(B, C)), eps_mc=rng.normal(size=(L, B, C)))
+    a = rng.normal(size=(K, C, C))
+    gm = (rng.normal(size=(K, C)), a @ a.transpose(0, 2, 1) / C + 0.1 * np.eye(C), rng.uniform(0.1, 1, size=K))
+    feeds = steps.compute_feeds(cfg, cfg['sg_pretraining'] + 1, gm)
+    Pv, o = nets.build(cfg, P, x, nz, feeds)
+    if prior == 'vampPrior':
+        assert o['loss_prior'] is o['negative_elbo'] and 'prior/Variable' in P
+        assert float(o['crossEntropy_prior'].v) == float(o['vampPrior_crossEntropy'].v)
+    names = list(P.keys())
+    g = nets.grads_of(o['loss_ae'], Pv, names)
+    h = 1e-6
+    for n in names:
+        flat = P[n].reshape(-1)
+        for idx in rng.choice(flat.size, size=min(2, flat.size), replace=False):
+            vals = []
+            for sgn in (+1, -1):
+                P2 = {k: v.copy() for k, v in P.items()}
+                P2[n].reshape(-1)[idx] += sgn * h
+                vals.append(float(nets.build(cfg, P2, x, nz, feeds)[1]['loss_ae'].v))
+            fd = (vals[0] - vals[1]) / (2 * h)
+            an = g[n].reshape(-1)[idx]
+            assert abs(fd - an) <= 2e-5 * max(1.0, abs(fd), abs(an)), (n, idx, fd, an)
+
+
+def test_vamp_prior_mixture_matches_pinned_canonical_form():
+    """diag_mixture_logprob_var (VampPrior) evaluates the same density as the canonical form pinned against
+    scikit-learn / SciPy (oracle.mixture.mixture_logprob via canonical_from_diag)."""
+    from oracle import mixture as OM
+    rng = np.random.default_rng(0)
+    K, D, N = 6, 5, 40
+    mean, std, t = rng.normal(size=(K, D)), rng.uniform(0.2, 2, size=(K, D)), rng.normal(size=(N, D)) * 2
+    lp = OM.diag_mixture_logprob_var(T.Var(t), T.Var(mean), T.Var(std))
+    mu, A, c = OM.canonical_from_diag(mean, std)
+    np.testing.assert_allclose(lp.v, OM.mixture_logprob(t, mu, A, c), rtol=1e-12, atol=1e-12)
+
+
+def test_vamp_prior_trainer_updates_pseudo_inputs_only_in_prior_step():
+    cfg = dict(small('mnist_digit'), prior='vampPrior', sg_pretraining=0)
+    rng = np.random.default_rng(1)
+    P = params.glorot_init(params.vae_param_specs(cfg) + params.prior_param_specs(cfg), cfg, 2)
+    P['encoder/code_std_dev/bias'] = P['encoder/code_std_dev/bias'] + 0.5
+    B, C, L = 2, cfg['code_size'], cfg['n_MC_samples']
+    x = rng.uniform(size=(B, 28, 28, 1))
+    nz = dict(eps_z=rng.normal(size=(B, C)), eps_mc=rng.normal(size=(L, B, C)))
+    feeds = steps.compute_feeds(cfg, 1)
+    assert feeds['use_standard_gaussian_prior'] is False
+    tr = steps.OracleTrainer(cfg, P)
+    before = {k: v.copy() for k, v in tr.params.items()}
+    tr.train_step_prior(x, nz, feeds, 1e-3)
+    for k in before:
+        assert (not np.array_equal(before[k], tr.params[k])) == (k == 'prior/Variable'), k
