@@ -190,7 +190,7 @@ int ladder_conv2d_wgrad_tma(const void* x_bf16, const void* dy_bf16, float* dw, 
 int ladder_tap_dgrad(const float* dy, const float* w, const void* act_out /*nullable*/, int act_out_bf16, void* dx,
                      int dx_bf16, int B, int H, int W, int C, int Co /* <= 32 */, int KH, int KW, int pad_t, int pad_l, int OH,
                      int OW, int act, int out_s2d, int accumulate /* dx += */, cudaStream_t stream);
-/* Short-reduction layers (KH*KW*Cin <= 32, Cout % 8 == 0, Cout <= 1024): the first encoder conv on the 1- / 3-channel image
+/* Short-reduction layers (KH*KW*Cin <= 16, Cout % 8 == 0, Cout <= 1024): the first encoder conv on the 1- / 3-channel image
  * (codes/models.py:52-56, 203-207, 398-404) and dense layers fed by a latent (decoder/dense, codes/base.py:174-176).
  * fp32 element-wise passes instead of GEMMs padded to a 64-wide k-block: fprop (bias + activation fused, y fp32 or bf16)
  * and wgrad (dw, dbias overwritten; dbias nullable).  ladder_thin_n_dgrad: dx[M,N] (+)= dy[M,K] . w[N,K]^T for a dense

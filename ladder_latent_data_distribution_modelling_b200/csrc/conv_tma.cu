@@ -282,6 +282,14 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(a.out);
     const float* auxf = reinterpret_cast<const float*>(a.aux);
     const __nv_bfloat16* auxh = reinterpret_cast<const __nv_bfloat16*>(a.aux);
+    // Row addressing of the permuted stores (depth_to_space / space_to_depth / parity-class scatter): the (b, y, x)
+    // decomposition of a tile's first row is done ONCE per tile with 32-bit divisions and then walked incrementally
+    // (+4 rows per store iteration).  Calling d2s_dest / s2d_dest per (row, column chunk) -- four 64-bit divisions each
+    // -- made the epilogue, not the MMA mainloop, the critical path of every decoder layer (4x on the 16x16 conv).
+    const bool need_bhw = MODE != WGRAD && (a.perm_r > 0 || (MODE == DGRAD && a.os > 1));
+    const int pr = a.perm_r > 0 ? a.perm_r : 1;
+    const int rsh = (pr & (pr - 1)) == 0 ? __ffs(pr) - 1 : -1;
+    const int GHr = a.GH / pr, GWr = a.GW / pr, Cp_d2s = Ng / (pr * pr);
     Tile T;
     decode_tile<MODE>(a, blockIdx.x, total, T);
     unsigned j = 0;
@@ -298,6 +306,14 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       mbar_wait(bar_tfull + acc * 8, (j >> 1) & 1);
       tc_fence_after();
       const long long mrow0 = (long long)T.m_tile * BM + quad * 32;
+      int w0 = 0, h0 = 0, b0 = 0;
+      if (need_bhw) {                                // rows < 2^31 (checked by ladder_conv2d_tma_supported)
+        const unsigned mu = (unsigned)(mrow0 + sub);
+        w0 = (int)(mu % (unsigned)a.GW);
+        const unsigned rq = mu / (unsigned)a.GW;
+        h0 = (int)(rq % (unsigned)a.GH);
+        b0 = (int)(rq / (unsigned)a.GH);
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
@@ -327,24 +343,35 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           coloff = ((long long)(ij / r) * a.GW * r + ij % r) * Cp + c;
           vec_ok = vec_ok && (Cp & 3) == 0;
         }
+        int pw = w0, ph = h0, pb = b0;
 #pragma unroll 2
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + sub;
           const long long m = mrow0 + r;
           const float4 q = *reinterpret_cast<const float4*>(stage + r * 36 + c4);
+          long long o, arow;                             // output row / row of the saved activation (aux)
+          if (!need_bhw) {
+            o = arow = m * Ng;
+          } else {
+            arow = (((long long)pb * a.GH + ph) * a.GW + pw) * Ng;
+            if (MODE == DGRAD && a.os > 1)               // parity class of a strided dgrad: scatter into the full map
+              arow = (((long long)pb * a.OHf + ph * a.os + a.opy) * a.OWf + pw * a.os + a.opx) * Ng;
+            o = arow;
+            if (a.perm_r > 0) {
+              if (MODE == FPROP) {                       // depth_to_space: row part of d2s_dest(m, 0, ...)
+                o = (((long long)pb * a.GH * pr + ph * pr) * ((long long)a.GW * pr) + pw * pr) * Cp_d2s;
+              } else {                                   // space_to_depth: s2d_dest(m, 0, ...)
+                const int yq = rsh >= 0 ? ph >> rsh : ph / pr, xq = rsh >= 0 ? pw >> rsh : pw / pr;
+                o = (((long long)pb * GHr + yq) * GWr + xq) * ((long long)Ng * pr * pr) + ((ph - yq * pr) * pr + (pw - xq * pr)) * Ng;
+              }
+            }
+            pw += 4;                                     // next store iteration: 4 rows further down the pixel grid
+            while (pw >= a.GW) {
+              pw -= a.GW;
+              if (++ph == a.GH) { ph = 0; ++pb; }
+            }
+          }
           if (m >= Mg || col >= Ng) continue;
-          long long o = m * Ng, arow = m * Ng;           // output row / row of the saved activation (aux)
-          if (MODE == DGRAD && a.os > 1) {               // parity class of a strided dgrad: scatter into the full map
-            const unsigned mu = (unsigned)m;
-            const int jx = (int)(mu % (unsigned)a.GW);
-            const unsigned rq = mu / (unsigned)a.GW;
-            const int iy = (int)(rq % (unsigned)a.GH), bb = (int)(rq / (unsigned)a.GH);
-            o = arow = (((long long)bb * a.OHf + iy * a.os + a.opy) * a.OWf + jx * a.os + a.opx) * Ng;
-          }
-          if (a.perm_r > 0) {
-            if (MODE == FPROP) o = d2s_dest(m, 0, a.GH, a.GW, Ng, a.perm_r);
-            if (MODE == DGRAD) o = s2d_dest(m, 0, a.GH, a.GW, Ng, a.perm_r);
-          }
           o += coloff;
           if (!vec_ok) {
             slow_store<MODE, OUT16>(a, q, m, col, o, arow, slope, is_tanh);

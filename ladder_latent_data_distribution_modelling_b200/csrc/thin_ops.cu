@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) thin_wgrad_1x1_kernel(const void* __restr
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// Short-reduction layers (K = KH*KW*Cin <= 32): the first encoder conv on the 1- or 3-channel image (models.py:52-56,
+// Short-reduction layers (K = KH*KW*Cin <= 16): the first encoder conv on the 1- or 3-channel image (models.py:52-56,
 // 203-207, 398-404) and the dense layers fed by a latent (decoder/dense on z, prior decoder on t, prior encoder on z).
 // As GEMMs they pad K to a 64-wide k-block and run at a few percent of any roofline; they are bandwidth-bound
 // element-wise passes: fp32 math on fp32 inputs, output fp32 or bf16.
@@ -377,13 +377,16 @@ int ladder_tap_dgrad(const float* dy, const float* w, const void* act_out, int a
 }
 
 int ladder_thin_k_supported(int KH, int KW, int Cin, int Cout) {
-  return KH * KW * Cin <= 32 && Cout % 8 == 0 && Cout / 4 <= 256;
+  // K <= 16: measured on B200, the element-wise passes beat the SIMT implicit GEMM for the K = 9 first conv of the MNIST
+  // encoders and the K = 2 / 16 latent dense layers, but lose at K = 27 (CelebA's first conv: 2x slower fprop, 4x slower
+  // wgrad -- instruction bound), which therefore stays on the GEMM path.
+  return KH * KW * Cin <= 16 && Cout % 8 == 0 && Cout / 4 <= 256;
 }
 
 int ladder_thin_k_fprop(const float* x, const float* w, const float* bias, void* y, int y_bf16, int B, int H, int W, int Cin,
                         int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act, cudaStream_t stream) {
   LADDER_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && stride >= 1, "thin_k_fprop: bad arguments");
-  LADDER_REQUIRE(ladder_thin_k_supported(KH, KW, Cin, Cout), "thin_k_fprop: needs KH*KW*Cin <= 32 and Cout %% 8 == 0");
+  LADDER_REQUIRE(ladder_thin_k_supported(KH, KW, Cin, Cout), "thin_k_fprop: needs KH*KW*Cin <= 16 and Cout %% 8 == 0");
   LADDER_REQUIRE(((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0 && (bias == nullptr || ((uintptr_t)bias & 15) == 0),
                  "thin_k_fprop: w, bias and y must be 16-byte aligned");
   ThinK a{x, w, bias, y, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, act, y_bf16};
@@ -396,7 +399,7 @@ int ladder_thin_k_fprop(const float* x, const float* w, const float* bias, void*
 int ladder_thin_k_wgrad(const float* x, const float* dy, float* dw, float* dbias, int B, int H, int W, int Cin, int KH, int KW,
                         int Cout, int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream) {
   LADDER_REQUIRE(x && dy && dw && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && stride >= 1, "thin_k_wgrad: bad arguments");
-  LADDER_REQUIRE(ladder_thin_k_supported(KH, KW, Cin, Cout), "thin_k_wgrad: needs KH*KW*Cin <= 32 and Cout %% 8 == 0");
+  LADDER_REQUIRE(ladder_thin_k_supported(KH, KW, Cin, Cout), "thin_k_wgrad: needs KH*KW*Cin <= 16 and Cout %% 8 == 0");
   LADDER_REQUIRE(((uintptr_t)dy & 15) == 0, "thin_k_wgrad: dy must be 16-byte aligned");
   const int K = KH * KW * Cin;
   cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)K * Cout * sizeof(float), stream);

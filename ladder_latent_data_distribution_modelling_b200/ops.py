@@ -415,9 +415,9 @@ def thin_dgrad(g):
 
 
 def thin_k(g):
-    """Short-reduction layers (K = KH*KW*Cin <= 32: first conv on the image, dense layers on a latent): fp32 element-wise
-    fprop / wgrad passes (csrc/thin_ops.cu) instead of GEMMs padded to a 64-wide k-block."""
-    return (MATH_MODE == 'bf16' and TMA and g.KH * g.KW * g.Cin <= 32 and not _is_tap_gemm(g)
+    """Short-reduction layers (K = KH*KW*Cin <= 16: first conv on a 1-channel image, dense layers on a latent): fp32
+    element-wise fprop / wgrad passes (csrc/thin_ops.cu) instead of GEMMs padded to a 64-wide k-block."""
+    return (MATH_MODE == 'bf16' and TMA and g.KH * g.KW * g.Cin <= 16 and not _is_tap_gemm(g)
             and bool(_L().ladder_thin_k_supported(g.KH, g.KW, g.Cin, g.Cout)))
 
 

@@ -13,6 +13,9 @@ import torch  # noqa: E402
 from ladder_latent_data_distribution_modelling_b200 import ops  # noqa: E402
 
 
+D2S = int(os.environ.get('LADDER_D2S', '2'))      # the step stores this layer's output in depth_to_space(2) layout
+
+
 def main():
     ops.set_math_mode('bf16')
     B, hw, ci, co = 1024, 16, 64, 256
@@ -23,12 +26,12 @@ def main():
     y = torch.empty(B, hw, hw, co, device='cuda', dtype=torch.bfloat16)
     wimg = ops.tma_pack(w, g, ops.FPROP)
     for _ in range(5):
-        ops.conv2d_fprop(x, w, b, y, g, 'leaky_relu', wimg=wimg)
+        ops.conv2d_fprop(x, w, b, y, g, 'leaky_relu', wimg=wimg, out_d2s=D2S)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20):
-        ops.conv2d_fprop(x, w, b, y, g, 'leaky_relu', wimg=wimg)
+        ops.conv2d_fprop(x, w, b, y, g, 'leaky_relu', wimg=wimg, out_d2s=D2S)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
