@@ -283,9 +283,9 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     const float* auxf = reinterpret_cast<const float*>(a.aux);
     const __nv_bfloat16* auxh = reinterpret_cast<const __nv_bfloat16*>(a.aux);
     // Row addressing of the permuted stores (depth_to_space / space_to_depth / parity-class scatter): the (b, y, x)
-    // decomposition of a tile's first row is done ONCE per tile with 32-bit divisions and then walked incrementally
-    // (+4 rows per store iteration).  Calling d2s_dest / s2d_dest per (row, column chunk) -- four 64-bit divisions each
-    // -- made the epilogue, not the MMA mainloop, the critical path of every decoder layer (4x on the 16x16 conv).
+    // decomposition is done ONCE per tile, one row per lane, with 32-bit divisions; the store loop fetches a row's offset
+    // with a warp shuffle.  Calling d2s_dest / s2d_dest per (row, column chunk) -- four 64-bit divisions each -- made the
+    // epilogue, not the MMA mainloop, the critical path of every decoder layer (4x on the 16x16 conv).
     const bool need_bhw = MODE != WGRAD && (a.perm_r > 0 || (MODE == DGRAD && a.os > 1));
     const int pr = a.perm_r > 0 ? a.perm_r : 1;
     const int rsh = (pr & (pr - 1)) == 0 ? __ffs(pr) - 1 : -1;
@@ -306,13 +306,25 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       mbar_wait(bar_tfull + acc * 8, (j >> 1) & 1);
       tc_fence_after();
       const long long mrow0 = (long long)T.m_tile * BM + quad * 32;
-      int w0 = 0, h0 = 0, b0 = 0;
+      // lane L owns the addressing of row L of this warp's 32-row slab; the store loop fetches it with a shuffle
+      long long my_o = 0, my_arow = 0;
       if (need_bhw) {                                // rows < 2^31 (checked by ladder_conv2d_tma_supported)
-        const unsigned mu = (unsigned)(mrow0 + sub);
-        w0 = (int)(mu % (unsigned)a.GW);
+        const unsigned mu = (unsigned)(mrow0 + lane);
+        const int pw = (int)(mu % (unsigned)a.GW);
         const unsigned rq = mu / (unsigned)a.GW;
-        h0 = (int)(rq % (unsigned)a.GH);
-        b0 = (int)(rq / (unsigned)a.GH);
+        const int ph = (int)(rq % (unsigned)a.GH), pb = (int)(rq / (unsigned)a.GH);
+        my_arow = (((long long)pb * a.GH + ph) * a.GW + pw) * Ng;
+        if (MODE == DGRAD && a.os > 1)               // parity class of a strided dgrad: scatter into the full map
+          my_arow = (((long long)pb * a.OHf + ph * a.os + a.opy) * a.OWf + pw * a.os + a.opx) * Ng;
+        my_o = my_arow;
+        if (a.perm_r > 0) {
+          if (MODE == FPROP) {                       // depth_to_space: row part of d2s_dest(m, 0, ...)
+            my_o = (((long long)pb * a.GH * pr + ph * pr) * ((long long)a.GW * pr) + pw * pr) * Cp_d2s;
+          } else {                                   // space_to_depth: s2d_dest(m, 0, ...)
+            const int yq = rsh >= 0 ? ph >> rsh : ph / pr, xq = rsh >= 0 ? pw >> rsh : pw / pr;
+            my_o = (((long long)pb * GHr + yq) * GWr + xq) * ((long long)Ng * pr * pr) + ((ph - yq * pr) * pr + (pw - xq * pr)) * Ng;
+          }
+        }
       }
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -343,7 +355,6 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           coloff = ((long long)(ij / r) * a.GW * r + ij % r) * Cp + c;
           vec_ok = vec_ok && (Cp & 3) == 0;
         }
-        int pw = w0, ph = h0, pb = b0;
 #pragma unroll 2
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + sub;
@@ -352,24 +363,9 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           long long o, arow;                             // output row / row of the saved activation (aux)
           if (!need_bhw) {
             o = arow = m * Ng;
-          } else {
-            arow = (((long long)pb * a.GH + ph) * a.GW + pw) * Ng;
-            if (MODE == DGRAD && a.os > 1)               // parity class of a strided dgrad: scatter into the full map
-              arow = (((long long)pb * a.OHf + ph * a.os + a.opy) * a.OWf + pw * a.os + a.opx) * Ng;
-            o = arow;
-            if (a.perm_r > 0) {
-              if (MODE == FPROP) {                       // depth_to_space: row part of d2s_dest(m, 0, ...)
-                o = (((long long)pb * a.GH * pr + ph * pr) * ((long long)a.GW * pr) + pw * pr) * Cp_d2s;
-              } else {                                   // space_to_depth: s2d_dest(m, 0, ...)
-                const int yq = rsh >= 0 ? ph >> rsh : ph / pr, xq = rsh >= 0 ? pw >> rsh : pw / pr;
-                o = (((long long)pb * GHr + yq) * GWr + xq) * ((long long)Ng * pr * pr) + ((ph - yq * pr) * pr + (pw - xq * pr)) * Ng;
-              }
-            }
-            pw += 4;                                     // next store iteration: 4 rows further down the pixel grid
-            while (pw >= a.GW) {
-              pw -= a.GW;
-              if (++ph == a.GH) { ph = 0; ++pb; }
-            }
+          } else {                                       // warp-uniform branch: every lane takes part in the shuffles
+            o = __shfl_sync(0xffffffffu, my_o, r);
+            arow = MODE == DGRAD ? __shfl_sync(0xffffffffu, my_arow, r) : o;
           }
           if (m >= Mg || col >= Ng) continue;
           o += coloff;

@@ -1017,10 +1017,23 @@ class LadderEngine:
             n0 = ops.launch_count()
             if hasattr(g, 'register_generator_state'):
                 g.register_generator_state(self.gen)
-            # thread_local: the NCCL watchdog thread of torch.distributed may touch CUDA while this thread captures
-            with torch.cuda.graph(g, capture_error_mode='thread_local' if self.world > 1 else 'global'):
+            try:
+                # thread_local: the NCCL watchdog thread of torch.distributed may touch CUDA while this thread captures
+                with torch.cuda.graph(g, capture_error_mode='thread_local' if self.world > 1 else 'global'):
+                    self.draw_noise(**self._STEP_NOISE[name])
+                    fn(self._static_x)
+            except Exception as e:                       # noqa: BLE001
+                if self.world == 1:
+                    raise
+                # data-parallel capture of the NCCL collectives failed on this stack: launch the sub-steps eagerly
+                import sys
+                print('[ladder] CUDA-graph capture with NCCL failed (%s: %s); data-parallel sub-steps run eagerly'
+                      % (type(e).__name__, str(e).splitlines()[0] if str(e) else ''), file=sys.stderr)
+                self.use_graphs = False
+                torch.cuda.synchronize()
                 self.draw_noise(**self._STEP_NOISE[name])
-                fn(self._static_x)
+                fn(x)
+                return
             self._graphs = {k: v for k, v in self._graphs.items() if k[1] == self._feed_version}
             self._graphs[key] = g
             self._graph_launches[key] = ops.launch_count() - n0      # kernels captured in this graph
