@@ -27,7 +27,7 @@ METRIC = 'train imgs/sec (ELBO fwd+bwd, 4 sub-steps per image batch)'
 
 
 # dram bytes (read+write) per launch of the roofline kernel from the committed `ncu --set full` capture (profiles/)
-TRAFFIC = {}
+TRAFFIC = {('mnist_fashion', 'bf16', 1024): 33.90e6 + 84.29e6}    # profiles/r1d_ncu_dominant_kernel.md (read + write)
 
 WORKLOAD = 'mnist_fashion'       # set from --workload; the default is BASELINE.json configs[1]
 
