@@ -572,7 +572,11 @@ class PriorVAE:
         self.head_std.forward(h)
         ops.gauss_head_fwd(self.mean, self.std, eps_t, self.t, float(self.cfg['latent_variance_precision']), stats_t)
         self.eps_t = eps_t
-        h = self.t.view(B, 1, 1, self.R)
+        return self.decode(self.t)
+
+    def decode(self, t):
+        """Decoder half only: `decoded_code` for a given representation (is_representation_input, base.py:171-186)."""
+        h = t.view(self.B, 1, 1, self.R)
         for l in self.dec:
             h = l.forward(h)
         self.out.forward(h)
@@ -911,6 +915,44 @@ class LadderEngine:
                          float(cfg.get('inner_sigma_lb', 0.0)), float(cfg.get('inner_sigma_ub', 1.0)), kind,
                          self.use_sg)
         return s
+
+    # ---- decoder-only / encoder-only passes on arbitrary point sets (demo path: notebook cells 14-25, demo_tools.py:41-77)
+    def _chunks(self, pts, width):
+        pts = torch.as_tensor(np.asarray(pts) if not torch.is_tensor(pts) else pts, dtype=torch.float32, device=self.dev)
+        pts = pts.reshape(-1, *width) if isinstance(width, tuple) else pts.reshape(-1, width)
+        for i in range(0, pts.shape[0], self.B):
+            chunk = pts[i:i + self.B]
+            buf = torch.zeros(self.B, *chunk.shape[1:], device=self.dev)
+            buf[:chunk.shape[0]] = chunk
+            yield buf, chunk.shape[0]
+
+    def decode_code(self, code):
+        """`sess.run(model.decoded, {is_code_input: True, code_input: code})` (models.py:103-148): decoder-only forward of
+        any number of codes [n, C] -> images [n, H, W, ch] (evaluated in batches of the engine's batch size)."""
+        self.ae.repack()
+        out = [self.outer.decode(buf)[:n].float().clone() for buf, n in self._chunks(code, self.C)]
+        return torch.cat(out) if out else torch.empty(0, *self.outer.decoded.shape[1:], device=self.dev)
+
+    def decode_representation(self, t):
+        """`sess.run(model.decoded_code, {is_representation_input: True, representation_input: t})` (base.py:171-186):
+        prior-VAE decoder only, [n, R] -> decoded codes [n, C]."""
+        if not self.has_prior:
+            raise RuntimeError('decode_representation: prior=%r has no prior VAE' % self.prior)
+        self.prior_g.repack()
+        out = [self.pvae.decode(buf)[:n].clone() for buf, n in self._chunks(t, self.R)]
+        return torch.cat(out) if out else torch.empty(0, self.C, device=self.dev)
+
+    def embed(self, x, space='t'):
+        """Posterior means of images [n, H, W, ch]: `representation_mean` (space 't') or `code_mean` (space 'z') with the
+        decoder skipped (demo_tools.py:41-77).  BatchNorm models normalise each padded chunk with its own statistics, as the
+        reference does for whatever batch is fed."""
+        shape = tuple(self.outer.decoded.shape[1:])
+        out = []
+        for buf, n in self._chunks(x, shape):
+            self.draw_noise(mc=False)
+            self.forward(buf, dec=False, prior=(space == 't'), mix=False)
+            out.append((self.pvae.mean if space == 't' else self.outer.mean)[:n].clone())
+        return torch.cat(out)
 
     # ---- backward pieces
     def _prior_backward(self, dz, wgrad):
