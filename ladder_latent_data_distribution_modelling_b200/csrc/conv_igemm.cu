@@ -537,12 +537,12 @@ int ladder_colsum(const float* g, long long rows, int cols, float* out, cudaStre
 // GEMM half can run on either GEMM backend:  y = act(bias + sum_tap Z[p + tap, tap])  and  DYS[p, tap] = dy[p - tap].
 // Z / DYS are [B*H*W, ldz] with ldz >= KH*KW (columns beyond KH*KW are ignored / zero-filled).
 __global__ void tap_sum_ld_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ bias, float* __restrict__ y, ConvArgs a) {
-  const long long pixels = (long long)a.B * a.OH * a.OW;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(p % a.OW);
-    long long r = p / a.OW;
-    const int oy = (int)(r % a.OH);
-    const int b = (int)(r / a.OH);
+  const unsigned pixels = (unsigned)a.B * a.OH * a.OW;            // < 2^31 (checked on the host): 32-bit index arithmetic
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += gridDim.x * blockDim.x) {
+    const int ox = (int)(p % (unsigned)a.OW);
+    const unsigned r = p / (unsigned)a.OW;
+    const int oy = (int)(r % (unsigned)a.OH);
+    const int b = (int)(r / (unsigned)a.OH);
     float acc = bias != nullptr ? __ldg(bias) : 0.f;
     for (int kh = 0; kh < a.KH; ++kh) {
       const int iy = oy * a.stride - a.pad_t + kh;
@@ -581,6 +581,7 @@ __global__ void tap_scatter_ld_kernel(const float* __restrict__ dy, float* __res
 int ladder_tap_sum(const float* z, int ldz, const float* bias, float* y, int B, int H, int W, int KH, int KW, int stride,
                    int pad_t, int pad_l, int OH, int OW, int act, cudaStream_t stream) {
   LADDER_REQUIRE(z && y && ldz >= KH * KW && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && stride > 0, "tap_sum: bad arguments");
+  LADDER_REQUIRE((long long)B * OH * OW < (1LL << 31), "tap_sum: more than 2^31 pixels");
   ConvArgs a{z, nullptr, bias, nullptr, y, B, H, W, 1, KH, KW, 1, stride, pad_t, pad_l, OH, OW, act, 0, 0};
   long long blocks = ceil_div64((long long)B * OH * OW, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;

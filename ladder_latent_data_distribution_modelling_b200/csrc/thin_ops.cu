@@ -33,16 +33,17 @@ __global__ void __launch_bounds__(256) tap_dgrad_kernel(TapArgs a) {
     sw[(tap * a.Co + co) * a.C + c] = a.w[i];
   }
   __syncthreads();
-  const int c8 = a.C / 8;
-  const long long total = (long long)a.B * a.H * a.W * c8;
+  const unsigned c8 = a.C / 8;
+  const unsigned total = (unsigned)a.B * a.H * a.W * c8;          // < 2^31 (checked on the host): 32-bit index arithmetic
   const float slope = a.act == ACT_LEAKY ? 0.2f : (a.act == ACT_RELU ? 0.f : 1.f);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c0 = (int)(i % c8) * 8;
-    const long long m = i / c8;
-    const int x = (int)(m % a.W);
-    const long long r = m / a.W;
-    const int y = (int)(r % a.H);
-    const long long b = r / a.H;
+    const unsigned mu = i / c8;
+    const int x = (int)(mu % (unsigned)a.W);
+    const unsigned r = mu / (unsigned)a.W;
+    const int y = (int)(r % (unsigned)a.H);
+    const long long b = r / (unsigned)a.H;
+    const long long m = mu;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int kh = 0; kh < a.KH; ++kh) {
       const int ny = y + a.pad_t - kh;
@@ -108,15 +109,17 @@ __global__ void __launch_bounds__(256) tap_dgrad_kernel(TapArgs a) {
 __global__ void __launch_bounds__(256) tap_scatter_bf16_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dys,
                                                                int ld, int B, int H, int W, int KH, int KW, int pad_t,
                                                                int pad_l, int OH, int OW) {
-  const int T = KH * KW, l8 = ld / 8;
-  const long long total = (long long)B * H * W * l8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const int T = KH * KW;
+  const unsigned l8 = ld / 8;
+  const unsigned total = (unsigned)B * H * W * l8;                 // < 2^31 (checked on the host): 32-bit index arithmetic
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int t0 = (int)(i % l8) * 8;
-    const long long m = i / l8;
-    const int x = (int)(m % W);
-    const long long r = m / W;
-    const int y = (int)(r % H);
-    const long long b = r / H;
+    const unsigned mu = i / l8;
+    const int x = (int)(mu % (unsigned)W);
+    const unsigned r = mu / (unsigned)W;
+    const int y = (int)(r % (unsigned)H);
+    const long long b = r / (unsigned)H;
+    const long long m = mu;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -202,16 +205,17 @@ struct ThinK {
 
 // one thread = one output pixel x 8 output channels; weights / bias through the read-only cache
 __global__ void __launch_bounds__(256) thin_k_fprop_kernel(ThinK a) {
-  const int n8 = a.Cout / 8;
-  const long long total = (long long)a.B * a.OH * a.OW * n8;
+  const unsigned n8 = a.Cout / 8;
+  const unsigned total = (unsigned)a.B * a.OH * a.OW * n8;         // < 2^31 (checked on the host): 32-bit index arithmetic
   const float slope = a.act == ACT_LEAKY ? 0.2f : (a.act == ACT_RELU ? 0.f : 1.f);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n0 = (int)(i % n8) * 8;
-    const long long m = i / n8;
-    const int ox = (int)(m % a.OW);
-    const long long r = m / a.OW;
-    const int oy = (int)(r % a.OH);
-    const long long b = r / a.OH;
+    const unsigned mu = i / n8;
+    const int ox = (int)(mu % (unsigned)a.OW);
+    const unsigned r = mu / (unsigned)a.OW;
+    const int oy = (int)(r % (unsigned)a.OH);
+    const long long b = r / (unsigned)a.OH;
+    const long long m = mu;
     float acc[8];
     if (a.bias != nullptr) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + n0)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + 4));
@@ -281,10 +285,11 @@ __global__ void __launch_bounds__(256) thin_k_wgrad_kernel(ThinK a, const float*
     for (long long p = lo + pl; p < hi; p += lanes) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(dy + p * a.Cout + ng * 4));
       accb[0] += g.x; accb[1] += g.y; accb[2] += g.z; accb[3] += g.w;
-      const int ox = (int)(p % a.OW);
-      const long long r = p / a.OW;
-      const int oy = (int)(r % a.OH);
-      const long long b = r / a.OH;
+      const unsigned pu = (unsigned)p;                               // P < 2^31 (checked on the host)
+      const int ox = (int)(pu % (unsigned)a.OW);
+      const unsigned r = pu / (unsigned)a.OW;
+      const int oy = (int)(r % (unsigned)a.OH);
+      const long long b = r / (unsigned)a.OH;
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
@@ -369,6 +374,7 @@ int ladder_tap_dgrad(const float* dy, const float* w, const void* act_out, int a
   LADDER_REQUIRE(out_s2d == 0 || (H % out_s2d == 0 && W % out_s2d == 0), "tap_dgrad: space_to_depth(%d) needs H, W divisible by r", out_s2d);
   const size_t smem = (size_t)KH * KW * C * Co * sizeof(float);
   LADDER_REQUIRE(smem <= 48 * 1024, "tap_dgrad: KH*KW*C*Co = %d weights do not fit in 48 KB of shared memory", KH * KW * C * Co);
+  LADDER_REQUIRE((long long)B * H * W * (C / 8) < (1LL << 31), "tap_dgrad: more than 2^31 work items");
   TapArgs a{dy, w, act_out, dx, B, H, W, C, Co, KH, KW, pad_t, pad_l, OH, OW, act, act_out_bf16, dx_bf16, out_s2d, accumulate};
   long long blocks = ceil_div64((long long)B * H * W * (C / 8), 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -389,6 +395,7 @@ int ladder_thin_k_fprop(const float* x, const float* w, const float* bias, void*
   LADDER_REQUIRE(ladder_thin_k_supported(KH, KW, Cin, Cout), "thin_k_fprop: needs KH*KW*Cin <= 16 and Cout %% 8 == 0");
   LADDER_REQUIRE(((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 15) == 0 && (bias == nullptr || ((uintptr_t)bias & 15) == 0),
                  "thin_k_fprop: w, bias and y must be 16-byte aligned");
+  LADDER_REQUIRE((long long)B * OH * OW * (Cout / 8) < (1LL << 31), "thin_k_fprop: more than 2^31 work items");
   ThinK a{x, w, bias, y, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, act, y_bf16};
   long long blocks = ceil_div64((long long)B * OH * OW * (Cout / 8), 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -402,6 +409,7 @@ int ladder_thin_k_wgrad(const float* x, const float* dy, float* dw, float* dbias
   LADDER_REQUIRE(ladder_thin_k_supported(KH, KW, Cin, Cout), "thin_k_wgrad: needs KH*KW*Cin <= 16 and Cout %% 8 == 0");
   LADDER_REQUIRE(((uintptr_t)dy & 15) == 0, "thin_k_wgrad: dy must be 16-byte aligned");
   const int K = KH * KW * Cin;
+  LADDER_REQUIRE((long long)B * OH * OW < (1LL << 31), "thin_k_wgrad: more than 2^31 pixels");
   cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)K * Cout * sizeof(float), stream);
   if (e == cudaSuccess && dbias != nullptr) e = cudaMemsetAsync(dbias, 0, (size_t)Cout * sizeof(float), stream);
   if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "thin_k_wgrad memset: %s", cudaGetErrorString(e));
@@ -435,6 +443,7 @@ int ladder_tap_scatter_bf16(const float* dy, void* dys_bf16, int ld, int B, int 
                             int OH, int OW, cudaStream_t stream) {
   LADDER_REQUIRE(dy && dys_bf16 && ld >= KH * KW && ld % 8 == 0 && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0,
                  "tap_scatter_bf16: bad arguments");
+  LADDER_REQUIRE((long long)B * H * W * (ld / 8) < (1LL << 31), "tap_scatter_bf16: more than 2^31 work items");
   long long blocks = ceil_div64((long long)B * H * W * (ld / 8), 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   tap_scatter_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dy, static_cast<__nv_bfloat16*>(dys_bf16), ld, B, H, W, KH, KW,
