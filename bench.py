@@ -444,7 +444,7 @@ def run_ours(args):
         hyper = {'pairs_per_s_fwd': hp['fwd'], 'pairs_per_s_fwd_grad': hp['fwd_grad'], 'N': N, 'K': N, 'D': 2,
                  'bound': 'sfu (1 MUFU.EX2 per pair)', 'ex2_peak_per_s_measured': ex2_peak,
                  'frac_fwd': hp['fwd'] / ex2_peak, 'frac_fwd_grad': hp['fwd_grad'] / ex2_peak}
-        cpu = cpu_reference(cfg, args.cpu_sample, 1, 1)
+        cpu = cpu_reference(cfg, args.cpu_sample, 2, 1)
         line = {'metric': METRIC, 'value': value, 'unit': 'imgs/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16' if args.dtype == 'bf16' else 'f32', 'data': 'synthetic',
@@ -474,7 +474,8 @@ def main():
     ap.add_argument('--batch', type=int, default=1024, help='images per GPU')
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of CUDA-graph replay')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'], help='GEMM math: bf16 tcgen05 or fp32 SIMT')
-    ap.add_argument('--cpu-sample', type=int, default=32, help='batch of the bounded CPU-baseline sample')
+    ap.add_argument('--cpu-sample', type=int, default=0,
+                    help='batch of the bounded CPU-baseline sample (0 = 256 images for the MNIST workloads, 8 for celeba: ~10-20 s)')
     ap.add_argument('--celeba-batch', type=int, default=64, help='per-GPU batch of the secondary CelebA-shape leg (0 = skip)')
     ap.add_argument('--celeba-steps', type=int, default=10)
     ap.add_argument('--workload', default='mnist_fashion', choices=['mnist_fashion', 'mnist_digit', 'celeba'],
@@ -482,6 +483,8 @@ def main():
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload
+    if args.cpu_sample <= 0:
+        args.cpu_sample = 8 if WORKLOAD == 'celeba' else 256
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
         run_reference(args)
