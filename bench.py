@@ -174,16 +174,18 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def celeba_leg(args, dev, rank, world, group):
+def celeba_leg(args, dev, rank, world, group, B, code_size=None, steps=None):
     """Same 4-sub-step iteration on codes/celeba_config.json (128x128x3 conv VAE + prior VAE + hyper-prior), synthetic
-    batches of --celeba-batch images per GPU resident in HBM; max over ranks of the CUDA-event time."""
+    batches of B images per GPU resident in HBM; max over ranks of the CUDA-event time.  code_size overrides the JSON
+    (BASELINE.json configs[4]: latent dim 128 at batch 512 per GPU)."""
     import torch
     import torch.distributed as dist
     from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
     with open(os.path.join(ROOT, 'codes', 'celeba_config.json')) as f:
         cfg = json.load(f)
-    B = args.celeba_batch
     cfg.update(batch_size=B, seed=1234, compute_dtype=args.dtype)
+    if code_size:
+        cfg['code_size'] = int(code_size)
     if args.no_graphs:
         cfg['cuda_graphs'] = False
     eng = LadderEngine(cfg, B, dev, seed=4321 + rank, dist_group=group)
@@ -197,7 +199,7 @@ def celeba_leg(args, dev, rank, world, group):
     gen = torch.Generator(device=dev)
     gen.manual_seed(7 + rank)
     pool = [torch.rand(B, 128, 128, 3, device=dev, generator=gen) for _ in range(4)]
-    steps = args.celeba_steps
+    steps = steps or args.celeba_steps
 
     def sync():
         if world > 1:
@@ -220,7 +222,7 @@ def celeba_leg(args, dev, rank, world, group):
     ms = float(t.item())
     fl = 3 * 10.04e9          # algorithmic fwd+bwd flop per image (one fused pass; the 4-sub-step protocol runs more)
     v = B * world * steps / (ms * 1e-3)
-    out = {'workload': 'codes/celeba_config.json @ batch %d per GPU (128x128x3, H=512, C=256), all 4 sub-steps' % B,
+    out = {'workload': 'codes/celeba_config.json @ batch %d per GPU (128x128x3, H=512, C=%d), all 4 sub-steps' % (B, cfg['code_size']),
            'value': v, 'unit': 'imgs/s', 'ms_per_step': ms / steps, 'steps': steps, 'warmup': 3, 'global_batch': B * world,
            'algorithmic_tflops': v * fl / 1e12 / world, 'loss_ae': eng.fetch(['loss_ae'])['loss_ae']}
     eng.release_graphs()
@@ -364,14 +366,6 @@ def run_ours(args):
     windows.append((w0, time.time()))               # second sampling window: the end-to-end timed region
     clocks = sampler.summary(windows) if rank == 0 else None
 
-    # ---- secondary workload: CelebA-shape (128x128x3) training step, BASELINE.json configs[3] per-GPU batch
-    celeba = None
-    if WORKLOAD != 'celeba' and args.celeba_batch > 0:
-        del model, trainer
-        eng.release_graphs()
-        torch.cuda.empty_cache()
-        celeba = celeba_leg(args, dev, rank, world, group)
-
     line = None
     if rank == 0:
         peaks = measured_peaks()
@@ -457,10 +451,35 @@ def run_ours(args):
                         'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps,
                         'api': '*Trainer_joint_training.train_step_ae + train_step_prior on pinned host batches'},
                 'roofline': roofline, 'cpu_baseline': {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
-                'hyper_prior': hyper, 'celeba_shape': celeba, 'loss_prior_last': loss_check, 'loss_ae_last_e2e': last}
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+                'hyper_prior': hyper, 'celeba_shape': None, 'loss_prior_last': loss_check, 'loss_ae_last_e2e': last}
+    # ---- secondary workload: CelebA-shape (128x128x3) training step, BASELINE.json configs[3] per-GPU batch
+    celeba = None
+    if WORKLOAD != 'celeba' and args.celeba_batch > 0:
+        del model, trainer
+        eng.release_graphs()
+        torch.cuda.empty_cache()
+        celeba = {}
+        for key, b, cs, st in (('reference_batch', args.celeba_batch, None, args.celeba_steps),
+                               ('weak_scaling_config', args.celeba_big_batch, 128, max(3, args.celeba_steps // 2))):
+            if b <= 0:
+                continue
+            try:                                      # a secondary leg must never take the headline line down with it
+                celeba[key] = celeba_leg(args, dev, rank, world, group, b, cs, st)
+            except Exception as e:                    # noqa: BLE001
+                celeba[key] = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:200] if str(e) else '')}
+                try:
+                    torch.cuda.synchronize()
+                except Exception:                     # noqa: BLE001
+                    break
+
+    if line is not None:
+        line['celeba_shape'] = celeba
+    try:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+    except Exception:                                 # noqa: BLE001
+        pass
     if line is not None:
         print(json.dumps(line))
 
@@ -477,6 +496,8 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=0,
                     help='batch of the bounded CPU-baseline sample (0 = 256 images for the MNIST workloads, 8 for celeba: ~10-20 s)')
     ap.add_argument('--celeba-batch', type=int, default=64, help='per-GPU batch of the secondary CelebA-shape leg (0 = skip)')
+    ap.add_argument('--celeba-big-batch', type=int, default=512,
+                    help='per-GPU batch of the CelebA-shape weak-scaling leg (BASELINE.json configs[4]: 4096 over 8 GPUs, code_size 128)')
     ap.add_argument('--celeba-steps', type=int, default=10)
     ap.add_argument('--workload', default='mnist_fashion', choices=['mnist_fashion', 'mnist_digit', 'celeba'],
                     help='config file under codes/ (default: BASELINE.json configs[1])')
