@@ -203,6 +203,11 @@ int ladder_thin_k_wgrad(const float* x, const float* dy, float* dw, float* dbias
                         int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, cudaStream_t stream);
 int ladder_thin_n_dgrad(const float* dy, const float* w, float* dx, long long M, int N, int K, int accumulate,
                         cudaStream_t stream);
+/* Patch matrix of a tiny-Cin conv (KH*KW*Cin <= 64: the first encoder conv on the RGB / grey image, codes/models.py:398-404,
+ * 52-56, 203-207): A[p, (kh, kw, c)] over the OUTPUT pixels p, bf16, zero padded to 64 columns, so that its fprop / wgrad run
+ * as dense TMA-fed GEMMs (ladder_conv2d_fprop_tma / _wgrad_tma on [P,1,1,64]). */
+int ladder_im2col64_bf16(const float* x, void* patches_bf16, int B, int H, int W, int Cin, int KH, int KW, int stride,
+                         int pad_t, int pad_l, int OH, int OW, cudaStream_t stream);
 /* dw[c, co] = sum_p x[p, c] dy[p, co] for a 1x1 conv with <= 8 outputs; x fp32 or bf16, dw (HWIO) overwritten */
 int ladder_thin_wgrad_1x1(const void* x, int x_bf16, const float* dy, float* dw, long long P, int C, int Co,
                           cudaStream_t stream);

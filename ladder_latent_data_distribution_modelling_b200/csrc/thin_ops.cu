@@ -359,6 +359,44 @@ __global__ void __launch_bounds__(256) thin_n_dgrad_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tiny-Cin first conv (CelebA: 3x3 stride 2 on the RGB image, K = 27; MNIST: K = 9) on the tensor cores: the patch
+// matrix A[p, k] (k = (kh, kw, c), zero padded to 64 columns, bf16) is materialised ONCE -- it is only 64 columns wide --
+// and fprop / wgrad become dense TMA-fed GEMMs [P x 64] x [64 x Cout] / [64 x P] x [P x Cout].  One thread = one output
+// pixel x 8 consecutive patch entries (one 16-byte store).
+__global__ void __launch_bounds__(256) im2col64_bf16_kernel(ThinK a, __nv_bfloat16* __restrict__ out) {
+  const unsigned total = (unsigned)a.B * a.OH * a.OW * 8u;           // < 2^31 (checked on the host)
+  const int K = a.KH * a.KW * a.Cin;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k0 = (int)(i & 7u) * 8;
+    const unsigned p = i >> 3;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (k0 < K) {
+      const int ox = (int)(p % (unsigned)a.OW);
+      const unsigned r = p / (unsigned)a.OW;
+      const int oy = (int)(r % (unsigned)a.OH);
+      const long long b = r / (unsigned)a.OH;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + j;
+        v[j] = 0.f;
+        if (k < K) {
+          const int tap = k / a.Cin, c = k - tap * a.Cin;
+          const int kh = tap / a.KW, kw = tap - kh * a.KW;
+          const int iy = oy * a.stride - a.pad_t + kh, ix = ox * a.stride - a.pad_l + kw;
+          if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v[j] = __ldg(a.x + ((b * a.H + iy) * a.W + ix) * a.Cin + c);
+        }
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)p * 64 + k0) = u;
+  }
+}
+
 }  // namespace ladder
 
 using namespace ladder;
@@ -437,6 +475,19 @@ int ladder_thin_n_dgrad(const float* dy, const float* w, float* dx, long long M,
   if (blocks > 148 * 8) blocks = 148 * 8;
   thin_n_dgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dy, w, dx, M, N, K, accumulate);
   return check_launch("thin_n_dgrad");
+}
+
+int ladder_im2col64_bf16(const float* x, void* patches_bf16, int B, int H, int W, int Cin, int KH, int KW, int stride,
+                         int pad_t, int pad_l, int OH, int OW, cudaStream_t stream) {
+  LADDER_REQUIRE(x && patches_bf16 && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && stride >= 1, "im2col64_bf16: bad arguments");
+  LADDER_REQUIRE(KH * KW * Cin <= 64 && Cin >= 1, "im2col64_bf16: needs KH*KW*Cin <= 64");
+  LADDER_REQUIRE((long long)B * OH * OW * 8 < (1LL << 31), "im2col64_bf16: more than 2^31 work items");
+  LADDER_REQUIRE(((uintptr_t)patches_bf16 & 15) == 0, "im2col64_bf16: output must be 16-byte aligned");
+  ThinK a{x, nullptr, nullptr, nullptr, B, H, W, Cin, KH, KW, 0, stride, pad_t, pad_l, OH, OW, 0, 0};
+  long long blocks = ceil_div64((long long)B * OH * OW * 8, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  im2col64_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, static_cast<__nv_bfloat16*>(patches_bf16));
+  return check_launch("im2col64_bf16");
 }
 
 int ladder_tap_scatter_bf16(const float* dy, void* dys_bf16, int ld, int B, int H, int W, int KH, int KW, int pad_t, int pad_l,

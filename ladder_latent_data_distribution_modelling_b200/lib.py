@@ -56,6 +56,7 @@ SIGNATURES = {
     'ladder_conv2d_dgrad_tma': (C.c_int, [ptr, ptr, ptr, C.c_int, ptr, C.c_int] + [C.c_int] * 15 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_wgrad_tma': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [stream_t]),
     'ladder_tap_dgrad': (C.c_int, [ptr, ptr, ptr, C.c_int, ptr, C.c_int] + [C.c_int] * 14 + [stream_t]),
+    'ladder_im2col64_bf16': (C.c_int, [ptr, ptr] + [C.c_int] * 11 + [stream_t]),
     'ladder_thin_k_supported': (C.c_int, [C.c_int] * 4),
     'ladder_thin_k_fprop': (C.c_int, [ptr, ptr, ptr, ptr, C.c_int] + [C.c_int] * 13 + [stream_t]),
     'ladder_thin_k_wgrad': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 12 + [stream_t]),

@@ -421,6 +421,49 @@ def thin_k(g):
             and bool(_L().ladder_thin_k_supported(g.KH, g.KW, g.Cin, g.Cout)))
 
 
+# first conv on the tiny-Cin image as [P x 64] patch matrix + dense tensor-core GEMMs (LADDER_IM2COL=0: SIMT / thin kernels)
+IM2COL = os.environ.get('LADDER_IM2COL', '1') != '0'
+
+
+def _im2col_geom(g):
+    return ConvGeom.dense(g.B * g.OH * g.OW, 64, g.Cout)
+
+
+def im2col_ok(g):
+    """Tiny-Cin KxK conv (first encoder layer): K = KH*KW*Cin <= 64 patch entries, Cout a multiple of 64."""
+    if not (IM2COL and MATH_MODE == 'bf16' and TMA and g.Cin < 8 and g.KH * g.KW > 1 and g.KH * g.KW * g.Cin <= 64
+            and g.Cout % 64 == 0 and g.B * g.OH * g.OW * 8 < 2 ** 31):
+        return False
+    gd = _im2col_geom(g)
+    return tma_supported(gd, FPROP) and tma_supported(gd, WGRAD)
+
+
+def _im2col(x, g):
+    P = g.B * g.OH * g.OW
+    a = _workspace(x.device, P * 64 * 2, 'im2col').view(torch.bfloat16)[:P * 64].view(P, 1, 1, 64)
+    _lib.check(_L().ladder_im2col64_bf16(_p(_f32(x)), _p(a), g.B, g.H, g.W, g.Cin, g.KH, g.KW, g.stride, g.pad_t, g.pad_l,
+                                         g.OH, g.OW, _stream()), 'im2col64_bf16')
+    return a
+
+
+def _im2col_fprop(x, w, bias, y, g, act):
+    K = g.KH * g.KW * g.Cin
+    wp = _workspace(x.device, 64 * g.Cout * 4, 'im2col_w').view(torch.float32)[:64 * g.Cout].view(64, g.Cout)
+    wp[K:].zero_()
+    wp[:K].copy_(w.view(K, g.Cout))
+    gd = _im2col_geom(g)
+    return conv2d_fprop(_im2col(x, g), wp.view(1, 1, 64, g.Cout), bias, y.view(gd.B, 1, 1, g.Cout), gd, act)
+
+
+def _im2col_wgrad(x, dy, dw, dbias, g):
+    K = g.KH * g.KW * g.Cin
+    gd = _im2col_geom(g)
+    dwp = _workspace(x.device, 64 * g.Cout * 4, 'im2col_dw').view(torch.float32)[:64 * g.Cout].view(1, 1, 64, g.Cout)
+    conv2d_wgrad(_im2col(x, g), dy.view(gd.B, 1, 1, g.Cout), dwp, dbias, gd)
+    dw.view(K, g.Cout).copy_(dwp.view(64, g.Cout)[:K])
+    return dw
+
+
 def thin_n(g):
     """Dense layers with <= 16 inputs: the gradient w.r.t. the latent is a warp-per-row dot-product pass."""
     return MATH_MODE == 'bf16' and TMA and g.KH == 1 and g.KW == 1 and g.stride == 1 and g.Cin <= 16
@@ -504,6 +547,9 @@ def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0, wimg=None):
     _act_t(x, 'x'), _act_t(y, 'y')
     if MATH_MODE == 'bf16' and _is_tap_gemm(g) and g.Cin % 64 == 0 and not out_d2s:
         return _tap_gemm_fprop_tc(x, w, bias, y, g, act)
+    if x.dtype == torch.float32 and not out_d2s and im2col_ok(g):
+        _im2col_fprop(x, w, bias, y, g, act)
+        return y
     if thin_k(g) and x.dtype == torch.float32 and not out_d2s:
         _lib.check(_L().ladder_thin_k_fprop(_p(x), _p(_f32(w)), _p(bias), _p(y), _is16(y), *g.args(), ACT[act], _stream()),
                    'thin_k_fprop')
@@ -578,6 +624,8 @@ def conv2d_wgrad(x, dy, dw, dbias, g, dys=None):
         if dbias is not None:
             colsum(dy, g.B * g.OH * g.OW, g.Cout, dbias)
         return dw
+    if x.dtype == torch.float32 and im2col_ok(g):
+        return _im2col_wgrad(x, dy, dw, dbias, g)
     if thin_k(g) and x.dtype == torch.float32 and dy.dtype == torch.float32:
         _lib.check(_L().ladder_thin_k_wgrad(_p(x), _p(dy), _p(_f32(dw)), _p(dbias), *g.args(), _stream()), 'thin_k_wgrad')
         return dw

@@ -18,6 +18,8 @@ def main():
     bench.WORKLOAD = workload
     cfg = bench.load_config(B)
     cfg['seed'] = 1234
+    if len(sys.argv) > 4:
+        cfg['code_size'] = int(sys.argv[4])
     dev = torch.device('cuda', 0)
     eng = LadderEngine(cfg, B, dev, seed=1234)
     gm = bench.synthetic_mixture(cfg['n_mixtures'], cfg['representation_size'])
