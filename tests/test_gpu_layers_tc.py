@@ -33,8 +33,8 @@ TC_CASES = CASES + [
     (2, 16, 16, 128, 3, 128, 1, 'same', 'leaky_relu'),    # CelebA-like
     (300, 1, 1, 512, 1, 512, 1, 'valid', 'leaky_relu'),   # dense, M not a tile multiple, several k-blocks
     (3, 8, 8, 64, 3, 300, 2, 'same', None),               # N > 256: two N tiles with a ragged tail
-    (3, 32, 32, 1, 3, 64, 2, 'same', 'leaky_relu'),       # fashion enc conv 1: [P x 64] patch matrix + dense GEMMs
-    (2, 16, 16, 3, 3, 128, 2, 'same', 'leaky_relu'),      # CelebA enc conv 1 (RGB, K = 27), same path
+    (3, 32, 32, 1, 3, 64, 2, 'same', 'leaky_relu'),       # fashion enc conv 1 (K = 9: thin element-wise kernels)
+    (2, 16, 16, 3, 3, 128, 2, 'same', 'leaky_relu'),      # CelebA enc conv 1 (RGB, K = 27): [P x 64] patch matrix + dense GEMMs
     (2, 12, 10, 3, 3, 64, 1, 'valid', None),              # tiny-Cin, stride 1, valid, ragged pixel count
 ]
 
