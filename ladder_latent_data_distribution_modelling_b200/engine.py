@@ -119,6 +119,20 @@ def glorot_uniform_(t, shape, gen):
 
 
 # ------------------------------------------------------------------------------ layers
+BF16_HIDDEN = os.environ.get('LADDER_BF16_HIDDEN', '1') != '0'
+
+
+def hidden_dtype(g, consumers):
+    """Storage type of a hidden activation: bf16 when the layer can write it (TMA-fed or thin short-reduction kernel) and
+    every consumer layer reads bf16 natively -- the GEMMs round their operands to bf16 anyway, so the numbers entering every
+    MMA are unchanged; what disappears is the fp32 copy and its conversion launch."""
+    if not BF16_HIDDEN or ops.MATH_MODE != 'bf16':
+        return torch.float32
+    if not (ops.tma_supported(g, ops.FPROP) or ops.thin_k(g)):
+        return torch.float32
+    return torch.bfloat16 if all(ops.reads_bf16(c) for c in consumers) else torch.float32
+
+
 class Conv:
     """conv2d (or dense) + bias + activation with preallocated output and gradients.
 
@@ -137,7 +151,7 @@ class Conv:
         self.db = group.g(wname + '/bias')
         g = geom
         self.tma = [ops.tma_supported(g, m) for m in (ops.FPROP, ops.DGRAD, ops.WGRAD)]
-        if out_dtype != torch.float32 and not self.tma[0]:
+        if out_dtype != torch.float32 and not (self.tma[0] or ops.thin_k(g)):
             raise RuntimeError('engine: bf16 activations need the TMA path for %s' % wname)
         self.y = torch.empty(g.B, g.OH, g.OW, g.Cout, device=device, dtype=out_dtype)
         self.x = None
@@ -209,20 +223,21 @@ class MnistOuterVAE:
         G = ops.ConvGeom
         self.buf = Buffers(device)
         self.xpad = torch.empty(B, 32, 32, 1, device=device)
-        enc = []
         if exp == 'mnist_digit':
-            enc.append(Conv(group, 'encoder/conv2d', G(B, 32, 32, 1, k, k, H // 16, 2, 'same'), LEAKY, device))
-            enc.append(Conv(group, 'encoder/conv2d_1', G(B, 16, 16, H // 16, k, k, H // 4, 2, 'same'), LEAKY, device))
-            enc.append(Conv(group, 'encoder/conv2d_2', G(B, 8, 8, H // 4, k, k, H, 2, 'same'), LEAKY, device))
+            egeoms = [G(B, 32, 32, 1, k, k, H // 16, 2, 'same'), G(B, 16, 16, H // 16, k, k, H // 4, 2, 'same'),
+                      G(B, 8, 8, H // 4, k, k, H, 2, 'same')]
             flat, feat = 16 * H, H // 4
         else:
-            enc.append(Conv(group, 'encoder/conv2d', G(B, 32, 32, 1, 3, 3, H // 4, 2, 'same'), LEAKY, device))
-            enc.append(Conv(group, 'encoder/conv2d_1', G(B, 16, 16, H // 4, 3, 3, H // 4, 2, 'same'), LEAKY, device))
-            enc.append(Conv(group, 'encoder/conv2d_2', G(B, 8, 8, H // 4, 3, 3, H // 2, 2, 'same'), LEAKY, device))
-            enc.append(Conv(group, 'encoder/conv2d_3', G(B, 4, 4, H // 2, 3, 3, H // 2, 1, 'valid'), LEAKY, device))
+            egeoms = [G(B, 32, 32, 1, 3, 3, H // 4, 2, 'same'), G(B, 16, 16, H // 4, 3, 3, H // 4, 2, 'same'),
+                      G(B, 8, 8, H // 4, 3, 3, H // 2, 2, 'same'), G(B, 4, 4, H // 2, 3, 3, H // 2, 1, 'valid')]
             flat, feat = 2 * H, H
+        gdense = G.dense(B, flat, feat)
+        enames = ['encoder/conv2d'] + ['encoder/conv2d_%d' % i for i in range(1, len(egeoms))]
+        # hidden encoder maps are bf16-resident where the next layer reads bf16 (see hidden_dtype)
+        enc = [Conv(group, enames[i], g, LEAKY, device,
+                    out_dtype=hidden_dtype(g, [egeoms[i + 1] if i + 1 < len(egeoms) else gdense])) for i, g in enumerate(egeoms)]
         self.enc_convs = enc
-        self.enc_dense = Conv(group, 'encoder/dense', G.dense(B, flat, feat), LEAKY, device)
+        self.enc_dense = Conv(group, 'encoder/dense', gdense, LEAKY, device)
         self.head_mean = Conv(group, 'encoder/code_mean', G.dense(B, feat, C), None, device)
         self.head_std = Conv(group, 'encoder/code_std_dev', G.dense(B, feat, C), None, device)
         self.flat, self.feat, self.C = flat, feat, C
@@ -549,13 +564,19 @@ class PriorVAE:
         act = config['inner_activation']
         G = ops.ConvGeom
         names = ['prior/dense'] + ['prior/dense_%d' % i for i in range(1, 2 * nl + 3)]
-        self.enc = [Conv(group, names[0], G.dense(B, C, Hi), act, device)]
-        self.enc += [Conv(group, names[i], G.dense(B, Hi, Hi), act, device) for i in range(1, nl)]
-        self.head_mean = Conv(group, names[nl], G.dense(B, Hi, R), None, device)
-        self.head_std = Conv(group, names[nl + 1], G.dense(B, Hi, R), None, device)
-        self.dec = [Conv(group, names[nl + 2], G.dense(B, R, Hi), act, device)]
-        self.dec += [Conv(group, names[nl + 2 + i], G.dense(B, Hi, Hi), act, device) for i in range(1, nl)]
-        self.out = Conv(group, names[2 * nl + 2], G.dense(B, Hi, C), None, device)
+        g_in, g_hid, g_head = G.dense(B, C, Hi), G.dense(B, Hi, Hi), G.dense(B, Hi, R)
+        g_t, g_out = G.dense(B, R, Hi), G.dense(B, Hi, C)
+        # hidden activations are bf16-resident where every consumer reads bf16 (see hidden_dtype)
+        dt_hid, dt_pre_head, dt_pre_out = hidden_dtype(g_hid, [g_hid]), hidden_dtype(g_hid, [g_head, g_head]), hidden_dtype(g_hid, [g_out])
+        last = lambda i, d: d if i == nl - 1 else dt_hid                                   # noqa: E731
+        first_consumers = lambda tail: [g_hid] if nl > 1 else tail                         # noqa: E731
+        self.enc = [Conv(group, names[0], g_in, act, device, out_dtype=hidden_dtype(g_in, first_consumers([g_head, g_head])))]
+        self.enc += [Conv(group, names[i], g_hid, act, device, out_dtype=last(i, dt_pre_head)) for i in range(1, nl)]
+        self.head_mean = Conv(group, names[nl], g_head, None, device)
+        self.head_std = Conv(group, names[nl + 1], g_head, None, device)
+        self.dec = [Conv(group, names[nl + 2], g_t, act, device, out_dtype=hidden_dtype(g_t, first_consumers([g_out])))]
+        self.dec += [Conv(group, names[nl + 2 + i], g_hid, act, device, out_dtype=last(i, dt_pre_out)) for i in range(1, nl)]
+        self.out = Conv(group, names[2 * nl + 2], g_out, None, device)
         self.C, self.R, self.Hi, self.act = C, R, Hi, act
         self.mean = self.head_mean.y.view(B, R)
         self.std = self.head_std.y.view(B, R)
