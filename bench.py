@@ -27,7 +27,8 @@ METRIC = 'train imgs/sec (ELBO fwd+bwd, 4 sub-steps per image batch)'
 
 
 # dram bytes (read+write) per launch of the roofline kernel from the committed `ncu --set full` capture (profiles/)
-TRAFFIC = {('mnist_fashion', 'bf16', 1024): 33.90e6 + 84.29e6}    # profiles/r1d_ncu_dominant_kernel.md (read + write)
+TRAFFIC = {('mnist_fashion', 'bf16', 1024): 33.90e6 + 84.29e6,             # fprop: profiles/r1d_ncu_dominant_kernel.md (read + write)
+           ('mnist_fashion', 'bf16', 1024, 'dgrad'): 168.10e6 + 25.31e6}   # dgrad: profiles/r1g_ncu_dgrad_kernel.md
 
 WORKLOAD = 'mnist_fashion'       # set from --workload; the default is BASELINE.json configs[1]
 
@@ -412,6 +413,41 @@ def run_ours(args):
                     'note': 'bf16 activations and pre-packed bf16 weights in HBM, fp32 accumulation in TMEM, fused bias + leaky_relu%s, '
                             'exactly the launch the step makes' % (' + depth_to_space(2) store' if d2s else '')
                     if tma else 'denominator is the bf16 tensor peak'}
+        if tma and ops.tma_supported(g, ops.DGRAD):
+            # The largest kernel of the step (ncu launch list / CUPTI, profiles/): the decoder data gradients,
+            # tma_kernel<DGRAD, BN=64, bf16>.  Its largest launch is the dgrad of this same layer, with the fused producer
+            # leaky_relu' and (MNIST decoders) space_to_depth scatter -- it becomes `roofline`, the fprop above `roofline_fprop`.
+            dyk = torch.randn(B, hw, hw, co, device=dev).to(adt)
+            auxk = torch.randn(B, hw, hw, ci, device=dev).to(adt)
+            dxk = torch.empty(B * hw * hw * ci, device=dev, dtype=adt)
+            dxk = dxk.view(B, hw // d2s, hw // d2s, ci * d2s * d2s) if d2s else dxk.view(B, hw, hw, ci)
+            wimg_d = ops.tma_pack(wk, g, ops.DGRAD)
+            for _ in range(3):
+                ops.conv2d_dgrad(dyk, wk, dxk, g, act_out=auxk, act='leaky_relu', out_s2d=d2s, wimg=wimg_d)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                ops.conv2d_dgrad(dyk, wk, dxk, g, act_out=auxk, act='leaky_relu', out_s2d=d2s, wimg=wimg_d)
+            e1.record()
+            torch.cuda.synchronize()
+            d_ms = e0.elapsed_time(e1) / reps
+            d_bytes = 2 * B * hw * hw * (co + 2 * ci) + 2 * 9 * ci * co          # dy + saved activation + dx + weights, bf16
+            d_ach = flops / (d_ms * 1e-3) / 1e12
+            roofline_fprop = roofline
+            roofline = {'kernel': 'tma_kernel<DGRAD,64> (TMA im2col + tcgen05, bf16 in/out) %s [B,%d,%d,%d]<-%d 3x3'
+                                  % (dom_name, hw, hw, ci, co),
+                        'bound': 'tensor', 'achieved': d_ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                        'frac': d_ach / peaks['bf16_tflops'], 'traffic': TRAFFIC.get((WORKLOAD, args.dtype, B, 'dgrad')),
+                        'peak_source': peaks['source'] + ' bf16 burst (kernel timed alone)',
+                        'ms_per_launch': d_ms, 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': d_bytes,
+                        'hbm_floor_ms': d_bytes / (peaks['hbm_gbs'] * 1e9) * 1e3,
+                        'tensor_floor_ms': flops / (peaks['bf16_tflops'] * 1e12) * 1e3,
+                        'timed': 'CUDA events on the launch stream around %d back-to-back launches; dy + aux + dx = %d MB (%s the '
+                                 '126 MB L2)' % (reps, d_bytes >> 20, 'exceeds' if d_bytes > 126 << 20 else 'FITS in'),
+                        'note': 'largest launch of the largest kernel of the step (15-17 %% of the step, profiles/); fused producer '
+                                'leaky_relu\'%s; bound by L2->SM operand traffic at N = 64 (profiles/r1g_ncu_dgrad_kernel.md)'
+                                % (' + space_to_depth(2) scatter' if d2s else ''),
+                        'roofline_fprop': roofline_fprop}
         # ---- hyper-prior micro-benchmark (second half of the metric): 65 536 x 65 536 pairs, D = 2
         rng = np.random.default_rng(1234)
         N = 65536
