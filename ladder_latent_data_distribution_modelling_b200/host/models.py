@@ -125,8 +125,14 @@ class BaseModel:
             f.write('ladder_b200 checkpoint: trainable variables in %s.npz\n' % os.path.basename(path))
 
     def _load(self, path):
-        d = np.load(path + '.npz')
-        self.engine.load_parameters({k.replace('__', '/'): d[k] for k in d.files})
+        if os.path.isfile(path + '.npz'):
+            d = np.load(path + '.npz')
+            self.engine.load_parameters({k.replace('__', '/'): d[k] for k in d.files})
+            return
+        # a checkpoint written by the reference's tf.train.Saver (<path>.index + <path>.data-00000-of-00001, same variable names)
+        from .tf_checkpoint import read_tf_checkpoint
+        mine = {n for n, _ in self.engine.named_parameters()}
+        self.engine.load_parameters({k: v for k, v in read_tf_checkpoint(path).items() if k in mine})
 
     def save(self, sess, model):
         print("Saving model...")

@@ -6,6 +6,7 @@ Run once in the build container (needs /root/reference, scikit-learn, SciPy):
 
 Outputs (committed):
   ref_variables.json    variable names/shapes of the six pretrained_models/*.index files
+  tf_index/*.index      the four MNIST bundle index files (1 KB each), copied verbatim
   gm_prior_golden.npz   the reference's fitted hyper-prior (figures/mnist_digit/result/
                         GM_prior_info.npz) + query points + log-densities computed with the
                         reference's own dependencies: sklearn GaussianMixture.score_samples
@@ -70,7 +71,18 @@ def mixture():
     np.savez(os.path.join(HERE, 'gm_prior_golden.npz'), **out)
 
 
+def index_files():
+    """The MNIST checkpoints' bundle index files themselves (1 KB each): fixtures of tests/test_tf_checkpoint.py."""
+    import shutil
+    dst = os.path.join(HERE, 'tf_index')
+    os.makedirs(dst, exist_ok=True)
+    for exp in ('mnist_digit', 'mnist_fashion'):
+        for stem in ('vae-model', 'prior-model'):
+            shutil.copy(os.path.join(REF, 'pretrained_models', exp, stem + '.index'), os.path.join(dst, '%s_%s.index' % (exp, stem)))
+
+
 if __name__ == '__main__':
     variables()
     mixture()
+    index_files()
     print('golden fixtures written to', HERE)
