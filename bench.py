@@ -367,6 +367,32 @@ def run_ours(args):
     windows.append((w0, time.time()))               # second sampling window: the end-to-end timed region
     clocks = sampler.summary(windows) if rank == 0 else None
 
+    # ---- component-sharded hyper-prior (BASELINE.json configs[2]): every rank evaluates K / world components
+    # of the 65 536 x 65 536 problem, (m, s[, g]) partials are all-gathered over NCCL and combined; max over ranks
+    sharded = None
+    if world > 1:
+        try:
+            from ladder_latent_data_distribution_modelling_b200 import parallel
+            rng = np.random.default_rng(1234)                        # same queries and components on every rank
+            Ns = 65536
+            tq_s = torch.tensor(rng.normal(size=(Ns, 2)).astype(np.float32), device=dev)
+            tab_s = ops.mixture_pack_diag(rng.normal(size=(Ns, 2)), 1.0, None, dev)
+            sharded = {'N': Ns, 'K': Ns, 'D': 2, 'components_per_rank': -(-Ns // world)}
+            for grad in (False, True):
+                for _ in range(3):
+                    parallel.sharded_mixture_logprob(tq_s, tab_s, group=group, want_grad=grad)
+                barrier()
+                e0.record()
+                for _ in range(5):
+                    parallel.sharded_mixture_logprob(tq_s, tab_s, group=group, want_grad=grad)
+                e1.record()
+                barrier()
+                ts = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+                sharded['pairs_per_s_fwd_grad' if grad else 'pairs_per_s_fwd'] = Ns * Ns / (float(ts.item()) * 1e-3)
+        except Exception as e:                                       # noqa: BLE001
+            sharded = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:200] if str(e) else '')}
+
     line = None
     if rank == 0:
         peaks = measured_peaks()
@@ -487,7 +513,7 @@ def run_ours(args):
                         'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps,
                         'api': '*Trainer_joint_training.train_step_ae + train_step_prior on pinned host batches'},
                 'roofline': roofline, 'cpu_baseline': {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
-                'hyper_prior': hyper, 'celeba_shape': None, 'loss_prior_last': loss_check, 'loss_ae_last_e2e': last}
+                'hyper_prior': hyper, 'hyper_prior_component_sharded': sharded, 'celeba_shape': None, 'loss_prior_last': loss_check, 'loss_ae_last_e2e': last}
     # ---- secondary workload: CelebA-shape (128x128x3) training step, BASELINE.json configs[3] per-GPU batch
     celeba = None
     if WORKLOAD != 'celeba' and args.celeba_batch > 0:
