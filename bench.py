@@ -129,7 +129,10 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ CPU arm
 def cpu_reference(cfg_full, sample_B, steps, warmup):
-    """The oracle port of one reference iteration, float32, all host threads numpy/BLAS will use."""
+    """The oracle port of one reference iteration on the host cores, float32: for the MNIST models the torch-CPU
+    restatement (`oracle/torch_cpu.py`: oneDNN convolutions + autograd, all host threads -- a multi-threaded framework graph
+    like the reference's TF1.15 one; pinned to the float64 NumPy oracle by tests/test_oracle_torch_cpu.py), for CelebA the
+    NumPy tape oracle."""
     from oracle import params as oparams, steps as osteps
     cfg = dict(cfg_full)
     cfg['batch_size'] = sample_B
@@ -140,7 +143,16 @@ def cpu_reference(cfg_full, sample_B, steps, warmup):
     x = rng.uniform(size=(sample_B,) + image_shape(cfg)).astype(np.float32)
     epoch = cfg['sg_pretraining'] + 1
     feeds = osteps.compute_feeds(cfg, epoch, synthetic_mixture(K, R))
-    tr = osteps.OracleTrainer(cfg, P, dtype=np.float32)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
+    if cfg['exp_name'] != 'celeba':
+        import torch
+        from oracle import torch_cpu
+        torch.set_num_threads(cores)
+        tr = torch_cpu.TorchTrainer(cfg, P)
+        how = 'fp32 torch-CPU restatement of the reference graph (oneDNN + autograd, %d threads)' % torch.get_num_threads()
+    else:
+        tr = osteps.OracleTrainer(cfg, P, dtype=np.float32)
+        how = 'fp32 NumPy oracle (BLAS threads = host default)'
 
     def noise():
         return [dict(eps_z=rng.normal(size=(sample_B, C)), eps_t=rng.normal(size=(sample_B, R)),
@@ -151,10 +163,9 @@ def cpu_reference(cfg_full, sample_B, steps, warmup):
     for _ in range(steps):
         tr.iteration(x, noise(), feeds, epoch)
     dt = time.perf_counter() - t0
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
     return {'value': sample_B * steps / dt, 'unit': 'imgs/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d iteration(s) of the 4-sub-step protocol on a %d-image batch of the same config, fp32 NumPy '
-                      'oracle (BLAS threads = host default)' % (steps, sample_B), 'seconds': dt}
+            'sample': '%d iteration(s) of the 4-sub-step protocol on a %d-image batch of the same config, %s'
+                      % (steps, sample_B, how), 'seconds': dt}
 
 
 def run_reference(args):
@@ -556,7 +567,7 @@ def main():
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of CUDA-graph replay')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'], help='GEMM math: bf16 tcgen05 or fp32 SIMT')
     ap.add_argument('--cpu-sample', type=int, default=0,
-                    help='batch of the bounded CPU-baseline sample (0 = 256 images for the MNIST workloads, 8 for celeba: ~10-20 s)')
+                    help='batch of the bounded CPU-baseline sample (0 = the full batch, at most 1024 images, for the MNIST workloads; 8 for celeba: ~10-20 s)')
     ap.add_argument('--celeba-batch', type=int, default=64, help='per-GPU batch of the secondary CelebA-shape leg (0 = skip)')
     ap.add_argument('--celeba-big-batch', type=int, default=512,
                     help='per-GPU batch of the CelebA-shape weak-scaling leg (BASELINE.json configs[4]: 4096 over 8 GPUs, code_size 128)')
@@ -567,7 +578,7 @@ def main():
     global WORKLOAD
     WORKLOAD = args.workload
     if args.cpu_sample <= 0:
-        args.cpu_sample = 8 if WORKLOAD == 'celeba' else 256
+        args.cpu_sample = 8 if WORKLOAD == 'celeba' else min(args.batch, 1024)
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
         run_reference(args)
