@@ -129,10 +129,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ CPU arm
 def cpu_reference(cfg_full, sample_B, steps, warmup):
-    """The oracle port of one reference iteration on the host cores, float32: for the MNIST models the torch-CPU
-    restatement (`oracle/torch_cpu.py`: oneDNN convolutions + autograd, all host threads -- a multi-threaded framework graph
-    like the reference's TF1.15 one; pinned to the float64 NumPy oracle by tests/test_oracle_torch_cpu.py), for CelebA the
-    NumPy tape oracle."""
+    """The oracle port of one reference iteration on the host cores, float32: the torch-CPU restatement
+    (`oracle/torch_cpu.py`: oneDNN convolutions + autograd, all host threads -- a multi-threaded framework graph like the
+    reference's TF1.15 one; pinned to the float64 NumPy oracle at 1e-8 by tests/test_oracle_torch_cpu.py)."""
     from oracle import params as oparams, steps as osteps
     cfg = dict(cfg_full)
     cfg['batch_size'] = sample_B
@@ -144,15 +143,11 @@ def cpu_reference(cfg_full, sample_B, steps, warmup):
     epoch = cfg['sg_pretraining'] + 1
     feeds = osteps.compute_feeds(cfg, epoch, synthetic_mixture(K, R))
     cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
-    if cfg['exp_name'] != 'celeba':
-        import torch
-        from oracle import torch_cpu
-        torch.set_num_threads(cores)
-        tr = torch_cpu.TorchTrainer(cfg, P)
-        how = 'fp32 torch-CPU restatement of the reference graph (oneDNN + autograd, %d threads)' % torch.get_num_threads()
-    else:
-        tr = osteps.OracleTrainer(cfg, P, dtype=np.float32)
-        how = 'fp32 NumPy oracle (BLAS threads = host default)'
+    import torch
+    from oracle import torch_cpu
+    torch.set_num_threads(cores)
+    tr = torch_cpu.TorchTrainer(cfg, P)
+    how = 'fp32 torch-CPU restatement of the reference graph (oneDNN + autograd, %d threads)' % torch.get_num_threads()
 
     def noise():
         return [dict(eps_z=rng.normal(size=(sample_B, C)), eps_t=rng.normal(size=(sample_B, R)),
@@ -567,7 +562,7 @@ def main():
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of CUDA-graph replay')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'], help='GEMM math: bf16 tcgen05 or fp32 SIMT')
     ap.add_argument('--cpu-sample', type=int, default=0,
-                    help='batch of the bounded CPU-baseline sample (0 = the full batch, at most 1024 images, for the MNIST workloads; 8 for celeba: ~10-20 s)')
+                    help='batch of the bounded CPU-baseline sample (0 = the full batch, at most 1024 images, for the MNIST workloads; 16 for celeba: ~10-20 s)')
     ap.add_argument('--celeba-batch', type=int, default=64, help='per-GPU batch of the secondary CelebA-shape leg (0 = skip)')
     ap.add_argument('--celeba-big-batch', type=int, default=512,
                     help='per-GPU batch of the CelebA-shape weak-scaling leg (BASELINE.json configs[4]: 4096 over 8 GPUs, code_size 128)')
@@ -578,7 +573,7 @@ def main():
     global WORKLOAD
     WORKLOAD = args.workload
     if args.cpu_sample <= 0:
-        args.cpu_sample = 8 if WORKLOAD == 'celeba' else min(args.batch, 1024)
+        args.cpu_sample = 16 if WORKLOAD == 'celeba' else min(args.batch, 1024)
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
         run_reference(args)

@@ -11,7 +11,7 @@ baseline) of the reference's TF1.15 graph for this path -- `codes/models.py`,
 `codes/base.py:88-517`, `codes/modules.py:6-10` of
 lin-shuyu/ladder-latent-data-distribution-modelling -- with a small reverse-mode
 tape (`oracle/tape.py`) providing the gradients TF's `compute_gradients` would.
-`oracle/torch_cpu.py` restates the MNIST graphs a second time with torch CPU ops +
+`oracle/torch_cpu.py` restates the three models' graphs a second time with torch CPU ops +
 autograd (oneDNN convolutions, all host threads): it is the multi-threaded fp32 CPU
 baseline `bench.py` times, and an independent cross-check of the NumPy tape (losses,
 gradients of all four optimiser groups and two full iterations agree to 1e-8,

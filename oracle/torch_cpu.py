@@ -1,9 +1,9 @@
-"""Oracle, CPU-baseline flavour (test infrastructure only): the same graph as `oracle/nets.py` for the MNIST models and the
+"""Oracle, CPU-baseline flavour (test infrastructure only): the same graph as `oracle/nets.py` for all three models and the
 `prior in {ours, standard_gaussian, hierarchical}` branches, written with torch CPU ops + autograd (oneDNN convolutions, all host
 threads) so that the "reference CPU path" timed by `bench.py` is a multi-threaded float32 framework graph like the TF1.15 one,
 not a NumPy loop.  SURVEY 8(d) "CPU baseline": a restatement of the reference on host CPU -- not TF1.15 itself.
 
-Restates models.py:46-160 (digit), 199-327 (fashion), base.py:127-213 (prior VAE), base.py:109-124 + 308-313 (mixture, K-unrolled as
+Restates models.py:46-160 (digit), 199-327 (fashion), 392-598 + modules.py:6-10 (CelebA), base.py:127-213 (prior VAE), base.py:109-124 + 308-313 (mixture, K-unrolled as
 the reference does it: one Cholesky-whitened Gaussian per component, stacked, logsumexp), base.py:257-413 (ELBO), base.py:457-517
 (clip + TF-Adam).  PARITY: checked against `oracle/nets.py` (float64 NumPy tape) in tests/test_oracle_torch_cpu.py.
 """
@@ -63,7 +63,76 @@ def _conv(P, scope, idx, x, stride=1, padding='same', act=None):
     return act(y) if act is not None else y
 
 
+def batch_norm_train(x, gamma, beta, eps=1e-3):
+    """tf.layers.batch_normalization(training=True): biased batch statistics over (N, H, W) (models.py:398-460)."""
+    mean = x.mean((0, 1, 2), keepdim=True)
+    xc = x - mean
+    var = (xc * xc).mean((0, 1, 2), keepdim=True)
+    return xc / torch.sqrt(var + eps) * gamma + beta
+
+
+def instance_norm(x, eps=1e-6):
+    """tf.contrib.layers.instance_norm(center=False, scale=False): per-sample, per-channel moments over (H, W)."""
+    mean = x.mean((1, 2), keepdim=True)
+    xc = x - mean
+    return xc / torch.sqrt((xc * xc).mean((1, 2), keepdim=True) + eps)
+
+
+def _legacy_matrix(n_in, n_out, dtype):
+    """TF1 ResizeBilinear (align_corners=False, no half-pixel centres): src = dst * n_in / n_out."""
+    R = torch.zeros(n_out, n_in, dtype=dtype)
+    for o in range(n_out):
+        src = o * n_in / n_out
+        lo = int(math.floor(src))
+        hi = min(lo + 1, n_in - 1)
+        R[o, lo] += 1.0 - (src - lo)
+        R[o, hi] += src - lo
+    return R
+
+
+def resize_bilinear_legacy(x, oh, ow):
+    Rh, Rw = _legacy_matrix(x.shape[1], oh, x.dtype), _legacy_matrix(x.shape[2], ow, x.dtype)
+    return torch.einsum('qw,bpwc->bpqc', Rw, torch.einsum('ph,bhwc->bpwc', Rh, x))
+
+
+def style_mod(P, x, dlatent, num):
+    """modules.py:6-10"""
+    Cx = x.shape[3]
+    s = _dense(P, 'decoder/StyleMod_%d/dense' % num, dlatent)
+    return x * (s[:, :Cx].reshape(-1, 1, 1, Cx) + 1.0) + s[:, Cx:].reshape(-1, 1, 1, Cx)
+
+
+def encoder_celeba(cfg, P, x):
+    """models.py:392-464"""
+    h = x
+    for i in range(6):
+        h = _conv(P, 'encoder', i, h, 2 if i < 5 else 1, 'same' if i < 5 else 'valid')
+        bn = 'encoder/batch_normalization' if i == 0 else 'encoder/batch_normalization_%d' % i
+        h = leaky(batch_norm_train(h, P[bn + '/gamma'], P[bn + '/beta']))
+    return h.reshape(h.shape[0], -1)
+
+
+def decoder_celeba(cfg, P, z):
+    """models.py:499-587"""
+    H = int(cfg['num_hidden_units'])
+    encoded = _dense(P, 'decoder/dense', z, leaky)
+    dl = encoded
+    for i in range(1, 9):
+        dl = _dense(P, 'decoder/dense_%d' % i, dl, leaky)
+    h = resize_bilinear_legacy(_conv(P, 'decoder', 0, encoded.reshape(-1, 1, 1, H)), 2, 2)
+    h = leaky(style_mod(P, instance_norm(_conv(P, 'decoder', 1, h)), dl, 0))
+    h = leaky(style_mod(P, instance_norm(_conv(P, 'decoder', 2, h)), dl, 1))
+    h = _conv(P, 'decoder', 3, resize_bilinear_legacy(h, 8, 8), act=leaky)
+    h = leaky(style_mod(P, instance_norm(_conv(P, 'decoder', 4, resize_bilinear_legacy(h, 16, 16))), dl, 2))
+    h = _conv(P, 'decoder', 5, resize_bilinear_legacy(h, 32, 32), act=leaky)
+    h = leaky(style_mod(P, instance_norm(_conv(P, 'decoder', 6, resize_bilinear_legacy(h, 64, 64))), dl, 3))
+    h = _conv(P, 'decoder', 7, resize_bilinear_legacy(h, 128, 128), act=leaky)
+    return _conv(P, 'decoder', 8, h)
+
+
 def encoder(cfg, P, x):
+    if cfg['exp_name'] == 'celeba':
+        return encoder_celeba(cfg, P, x)
     h = sym_pad(x, 2)
     if cfg['exp_name'] == 'mnist_digit':
         for i in range(3):
@@ -76,6 +145,8 @@ def encoder(cfg, P, x):
 
 
 def decoder(cfg, P, z):
+    if cfg['exp_name'] == 'celeba':
+        return decoder_celeba(cfg, P, z)
     H = int(cfg['num_hidden_units'])
     h = _dense(P, 'decoder/dense', z, leaky)
     if cfg['exp_name'] == 'mnist_digit':
@@ -116,7 +187,7 @@ def losses(cfg, P, x, noise, feeds):
     xhat = decoder(cfg, P, z)
     mpe = (xhat - x).abs().mean()
     sigma = P['sigma/Variable'].abs()
-    if int(cfg['TRAIN_sigma']) == 1:
+    if cfg['exp_name'] == 'celeba' or int(cfg['TRAIN_sigma']) == 1:          # models.py:158-159, 597
         sigma = torch.maximum(sigma, mpe)
     entropy_z = ((-0.5 * C * LOG_2PI - 0.5 * C) - 0.5 * (2.0 * torch.log(std)).sum(1)).mean()
     ce_sg = (-0.5 * C * LOG_2PI - 0.5 * ((mean ** 2).sum(1) + (std ** 2).sum(1))).mean()

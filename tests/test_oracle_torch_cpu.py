@@ -8,7 +8,7 @@ from oracle import nets, steps, torch_cpu
 from test_oracle_nets import setup
 
 
-@pytest.mark.parametrize('exp', ['mnist_digit', 'mnist_fashion'])
+@pytest.mark.parametrize('exp', ['mnist_digit', 'mnist_fashion', 'celeba'])
 @pytest.mark.parametrize('pretrain', [False, True])
 def test_losses_and_gradients_match_numpy_oracle(exp, pretrain):
     cfg, P, x, nz, feeds = setup(exp, B=3, seed=2, pretrain=pretrain)
