@@ -1,5 +1,5 @@
 """Oracle, CPU-baseline flavour (test infrastructure only): the same graph as `oracle/nets.py` for all three models and the
-`prior in {ours, standard_gaussian, hierarchical}` branches, written with torch CPU ops + autograd (oneDNN convolutions, all host
+all five `prior` branches, written with torch CPU ops + autograd (oneDNN convolutions, all host
 threads) so that the "reference CPU path" timed by `bench.py` is a multi-threaded float32 framework graph like the TF1.15 one,
 not a NumPy loop.  SURVEY 8(d) "CPU baseline": a restatement of the reference on host CPU -- not TF1.15 itself.
 
@@ -194,6 +194,18 @@ def losses(cfg, P, x, noise, feeds):
     use_sg = bool(feeds.get('use_standard_gaussian_prior', False))
     if prior == 'standard_gaussian':
         ce_prior = ce_sg
+    elif prior == 'GMM':                                   # base.py:323-329: fed full-covariance mixture in z-space
+        samples = mean + std * noise['eps_mc']
+        ce_prior = mixture_logprob(samples, feeds['prior_mean'], feeds['prior_cov'], feeds['prior_weight']).mean()
+    elif prior == 'vampPrior':                             # base.py:215-254, 362-370, 407-408
+        fp = encoder(cfg, P, P['prior/Variable'])
+        mp = _dense(P, 'encoder/code_mean', fp)
+        sp = _dense(P, 'encoder/code_std_dev', fp, F.relu) + floor
+        samples = (mean + std * noise['eps_mc']).reshape(-1, 1, C)
+        e = (-math.log(mp.shape[0]) - 0.5 * C * LOG_2PI - torch.log(sp).sum(1)[None]
+             - 0.5 * (((samples - mp[None]) / sp[None]) ** 2).sum(2))
+        o['vampPrior_crossEntropy'] = torch.logsumexp(e, 1).mean()
+        ce_prior = ce_sg if use_sg else o['vampPrior_crossEntropy']
     else:
         nl = int(cfg['n_layers_inner_VAE'])
         names = ['prior/dense'] + ['prior/dense_%d' % i for i in range(1, 2 * nl + 3)]
@@ -229,6 +241,8 @@ def losses(cfg, P, x, noise, feeds):
     recon = -(xhat - x).abs().sum((1, 2, 3)).mean() / sigma
     o['elbo'] = recon - D_in * torch.log(2.0 * sigma) - entropy_z + ce_prior
     o['loss_ae'] = -o['elbo']
+    if prior == 'vampPrior':
+        o['loss_prior'] = o['loss_ae']
     o['sigma'], o['entropy_z'], o['crossEntropy_prior'] = sigma, entropy_z, ce_prior
     return o
 
@@ -276,9 +290,10 @@ class TorchTrainer:
             out['ae'], _ = self._step('ae', 'loss_ae', x, noises[0], feeds, lr_ae)
             if int(cfg['TRAIN_sigma']) == 1:
                 out['sigma'], _ = self._step('sigma', 'loss_ae', x, noises[1], feeds, lr_sigma)
-        if cur_epoch > int(cfg['sg_pretraining']) - 1 and cfg['prior'] in ('ours', 'hierarchical') and int(cfg['TRAIN_prior']) == 1:
+        if cur_epoch > int(cfg['sg_pretraining']) - 1 and cfg['prior'] in ('ours', 'hierarchical', 'vampPrior') \
+                and int(cfg['TRAIN_prior']) == 1:
             out['prior'], _ = self._step('prior', 'loss_prior', x, noises[2], feeds, lr_prior)
-            if int(cfg['TRAIN_inner_sigma']) == 1:
+            if cfg['prior'] != 'vampPrior' and int(cfg['TRAIN_inner_sigma']) == 1:
                 out['inner_sigma'], _ = self._step('inner_sigma', 'loss_prior', x, noises[3], feeds, lr_is)
         return out
 
