@@ -58,3 +58,62 @@ def test_shard_range_covers_everything():
             spans = [shard_range(n, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+class _FakeTable:
+    """Stands in for ops.MixtureTable on CPU: canonical (mu, A, c) arrays with the same shard() rule."""
+
+    def __init__(self, mu, A, c):
+        self.mu, self.A, self.c, self.K = mu, A, c, len(c)
+
+    def shard(self, rank, world):
+        per = -(-self.K // world)
+        lo, hi = min(rank * per, self.K), min((rank + 1) * per, self.K)
+        return _FakeTable(self.mu[lo:hi], self.A[lo:hi], self.c[lo:hi])
+
+
+def _sharded_worker(rank, world, port, golden, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from ladder_latent_data_distribution_modelling_b200 import ops, parallel
+    d = np.load(golden)
+    mu, A, c = OM.canonical_from_full(d['m_full'], d['K_full'], d['w_full'])
+
+    def fake_logprob(t, tab, want_grad=False, partial=False, **kw):       # the kernel's shard-partial contract on CPU
+        assert partial
+        e, y = OM.component_exponents(t.numpy(), tab.mu, tab.A, tab.c)
+        m = e.max(axis=1)
+        p = np.exp(e - m[:, None])
+        g = -(p[:, :, None] * np.einsum('kij,nki->nkj', tab.A, y)).sum(axis=1)   # unnormalised, in this shard's frame
+        res = (torch.tensor(m), torch.tensor(p.sum(axis=1)))
+        return res + (torch.tensor(g),) if want_grad else res
+
+    def fake_combine(m, s, g=None):
+        M = m.max(dim=0).values
+        w = torch.exp(m - M[None])
+        S = (s * w).sum(dim=0)
+        lp = M + torch.log(S)
+        return (lp, (g * w[:, :, None]).sum(dim=0) / S[:, None]) if g is not None else lp
+    ops.mixture_logprob, ops.mixture_combine = fake_logprob, fake_combine
+    t = torch.tensor(d['t_full'])
+    lp = parallel.sharded_mixture_logprob(t, _FakeTable(mu, A, c), group=dist.group.WORLD, want_grad=False)
+    lp2, g = parallel.sharded_mixture_logprob(t, _FakeTable(mu, A, c), group=dist.group.WORLD, want_grad=True)
+    if rank == 0:
+        np.savez(out, lp=lp.numpy(), lp2=lp2.numpy(), g=g.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_mixture_logprob_glue_world2(tmp_path, golden_dir):
+    """parallel.sharded_mixture_logprob exactly as bench.py's component-sharded leg calls it (group=WORLD, with and without the
+    gradient), over real gloo collectives, with the kernel and the combine replaced by their oracle contracts."""
+    golden = os.path.join(golden_dir, 'gm_prior_golden.npz')
+    out = str(tmp_path / 'sharded.npz')
+    mp.spawn(_sharded_worker, args=(2, _free_port(), golden, out), nprocs=2, join=True)
+    r, d = np.load(out), np.load(golden)
+    mu, A, c = OM.canonical_from_full(d['m_full'], d['K_full'], d['w_full'])
+    ref, gref = OM.mixture_logprob(d['t_full'], mu, A, c, with_grad=True)
+    np.testing.assert_allclose(r['lp'], ref, rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(r['lp2'], ref, rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(r['g'], gref, rtol=1e-8, atol=1e-8)
