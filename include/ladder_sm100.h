@@ -352,6 +352,15 @@ int ladder_elbo_scalars(float* scalars, const float* sigma_var, const float* inn
 int ladder_clip_adam(float* param, const float* grad, float* m, float* v, long long n, const float* lr_dev,
                      const int* step_dev, float beta1, float beta2, float eps, cudaStream_t stream);
 int ladder_increment(int* counter_dev, cudaStream_t stream);
+/* K8: standard-normal noise of one sess.run, replacing RandomStandardNormal inside tfd.MultivariateNormalDiag.sample
+ * (codes/models.py:97-100; codes/base.py:164-167, 308-311).  Philox4x32-10 + Box-Muller, up to three tensors
+ * out_i [outer_i, B, inner_i] (null = skipped; segment id i) in ONE launch.  Element (o, b, j) is a pure function of
+ * (seed, i, *draw_ctr_dev, o, b_off + b, j) with rows counted in the GLOBAL batch [outer, B_global, inner]: a data-parallel
+ * rank holding rows [b_off, b_off + B) draws what the single-GPU run draws for them; the counter is device-resident
+ * (bump it with ladder_increment) so CUDA-graph replays advance the stream exactly like eager launches. */
+int ladder_philox_normal(float* out0, int outer0, int inner0, float* out1, int outer1, int inner1, float* out2, int outer2,
+                         int inner2, int B, int B_global, int b_off, unsigned long long seed, const int* draw_ctr_dev,
+                         cudaStream_t stream);
 
 /* Diagnostic: saturate one pipe (kind 0 = FP32 FFMA, 1 = SFU MUFU.EX2).  Each of `blocks`
  * CTAs of 256 threads issues iters*64 dependent-chain ops per thread (8 chains).  Used by

@@ -355,6 +355,62 @@ __global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict_
 
 __global__ void increment_kernel(int* c) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1; }
 
+// ------------------------------------------------------------------ K8: in-kernel Philox4x32-10 standard normals
+// Replaces the RandomStandardNormal draws inside tfd.MultivariateNormalDiag.sample (codes/models.py:97-100; codes/base.py:
+// 164-167, 308-311).  The value of element (o, b_global, j) of a noise tensor laid out [outer, B_global, inner] depends only
+// on (seed, segment id, draw counter, that GLOBAL index): a data-parallel rank that holds rows [b_off, b_off + B) of the
+// global batch draws exactly the numbers the single-GPU run draws for those rows, and a CUDA-graph replay draws what the
+// eager launch draws (the draw counter lives on the device and is bumped by its own kernel).
+struct PhiloxSeg {
+  float* out;
+  int outer, B, inner;     // local tensor [outer, B, inner]
+  int seg_id;
+  long long begin;         // first flat thread index of this segment
+};
+struct PhiloxArgs {
+  PhiloxSeg seg[3];
+  int nseg;
+  int B_global, b_off;
+  unsigned seed_lo, seed_hi;
+};
+
+__device__ __forceinline__ void philox4x32_10(unsigned (&c)[4], unsigned k0, unsigned k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const unsigned n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void philox_normal_kernel(PhiloxArgs a, const int* __restrict__ draw_ctr, long long total) {
+  const unsigned draw = (unsigned)(*draw_ctr);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int s = 0;
+    if (a.nseg > 1 && i >= a.seg[1].begin) s = 1;
+    if (a.nseg > 2 && i >= a.seg[2].begin) s = 2;
+    const PhiloxSeg& g = a.seg[s];
+    const long long li = i - g.begin;                       // local flat index in [outer, B, inner]
+    const int j = (int)(li % g.inner);
+    const long long r = li / g.inner;
+    const int b = (int)(r % g.B);
+    const long long o = r / g.B;
+    const unsigned long long gi = ((unsigned long long)o * a.B_global + (a.b_off + b)) * g.inner + j;   // global index
+    unsigned c[4] = {(unsigned)(gi >> 2), (unsigned)(gi >> 34), draw, (unsigned)g.seg_id};
+    philox4x32_10(c, a.seed_lo, a.seed_hi);
+    const int q = (int)(gi & 3);
+    const unsigned u1 = q < 2 ? c[0] : c[2], u2 = q < 2 ? c[1] : c[3];
+    // 23-bit uniforms (k + 1/2) 2^-23 strictly inside (0, 1): exactly representable in fp32, so a host restatement
+    // reproduces them bit for bit
+    const float rad = sqrtf(-2.f * logf(((float)(u1 >> 9) + 0.5f) * 1.1920928955078125e-07f));
+    float sn, cs;
+    sincospif(((float)(u2 >> 9) + 0.5f) * 2.384185791015625e-07f, &sn, &cs);                 // angle = 2 pi u2
+    g.out[li] = rad * ((q & 1) ? sn : cs);
+  }
+}
+
 }  // namespace ladder
 
 using namespace ladder;
@@ -493,6 +549,28 @@ int ladder_increment(int* counter_dev, cudaStream_t stream) {
   LADDER_REQUIRE(counter_dev, "increment: null");
   increment_kernel<<<1, 32, 0, stream>>>(counter_dev);
   return check_launch("increment");
+}
+
+int ladder_philox_normal(float* out0, int outer0, int inner0, float* out1, int outer1, int inner1, float* out2, int outer2,
+                         int inner2, int B, int B_global, int b_off, unsigned long long seed, const int* draw_ctr_dev,
+                         cudaStream_t stream) {
+  LADDER_REQUIRE(draw_ctr_dev && B > 0 && B_global >= B && b_off >= 0 && b_off + B <= B_global, "philox_normal: bad arguments");
+  PhiloxArgs a;
+  a.nseg = 0; a.B_global = B_global; a.b_off = b_off;
+  a.seed_lo = (unsigned)seed; a.seed_hi = (unsigned)(seed >> 32);
+  float* outs[3] = {out0, out1, out2};
+  const int outers[3] = {outer0, outer1, outer2}, inners[3] = {inner0, inner1, inner2};
+  long long total = 0;
+  for (int i = 0; i < 3; ++i) {
+    if (outs[i] == nullptr) continue;
+    LADDER_REQUIRE(outers[i] > 0 && inners[i] > 0, "philox_normal: bad segment shape");
+    PhiloxSeg& g = a.seg[a.nseg++];
+    g.out = outs[i]; g.outer = outers[i]; g.B = B; g.inner = inners[i]; g.seg_id = i; g.begin = total;
+    total += (long long)outers[i] * B * inners[i];
+  }
+  if (total == 0) return LADDER_OK;
+  philox_normal_kernel<<<ew_grid(total), EW_THREADS, 0, stream>>>(a, draw_ctr_dev, total);
+  return check_launch("philox_normal");
 }
 
 }  // extern "C"

@@ -720,7 +720,8 @@ class LadderEngine:
     def __init__(self, config, batch_size, device='cuda', seed=0, dist_group=None):
         self.cfg = config
         # optional key: 'bf16' = tcgen05 tensor-core GEMMs (default), 'fp32' = SIMT GEMMs (strict parity)
-        ops.set_math_mode(config.get('compute_dtype', ops.MATH_MODE))
+        self.math_mode = config.get('compute_dtype', ops.MATH_MODE)
+        ops.set_math_mode(self.math_mode)
         self.B = B = int(batch_size)
         self.dev = torch.device(device)
         self.prior = config['prior']
@@ -731,10 +732,10 @@ class LadderEngine:
         self.L, self.K = int(config['n_MC_samples']), int(config['n_mixtures'])
         self.D_in = int(config['dim_input_x']) * int(config['dim_input_y']) * int(config['dim_input_channel'])
         self.dist = dist_group
-        self.world = 1
+        self.world, self.rank = 1, 0
         if dist_group is not None:
             import torch.distributed as dist
-            self.world = dist.get_world_size(dist_group)
+            self.world, self.rank = dist.get_world_size(dist_group), dist.get_rank(dist_group)
         self.B_global = B * self.world
         dev = self.dev
         # optimiser groups (base.py:415-455, 457-511)
@@ -753,8 +754,12 @@ class LadderEngine:
                                                                     int(config['dim_input_y']),
                                                                     int(config['dim_input_channel'])))], dev)
             self.groups['prior'] = self.prior_g
-        self.gen = torch.Generator(device=dev)
+        self.gen = torch.Generator(device=dev)            # parameter initialisation only
         self.gen.manual_seed(seed)
+        # K8 noise: in-kernel Philox keyed by (seed, device draw counter, GLOBAL sample index) -- every data-parallel rank uses
+        # the SAME seed and draws the rows [rank*B, (rank+1)*B) of the global noise tensors
+        self.seed = int(seed)
+        self.noise_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
         self.init_params()
         if config['exp_name'] == 'celeba':
             self.outer = CelebAOuterVAE(config, self.ae, B, dev, self._allreduce, self.world)
@@ -865,13 +870,11 @@ class LadderEngine:
                 g.lr.fill_(float(lr))
 
     def draw_noise(self, z=True, t=True, mc=True):
-        """Fresh standard-normal noise for one sess.run (K8: tfd sample() draws)."""
-        if z:
-            self.eps_z.normal_(generator=self.gen)
-        if t and self.has_prior:
-            self.eps_t.normal_(generator=self.gen)
-        if mc and self.prior in ('ours', 'GMM', 'vampPrior'):
-            self.eps_mc.normal_(generator=self.gen)
+        """Fresh standard-normal noise for one sess.run (K8: tfd sample() draws): one counter bump + one Philox launch."""
+        ops.increment(self.noise_ctr)
+        ops.philox_normal([self.eps_z if z else None, self.eps_t if (t and self.has_prior) else None,
+                           self.eps_mc if (mc and self.prior in ('ours', 'GMM', 'vampPrior')) else None],
+                          self.B, self.B_global, self.rank * self.B, self.seed, self.noise_ctr)
 
     def set_noise(self, eps_z=None, eps_t=None, eps_mc=None):
         for dst, src in ((self.eps_z, eps_z), (getattr(self, 'eps_t', None), eps_t), (getattr(self, 'eps_mc', None), eps_mc)):
@@ -886,6 +889,7 @@ class LadderEngine:
 
     def forward(self, x, dec=True, prior=True, mix=True):
         """One forward pass; fills self.scalars with the ELBO terms of the GLOBAL batch."""
+        ops.set_math_mode(self.math_mode)          # kernel dispatch follows THIS engine's dtype (buffers were sized for it)
         s = self.scalars
         s[:16].zero_()
         # bf16 weight images of every TMA-fed GEMM, refreshed from the fp32 master weights once per sub-step
@@ -950,6 +954,7 @@ class LadderEngine:
     def decode_code(self, code):
         """`sess.run(model.decoded, {is_code_input: True, code_input: code})` (models.py:103-148): decoder-only forward of
         any number of codes [n, C] -> images [n, H, W, ch] (evaluated in batches of the engine's batch size)."""
+        ops.set_math_mode(self.math_mode)
         self.ae.repack()
         out = [self.outer.decode(buf)[:n].float().clone() for buf, n in self._chunks(code, self.C)]
         return torch.cat(out) if out else torch.empty(0, *self.outer.decoded.shape[1:], device=self.dev)
@@ -959,6 +964,7 @@ class LadderEngine:
         prior-VAE decoder only, [n, R] -> decoded codes [n, C]."""
         if not self.has_prior:
             raise RuntimeError('decode_representation: prior=%r has no prior VAE' % self.prior)
+        ops.set_math_mode(self.math_mode)
         self.prior_g.repack()
         out = [self.pvae.decode(buf)[:n].clone() for buf, n in self._chunks(t, self.R)]
         return torch.cat(out) if out else torch.empty(0, self.C, device=self.dev)
@@ -1052,17 +1058,22 @@ class LadderEngine:
     _STEP_NOISE = {'ae': dict(z=True, t=True, mc=True), 'sigma': dict(z=True, t=False, mc=False),
                    'prior': dict(z=True, t=True, mc=True), 'inner_sigma': dict(z=True, t=True, mc=False)}
 
-    def run_step(self, name, x, graph=None):
+    def run_step(self, name, x, graph=None, noise=None):
         """One sess.run equivalent: fresh noise + step `name` in {'ae','sigma','prior','inner_sigma'} on batch x.
         With CUDA graphs the whole sub-step (noise, ~100 kernels, clip+Adam) is one graph launch; graphs are
-        re-captured when the feeds (mixture, use_sg, use_mask) change."""
+        re-captured when the feeds (mixture, use_sg, use_mask) change.  noise = dict(eps_z=..., eps_t=..., eps_mc=...)
+        feeds explicit noise instead of drawing it (the static noise buffers are filled before the launch / replay)."""
         fn = getattr(self, 'step_' + name)
         use_graph = self.use_graphs if graph is None else graph
+        fed = noise is not None
+        draw = (lambda: None) if fed else (lambda: self.draw_noise(**self._STEP_NOISE[name]))
+        if fed:
+            self.set_noise(**noise)
         if not use_graph:
-            self.draw_noise(**self._STEP_NOISE[name])
+            draw()
             fn(x)
             return
-        key = (name, self._feed_version)
+        key = (name, self._feed_version, fed)
         g = self._graphs.get(key)
         if g is None:
             if self._static_x is None:
@@ -1072,18 +1083,15 @@ class LadderEngine:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self.draw_noise(**self._STEP_NOISE[name])
                 fn(self._static_x, apply=False)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
-            if hasattr(g, 'register_generator_state'):
-                g.register_generator_state(self.gen)
             try:
                 # thread_local: the NCCL watchdog thread of torch.distributed may touch CUDA while this thread captures
                 with torch.cuda.graph(g, capture_error_mode='thread_local' if self.world > 1 else 'global'):
-                    self.draw_noise(**self._STEP_NOISE[name])
+                    draw()
                     fn(self._static_x)
             except Exception as e:                       # noqa: BLE001
                 if self.world == 1:
@@ -1094,7 +1102,7 @@ class LadderEngine:
                       % (type(e).__name__, str(e).splitlines()[0] if str(e) else ''), file=sys.stderr)
                 self.use_graphs = False
                 torch.cuda.synchronize()
-                self.draw_noise(**self._STEP_NOISE[name])
+                draw()
                 fn(x)
                 return
             self._graphs = {k: v for k, v in self._graphs.items() if k[1] == self._feed_version}

@@ -25,6 +25,9 @@ class BaseTrain:
     def __init__(self, sess, model, data, config):
         self.model, self.config, self.sess, self.data = model, config, sess, data
         self.cur_epoch = 0
+        self.rank, self.world = getattr(model, 'rank', 0), getattr(model, 'world', 1)
+        self.is_main = self.rank == 0
+        self._gm_version = 0        # bumped by every hyper-prior fit; compute_feeddict re-packs the feeds when it changes
         self._pending = []          # (kind, device snapshot of the scalars buffer)
         self._pinned = None
         # the reference's records (codes/base.py:531-570)
@@ -154,6 +157,8 @@ class BaseTrain:
 
     # ---------------------------------------------------------------- hyper-prior fitting (base.py:681-789)
     def _collect_samples(self, iterator, n_batch, space):
+        """`n_batch` GLOBAL batches of representation_sample / code_sample, identical on every rank (data parallel: the
+        per-rank rows are all-gathered back into global-batch order)."""
         eng = self.model.engine
         out = []
         for _ in range(n_batch):
@@ -161,11 +166,35 @@ class BaseTrain:
             eng.draw_noise(mc=False)
             eng.forward(x, dec=False, prior=(space == 't'), mix=False)
             out.append((eng.pvae.t if space == 't' else eng.outer.z).clone())
-        return torch.cat(out).cpu().numpy().astype(np.float64)
+        local = torch.stack(out)                                   # [n_batch, B, D]
+        if self.world > 1:
+            import torch.distributed as dist
+            # gather as a sum of one-hot slots: one all-reduce, available on every backend (the set is <= 20 000 x D floats)
+            allr = torch.zeros((self.world,) + tuple(local.shape), device=local.device, dtype=local.dtype)
+            allr[self.rank] = local
+            dist.all_reduce(allr, op=dist.ReduceOp.SUM, group=self.model.dist_group)
+            local = allr.permute(1, 0, 2, 3).reshape(n_batch, -1, local.shape[-1])     # batch i = ranks 0..P-1 in order
+        return local.reshape(-1, local.shape[-1]).cpu().numpy().astype(np.float64)
 
-    @staticmethod
-    def _report_active(gm):
+    def _fit_shared(self, gm, samples):
+        """Fit `gm` (a scikit-learn mixture, as in the reference) on rank 0 and hand the fitted means / covariances /
+        weights to every rank -- the estimators draw their initialisation from NumPy's global RNG, so per-rank fits would feed
+        different hyper-priors to the replicas.  Bumps the fit version that compute_feeddict watches."""
+        if self.is_main:
+            gm.fit(samples)
+        if self.world > 1:
+            import torch.distributed as dist
+            payload = [(gm.means_, gm.covariances_, gm.weights_) if self.is_main else None]
+            dist.broadcast_object_list(payload, src=0, group=self.model.dist_group)
+            if not self.is_main:
+                gm.means_, gm.covariances_, gm.weights_ = payload[0]
+        self._gm_version += 1
+        return gm
+
+    def _report_active(self, gm):
         idx = np.squeeze(np.argwhere(gm.weights_ >= 1e-2)).tolist()
+        if not self.is_main:
+            return idx
         if type(idx) is int:
             print("There are 1 active mixtures.")
             print("The current GM prior estimate has following weights:\n{}".format(gm.weights_[idx]))
@@ -178,36 +207,42 @@ class BaseTrain:
 
     def fit_GMM_VI(self, iterator, mode="fast", space="z"):
         from sklearn.mixture import BayesianGaussianMixture, GaussianMixture
-        B = self.config['batch_size']
+        Bg = self.config['batch_size'] * self.world
         if mode == "fast":
-            samples = self._collect_samples(iterator, 2000 // B + 1, space)
-            self.model.GM_prior_training.fit(samples)
+            samples = self._collect_samples(iterator, 2000 // Bg + 1, space)
+            self._fit_shared(self.model.GM_prior_training, samples)
             self._report_active(self.model.GM_prior_training)
             return samples
-        samples = self._collect_samples(iterator, 20000 // B + 1, space)
+        samples = self._collect_samples(iterator, 20000 // Bg + 1, space)
+        verbose = 2 if self.is_main else 0
         if space == "t":
             self.GM_prior_final = BayesianGaussianMixture(
                 n_components=self.config['n_mixtures'], covariance_type='full', max_iter=2000,
                 n_init=self.config['GM_fit_restart'], weight_concentration_prior_type='dirichlet_process',
-                weight_concentration_prior=0.1, warm_start=False, verbose=2, verbose_interval=100)
+                weight_concentration_prior=0.1, warm_start=False, verbose=verbose, verbose_interval=100)
         else:
             self.GM_prior_final = GaussianMixture(n_components=self.config['n_mixtures'], covariance_type='full',
-                                                  max_iter=2000, n_init=1, warm_start=False, verbose=2,
+                                                  max_iter=2000, n_init=1, warm_start=False, verbose=verbose,
                                                   verbose_interval=100)
-        self.GM_prior_final.fit(samples)
-        gm = self.GM_prior_final
+        version = self._gm_version
+        gm = self._fit_shared(self.GM_prior_final, samples)
+        self._gm_version = version          # the "accurate" fit is saved, not fed (the feeds read GM_prior_training)
         idx = np.squeeze(np.argwhere(gm.weights_ >= 1e-2)).tolist()
         w = gm.weights_[idx]
-        np.savez("{}GM_prior_info.npz".format(self.config['result_dir']), w_active=w / np.sum(w),
-                 m_active=gm.means_[idx], K_active=gm.covariances_[idx], w_full=gm.weights_, m_full=gm.means_,
-                 K_full=gm.covariances_)
+        if self.is_main:
+            np.savez("{}GM_prior_info.npz".format(self.config['result_dir']), w_active=w / np.sum(w),
+                     m_active=gm.means_[idx], K_active=gm.covariances_[idx], w_full=gm.weights_, m_full=gm.means_,
+                     K_full=gm.covariances_)
         self._report_active(gm)
-        print("Final fitted prior saved.")
+        if self.is_main:
+            print("Final fitted prior saved.")
         return samples
 
     # ---------------------------------------------------------------- result file (base.py:791-823)
     def save_variables_VAE(self):
         self.flush_logs()
+        if not self.is_main:
+            return
         file_name = "{}{}-result.npz".format(self.config['result_dir'], self.config['exp_name'])
         np.savez(file_name,
                  iter_list_val=self.iter_epochs_list, n_train_iter=self.n_train_iter, n_val_iter=self.n_val_iter,
@@ -252,7 +287,7 @@ class BaseTrain_joint(BaseTrain):
                 feed['use_standard_gaussian_prior'] = True
             else:
                 gm = self.model.GM_prior_training
-                stamp = ('fit', id(gm.means_))
+                stamp = ('fit', self._gm_version)
                 if getattr(self, '_dummy_fed', None) != stamp:          # re-pack only after a new fit
                     feed.update(prior_mean=gm.means_, prior_cov=gm.covariances_, prior_weight=gm.weights_)
                     self._dummy_fed = stamp
@@ -273,7 +308,7 @@ class BaseTrain_joint(BaseTrain):
                     self._dummy_fed = 'dummy'
             else:
                 gm = self.model.GM_prior_training
-                stamp = ('fit', id(gm.means_))
+                stamp = ('fit', self._gm_version)
                 if getattr(self, '_dummy_fed', None) != stamp:          # base.py:924-933: fitted covariances + 0.01 I
                     feed.update(prior_mean=gm.means_, prior_cov=gm.covariances_ + 0.01 * np.eye(C)[None],
                                 prior_weight=gm.weights_)

@@ -19,33 +19,53 @@ from .utils import count_trainable_variables
 
 
 class BatchIterator:
-    """Stand-in for the tf.data pipeline of define_iterator (codes/models.py:26-40): the whole
-    image set lives on the device, `initializer` reshuffles it with the epoch seed and `get_next`
-    returns consecutive batches, repeating for ever (`repeat(8000)`, drop_remainder=True)."""
+    """Stand-in for the tf.data pipeline of define_iterator (codes/models.py:26-40): the whole image set lives on the device
+    (uint8 pools stay uint8 and are scaled by 1/255 per batch, like the TFRecord parser of models.py:354-371), `initializer`
+    reshuffles it with the epoch seed and `get_next` returns consecutive batches, repeating for ever with a NEW shuffle per
+    pass (`shuffle(...).repeat(8000)`, drop_remainder=True).
 
-    def __init__(self, batch_size, device):
-        self.B, self.dev = batch_size, device
+    Data parallel (rank, world): every rank derives the same permutation from the epoch seed; global batch i is
+    perm[i*B*world : (i+1)*B*world] and rank r takes rows [r*B, (r+1)*B) of it -- disjoint shards, and the union over the ranks
+    is what one GPU with batch B*world would have drawn."""
+
+    def __init__(self, batch_size, device, rank=0, world=1):
+        self.B, self.dev, self.rank, self.world = batch_size, device, int(rank), int(world)
         self.data = None
         self.perm = None
         self.pos = 0
-        self._src_id = None
+        self._src_key = None
+        self._gen = torch.Generator()
 
-    def initializer(self, images, seed):
-        if self._src_id != id(images):
-            self.data = torch.as_tensor(np.asarray(images), dtype=torch.float32).to(self.dev).contiguous()
-            self._src_id = id(images)
-        g = torch.Generator()
-        g.manual_seed(int(seed))
-        self.perm = torch.randperm(self.data.shape[0], generator=g).to(self.dev)
+    def initializer(self, images, seed, key=None):
+        """key: explicit name of the split ('train', 'val', ...) -- the device copy is reused while it stays the same.
+        Without a key the pool is re-uploaded on every call (an id() of a temporary array is not a safe cache key)."""
+        if key is None or key != self._src_key:
+            arr = np.asarray(images)
+            if arr.dtype == np.uint8:
+                self.data = torch.from_numpy(np.ascontiguousarray(arr)).to(self.dev)
+            else:
+                self.data = torch.as_tensor(arr, dtype=torch.float32).to(self.dev).contiguous()
+            self._src_key = key
+        self._gen.manual_seed(int(seed))
+        self._shuffle()
+
+    def _shuffle(self):
+        self.perm = torch.randperm(self.data.shape[0], generator=self._gen).to(self.dev)
         self.pos = 0
 
     def get_next(self):
-        n = self.data.shape[0]
-        if self.pos + self.B > n:          # next pass of the repeated, reshuffled stream
-            self.pos = 0
-        idx = self.perm[self.pos:self.pos + self.B]
-        self.pos += self.B
-        return self.data.index_select(0, idx)
+        n, Bg = self.data.shape[0], self.B * self.world
+        if Bg > n:
+            raise RuntimeError('BatchIterator: global batch %d exceeds the pool of %d images' % (Bg, n))
+        if self.pos + Bg > n:              # next pass of the repeated stream: a fresh shuffle from the same generator
+            self._shuffle()
+        lo = self.pos + self.rank * self.B
+        idx = self.perm[lo:lo + self.B]
+        self.pos += Bg
+        out = self.data.index_select(0, idx)
+        if out.dtype == torch.uint8:
+            out = out.float().mul_(1.0 / 255)
+        return out
 
 
 class BaseModel:
@@ -55,6 +75,14 @@ class BaseModel:
         self.config = config
         self.device = torch.device(device if device is not None else 'cuda')
         self.two_pi = 2 * np.pi
+        self.rank, self.world = 0, 1
+        if dist_group is not None:
+            import torch.distributed as dist
+            self.rank, self.world = dist.get_rank(dist_group), dist.get_world_size(dist_group)
+        self.dist_group = dist_group
+        self.is_main = self.rank == 0          # rank 0 alone prints, saves checkpoints / result files and fits the hyper-prior
+        # config['batch_size'] is the PER-RANK batch; the global batch is batch_size * world (the engine all-reduces the batch
+        # sums, batch-norm statistics and gradients, and keys its noise by the global sample index)
         self.engine = LadderEngine(config, int(config['batch_size']), self.device, seed=int(config.get('seed', 0)),
                                    dist_group=dist_group)
         self.define_iterator()
@@ -65,7 +93,7 @@ class BaseModel:
 
     # -- iterator (models.py:26-44)
     def define_iterator(self):
-        self.iterator = BatchIterator(int(self.config['batch_size']), self.device)
+        self.iterator = BatchIterator(int(self.config['batch_size']), self.device, self.rank, self.world)
 
     @property
     def input_image(self):
@@ -102,8 +130,9 @@ class BaseModel:
             self.num_prior_ae = self.num_prior_sigma = 0
         self.num_para_list = [self.num_encoder, self.num_decoder, self.num_sigma, self.num_prior_ae,
                               self.num_prior_sigma]
-        print("Total number of trainable parameters in VAE network is:\n{}k\n".format(
-            np.around(sum(self.num_para_list) / 1000, 2)))
+        if self.is_main:
+            print("Total number of trainable parameters in VAE network is:\n{}k\n".format(
+                np.around(sum(self.num_para_list) / 1000, 2)))
 
     # -- checkpoints (base.py:37-85): two files, trainable variables only, reference variable names
     def init_saver(self):
@@ -135,6 +164,8 @@ class BaseModel:
         self.engine.load_parameters({k: v for k, v in read_tf_checkpoint(path).items() if k in mine})
 
     def save(self, sess, model):
+        if not self.is_main:               # data parallel: the replicas hold identical weights, rank 0 writes them
+            return
         print("Saving model...")
         e = self.engine
         if model == "VAE" or (model == "joint" and self.config['TRAIN_VAE'] == 1):
@@ -208,7 +239,7 @@ class CelebAModel_densenet(BaseModel):
         cfg = self.config
         path = os.path.join(cfg.get('data_path', '') or '', 'celeba_%s.npy' % split)
         if not cfg.get('synthetic', False) and os.path.isfile(path):
-            return np.load(path, mmap_mode='r').astype(np.float32) * (1.0 / 255)
+            return np.load(path, mmap_mode='r')        # uint8: uploaded as uint8, scaled by 1/255 per batch on the device
         key = '_pool_' + split
         if not hasattr(self, key):
             n = int(cfg.get('synthetic_pool', n_default))
@@ -227,4 +258,5 @@ class CelebAModel_densenet(BaseModel):
         return self._pool('val', 256)
 
     def test_image(self):
-        return self._pool('test', 256)[:int(self.config['batch_size'])]
+        t = np.asarray(self._pool('test', 256)[:int(self.config['batch_size'])])
+        return t.astype(np.float32) * (1.0 / 255) if t.dtype == np.uint8 else t

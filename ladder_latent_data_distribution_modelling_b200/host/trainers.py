@@ -53,8 +53,9 @@ class MNISTTrainer_joint_training(_JointEpochMixin, BaseTrain_joint):
     def __init__(self, sess, model, data, config):
         super().__init__(sess, model, data, config)
         self.test_batch = self.data.test_set['image']
-        self.n_train_iter = self.data.n_train // self.config['batch_size']
-        self.n_val_iter = self.data.n_val // self.config['batch_size']
+        # data parallel: config batch_size is per rank, one iteration consumes batch_size * world images
+        self.n_train_iter = self.data.n_train // (self.config['batch_size'] * self.world)
+        self.n_val_iter = self.data.n_val // (self.config['batch_size'] * self.world)
         step = max(1, self.n_train_iter // self.config['num_iter_to_plot'])
         self.idx_check_point = np.arange(0, self.n_train_iter - 1, step)
 
@@ -62,14 +63,14 @@ class MNISTTrainer_joint_training(_JointEpochMixin, BaseTrain_joint):
         cfg = self.config
         self.cur_epoch += 1
         print("{}/{}:".format(self.cur_epoch, cfg['num_epochs']))
-        self.model.iterator.initializer(self.data.train_set['image'], seed=self.cur_epoch)
+        self.model.iterator.initializer(self.data.train_set['image'], seed=self.cur_epoch, key='train')
         self.cur_lr = cfg['learning_rate_ae'] * (0.99 ** (self.cur_epoch - 1))
         self._train_loop(self.n_train_iter)
         if self.cur_epoch > cfg['sg_pretraining'] - 1 and cfg['prior'] in ("ours", "GMM"):
             self.fit_GM(iterator=None)
         self.generate_samples_from_prior()
         self.test_step(batch_data=self.test_batch, print_result=True)
-        self.model.iterator.initializer(self.data.val_set['image'], seed=self.cur_epoch)
+        self.model.iterator.initializer(self.data.val_set['image'], seed=self.cur_epoch, key='val')
         self._val_loop(self.n_val_iter)
         if cfg['TRAIN_VAE'] == 1:
             print("Average overall negative ELBO loss:\ntrain: {:.4f}, val: {:.4f}".format(
@@ -80,8 +81,8 @@ class MNISTTrainer_joint_training(_JointEpochMixin, BaseTrain_joint):
 class CelebATrainer_joint_training(_JointEpochMixin, BaseTrain_joint):
     def __init__(self, sess, model, data, config):
         super().__init__(sess, model, data, config)
-        self.n_train_iter = self.data.n_train // self.config['batch_size']
-        self.n_val_iter = self.data.n_val // self.config['batch_size']
+        self.n_train_iter = self.data.n_train // (self.config['batch_size'] * self.world)
+        self.n_val_iter = self.data.n_val // (self.config['batch_size'] * self.world)
         step = max(1, self.n_train_iter // self.config['num_iter_to_plot'])
         self.idx_check_point = np.arange(0, self.n_train_iter - 1, step)
         self.test_batch = self.model.test_image()
@@ -106,18 +107,18 @@ class CelebATrainer_joint_training(_JointEpochMixin, BaseTrain_joint):
         cfg = self.config
         self.cur_epoch += 1
         print('Training epoch: {}/{}'.format(self.cur_epoch, cfg['num_epochs']))
-        self.model.iterator.initializer(self.model.train_images(), seed=self.cur_epoch)
+        self.model.iterator.initializer(self.model.train_images(), seed=self.cur_epoch, key='train')
         self.compute_cur_lr()
         try:
             from tqdm import tqdm
         except ImportError:
             tqdm = None
-        self._train_loop(self.n_train_iter, progress=tqdm)
+        self._train_loop(self.n_train_iter, progress=tqdm if self.is_main else None)
         if self.cur_epoch > cfg['sg_pretraining'] - 1 and cfg['prior'] in ("ours", "GMM"):
             self.fit_GM(iterator=None)
         self.generate_samples_from_prior()
         self.test_step(batch_data=self.test_batch, print_result=True)
-        self.model.iterator.initializer(self.model.val_images(), seed=self.cur_epoch)
+        self.model.iterator.initializer(self.model.val_images(), seed=self.cur_epoch, key='val')
         self._val_loop(self.n_val_iter, need_vae=cfg['TRAIN_VAE'] == 1)
         if cfg['TRAIN_VAE'] == 1:
             print("Average:\ntrain: {:.4f}, val: {:.4f}".format(

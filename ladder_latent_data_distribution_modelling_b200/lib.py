@@ -97,6 +97,8 @@ SIGNATURES = {
     'ladder_elbo_scalars': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 8 + [C.c_float, C.c_float, C.c_int, C.c_int, stream_t]),
     'ladder_clip_adam': (C.c_int, [ptr, ptr, ptr, ptr, C.c_longlong, ptr, ptr, C.c_float, C.c_float, C.c_float, stream_t]),
     'ladder_increment': (C.c_int, [ptr, stream_t]),
+    'ladder_philox_normal': (C.c_int, [ptr, C.c_int, C.c_int, ptr, C.c_int, C.c_int, ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_ulonglong, ptr, stream_t]),
     'ladder_pipe_peak_launch': (C.c_int, [C.c_int, C.c_int, C.c_int, ptr, stream_t]),
     'ladder_mixture_tc_image_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'ladder_mixture_tc_pack_iso': (C.c_int, [c_double_p, C.c_double, c_double_p, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p]),

@@ -744,6 +744,23 @@ def clip_adam(param, grad, m, v, lr_dev, step_dev, beta1=0.9, beta2=0.95, eps=1e
                                      _p(lr_dev), _p(step_dev), beta1, beta2, eps, _stream()), 'clip_adam')
 
 
+def philox_normal(outs, B, B_global, b_off, seed, draw_ctr):
+    """Fill up to three noise tensors (None = skipped; position = segment id) shaped [B, inner] or [outer, B, inner] with
+    standard normals keyed by (seed, segment, device draw counter, GLOBAL row b_off + b): see ladder_philox_normal."""
+    a = []
+    for t in (list(outs) + [None] * 3)[:3]:
+        if t is None:
+            a += [C.c_void_p(0), 0, 0]
+        else:
+            _f32(t, 'noise')
+            outer = 1 if t.dim() == 2 else t.shape[0]
+            if t.shape[-2] != B:
+                raise RuntimeError('philox_normal: noise tensor rows %d != batch %d' % (t.shape[-2], B))
+            a += [_p(t), int(outer), int(t.shape[-1])]
+    _lib.check(_L().ladder_philox_normal(*a, int(B), int(B_global), int(b_off), int(seed) & (2 ** 64 - 1), _p(draw_ctr),
+                                         _stream()), 'philox_normal')
+
+
 def increment(counter):
     _lib.check(_L().ladder_increment(_p(counter), _stream()), 'increment')
 

@@ -1,6 +1,12 @@
-"""Data-parallel invariance on 2 GPUs (NCCL): two ranks with half of the batch each reproduce the ELBO terms and
-the gradients of one GPU running the whole batch -- the 12 batch sums are all-reduced before the scalar ELBO
-assembly (sigma = max(|sigma_var|, mean|x - xhat|) is a batch-global scalar) and gradients are summed."""
+"""Data-parallel invariance: P ranks with B/P rows each reproduce one GPU running the whole batch -- the 12 batch sums are
+all-reduced before the scalar ELBO assembly (sigma = max(|sigma_var|, mean|x - xhat|) is a batch-global scalar), CelebA's
+batch-norm statistics are cross-replica (codes/models.py:398-460 on the GLOBAL batch), gradients are summed, and the Philox
+noise is keyed by the global sample index, so a full reference iteration through `run_step` (4 sub-steps, updates applied)
+lands on the same weights.
+
+Two transports: NCCL on 2 GPUs with the collectives CAPTURED in the sub-step CUDA graphs (what bench.py --gpus N and
+`torchrun train.py` run; skipped on a 1-GPU box), and gloo with both ranks on ONE GPU, launched eagerly (the same engine logic,
+exercised wherever a single GPU is visible)."""
 import os
 import socket
 
@@ -9,6 +15,8 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+
+STEPS = ('ae', 'sigma', 'prior', 'inner_sigma')
 
 
 def _free_port():
@@ -19,59 +27,98 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _case(exp):
+    if exp == 'celeba':
+        from test_gpu_parity_r2 import celeba_case
+        cfg, P, x, nz, feeds = celeba_case(4, 256, 64)            # 64-aligned widths: the TMA-fed bf16 production kernels
+        cfg['n_MC_samples'] = 4
+        return cfg, P, x, feeds, cfg['sg_pretraining'] + 1
+    from test_gpu_engine import make_case
+    cfg, P, x, noises, feeds, epoch = make_case(exp, 8, 41)
+    return cfg, P, x, feeds, epoch
+
+
+def _run(cfg, P, x, feeds, epoch, B, dev, graphs, group=None):
+    from oracle import steps
+    from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
+    eng = LadderEngine(dict(cfg, batch_size=B, cuda_graphs=graphs), B, dev, seed=7, dist_group=group)
+    eng.load_parameters(P)
+    eng.set_feeds(**feeds)
+    eng.set_lrs(*steps.lr_schedule(cfg, epoch))
+    xd = torch.tensor(x, device=dev)
+    out = {}
+    for name in STEPS:
+        eng.run_step(name, xd)
+        out['scal_' + name] = eng.scalars.cpu().numpy()
+        if name == 'ae':
+            out['g_ae'] = eng.ae.grad.cpu().numpy()
+        if name == 'prior':
+            out['g_prior'] = eng.prior_g.grad.cpu().numpy()
+    out['p_ae'] = eng.ae.param.cpu().numpy()
+    out['p_prior'] = eng.prior_g.param.cpu().numpy()
+    out['graphs'] = np.array(len(eng._graphs))
+    return out
+
+
+def _worker(rank, world, port, out, backend, exp, graphs):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
-    from test_gpu_engine import make_case
-    from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
-    B = 8
-    cfg, P, x, noises, feeds, epoch = make_case('mnist_digit', B, 41)
-    nz = noises[0]
-    half = B // world
-    sl = slice(rank * half, (rank + 1) * half)
-    eng = LadderEngine(dict(cfg, batch_size=half, cuda_graphs=False), half, 'cuda:%d' % rank, seed=0, dist_group=dist.group.WORLD)
-    eng.load_parameters(P)
-    eng.set_feeds(**feeds)
-    eng.set_noise(eps_z=nz['eps_z'][sl], eps_t=nz['eps_t'][sl], eps_mc=nz['eps_mc'][:, sl])
-    eng.step_ae(torch.tensor(x[sl], device='cuda:%d' % rank), apply=False)
-    scal = eng.scalars.cpu().numpy()
-    g_ae = eng.ae.grad.cpu().numpy()
-    eng.step_prior(torch.tensor(x[sl], device='cuda:%d' % rank), apply=False)
-    g_pr = eng.prior_g.grad.cpu().numpy()
+    d = rank if backend == 'nccl' else 0
+    torch.cuda.set_device(d)
+    if backend == 'nccl':
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', d))
+    else:
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+    cfg, P, x, feeds, epoch = _case(exp)
+    half = x.shape[0] // world
+    r = _run(cfg, P, x[rank * half:(rank + 1) * half], feeds, epoch, half, 'cuda:%d' % d, graphs, dist.group.WORLD)
     if rank == 0:
-        np.savez(out, scal=scal, g_ae=g_ae, g_pr=g_pr)
+        np.savez(out, **r)
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-def test_two_gpu_equals_one_gpu(tmp_path):
-    import torch.multiprocessing as mp
-    from test_gpu_engine import make_case
-    from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
+def _compare(r, one, exp):
     from ladder_latent_data_distribution_modelling_b200 import ops
+    # fp32 kernels: atomics order only.  bf16 CelebA: an fp32-noise difference in a batch statistic can flip single bf16
+    # roundings of a normalised activation, i.e. isolated 2^-9 relative changes
+    st, gt = (2e-5, 2e-4) if exp != 'celeba' else (2e-3, 1e-2)
+    for name in STEPS:
+        a, b = one['scal_' + name], r['scal_' + name]
+        for k, i in ops.O.items():
+            assert abs(a[i] - b[i]) <= st * max(1.0, abs(a[i])), (name, k, a[i], b[i])
+    for k in ('g_ae', 'g_prior'):
+        assert np.abs(one[k] - r[k]).max() <= gt * np.abs(one[k]).max(), k
+    for k in ('p_ae', 'p_prior'):          # after clip + Adam: sign-like first step, compare the bulk
+        frac = (np.abs(one[k] - r[k]) > 1e-5).mean()
+        assert frac <= (5e-3 if exp != 'celeba' else 5e-2), (k, frac)
+
+
+@pytest.mark.parametrize('exp', ['mnist_digit', 'celeba'])
+def test_two_ranks_on_one_gpu_equal_one_rank(tmp_path, exp):
+    """gloo transport, both ranks on cuda:0, eager launches: batch sums, cross-replica BN, gradient sums, global noise rows."""
+    import torch.multiprocessing as mp
     out = str(tmp_path / 'dp.npz')
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    r = np.load(out)
-    B = 8
-    cfg, P, x, noises, feeds, epoch = make_case('mnist_digit', B, 41)
-    eng = LadderEngine(dict(cfg, cuda_graphs=False), B, 'cuda:0', seed=0)
-    eng.load_parameters(P)
-    eng.set_feeds(**feeds)
-    eng.set_noise(**noises[0])
-    xd = torch.tensor(x, device='cuda:0')
-    eng.step_ae(xd, apply=False)
-    scal = eng.scalars.cpu().numpy()
-    for name, i in ops.O.items():
-        assert abs(scal[i] - r['scal'][i]) <= 2e-5 * max(1.0, abs(scal[i])), name
-    g = eng.ae.grad.cpu().numpy()
-    assert np.abs(g - r['g_ae']).max() <= 2e-4 * np.abs(g).max()
-    eng.step_prior(xd, apply=False)
-    g = eng.prior_g.grad.cpu().numpy()
-    assert np.abs(g - r['g_pr']).max() <= 2e-4 * np.abs(g).max()
+    mp.spawn(_worker, args=(2, _free_port(), out, 'gloo', exp, False), nprocs=2, join=True)
+    r = dict(np.load(out))
+    cfg, P, x, feeds, epoch = _case(exp)
+    one = _run(cfg, P, x, feeds, epoch, x.shape[0], 'cuda:0', False)
+    _compare(r, one, exp)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.parametrize('exp', ['mnist_digit', 'celeba'])
+def test_two_gpus_with_graph_captured_nccl_equal_one_gpu(tmp_path, exp):
+    """NCCL on 2 GPUs, collectives captured inside the sub-step CUDA graphs (the bench / train.py configuration)."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'dp.npz')
+    mp.spawn(_worker, args=(2, _free_port(), out, 'nccl', exp, True), nprocs=2, join=True)
+    r = dict(np.load(out))
+    assert int(r['graphs']) >= 4, 'the data-parallel sub-steps must have been captured (NCCL inside the graph)'
+    cfg, P, x, feeds, epoch = _case(exp)
+    one = _run(cfg, P, x, feeds, epoch, x.shape[0], 'cuda:0', True)
+    _compare(r, one, exp)
 
 
 def _shard_worker(rank, world, port, out):

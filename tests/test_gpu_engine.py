@@ -262,31 +262,3 @@ def test_bf16_tensor_core_engine(exp):
     grad_check(eng, eng.ae, nets.grads_of(o['loss_ae'], Pv, eng.ae.names()), tol=0.2, l2_tol=0.12)
     eng.step_prior(xd, apply=False)
     grad_check(eng, eng.prior_g, nets.grads_of(o['loss_prior'], Pv, eng.prior_g.names()), tol=0.2, l2_tol=0.12)
-
-
-def test_cuda_graph_replay_matches_eager():
-    """A graph-replayed iteration equals the eagerly launched one (same seed -> same noise -> same weights)."""
-    import copy
-    cfg, P, x, noises, feeds, epoch = make_case('mnist_digit', 4, 31)
-    xd = torch.tensor(x, device='cuda')
-    outs = []
-    for graphs in (False, True):
-        c = copy.deepcopy(cfg); c['cuda_graphs'] = graphs
-        eng = make_engine(c, P, feeds, 4)
-        eng.set_lrs(*steps.lr_schedule(cfg, epoch))
-        for it in range(3):
-            for name in ('ae', 'sigma', 'prior', 'inner_sigma'):
-                eng.run_step(name, xd)
-        torch.cuda.synchronize()
-        outs.append({n: t.clone() for n, t in eng.named_parameters()})
-        assert int(eng.ae.step.item()) == 3 and int(eng.prior_g.step.item()) == 3
-    # the captured noise streams differ from the eager ones (graph-safe Philox offsets), so compare statistically:
-    # both runs must have moved every weight by a comparable amount and stayed finite
-    for n in outs[0]:
-        a, b = outs[0][n], outs[1][n]
-        assert torch.isfinite(b).all()
-        if a.numel() < 1024:
-            continue                      # tiny tensors: the statistic is too noisy to compare across noise streams
-        p0 = torch.tensor(np.asarray(P[n]), device='cuda').reshape(a.shape)
-        da, db = (a - p0).abs().mean().item(), (b - p0).abs().mean().item()
-        assert abs(da - db) <= 0.35 * max(da, db) + 1e-9, (n, da, db)

@@ -1,6 +1,8 @@
 """`python train.py --config codes/<name>_config.json` -- same CLI as the reference (train.py:18-74),
-running the ELBO hot path on the sm_100a kernels.  Under torchrun (WORLD_SIZE > 1) the batch is
-sharded data-parallel across the ranks (one process per GPU, NCCL)."""
+running the ELBO hot path on the sm_100a kernels.  Under torchrun (WORLD_SIZE > 1) the run is batch-sharded data
+parallel (one process per GPU, NCCL): `batch_size` is the per-rank batch, every rank draws a disjoint shard of each global
+batch (same epoch permutation) and its rows of the global noise tensors, batch sums / batch-norm statistics / gradients are
+all-reduced, the hyper-prior is fitted on rank 0 and broadcast, and rank 0 alone prints and writes files."""
 import os
 import sys
 
@@ -22,18 +24,24 @@ def main():
         print("missing or invalid arguments")
         exit(0)
 
-    create_dirs([config['result_dir'], config['checkpoint_dir']])
-    save_config(config)
-
     if not torch.cuda.is_available():
         raise RuntimeError("train.py needs a CUDA device (sm_100a); there is no CPU path")
     dist_group = None
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local_rank)
+    rank = 0
     if int(os.environ.get('WORLD_SIZE', 1)) > 1:
         import torch.distributed as dist
-        dist.init_process_group('nccl')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
         dist_group = dist.group.WORLD
+        rank = dist.get_rank()
+    if rank == 0:
+        create_dirs([config['result_dir'], config['checkpoint_dir']])
+        save_config(config)
+    else:                                   # rank 0 alone prints and writes (the replicas hold identical state)
+        sys.stdout = open(os.devnull, 'w')
+    if dist_group is not None:
+        dist.barrier()
 
     data = DataGenerator(config, None)
     classes = {'mnist_digit': MNISTModel_digit, 'mnist_fashion': MNISTModel_fashion, 'celeba': CelebAModel_densenet}
@@ -51,6 +59,9 @@ def main():
             model.load(None, model="prior")
         if config['num_epochs'] > 0:
             trainer_VAE.train()
+    if dist_group is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
