@@ -174,10 +174,13 @@ int ladder_conv2d_tma_pack(const float* w, void* image, size_t image_bytes, int 
  * total = number of units over all entries */
 int ladder_pack_weights_multi(const float* params, void* images, const void* desc_dev, int n, long long total,
                               cudaStream_t stream);
+/* stat_sums (nullable): the epilogue also accumulates the per-channel sum and sum of squares of the fp32 output (act none)
+ * into stat_sums [2][stat_groups][Cout] (zeroed by the call): stat_groups = 1 -> over all rows (the batch-norm statistics of
+ * codes/models.py:398-460), stat_groups = B -> per sample (instance norm, models.py:522-570; needs OH*OW % 128 == 0). */
 int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w /*NULL: prepacked*/, const float* bias /*nullable*/, void* y, int y_bf16,
                             int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l,
                             int OH, int OW, int act, int out_d2s, void* workspace, size_t workspace_bytes,
-                            cudaStream_t stream);
+                            float* stat_sums /*nullable*/, int stat_groups, cudaStream_t stream);
 int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w /*NULL: prepacked*/, const void* act_out /*nullable*/, int act_out_bf16,
                             void* dx, int dx_bf16, int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride,
                             int pad_t, int pad_l, int OH, int OW, int act, int accumulate, int out_s2d,
@@ -267,6 +270,32 @@ int ladder_resize_bilinear_fwd_ex(const void* x, int x_bf16, void* y, int y_bf16
 int ladder_resize_bilinear_bwd_ex(const void* dy, int dy_bf16, void* dx, int dx_bf16, const void* act_out /*nullable*/,
                                   int act_out_bf16, int act, int B, int H, int W, int C, int OH, int OW,
                                   cudaStream_t stream);
+
+/* ---- the same layers on bf16-resident maps, one HBM pass per direction (csrc/norm_fused.cu).  Statistics are RAW sums:
+ * batch norm sums2c [2][C] = (sum, sum of squares) over the `count` rows of the GLOBAL batch (the conv epilogue of
+ * ladder_conv2d_fprop_tma produces them; data-parallel ranks all-reduce them); instance norm insum [2][B][C] per sample.
+ * All need C % 8 == 0 and 256 % (C/8) == 0 (ladder_norm_fused_supported).
+ *   bn_apply_bf16      y = act(batch_norm(c))                                             codes/models.py:398-460
+ *   bn_bwd_stats_bf16  dsums2c = (sum g, sum g * xhat), g = d loss / d BN output (bf16 or fp32)
+ *   bn_bwd_apply_bf16  dc = gamma rstd (g - sum_g/n - xhat sum_gx/n); dbias (nullable) = column sums of dc
+ *   in_sums_bf16       insum of a map too small for the conv-epilogue statistics (2x2)
+ *   in_style_resize_bf16  out [B,OH,OW,C] = legacy_bilinear( act( instance_norm(c) * (s0 + 1) + s1 ) ), style [B,2C] = [s0|s1]
+ *                         (models.py:522-578 + codes/modules.py:6-10; OH == H: no resize)
+ *   in_style_bwd_bf16  da = d loss / d (block output before the resize): dstyle [B,2C], dc, dbias (nullable)          */
+int ladder_norm_fused_supported(int C);
+int ladder_bn_apply_bf16(const void* c_bf16, const float* sums2c, const float* gamma, const float* beta, void* y_bf16,
+                         long long rows, int C, long long count, float eps, int act, cudaStream_t stream);
+int ladder_bn_bwd_stats_bf16(const void* g, int g_bf16, const void* c_bf16, const float* sums2c, long long rows, int C,
+                             long long count, float eps, float* dsums2c, cudaStream_t stream);
+int ladder_bn_bwd_apply_bf16(const void* g, int g_bf16, const void* c_bf16, const float* sums2c, const float* dsums2c,
+                             const float* gamma, void* dc_bf16, long long rows, int C, long long count, float eps,
+                             float* dbias /*nullable*/, cudaStream_t stream);
+int ladder_in_sums_bf16(const void* c_bf16, int B, int HW, int C, float* insum, cudaStream_t stream);
+int ladder_in_style_resize_bf16(const void* c_bf16, const float* insum, const float* style, void* out_bf16, int B, int H, int W,
+                                int C, int OH, int OW, float eps, int act, cudaStream_t stream);
+int ladder_in_style_bwd_bf16(const void* da, int da_bf16, const void* c_bf16, const float* insum, const float* style,
+                             float* dstyle, void* dc_bf16, float* dbias /*nullable*/, int B, int HW, int C, float eps, int act,
+                             cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * The `scalars` buffer: LADDER_SCALARS_LEN floats on the device.  [0,16) are running sums the

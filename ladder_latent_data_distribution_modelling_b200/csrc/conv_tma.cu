@@ -32,11 +32,12 @@ constexpr int NTHREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int EPI_BYTES = 4 * 32 * 36 * 4;
 constexpr int BIAS_BYTES = 256 * 4;
+constexpr int STAT_BYTES = 4 * 2 * 256 * 4;     // per epilogue warp: running (sum, sum of squares) of up to 256 output columns
 __host__ __device__ constexpr int stages_for(int bn) {
-  // 227 KB - alignment slack - barriers - epilogue staging, divided by the stage size
-  return (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES) / (A_STAGE_BYTES + bn * BK * 2) > 8
+  // 227 KB - alignment slack - barriers - epilogue staging - statistics, divided by the stage size
+  return (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES - STAT_BYTES) / (A_STAGE_BYTES + bn * BK * 2) > 8
              ? 8
-             : (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES) / (A_STAGE_BYTES + bn * BK * 2);
+             : (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES - STAT_BYTES) / (A_STAGE_BYTES + bn * BK * 2);
 }
 
 enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
@@ -59,6 +60,9 @@ struct Args {
   int m_valid;               // WGRAD: rows of dw that exist (= KH*KW*C)
   int m_tiles, n_tiles, splits;
   int perm_r;                // fused depth_to_space (FPROP) / space_to_depth (DGRAD) store, 0 = off
+  float* stat;               // FPROP: per-channel (sum, sum of squares) of the output, accumulated in the epilogue (null = off):
+  int stat_groups;           //   [2][groups][Ng]; groups = 1 (batch norm: all rows) or B (instance norm: rows of one sample)
+  int stat_group_rows;       //   rows per group (a multiple of 128 when groups > 1, so a tile never straddles two samples)
   int os, opy, opx, OHf, OWf; // DGRAD of a strided conv, one output-parity class: row (b, i, j) of the [B, GH, GW] grid is
                              // dx pixel (b, i*os + opy, j*os + opx) of the full [B, OHf, OWf] map (os = 0/1: off)
 };
@@ -124,6 +128,21 @@ __device__ __noinline__ void slow_store(const Args& a, float4 q, long long m, in
     if (MODE == WGRAD) atomicAdd(outf + oo, e);
     else if (OUT16) outh[oo] = __float2bfloat16_rn(e);
     else outf[oo] = e;
+  }
+}
+
+// add one warp's running column sums to the global statistics and clear them (lane i owns columns i, i + 32, ...)
+template <int BN>
+__device__ __forceinline__ void stat_flush(const Args& a, float* wstat, int n_tile, int group, int lane) {
+  const long long base = (long long)group * a.Ng, sq = (long long)a.stat_groups * a.Ng;
+  for (int i = lane; i < BN; i += 32) {
+    const int col = n_tile * BN + i;
+    if (col < a.Ng) {
+      atomicAdd(a.stat + base + col, wstat[i]);
+      atomicAdd(a.stat + sq + base + col, wstat[256 + i]);
+    }
+    wstat[i] = 0.f;
+    wstat[256 + i] = 0.f;
   }
 }
 
@@ -274,6 +293,11 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     const int quad = warp & 3;                     // tcgen05.ld: warp w may touch TMEM lanes 32*(w%4)..+31
     float* stage = reinterpret_cast<float*>(smem + stage_off) + quad * (32 * 36);
     float* sbias = reinterpret_cast<float*>(smem + stage_off + EPI_BYTES);
+    float* wstat = reinterpret_cast<float*>(smem + stage_off + EPI_BYTES + BIAS_BYTES) + quad * (2 * 256);   // this warp's sums
+    const bool do_stat = MODE == FPROP && a.stat != nullptr;
+    if (do_stat)
+      for (int i = lane; i < 2 * 256; i += 32) wstat[i] = 0.f;
+    int stat_tile = -1, stat_group = 0;            // (n_tile, group) the running sums belong to
     const int etid = tid - 64;                     // 0..127 among the epilogue warps
     const int sub = lane >> 3, c4 = (lane & 7) * 4;
     const float slope = a.act == ACT_LEAKY ? 0.2f : (a.act == ACT_RELU ? 0.f : 1.f);
@@ -302,6 +326,12 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         for (int i = etid; i < BN; i += 128) sbias[i] = (a.bias != nullptr && n0 + i < Ng) ? __ldg(a.bias + n0 + i) : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         bias_tile = T.n_tile;
+      }
+      if (do_stat) {                                 // running sums follow (n_tile, group): flush when either changes
+        const int grp = a.stat_groups > 1 ? (int)(((long long)T.m_tile * BM) / a.stat_group_rows) : 0;
+        if (stat_tile >= 0 && (stat_tile != T.n_tile || stat_group != grp)) stat_flush<BN>(a, wstat, stat_tile, stat_group, lane);
+        stat_tile = T.n_tile;
+        stat_group = grp;
       }
       mbar_wait(bar_tfull + acc * 8, (j >> 1) & 1);
       tc_fence_after();
@@ -347,6 +377,18 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         __syncwarp();
+        if (do_stat) {                               // lane = column: sum the fp32 values of this warp's (valid) rows
+          const long long left = Mg - mrow0;
+          const int rows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+          float s1 = 0.f, s2 = 0.f;
+          for (int r = 0; r < rows; ++r) {
+            const float u = stage[r * 36 + lane];      // bank (4 r + lane) % 32: conflict free
+            s1 += u;
+            s2 = fmaf(u, u, s2);
+          }
+          wstat[c0 + lane] += s1;
+          wstat[256 + c0 + lane] += s2;
+        }
         const int col = nb + c4;
         bool vec_ok = (Ng & 3) == 0 && col + 4 <= Ng;
         long long coloff = col;
@@ -419,6 +461,7 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       ++j;
       decode_tile<MODE>(a, T.t + gridDim.x, total, T);
     }
+    if (do_stat && stat_tile >= 0) stat_flush<BN>(a, wstat, stat_tile, stat_group, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -503,7 +546,7 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, Args& a, long lo
   const int sms = num_sms();
   const unsigned grid = (unsigned)(total < sms ? total : sms);
   auto go = [&](auto kern, int BNv) {
-    const size_t smem = (size_t)stages_for(BNv) * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256 + EPI_BYTES + BIAS_BYTES;
+    const size_t smem = (size_t)stages_for(BNv) * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256 + EPI_BYTES + BIAS_BYTES + STAT_BYTES;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, NTHREADS, smem, st>>>(mA, mB, a);
   };
@@ -670,13 +713,22 @@ int ladder_colsum_bf16(const void* g, long long rows, int cols, float* out, cuda
 
 int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bias, void* y, int y_bf16, int B, int H, int W,
                             int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l, int OH, int OW, int act,
-                            int out_d2s, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                            int out_d2s, void* workspace, size_t workspace_bytes, float* stat_sums, int stat_groups,
+                            cudaStream_t stream) {
   LADDER_REQUIRE(x_bf16 && y && Cin > 0 && Cout > 0 && KH > 0 && KW > 0, "conv2d_fprop_tma: bad arguments");
   LADDER_REQUIRE(ladder_conv2d_tma_supported(0, B, H, W, Cin, KH, KW, Cout, stride, OH, OW),
                  "conv2d_fprop_tma: unsupported geometry (see ladder_conv2d_tma_supported)");
   LADDER_REQUIRE(out_d2s == 0 || (out_d2s > 0 && Cout % (out_d2s * out_d2s) == 0),
                  "conv2d_fprop_tma: depth_to_space(%d) output needs Cout %% r^2 == 0", out_d2s);
   LADDER_REQUIRE(((uintptr_t)x_bf16 & 15) == 0, "conv2d_fprop_tma: x must be 16-byte aligned");
+  const int stat_group_rows = OH * OW;
+  if (stat_sums != nullptr) {
+    LADDER_REQUIRE(act == ACT_NONE && out_d2s == 0, "conv2d_fprop_tma: output statistics are those of the linear output (act none, no d2s)");
+    LADDER_REQUIRE(stat_groups == 1 || (stat_groups == B && stat_group_rows % BM == 0),
+                   "conv2d_fprop_tma: per-sample statistics need OH*OW %% 128 == 0 (got %d) and groups == B", stat_group_rows);
+    cudaError_t e = cudaMemsetAsync(stat_sums, 0, (size_t)2 * stat_groups * Cout * sizeof(float), stream);
+    if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "conv2d_fprop_tma memset: %s", cudaGetErrorString(e));
+  }
   dense_as_row(B, H, W, KH, KW, OH, OW);
   const int bn = choose_bn(FPROP, (long long)B * OH * OW, Cout);
   int rc = LADDER_OK;
@@ -697,6 +749,7 @@ int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bia
   a.GW = OW; a.GH = OH; a.B = B; a.C = Cin; a.KH = KH; a.KW = KW;
   a.off_y = -pad_t; a.off_x = -pad_l; a.sign = 1;
   a.Ng = Cout; a.act = act; a.nkb = KH * KW * (Cin / BK); a.splits = 1; a.perm_r = out_d2s;
+  a.stat = stat_sums; a.stat_groups = stat_sums ? stat_groups : 0; a.stat_group_rows = stat_group_rows;
   return launch<FPROP>(mA, mA, a, (long long)B * OH * OW, bn, stream);
 }
 

@@ -151,15 +151,16 @@ class Conv:
         self.db = group.g(wname + '/bias')
         g = geom
         self.tma = [ops.tma_supported(g, m) for m in (ops.FPROP, ops.DGRAD, ops.WGRAD)]
-        if out_dtype != torch.float32 and not (self.tma[0] or ops.thin_k(g)):
+        if out_dtype != torch.float32 and not (self.tma[0] or ops.thin_k(g) or ops.im2col_ok(g)):
             raise RuntimeError('engine: bf16 activations need the TMA path for %s' % wname)
         self.y = torch.empty(g.B, g.OH, g.OW, g.Cout, device=device, dtype=out_dtype)
         self.x = None
         self.x16 = None
 
-    def forward(self, x, d2s=0):
+    def forward(self, x, d2s=0, stats=None):
         """d2s = r: the output is written directly in depth_to_space(r) layout (self.y must then be viewed as
-        [B, OH*r, OW*r, Cout/r^2] by the caller)."""
+        [B, OH*r, OW*r, Cout/r^2] by the caller).  stats = (sums, groups): per-channel sum / sum of squares of the output
+        accumulated by the GEMM epilogue (batch norm: groups 1, instance norm: groups B)."""
         self.x = self.xw = x                 # xw: the copy wgrad reads (bf16 on the TMA path, else as given)
         if x.dtype == torch.float32 and self.tma[0]:
             if self.x16 is None or self.x16.shape != x.shape:
@@ -167,12 +168,14 @@ class Conv:
             x = ops.to_bf16(x, self.x16)
             if self.tma[2]:
                 self.xw = x
-        return ops.conv2d_fprop(x, self.w, self.b, self.y, self.geom, self.act, out_d2s=d2s, wimg=self.wimg[ops.FPROP])
+        return ops.conv2d_fprop(x, self.w, self.b, self.y, self.geom, self.act, out_d2s=d2s, wimg=self.wimg[ops.FPROP],
+                                stats=stats)
 
-    def backward(self, dpre, dx=None, producer=None, wgrad=True, accumulate=False, s2d=0):
+    def backward(self, dpre, dx=None, producer=None, wgrad=True, accumulate=False, s2d=0, colsum=True):
         """dpre: d loss / d pre-activation of this layer.  producer = (act_out, act) of the layer
         that produced x, whose activation derivative is fused into dx.  s2d = r: x was the depth_to_space(r)
-        of the producer's output, so dx is scattered back to the producer's layout in the epilogue."""
+        of the producer's output, so dx is scattered back to the producer's layout in the epilogue.  colsum=False: the bias
+        gradient was already produced by the kernel that made dpre (fused norm backward passes)."""
         g = self.geom
         dy = dpre
         if dpre.dtype == torch.float32 and ((wgrad and self.tma[2]) or (dx is not None and self.tma[1])):
@@ -183,9 +186,10 @@ class Conv:
         if wgrad:
             if self.tma[2]:
                 ops.conv2d_wgrad(self.xw, dy, self.dw, None, g)
-                ops.colsum(dpre, g.B * g.OH * g.OW, g.Cout, self.db)
+                if colsum:
+                    ops.colsum(dpre, g.B * g.OH * g.OW, g.Cout, self.db)
             else:
-                ops.conv2d_wgrad(self.xw, dpre, self.dw, self.db, g, dys=dys)
+                ops.conv2d_wgrad(self.xw, dpre, self.dw, self.db if colsum else None, g, dys=dys)
         if dx is not None:
             ao, act = producer if producer is not None else (None, None)
             ops.conv2d_dgrad(dy if self.tma[1] else dpre, self.w, dx, g, act_out=ao, act=act, accumulate=accumulate,
@@ -373,9 +377,9 @@ class BNBlock:
     def backward(self, dout, dx, world):
         c = self.conv.y
         ops.bn_bwd_stats(dout, self.y, c, self.sums, self.dsums, self.count * world, LEAKY)
-        self.allreduce(self.dsums)
-        self.dbeta.copy_(self.dsums[:self.C])
+        self.dbeta.copy_(self.dsums[:self.C])         # this rank's share: the flat gradient is all-reduced after the backward
         self.dgamma.copy_(self.dsums[self.C:])
+        self.allreduce(self.dsums)
         ops.bn_bwd_apply(dout, self.y, c, self.sums, self.dsums, self.gamma, self.dconv, self.count * world, LEAKY)
         self.conv.backward(self.dconv, dx=dx)
 
@@ -408,8 +412,87 @@ class StyleBlock:
         self.conv.backward(self.dconv, dx=dx, producer=conv_producer)
 
 
+class BNBlock16:
+    """conv -> batch_norm(training statistics) -> leaky_relu on bf16-resident maps (codes/models.py:398-460): the conv's GEMM
+    epilogue accumulates the batch statistics, ONE pass normalises + activates (bf16 -> bf16), and the backward is two passes
+    over (g, c) that also produce the conv's bias gradient.  Gradient convention: backward() takes g = d loss / d (BN output),
+    i.e. the consumer's dgrad has already applied this block's leaky_relu derivative (fused in its epilogue)."""
+    fused = True
+
+    def __init__(self, group, idx, geom, device, allreduce):
+        cname = 'encoder/conv2d' if idx == 0 else 'encoder/conv2d_%d' % idx
+        bname = 'encoder/batch_normalization' if idx == 0 else 'encoder/batch_normalization_%d' % idx
+        self.conv = Conv(group, cname, geom, None, device, out_dtype=torch.bfloat16)
+        self.gamma, self.beta = group.p(bname + '/gamma'), group.p(bname + '/beta')
+        self.dgamma, self.dbeta = group.g(bname + '/gamma'), group.g(bname + '/beta')
+        self.C = C = geom.Cout
+        self.sums = torch.zeros(2 * C, device=device)
+        self.dsums = torch.zeros(2 * C, device=device)
+        self.y = torch.empty_like(self.conv.y)
+        self.dc = torch.empty_like(self.conv.y)
+        self.allreduce = allreduce
+        self.count = geom.B * geom.OH * geom.OW       # rows per rank; x world for cross-replica statistics
+
+    def forward(self, x, world):
+        c = self.conv.forward(x, stats=(self.sums, 1))
+        self.allreduce(self.sums)
+        return ops.bn_apply16(c, self.sums, self.gamma, self.beta, self.y, self.count * world, LEAKY)
+
+    def _between(self, dsums):
+        self.dbeta.copy_(dsums[:self.C])              # this rank's share (the flat gradient is all-reduced after the backward)
+        self.dgamma.copy_(dsums[self.C:])
+        self.allreduce(dsums)
+
+    def backward(self, g, dx, world, producer=None):
+        ops.bn_bwd16(g, self.conv.y, self.sums, self.dsums, self.gamma, self.dc, self.count * world, dbias=self.conv.db,
+                     between=self._between)
+        self.conv.backward(self.dc, dx=dx, producer=producer, colsum=False)
+
+
+class StyleBlock16:
+    """conv -> instance_norm -> style_mod(dlatent) -> leaky_relu -> legacy bilinear resize to `out_hw` (codes/models.py:
+    522-578, modules.py:6-10) on bf16-resident maps: per-sample statistics from the conv epilogue (maps of >= 128 pixels) or
+    one small pass (2x2 maps), then ONE pass writes the resized block output, the next conv's input; the un-resized block
+    output is never materialised.  backward() takes da = d loss / d (block output before the resize)."""
+    fused = True
+
+    def __init__(self, group, conv_idx, style_idx, geom, B, H, device, out_hw):
+        bf = torch.bfloat16
+        self.conv = Conv(group, 'decoder/conv2d_%d' % conv_idx, geom, None, device, out_dtype=bf)
+        self.Cx = Cx = geom.Cout
+        self.B = B
+        self.style = Conv(group, 'decoder/StyleMod_%d/dense' % style_idx, ops.ConvGeom.dense(B, H, 2 * Cx), None, device)
+        self.insum = torch.zeros(2, B, Cx, device=device)
+        self.epilogue_stats = ops.stats_in_epilogue(geom, B)
+        self.out = torch.empty(B, out_hw, out_hw, Cx, device=device, dtype=bf)
+        self.dstyle = torch.empty(B, 2 * Cx, device=device)
+        self.dc = torch.empty_like(self.conv.y)
+
+    def forward(self, x, dlatent):
+        if self.epilogue_stats:
+            c = self.conv.forward(x, stats=(self.insum, self.B))
+        else:
+            c = self.conv.forward(x)
+            ops.in_sums16(c, self.insum)
+        s = self.style.forward(dlatent)
+        return ops.in_style_resize16(c, self.insum, s.view(self.B, -1), self.out, LEAKY)
+
+    def backward(self, da, dx, d_dlatent_pre, dlatent_out, first, conv_producer=None):
+        B = self.B
+        ops.in_style_bwd16(da, self.conv.y, self.insum, self.style.y.view(B, -1), self.dstyle, self.dc, dbias=self.conv.db,
+                           act=LEAKY)
+        self.style.backward(self.dstyle.view(B, 1, 1, -1), dx=d_dlatent_pre, producer=(dlatent_out, LEAKY),
+                            accumulate=not first)
+        self.conv.backward(self.dc, dx=dx, producer=conv_producer, colsum=False)
+
+
 class CelebAOuterVAE:
-    """CelebAModel_densenet encoder / decoder (codes/models.py:392-587) for a fixed batch size."""
+    """CelebAModel_densenet encoder / decoder (codes/models.py:392-587) for a fixed batch size.
+
+    Two realisations of the normalisation layers: the fused bf16-resident one (BNBlock16 / StyleBlock16; used when every conv
+    of the block runs on the TMA-fed tensor-core kernel, i.e. 64-aligned channel counts in bf16 mode -- the shipped config and
+    the benchmark widths) and the fp32 stand-alone passes (BNBlock / StyleBlock; compute_dtype fp32 and narrow test models).
+    Set LADDER_FUSED_NORM=0 to force the latter."""
     last_act = None
 
     def __init__(self, config, group, B, device, allreduce, world):
@@ -419,12 +502,22 @@ class CelebAOuterVAE:
         G = ops.ConvGeom
         self.buf = Buffers(device)
         widths = [H // 4, H // 4, H // 2, H // 2, H, H]
-        self.enc = []
+        egeoms = []
         cin, hw = ch, S
         for i, w in enumerate(widths):
             g = G(B, hw, hw, cin, k, k, w, 2 if i < 5 else 1, 'same' if i < 5 else 'valid')
-            self.enc.append(BNBlock(group, i, g, device, allreduce))
+            egeoms.append(g)
             cin, hw = w, g.OH
+        sgeoms = {1: G(B, 2, 2, H, 3, 3, H, 1, 'same'), 2: G(B, 2, 2, H, 3, 3, H, 1, 'same'),
+                  4: G(B, 16, 16, H, 3, 3, H // 2, 1, 'same'), 6: G(B, 64, 64, H // 2, 3, 3, H // 4, 1, 'same')}
+        fwd_ok = lambda g: ops.tma_supported(g, ops.FPROP) or ops.im2col_ok(g)               # noqa: E731
+        self.fused = (os.environ.get('LADDER_FUSED_NORM', '1') != '0' and ops.MATH_MODE == 'bf16'
+                      and all(fwd_ok(g) and ops.norm_fused_ok(g.Cout) for g in egeoms)
+                      and all(ops.tma_supported(g, ops.DGRAD) and ops.tma_supported(g, ops.WGRAD) for g in egeoms[1:])
+                      and all(ops.tma_supported(g, ops.FPROP) and ops.tma_supported(g, ops.DGRAD)
+                              and ops.tma_supported(g, ops.WGRAD) and ops.norm_fused_ok(g.Cout) for g in sgeoms.values()))
+        fused = self.fused
+        self.enc = [(BNBlock16 if fused else BNBlock)(group, i, g, device, allreduce) for i, g in enumerate(egeoms)]
         self.flat, self.C, self.H = hw * hw * cin, C, H
         self.head_mean = Conv(group, 'encoder/code_mean', G.dense(B, self.flat, C), None, device)
         self.head_std = Conv(group, 'encoder/code_std_dev', G.dense(B, self.flat, C), None, device)
@@ -435,8 +528,12 @@ class CelebAOuterVAE:
         self.dec_dense = Conv(group, 'decoder/dense', G.dense(B, C, H), LEAKY, device)
         self.mapping = [Conv(group, 'decoder/dense_%d' % i, G.dense(B, H, H), LEAKY, device) for i in range(1, 9)]
         self.conv0 = Conv(group, 'decoder/conv2d', G(B, 1, 1, H, 1, 1, H, 1, 'same'), None, device)
-        self.sb1 = StyleBlock(group, 1, 0, G(B, 2, 2, H, 3, 3, H, 1, 'same'), B, H, device)
-        self.sb2 = StyleBlock(group, 2, 1, G(B, 2, 2, H, 3, 3, H, 1, 'same'), B, H, device)
+        if fused:       # a style block owns the resized map it hands to the next conv
+            self.sb1 = StyleBlock16(group, 1, 0, sgeoms[1], B, H, device, 2)
+            self.sb2 = StyleBlock16(group, 2, 1, sgeoms[2], B, H, device, 8)
+        else:
+            self.sb1 = StyleBlock(group, 1, 0, sgeoms[1], B, H, device)
+            self.sb2 = StyleBlock(group, 2, 1, sgeoms[2], B, H, device)
         bf = torch.bfloat16
         g3, g5 = G(B, 8, 8, H, 3, 3, H, 1, 'same'), G(B, 32, 32, H // 2, 3, 3, H // 2, 1, 'same')
         g7, g8 = G(B, 128, 128, H // 4, 3, 3, H // 4, 1, 'same'), G(B, 128, 128, H // 4, 1, 1, ch, 1, 'same')
@@ -444,18 +541,24 @@ class CelebAOuterVAE:
         # are written in bf16 by the TMA-fed kernel; the resized maps (inputs of the big convs) exist only in bf16
         o16 = lambda g: bf if ops.tma_supported(g, ops.FPROP) else torch.float32           # noqa: E731
         self.conv3 = Conv(group, 'decoder/conv2d_3', g3, LEAKY, device, out_dtype=o16(g3))
-        self.sb4 = StyleBlock(group, 4, 2, G(B, 16, 16, H, 3, 3, H // 2, 1, 'same'), B, H, device)
+        self.sb4 = (StyleBlock16(group, 4, 2, sgeoms[4], B, H, device, 32) if fused
+                    else StyleBlock(group, 4, 2, sgeoms[4], B, H, device))
         self.conv5 = Conv(group, 'decoder/conv2d_5', g5, LEAKY, device, out_dtype=o16(g5))
-        self.sb6 = StyleBlock(group, 6, 3, G(B, 64, 64, H // 2, 3, 3, H // 4, 1, 'same'), B, H, device)
+        self.sb6 = (StyleBlock16(group, 6, 3, sgeoms[6], B, H, device, 128) if fused
+                    else StyleBlock(group, 6, 3, sgeoms[6], B, H, device))
         self.conv7 = Conv(group, 'decoder/conv2d_7', g7, LEAKY, device,
                           out_dtype=bf if ops.tma_supported(g7, ops.FPROP) and ops.reads_bf16(g8) else torch.float32)
         self.conv8 = Conv(group, 'decoder/conv2d_8', g8, None, device)
         self.decoded = self.conv8.y
         E = lambda conv, *shape: torch.empty(*shape, device=device,                        # noqa: E731
                                              dtype=bf if ops.reads_bf16(conv.geom) else torch.float32)
-        self.r0, self.r2, self.r3 = E(self.sb1.conv, B, 2, 2, H), E(self.conv3, B, 8, 8, H), E(self.sb4.conv, B, 16, 16, H)
-        self.r4, self.r5 = E(self.conv5, B, 32, 32, H // 2), E(self.sb6.conv, B, 64, 64, H // 2)
-        self.r6 = E(self.conv7, B, 128, 128, H // 4)
+        self.r0, self.r3 = E(self.sb1.conv, B, 2, 2, H), E(self.sb4.conv, B, 16, 16, H)
+        self.r5 = E(self.sb6.conv, B, 64, 64, H // 2)
+        if fused:
+            self.r2, self.r4, self.r6 = self.sb2.out, self.sb4.out, self.sb6.out
+        else:
+            self.r2, self.r4 = E(self.conv3, B, 8, 8, H), E(self.conv5, B, 32, 32, H // 2)
+            self.r6 = E(self.conv7, B, 128, 128, H // 4)
 
     def encode(self, x, eps_z, stats_z):
         B = self.B
@@ -477,6 +580,13 @@ class CelebAOuterVAE:
             dl = m.forward(dl)
         h = self.conv0.forward(enc)
         h = ops.resize_bilinear_fwd(h, self.r0)
+        if self.fused:      # style blocks emit the resized map directly
+            h = self.sb2.forward(self.sb1.forward(h, dl), dl)
+            h = self.conv3.forward(h)
+            h = self.sb4.forward(ops.resize_bilinear_fwd(h, self.r3), dl)
+            h = self.conv5.forward(h)
+            h = self.sb6.forward(ops.resize_bilinear_fwd(h, self.r5), dl)
+            return self.conv8.forward(self.conv7.forward(h))
         h = self.sb1.forward(h, dl)
         h = self.sb2.forward(h, dl)
         h = self.conv3.forward(ops.resize_bilinear_fwd(h, self.r2))
@@ -492,15 +602,18 @@ class CelebAOuterVAE:
         dl_out = self.mapping[-1].y
         d_dl = g('d_dl', B, 1, 1, H)                      # pre-activation gradient of the last mapping layer
         bf = torch.bfloat16
+        fused = self.fused
         # gradient dtypes: bf16 wherever the producing kernel can write it and the consumer reads it (TMA GEMMs, resize)
         gdt = lambda conv: bf if conv.tma[1] else torch.float32                              # noqa: E731
+        adt = bf if fused else torch.float32              # gradient w.r.t. a style block's (un-resized) output
+        hw = lambda sb: sb.conv.y.shape                                                      # noqa: E731
         c7 = self.conv7
         d7 = g('d7', *c7.y.shape, dtype=bf if ops.dgrad_writes_bf16(self.conv8.geom) and (c7.tma[1] or c7.tma[2])
                else torch.float32)
         self.conv8.backward(dpre_last, dx=d7, producer=(c7.y, LEAKY), wgrad=wgrad)
         dr6 = g('dr6', *self.r6.shape, dtype=gdt(c7))
         c7.backward(d7, dx=dr6, wgrad=wgrad)
-        da6 = g('da6', *self.sb6.y.shape)
+        da6 = g('da6', *hw(self.sb6), dtype=adt)
         ops.resize_bilinear_bwd(dr6, da6)
         dr5 = g('dr5', *self.r5.shape, dtype=gdt(self.sb6.conv))
         self.sb6.backward(da6, dr5, d_dl, dl_out, first=True)
@@ -509,7 +622,7 @@ class CelebAOuterVAE:
         ops.resize_bilinear_bwd(dr5, da5, act_out=c5.y, act=LEAKY)       # resize^T fused with conv5's leaky derivative
         dr4 = g('dr4', *self.r4.shape, dtype=gdt(c5))
         c5.backward(da5, dx=dr4, wgrad=wgrad)
-        da4 = g('da4', *self.sb4.y.shape)
+        da4 = g('da4', *hw(self.sb4), dtype=adt)
         ops.resize_bilinear_bwd(dr4, da4)
         dr3 = g('dr3', *self.r3.shape, dtype=gdt(self.sb4.conv))
         self.sb4.backward(da4, dr3, d_dl, dl_out, first=False)
@@ -518,9 +631,9 @@ class CelebAOuterVAE:
         ops.resize_bilinear_bwd(dr3, da3, act_out=c3.y, act=LEAKY)
         dr2 = g('dr2', *self.r2.shape, dtype=gdt(c3))
         c3.backward(da3, dx=dr2, wgrad=wgrad)
-        da2 = g('da2', *self.sb2.y.shape)
+        da2 = g('da2', *hw(self.sb2), dtype=adt)
         ops.resize_bilinear_bwd(dr2, da2)
-        da1 = g('da1', *self.sb1.y.shape)
+        da1 = g('da1', *hw(self.sb1), dtype=gdt(self.sb2.conv) if fused else torch.float32)
         self.sb2.backward(da2, da1, d_dl, dl_out, first=False)
         dr0 = g('dr0', *self.r0.shape, dtype=gdt(self.sb1.conv))
         self.sb1.backward(da1, dr0, d_dl, dl_out, first=False)
@@ -544,6 +657,25 @@ class CelebAOuterVAE:
         dmean, dstd = self.buf.get('dmean', B, C), self.buf.get('dstd', B, C)
         ops.gauss_head_bwd(dz, self.mean, self.std, self.eps_z, dmean_add, dstd_add, dmean, dstd, floor, c_entropy, c_sg)
         dflat = self.buf.get('dflat', B, 1, 1, self.flat)
+        if self.fused:
+            # every dgrad applies the leaky_relu derivative of the block that produced its input (aux = that block's output),
+            # so the blocks exchange d loss / d (batch-norm output)
+            last = self.enc[-1]
+            prod = (last.y.view(B, 1, 1, self.flat), LEAKY)
+            self.head_mean.backward(dmean.view(B, 1, 1, C), dx=dflat, producer=prod)
+            self.head_std.backward(dstd.view(B, 1, 1, C), dx=dflat, producer=prod, accumulate=True)
+            gcur = dflat.view(*last.y.shape)
+            for i in range(len(self.enc) - 1, -1, -1):
+                blk = self.enc[i]
+                if i > 0:
+                    prev = self.enc[i - 1]
+                    dx = self.buf.get('de%d' % i, *prev.y.shape, dtype=torch.bfloat16)
+                    blk.backward(gcur, dx, self.world, producer=(prev.y, LEAKY))
+                else:
+                    dx = None
+                    blk.backward(gcur, None, self.world)
+                gcur = dx
+            return
         self.head_mean.backward(dmean.view(B, 1, 1, C), dx=dflat)
         self.head_std.backward(dstd.view(B, 1, 1, C), dx=dflat, accumulate=True)
         dout = dflat.view(*self.enc[-1].y.shape)

@@ -52,7 +52,7 @@ SIGNATURES = {
     'ladder_conv2d_tma_pack_bytes': (C.c_size_t, [C.c_int] * 6),
     'ladder_conv2d_tma_pack': (C.c_int, [ptr, ptr, C.c_size_t] + [C.c_int] * 6 + [stream_t]),
     'ladder_pack_weights_multi': (C.c_int, [ptr, ptr, ptr, C.c_int, C.c_longlong, stream_t]),
-    'ladder_conv2d_fprop_tma': (C.c_int, [ptr, ptr, ptr, ptr, C.c_int] + [C.c_int] * 14 + [ptr, C.c_size_t, stream_t]),
+    'ladder_conv2d_fprop_tma': (C.c_int, [ptr, ptr, ptr, ptr, C.c_int] + [C.c_int] * 14 + [ptr, C.c_size_t, ptr, C.c_int, stream_t]),
     'ladder_conv2d_dgrad_tma': (C.c_int, [ptr, ptr, ptr, C.c_int, ptr, C.c_int] + [C.c_int] * 15 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_wgrad_tma': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [stream_t]),
     'ladder_tap_dgrad': (C.c_int, [ptr, ptr, ptr, C.c_int, ptr, C.c_int] + [C.c_int] * 14 + [stream_t]),
@@ -84,6 +84,15 @@ SIGNATURES = {
     'ladder_resize_bilinear_bwd': (C.c_int, [ptr, ptr] + [C.c_int] * 6 + [stream_t]),
     'ladder_resize_bilinear_fwd_ex': (C.c_int, [ptr, C.c_int, ptr, C.c_int] + [C.c_int] * 6 + [stream_t]),
     'ladder_resize_bilinear_bwd_ex': (C.c_int, [ptr, C.c_int, ptr, C.c_int, ptr, C.c_int, C.c_int] + [C.c_int] * 6 + [stream_t]),
+    'ladder_norm_fused_supported': (C.c_int, [C.c_int]),
+    'ladder_bn_apply_bf16': (C.c_int, [ptr, ptr, ptr, ptr, ptr, C.c_longlong, C.c_int, C.c_longlong, C.c_float, C.c_int, stream_t]),
+    'ladder_bn_bwd_stats_bf16': (C.c_int, [ptr, C.c_int, ptr, ptr, C.c_longlong, C.c_int, C.c_longlong, C.c_float, ptr, stream_t]),
+    'ladder_bn_bwd_apply_bf16': (C.c_int, [ptr, C.c_int, ptr, ptr, ptr, ptr, ptr, C.c_longlong, C.c_int, C.c_longlong, C.c_float,
+                                           ptr, stream_t]),
+    'ladder_in_sums_bf16': (C.c_int, [ptr, C.c_int, C.c_int, C.c_int, ptr, stream_t]),
+    'ladder_in_style_resize_bf16': (C.c_int, [ptr, ptr, ptr, ptr] + [C.c_int] * 6 + [C.c_float, C.c_int, stream_t]),
+    'ladder_in_style_bwd_bf16': (C.c_int, [ptr, C.c_int, ptr, ptr, ptr, ptr, ptr, ptr, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                           stream_t]),
     # ELBO pieces
     'ladder_gauss_head_fwd': (C.c_int, [ptr, ptr, ptr, ptr, C.c_longlong, C.c_float, ptr, stream_t]),
     'ladder_gauss_head_bwd': (C.c_int, [ptr] * 8 + [C.c_longlong, C.c_float, C.c_float, C.c_float, stream_t]),

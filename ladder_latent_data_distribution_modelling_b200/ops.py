@@ -439,6 +439,14 @@ def im2col_ok(g):
     return tma_supported(gd, FPROP) and tma_supported(gd, WGRAD)
 
 
+def stats_in_epilogue(g, groups):
+    """True if the fprop of geometry g runs on the TMA-fed kernel (directly or as the patch-matrix first conv) and can
+    accumulate output statistics for `groups` groups (1 = batch norm, B = instance norm: OH*OW a multiple of 128)."""
+    if not (tma_supported(g, FPROP) or im2col_ok(g)) or _is_tap_gemm(g):
+        return False
+    return groups == 1 or (groups == g.B and (g.OH * g.OW) % 128 == 0 and tma_supported(g, FPROP))
+
+
 def _im2col(x, g):
     P = g.B * g.OH * g.OW
     a = _workspace(x.device, P * 64 * 2, 'im2col').view(torch.bfloat16)[:P * 64].view(P, 1, 1, 64)
@@ -447,13 +455,13 @@ def _im2col(x, g):
     return a
 
 
-def _im2col_fprop(x, w, bias, y, g, act):
+def _im2col_fprop(x, w, bias, y, g, act, stats=None):
     K = g.KH * g.KW * g.Cin
     wp = _workspace(x.device, 64 * g.Cout * 4, 'im2col_w').view(torch.float32)[:64 * g.Cout].view(64, g.Cout)
     wp[K:].zero_()
     wp[:K].copy_(w.view(K, g.Cout))
     gd = _im2col_geom(g)
-    return conv2d_fprop(_im2col(x, g), wp.view(1, 1, 64, g.Cout), bias, y.view(gd.B, 1, 1, g.Cout), gd, act)
+    return conv2d_fprop(_im2col(x, g), wp.view(1, 1, 64, g.Cout), bias, y.view(gd.B, 1, 1, g.Cout), gd, act, stats=stats)
 
 
 def _im2col_wgrad(x, dy, dw, dbias, g):
@@ -541,15 +549,19 @@ def pack_weights_multi(params, images, desc, n, total):
                'pack_weights_multi')
 
 
-def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0, wimg=None):
+def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0, wimg=None, stats=None):
     """y = act(conv(x, w) + bias); out_d2s = r writes y directly in depth_to_space(r) layout.
     x and y may each be fp32 or bf16 when the layer runs on the TMA-fed kernel (tma_supported(g, FPROP));
-    wimg: pre-packed bf16 weight image of that kernel (tma_pack_plan) -- skips the per-call repack of w."""
+    wimg: pre-packed bf16 weight image of that kernel (tma_pack_plan) -- skips the per-call repack of w.
+    stats = (sums [2, groups, Cout] fp32, groups): the TMA kernel's epilogue also accumulates the per-channel sum / sum of
+    squares of y (groups = 1: over all rows, batch norm; groups = B: per sample, instance norm)."""
     _act_t(x, 'x'), _act_t(y, 'y')
+    if stats is not None and not (stats_in_epilogue(g, stats[1]) and act in (None, 'none') and not out_d2s):
+        raise RuntimeError('conv2d_fprop: epilogue statistics need the TMA path (geometry %r)' % (g.args(),))
     if MATH_MODE == 'bf16' and _is_tap_gemm(g) and g.Cin % 64 == 0 and not out_d2s:
         return _tap_gemm_fprop_tc(x, w, bias, y, g, act)
     if x.dtype == torch.float32 and not out_d2s and im2col_ok(g):
-        _im2col_fprop(x, w, bias, y, g, act)
+        _im2col_fprop(x, w, bias, y, g, act, stats)
         return y
     if thin_k(g) and x.dtype == torch.float32 and not out_d2s:
         _lib.check(_L().ladder_thin_k_fprop(_p(x), _p(_f32(w)), _p(bias), _p(y), _is16(y), *g.args(), ACT[act], _stream()),
@@ -560,8 +572,10 @@ def conv2d_fprop(x, w, bias, y, g, act=None, out_d2s=0, wimg=None):
             ws, n, wp = wimg, wimg.numel() * 2, None
         else:
             (ws, n), wp = _tma_ws(x, g), _f32(w)
+        st, groups = (_f32(stats[0], 'stats'), int(stats[1])) if stats is not None else (None, 0)
         _lib.check(_L().ladder_conv2d_fprop_tma(_p(_as16(x, 'x16')), _p(wp), _p(bias), _p(y), _is16(y), *g.args(),
-                                                ACT[act], int(out_d2s), _p(ws), n, _stream()), 'conv2d_fprop_tma')
+                                                ACT[act], int(out_d2s), _p(ws), n, _p(st), groups, _stream()),
+                   'conv2d_fprop_tma')
         return y
     x = _as32(x, 'x32')
     if y.dtype != torch.float32:
@@ -824,3 +838,58 @@ def resize_bilinear_bwd(dy, dx, act_out=None, act=None):
                                                   _is16(act_out), ACT[act], B, H, W, Cc, dy.shape[1], dy.shape[2], _stream()),
                'resize_bilinear_bwd')
     return dx
+
+
+# ---- bf16-resident forms (csrc/norm_fused.cu): raw-sum statistics, one HBM pass per direction
+def norm_fused_ok(Cc):
+    return MATH_MODE == 'bf16' and TMA and bool(_L().ladder_norm_fused_supported(int(Cc)))
+
+
+def _b16(t, name):
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()):
+        raise RuntimeError('%s must be a contiguous bf16 CUDA tensor' % name)
+    return t
+
+
+def bn_apply16(c, sums2c, gamma, beta, y, count, act='leaky_relu'):
+    Cc = c.shape[-1]
+    _lib.check(_L().ladder_bn_apply_bf16(_p(_b16(c, 'c')), _p(_f32(sums2c)), _p(gamma), _p(beta), _p(_b16(y, 'y')),
+                                         c.numel() // Cc, Cc, int(count), BN_EPS, ACT[act], _stream()), 'bn_apply_bf16')
+    return y
+
+
+def bn_bwd16(g, c, sums2c, dsums2c, gamma, dc, count, dbias=None, between=None):
+    """Batch-norm backward on the bf16 conv output c: dsums2c = (sum g, sum g xhat) [= (dbeta, dgamma)], then -- after
+    `between(dsums2c)` (the data-parallel all-reduce) -- dc and the conv's bias gradient."""
+    Cc = c.shape[-1]
+    rows = c.numel() // Cc
+    _lib.check(_L().ladder_bn_bwd_stats_bf16(_p(_act_t(g, 'g')), _is16(g), _p(_b16(c, 'c')), _p(_f32(sums2c)), rows, Cc,
+                                             int(count), BN_EPS, _p(_f32(dsums2c)), _stream()), 'bn_bwd_stats_bf16')
+    if between is not None:
+        between(dsums2c)
+    _lib.check(_L().ladder_bn_bwd_apply_bf16(_p(g), _is16(g), _p(c), _p(sums2c), _p(dsums2c), _p(gamma), _p(_b16(dc, 'dc')),
+                                             rows, Cc, int(count), BN_EPS, _p(dbias), _stream()), 'bn_bwd_apply_bf16')
+    return dc
+
+
+def in_sums16(c, insum):
+    B, H, W, Cc = c.shape
+    _lib.check(_L().ladder_in_sums_bf16(_p(_b16(c, 'c')), B, H * W, Cc, _p(_f32(insum)), _stream()), 'in_sums_bf16')
+    return insum
+
+
+def in_style_resize16(c, insum, style, out, act='leaky_relu'):
+    """out [B,OH,OW,C] = legacy_bilinear_resize(act(instance_norm(c) * (s0 + 1) + s1)) in one pass (OH == H: no resize)."""
+    B, H, W, Cc = c.shape
+    _lib.check(_L().ladder_in_style_resize_bf16(_p(_b16(c, 'c')), _p(_f32(insum)), _p(_f32(style)), _p(_b16(out, 'out')), B, H, W,
+                                                Cc, out.shape[1], out.shape[2], IN_EPS, ACT[act], _stream()),
+               'in_style_resize_bf16')
+    return out
+
+
+def in_style_bwd16(da, c, insum, style, dstyle, dc, dbias=None, act='leaky_relu'):
+    B, H, W, Cc = c.shape
+    _lib.check(_L().ladder_in_style_bwd_bf16(_p(_act_t(da, 'da')), _is16(da), _p(_b16(c, 'c')), _p(_f32(insum)), _p(_f32(style)),
+                                             _p(_f32(dstyle)), _p(_b16(dc, 'dc')), _p(dbias), B, H * W, Cc, IN_EPS, ACT[act],
+                                             _stream()), 'in_style_bwd_bf16')
+    return dc

@@ -15,6 +15,37 @@ import torch.nn.functional as F
 
 LOG_2PI = math.log(2.0 * math.pi)
 
+# --- bf16-operand emulation (checker for the tensor-core path) -------------------------------------------------------------
+# The sm_100a engine's GEMM layers round BOTH operands to bf16 and accumulate in fp32; everything else is fp32.  Against the
+# exact float64 graph such a path differs by ~2^-9 per activation in the forward pass, which flips the sign of the few
+# (leaky-)ReLU pre-activations that sit inside that band -- and a flipped unit changes its gradient by 80 %: a per-layer
+# relative gradient error of ~0.8 sqrt(fraction flipped), far above the rounding itself.  With BF16_OPERANDS = True this
+# restatement rounds the operands of the same layers (straight-through: the gradient w.r.t. the fp32 master value is that of
+# the rounded copy), so pre-activations agree to fp32 accumulation noise and the comparison isolates the kernels' own error.
+# BF16_STORED additionally rounds the conv outputs the engine keeps bf16-resident in front of batch / instance norm.
+BF16_OPERANDS = False
+BF16_STORED = False
+
+
+def _q(t):
+    return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+
+
+def _st(t):
+    """A tensor the engine keeps bf16-resident in HBM (CelebA: conv outputs in front of batch / instance norm, normalised
+    maps, resized maps, leaky conv outputs of the decoder)."""
+    return _q(t) if BF16_STORED else t
+
+
+def bf16_layer(kh, kw, cin, cout):
+    """Mirror of the engine's dispatch (ops._use_tc / thin_k / tap-GEMM / im2col): which layers multiply bf16 operands."""
+    K, taps = kh * kw * cin, kh * kw
+    if cout == 1 and taps > 1 and cin >= 4:          # single-output-channel KxK conv: tap-GEMM only for 64-aligned channels
+        return cin % 64 == 0
+    if K >= 32:
+        return True
+    return cin < 8 and taps > 1 and 16 < K <= 64 and cout % 64 == 0          # patch-matrix first conv
+
 
 def _same_pads(n, k, s):
     out = -(-n // s)
@@ -29,6 +60,8 @@ def conv2d(x, w, b, stride=1, padding='same'):
         pl, pr = _same_pads(x.shape[2], w.shape[1], stride)
     else:
         pt = pb = pl = pr = 0
+    if BF16_OPERANDS and bf16_layer(w.shape[0], w.shape[1], w.shape[2], w.shape[3]):
+        x, w = _q(x), _q(w)
     xn = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb)).contiguous()
     y = F.conv2d(xn, w.permute(3, 2, 0, 1).contiguous(), b, stride=stride)
     return y.permute(0, 2, 3, 1)
@@ -53,7 +86,10 @@ def leaky(x):
 
 
 def _dense(P, name, x, act=None):
-    y = x @ P[name + '/kernel'] + P[name + '/bias']
+    w = P[name + '/kernel']
+    if BF16_OPERANDS and bf16_layer(1, 1, w.shape[0], w.shape[1]):
+        x, w = _q(x), _q(w)
+    y = x @ w + P[name + '/bias']
     return act(y) if act is not None else y
 
 
@@ -106,9 +142,9 @@ def encoder_celeba(cfg, P, x):
     """models.py:392-464"""
     h = x
     for i in range(6):
-        h = _conv(P, 'encoder', i, h, 2 if i < 5 else 1, 'same' if i < 5 else 'valid')
+        h = _st(_conv(P, 'encoder', i, h, 2 if i < 5 else 1, 'same' if i < 5 else 'valid'))
         bn = 'encoder/batch_normalization' if i == 0 else 'encoder/batch_normalization_%d' % i
-        h = leaky(batch_norm_train(h, P[bn + '/gamma'], P[bn + '/beta']))
+        h = _st(leaky(batch_norm_train(h, P[bn + '/gamma'], P[bn + '/beta'])))
     return h.reshape(h.shape[0], -1)
 
 
@@ -119,14 +155,14 @@ def decoder_celeba(cfg, P, z):
     dl = encoded
     for i in range(1, 9):
         dl = _dense(P, 'decoder/dense_%d' % i, dl, leaky)
-    h = resize_bilinear_legacy(_conv(P, 'decoder', 0, encoded.reshape(-1, 1, 1, H)), 2, 2)
-    h = leaky(style_mod(P, instance_norm(_conv(P, 'decoder', 1, h)), dl, 0))
-    h = leaky(style_mod(P, instance_norm(_conv(P, 'decoder', 2, h)), dl, 1))
-    h = _conv(P, 'decoder', 3, resize_bilinear_legacy(h, 8, 8), act=leaky)
-    h = leaky(style_mod(P, instance_norm(_conv(P, 'decoder', 4, resize_bilinear_legacy(h, 16, 16))), dl, 2))
-    h = _conv(P, 'decoder', 5, resize_bilinear_legacy(h, 32, 32), act=leaky)
-    h = leaky(style_mod(P, instance_norm(_conv(P, 'decoder', 6, resize_bilinear_legacy(h, 64, 64))), dl, 3))
-    h = _conv(P, 'decoder', 7, resize_bilinear_legacy(h, 128, 128), act=leaky)
+    h = _st(resize_bilinear_legacy(_conv(P, 'decoder', 0, encoded.reshape(-1, 1, 1, H)), 2, 2))
+    h = _st(leaky(style_mod(P, instance_norm(_st(_conv(P, 'decoder', 1, h))), dl, 0)))
+    h = leaky(style_mod(P, instance_norm(_st(_conv(P, 'decoder', 2, h))), dl, 1))
+    h = _st(_conv(P, 'decoder', 3, _st(resize_bilinear_legacy(h, 8, 8)), act=leaky))
+    h = leaky(style_mod(P, instance_norm(_st(_conv(P, 'decoder', 4, _st(resize_bilinear_legacy(h, 16, 16))))), dl, 2))
+    h = _st(_conv(P, 'decoder', 5, _st(resize_bilinear_legacy(h, 32, 32)), act=leaky))
+    h = leaky(style_mod(P, instance_norm(_st(_conv(P, 'decoder', 6, _st(resize_bilinear_legacy(h, 64, 64))))), dl, 3))
+    h = _st(_conv(P, 'decoder', 7, _st(resize_bilinear_legacy(h, 128, 128)), act=leaky))
     return _conv(P, 'decoder', 8, h)
 
 

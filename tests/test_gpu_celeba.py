@@ -118,3 +118,138 @@ def test_celeba_engine_scalars_and_gradients():
         eng.draw_noise()
         fn(xd)
     assert all(torch.isfinite(t).all() for _, t in eng.named_parameters())
+
+
+# ------------------------------------------------------------------ fused bf16-resident norm layers (csrc/norm_fused.cu)
+def _bf16(a):
+    """round a float array to bf16 and back (the value the device tensor holds)."""
+    return torch.tensor(np.asarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy().astype(np.float64)
+
+
+def _dev16(a):
+    return torch.tensor(np.asarray(a, dtype=np.float32), device='cuda').to(torch.bfloat16).contiguous()
+
+
+def close16(got, want, rel=2.0 ** -7):
+    """bf16-stored result: within one bf16 ulp-ish (2^-7 of the tensor's largest magnitude covers rounding + fp32 math)."""
+    got = got.float().cpu().numpy().astype(np.float64)
+    scale = np.abs(want).max() + 1e-30
+    assert np.abs(got - want).max() <= rel * scale, (np.abs(got - want).max(), scale)
+
+
+@pytest.fixture(scope='module')
+def ops16():
+    from ladder_latent_data_distribution_modelling_b200 import ops
+    ops.set_math_mode('bf16')
+    yield ops
+    ops.set_math_mode('fp32')
+
+
+def test_conv_epilogue_statistics(ops16):
+    """ladder_conv2d_fprop_tma with stat_sums: per-channel (batch norm) and per-sample (instance norm) sum / sum of squares of
+    the fp32 conv output, accumulated by the GEMM epilogue -- against sums of the same conv's fp32 output."""
+    ops = ops16
+    rng = np.random.default_rng(11)
+    for (B, HW, Cin, Cout, stride, groups_b) in [(3, 16, 64, 128, 1, True), (2, 32, 64, 64, 2, True), (5, 8, 128, 256, 1, False),
+                                                 (130, 2, 64, 512, 1, False)]:
+        g = ops.ConvGeom(B, HW, HW, Cin, 3, 3, Cout, stride, 'same')
+        assert ops.tma_supported(g, ops.FPROP)
+        x = _dev16(rng.normal(size=(B, HW, HW, Cin)))
+        w = dev(rng.normal(size=(3, 3, Cin, Cout)) * 0.05); b = dev(rng.normal(size=Cout))
+        y32 = torch.empty(B, g.OH, g.OW, Cout, device='cuda')
+        ops.conv2d_fprop(x, w, b, y32, g, None)
+        for groups in ([1, B] if groups_b and (g.OH * g.OW) % 128 == 0 else [1]):
+            y16 = torch.empty(B, g.OH, g.OW, Cout, device='cuda', dtype=torch.bfloat16)
+            sums = torch.full((2, groups, Cout), 7.0, device='cuda')                     # the call zeroes it
+            ops.conv2d_fprop(x, w, b, y16, g, None, stats=(sums, groups))
+            yg = y32.double().reshape(groups, -1, Cout)
+            want = torch.stack([yg.sum(1), (yg * yg).sum(1)]).cpu().numpy()
+            got = sums.cpu().numpy()
+            assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max(), (groups, np.abs(got - want).max())
+            assert torch.equal(y16, y32.to(torch.bfloat16))
+
+
+def test_batch_norm_bf16_fused_fwd_bwd(ops16):
+    ops = ops16
+    rng = np.random.default_rng(12)
+    for shape in [(3, 8, 8, 128), (2, 5, 7, 64), (16, 2, 2, 512), (2, 16, 16, 8)]:
+        C = shape[-1]; P = int(np.prod(shape[:-1]))
+        c = _bf16(rng.normal(size=shape) * 2 + 0.5); gam = rng.normal(size=C); bet = rng.normal(size=C)
+        X, G, Bv = T.Var(c), T.Var(gam), T.Var(bet)
+        pre = T.batch_norm_train(X, G, Bv)
+        y = T.leaky_relu(pre)
+        up = _bf16(rng.normal(size=shape))                   # g = d loss / d (BN output), as the consumer's dgrad hands it over
+        T.backward(pre, seed=up)
+        cd = _dev16(c)
+        sums = torch.stack([cd.float().sum((0, 1, 2)), (cd.float() ** 2).sum((0, 1, 2))]).reshape(-1).contiguous()
+        yd = torch.empty(shape, device='cuda', dtype=torch.bfloat16)
+        ops.bn_apply16(cd, sums, dev(gam), dev(bet), yd, P)
+        close16(yd, y.v)
+        for g16 in (True, False):
+            gd = _dev16(up) if g16 else dev(up)
+            dsums = torch.zeros(2 * C, device='cuda'); dc = torch.empty(shape, device='cuda', dtype=torch.bfloat16)
+            db = torch.full((C,), 3.0, device='cuda')
+            seen = []
+            ops.bn_bwd16(gd, cd, sums, dsums, dev(gam), dc, P, dbias=db, between=lambda t: seen.append(t.clone()))
+            close(dsums[:C], Bv.g, 2e-4)
+            close(dsums[C:], G.g, 2e-4)
+            assert len(seen) == 1 and torch.equal(seen[0], dsums)
+            close16(dc, X.g)
+            # the conv bias in front of a batch norm has zero gradient: the fused column sum must be ~0 on the scale of dc
+            assert float(db.abs().max()) <= 1e-3 * np.abs(X.g).max() * np.sqrt(P) + 1e-6
+
+
+def test_instance_norm_style_resize_bf16_fused_fwd_bwd(ops16):
+    ops = ops16
+    rng = np.random.default_rng(13)
+    for (B, H, C, OH) in [(3, 2, 64, 2), (2, 2, 128, 8), (2, 16, 64, 32), (1, 8, 8, 16)]:
+        shape = (B, H, H, C)
+        c = _bf16(rng.normal(size=shape) * 1.5 + 0.3); st = rng.normal(size=(B, 2 * C))
+        X, S = T.Var(c), T.Var(st)
+        s0 = T.reshape(T.slice_last(S, 0, C), (B, 1, 1, C)); s1 = T.reshape(T.slice_last(S, C, 2 * C), (B, 1, 1, C))
+        y = T.leaky_relu(T.instance_norm(X) * (s0 + 1.0) + s1)
+        out = T.resize_bilinear_legacy(y, OH, OH) if OH != H else y
+        cd, sd = _dev16(c), dev(st)
+        insum = torch.zeros(2, B, C, device='cuda')
+        ops.in_sums16(cd, insum)
+        want_s = np.stack([c.sum((1, 2)), (c * c).sum((1, 2))])
+        close(insum, want_s, 1e-5)
+        od = torch.empty(B, OH, OH, C, device='cuda', dtype=torch.bfloat16)
+        ops.in_style_resize16(cd, insum, sd, od)
+        close16(od, out.v)
+        up = _bf16(rng.normal(size=shape))                   # da = d loss / d (un-resized block output)
+        T.backward(y, seed=up)
+        for g16 in (True, False):
+            dst = torch.empty(B, 2 * C, device='cuda'); dc = torch.empty(shape, device='cuda', dtype=torch.bfloat16)
+            db = torch.full((C,), 3.0, device='cuda')
+            ops.in_style_bwd16(_dev16(up) if g16 else dev(up), cd, insum, sd, dst, dc, dbias=db)
+            close(dst, S.g, 2e-4)
+            close16(dc, X.g)
+            assert float(db.abs().max()) <= 1e-3 * np.abs(X.g).max() * np.sqrt(B * H * H) + 1e-6
+
+
+def test_celeba_fused_engine_matches_unfused(monkeypatch):
+    """The fused bf16-resident normalisation path against the stand-alone fp32 passes on the same bf16 GEMMs (width 256, every
+    conv on the TMA kernel): ELBO terms and every gradient, tolerance = bf16 storage of the normalised maps."""
+    from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
+    from test_gpu_parity_r2 import celeba_case
+    cfg, P, x, nz, feeds = celeba_case(2, 256, 64)
+    xd = torch.tensor(x, device='cuda')
+    out = []
+    for fused in ('1', '0'):
+        monkeypatch.setenv('LADDER_FUSED_NORM', fused)
+        eng = LadderEngine(cfg, 2, 'cuda', seed=0)
+        assert eng.outer.fused == (fused == '1')
+        eng.load_parameters(P); eng.set_feeds(**feeds); eng.set_noise(**nz)
+        eng.step_ae(xd, apply=False)
+        out.append((eng.scalars.cpu().numpy().copy(), {n: t.clone() for n, t in eng.named_gradients()}))
+    from ladder_latent_data_distribution_modelling_b200 import ops
+    for name, i in ops.O.items():
+        a, b = out[0][0][i], out[1][0][i]
+        assert abs(a - b) <= 1e-2 * max(1.0, abs(b)), (name, a, b)
+    for n in out[0][1]:
+        if not (n.startswith('encoder') or n.startswith('decoder')):
+            continue
+        a, b = out[0][1][n].double(), out[1][1][n].double()
+        # the two paths round different tensors to bf16, so (leaky_relu kinks) they agree like two bf16 runs do
+        assert (a - b).norm() <= 0.3 * b.norm() + 1e-6 * float(b.numel()) ** 0.5, (n, float((a - b).norm() / (b.norm() + 1e-30)))

@@ -7,10 +7,16 @@
      Philox whose counter lives on the device);
  (d) the bf16 engine tolerance of the MNIST models stated per tensor from the depth of the bf16 GEMM chain.
 
-Tolerance model (stated, per tensor): one bf16 rounding has relative error <= 2^-9; a tensor's gradient passes through `d`
+Tolerance model (stated, per tensor).  One bf16 rounding has relative error <= 2^-9; a tensor's gradient passes through `d`
 bf16 GEMM stages (forward layers up to the loss plus backward layers down to the tensor), errors add in quadrature, so the
-expected relative L2 error is ~ sqrt(d) * 2^-9; the tests allow BF16_C times that.  The oracle is float64 (oracle/torch_cpu.py,
-itself checked against the NumPy tape at 1e-8); reference parity of network values stays UNPINNED (no TF1.15 here)."""
+expected relative L2 error of the ARITHMETIC is ~ sqrt(d) * 2^-9; the tests allow BF16_C times that -- against the float64
+oracle evaluated ON THE SAME bf16-ROUNDED OPERANDS (oracle/torch_cpu.py BF16_OPERANDS / BF16_STORED: the GEMM layers round
+both operands, bf16-resident maps are rounded where they are stored, straight-through gradients).  Against the EXACT float64
+graph a bf16 path additionally flips the sign of the leaky_relu pre-activations that lie within 2^-9 of zero, and a flipped
+unit changes its gradient by 80 %: measured 3-5 % relative L2 per 512-wide layer, 20 % after the 25 layers of the CelebA
+model (r2a, gpurun_out/parity_r2_*.json) -- inherent to bf16 training of a piecewise-linear net, so that comparison is kept
+only as a loose sanity bound (KINK_L2).  Reference parity of network values stays UNPINNED (no TF1.15 here); the oracle is
+oracle/torch_cpu.py in float64, itself checked against the NumPy tape at 1e-8."""
 import json
 import os
 
@@ -25,6 +31,7 @@ pytestmark = pytest.mark.gpu
 
 BF16_EPS = 2.0 ** -9
 BF16_C = 4.0                 # allowed multiple of sqrt(depth) * 2^-9 for the relative L2 error of a gradient tensor
+KINK_L2 = 0.35               # loose bound against the exact (unrounded) float64 graph, see above
 
 
 def _dump(name, table):
@@ -37,10 +44,19 @@ def _dump(name, table):
         pass
 
 
-def _oracle(cfg, P, x, nz, feeds):
-    """float64 losses + gradients of both objectives from the torch-CPU restatement."""
+def _oracle(cfg, P, x, nz, feeds, bf16=False):
+    """float64 losses + gradients of both objectives from the torch-CPU restatement; bf16=True evaluates it on the operands /
+    stored maps the tensor-core path rounds to bf16."""
     tr = torch_cpu.TorchTrainer(cfg, P, dtype=torch.float64)
     xt, nzt, fdt = tr._tensors(x, nz, feeds)
+    torch_cpu.BF16_OPERANDS = torch_cpu.BF16_STORED = bool(bf16)
+    try:
+        return _oracle_eval(cfg, tr, xt, nzt, fdt)
+    finally:
+        torch_cpu.BF16_OPERANDS = torch_cpu.BF16_STORED = False
+
+
+def _oracle_eval(cfg, tr, xt, nzt, fdt):
     o = torch_cpu.losses(cfg, tr.P, xt, nzt, fdt)
     out = {k: float(v.detach()) for k, v in o.items()}
     grads = {}
@@ -86,8 +102,11 @@ def _grad_table(group, want, depth):
     return rows
 
 
-def _assert_table(rows, what):
-    bad = {n: r for n, r in rows.items() if not (r['l2'] <= r['allowed'] and r['mx'] <= 6 * r['allowed'])}
+def _assert_table(rows, what, l2_cap=None):
+    if l2_cap is not None:
+        bad = {n: r for n, r in rows.items() if not r['l2'] <= l2_cap}
+    else:
+        bad = {n: r for n, r in rows.items() if not (r['l2'] <= r['allowed'] and r['mx'] <= 6 * r['allowed'])}
     assert not bad, (what, bad)
 
 
@@ -122,25 +141,32 @@ def test_celeba_engine_bf16_real_widths(H, C, B):
     """(a) celeba_config.json widths, the kernels `bench.py` times for the CelebA legs, as one graph against the oracle."""
     from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
     cfg, P, x, nz, feeds = celeba_case(B, H, C)
-    want, wgrads = _oracle(cfg, P, x, nz, feeds)
+    exact, egrads = _oracle(cfg, P, x, nz, feeds)
+    want, wgrads = _oracle(cfg, P, x, nz, feeds, bf16=True)
     eng = LadderEngine(cfg, B, 'cuda', seed=0)
-    assert eng.outer.enc[1].conv.tma[0] and eng.outer.conv7.tma[0], 'the production TMA path must be the one under test'
+    assert eng.outer.fused and eng.outer.enc[1].conv.tma[0] and eng.outer.conv7.tma[0], \
+        'the production path (TMA-fed GEMMs, fused bf16 norm layers) must be the one under test'
     eng.load_parameters(P)
     eng.set_feeds(**feeds)
     eng.set_noise(**nz)
     xd = torch.tensor(x, device='cuda')
     eng.step_ae(xd, apply=False)
     got = eng.fetch(SCALARS)
-    table = {'scalars': {k: [got[k], want[k]] for k in SCALARS}}
-    rows = _grad_table(eng.ae, wgrads['ae'], _depths(cfg, eng.ae.names()))
+    table = {'scalars': {k: [got[k], want[k], exact[k]] for k in SCALARS}}
+    d_ae = _depths(cfg, eng.ae.names())
+    rows, rows_x = _grad_table(eng.ae, wgrads['ae'], d_ae), _grad_table(eng.ae, egrads['ae'], d_ae)
     eng.step_prior(xd, apply=False)
-    rows_p = _grad_table(eng.prior_g, wgrads['prior'], _depths(cfg, eng.ae.names()[:14] + eng.prior_g.names()))
-    table.update(ae=rows, prior=rows_p)
+    d_pr = _depths(cfg, eng.ae.names()[:14] + eng.prior_g.names())
+    rows_p, rows_px = _grad_table(eng.prior_g, wgrads['prior'], d_pr), _grad_table(eng.prior_g, egrads['prior'], d_pr)
+    table.update(ae=rows, prior=rows_p, ae_vs_exact=rows_x, prior_vs_exact=rows_px)
     _dump('celeba_H%d_C%d' % (H, C), table)
     for k in SCALARS:        # ELBO terms: sums over 49 152 pixels / C latents of bf16-GEMM outputs
-        assert abs(got[k] - want[k]) <= 1e-2 * max(1.0, abs(want[k])), (k, got[k], want[k])
+        assert abs(got[k] - want[k]) <= 2e-3 * max(1.0, abs(want[k])), (k, got[k], want[k])
+        assert abs(got[k] - exact[k]) <= 1e-2 * max(1.0, abs(exact[k])), (k, got[k], exact[k])
     _assert_table(rows, 'ae')
     _assert_table(rows_p, 'prior')
+    _assert_table(rows_x, 'ae vs exact', KINK_L2)
+    _assert_table(rows_px, 'prior vs exact', KINK_L2)
 
 
 def mnist_case(exp, B, seed, **over):
@@ -154,21 +180,28 @@ def test_mnist_engine_bf16_per_tensor_tolerance(exp):
     from test_gpu_engine import make_engine
     B = 8
     cfg, P, x, noises, feeds, epoch = mnist_case(exp, B, 21, compute_dtype='bf16')
-    want, wgrads = _oracle(cfg, P, x, noises[0], feeds)
+    exact, egrads = _oracle(cfg, P, x, noises[0], feeds)
+    want, wgrads = _oracle(cfg, P, x, noises[0], feeds, bf16=True)
     eng = make_engine(cfg, P, feeds, B)
     xd = torch.tensor(x, device='cuda')
     eng.set_noise(**noises[0])
     eng.step_ae(xd, apply=False)
     got = eng.fetch(SCALARS)
-    rows = _grad_table(eng.ae, wgrads['ae'], _depths(cfg, eng.ae.names()))
+    d_ae = _depths(cfg, eng.ae.names())
+    rows, rows_x = _grad_table(eng.ae, wgrads['ae'], d_ae), _grad_table(eng.ae, egrads['ae'], d_ae)
     eng.step_prior(xd, apply=False)
     n_enc = len([n for n in eng.ae.names() if n.startswith('encoder/')])
-    rows_p = _grad_table(eng.prior_g, wgrads['prior'], _depths(cfg, eng.ae.names()[:n_enc] + eng.prior_g.names()))
-    _dump(exp, {'scalars': {k: [got[k], want[k]] for k in SCALARS}, 'ae': rows, 'prior': rows_p})
+    d_pr = _depths(cfg, eng.ae.names()[:n_enc] + eng.prior_g.names())
+    rows_p, rows_px = _grad_table(eng.prior_g, wgrads['prior'], d_pr), _grad_table(eng.prior_g, egrads['prior'], d_pr)
+    _dump(exp, {'scalars': {k: [got[k], want[k], exact[k]] for k in SCALARS}, 'ae': rows, 'prior': rows_p,
+                'ae_vs_exact': rows_x, 'prior_vs_exact': rows_px})
     for k in SCALARS:
-        assert abs(got[k] - want[k]) <= 1e-2 * max(1.0, abs(want[k])), (k, got[k], want[k])
+        assert abs(got[k] - want[k]) <= 2e-3 * max(1.0, abs(want[k])), (k, got[k], want[k])
+        assert abs(got[k] - exact[k]) <= 1e-2 * max(1.0, abs(exact[k])), (k, got[k], exact[k])
     _assert_table(rows, 'ae')
     _assert_table(rows_p, 'prior')
+    _assert_table(rows_x, 'ae vs exact', KINK_L2)
+    _assert_table(rows_px, 'prior vs exact', KINK_L2)
 
 
 def _run_iterations(cfg, P, feeds, B, xd, graphs, noises, n_iter, lrs):
