@@ -379,23 +379,33 @@ def run_ours(args):
     if world > 1:
         try:
             from ladder_latent_data_distribution_modelling_b200 import parallel
-            rng = np.random.default_rng(1234)                        # same queries and components on every rank
+            sharded = {'N': 65536, 'K': 65536, 'components_per_rank': -(-65536 // world),
+                       'exchange': 'one packed [N, 2+D] partial per rank, one all_gather_into_tensor, one combine kernel; the '
+                                   'three launches replayed as one CUDA graph'}
             Ns = 65536
-            tq_s = torch.tensor(rng.normal(size=(Ns, 2)).astype(np.float32), device=dev)
-            tab_s = ops.mixture_pack_diag(rng.normal(size=(Ns, 2)), 1.0, None, dev)
-            sharded = {'N': Ns, 'K': Ns, 'D': 2, 'components_per_rank': -(-Ns // world)}
-            for grad in (False, True):
-                for _ in range(3):
-                    parallel.sharded_mixture_logprob(tq_s, tab_s, group=group, want_grad=grad)
-                barrier()
-                e0.record()
-                for _ in range(5):
-                    parallel.sharded_mixture_logprob(tq_s, tab_s, group=group, want_grad=grad)
-                e1.record()
-                barrier()
-                ts = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
-                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-                sharded['pairs_per_s_fwd_grad' if grad else 'pairs_per_s_fwd'] = Ns * Ns / (float(ts.item()) * 1e-3)
+            for D in (2, 32, 64):                                    # BASELINE.json configs[2]: D = 2 / 32 / 64
+                rng = np.random.default_rng(1234 + D)                # same queries and components on every rank
+                sc = 1.0 if D == 2 else 1.0 / np.sqrt(D / 2.0)
+                tq_s = torch.tensor((rng.normal(size=(Ns, D)) * sc).astype(np.float32), device=dev)
+                tab_s = ops.mixture_pack_diag(rng.normal(size=(Ns, D)) * sc, 1.0, None, dev)
+                for grad in (False, True):
+                    sm = parallel.ShardedMixture(tab_s, Ns, group=group, want_grad=grad, graph=not args.no_graphs)
+                    for _ in range(3):
+                        sm(tq_s)
+                    barrier()
+                    reps = 5 if D == 2 else 2
+                    e0.record()
+                    for _ in range(reps):
+                        sm(tq_s)
+                    e1.record()
+                    barrier()
+                    ts = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+                    dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+                    key = 'pairs_per_s_fwd_grad' if grad else 'pairs_per_s_fwd'
+                    sharded[key if D == 2 else '%s_D%d' % (key, D)] = Ns * Ns / (float(ts.item()) * 1e-3)
+                    sharded['graph'] = bool(sm.use_graph)
+                    del sm
+            sharded['D'] = 2
         except Exception as e:                                       # noqa: BLE001
             sharded = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:200] if str(e) else '')}
 

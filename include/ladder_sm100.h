@@ -95,6 +95,14 @@ int ladder_mixture_diag_param_grad(const float* t, long long N, int D, const flo
 /* (max, sum-exp) combine of P shard partials laid out [P,N] (+ [P,N,D] gradients). */
 int ladder_mixture_combine(const float* m_parts, const float* s_parts, const float* g_parts, int P,
                            long long N, int D, float* logp, float* grad_t, cudaStream_t stream);
+/* One-exchange form of the component-sharded evaluation: the shard partial is written as ONE packed buffer
+ * pack [N, W], row n = (m, s, unnormalised g_0 .. g_{D-1}), W = 2 + D (W = 2 when with_grad == 0), so the ranks trade a single
+ * all-gather; ladder_mixture_combine_packed reduces parts [P, N, W] (rank-major) to logp [N] (+ grad_t [N, D]).            */
+int ladder_mixture_logprob_packed(const float* t, long long N, int D, const float* table, int K, int mode, float iso_scale,
+                                  float ref_log2, float* pack, int with_grad, void* workspace, size_t workspace_bytes,
+                                  cudaStream_t stream);
+int ladder_mixture_combine_packed(const float* parts, int P, long long N, int D, int with_grad, float* logp /*nullable*/,
+                                  float* grad_t /*nullable*/, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * K1/K2  conv2d + dense as implicit GEMM.  x NHWC [B,H,W,Cin], w HWIO [KH,KW,Cin,Cout],

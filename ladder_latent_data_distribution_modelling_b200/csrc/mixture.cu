@@ -228,6 +228,7 @@ struct MixArgs {
   float iso_scale;       // a' for MODE 0 (queries are pre-scaled in-kernel)
   float ref_log2;        // M
   const float* ref_dev;  // null, or M on the device (tables packed by ladder_mixture_pack_diag_device)
+  long long pstride;     // 0, or row stride of a PACKED shard partial: m_out / s_out / grad all point into one [N, 2 + D] buffer
 };
 
 template <int D, int MODE, int R, bool GRAD>
@@ -367,11 +368,12 @@ __global__ void __launch_bounds__(MIX_THREADS) mix_kernel(MixArgs a) {
       }
     }
     if (a.s_out != nullptr) {           // sharded: emit the partial (m, s) and the unnormalised gradient
-      a.m_out[n] = frame * LN2;
-      a.s_out[n] = s;
+      const long long ms = a.pstride > 0 ? n * a.pstride : n, gs = a.pstride > 0 ? n * a.pstride : n * D;
+      a.m_out[ms] = frame * LN2;
+      a.s_out[ms] = s;
       if constexpr (GRAD) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) a.grad[n * D + d] = gcoef * g[d];
+        for (int d = 0; d < D; ++d) a.grad[gs + d] = gcoef * g[d];
       }
     } else {
       if (a.logp != nullptr) a.logp[n] = LN2 * (frame + log2f(s));
@@ -577,6 +579,32 @@ static int param_grad_launch(const float* t, long long N, const float* mean, con
   return check_launch("mixture diag param-grad kernel");
 }
 
+// the same combine on PACKED partials parts [P, N, W], row = (m, s, g_0 .. g_{D-1}), W = 2 + D (2 without gradient)
+__global__ void mix_combine_packed_kernel(const float* __restrict__ parts, int P, long long N, int D, int W,
+                                          float* __restrict__ logp, float* __restrict__ grad) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float mx = -INFINITY;
+  for (int p = 0; p < P; ++p) mx = fmaxf(mx, __ldg(parts + ((size_t)p * N + n) * W));
+  float tot = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const float* r = parts + ((size_t)p * N + n) * W;
+    tot += __ldg(r + 1) * __expf(__ldg(r) - mx);
+  }
+  if (logp != nullptr) logp[n] = mx + logf(tot);
+  if (grad != nullptr) {
+    const float inv = 1.f / tot;
+    for (int d = 0; d < D; ++d) {
+      float acc = 0.f;
+      for (int p = 0; p < P; ++p) {
+        const float* r = parts + ((size_t)p * N + n) * W;
+        acc += __ldg(r + 2 + d) * __expf(__ldg(r) - mx);
+      }
+      grad[n * D + d] = acc * inv;
+    }
+  }
+}
+
 // (m, s[, g]) combine across P shards -> logp (and normalised gradient)
 __global__ void mix_combine_kernel(const float* __restrict__ m, const float* __restrict__ s,
                                    const float* __restrict__ g, int P, long long N, int D,
@@ -712,7 +740,8 @@ size_t ladder_mixture_workspace_bytes(long long N, int K, int D, int mode, int w
 
 static int mixture_logprob_impl(const float* t, long long N, int D, const float* table, int K, int mode,
                                 float iso_scale, float ref_log2, const float* ref_dev, float* logp, float* grad_t,
-                                float* m_out, float* s_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                                float* m_out, float* s_out, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                                long long pstride = 0) {
   LADDER_REQUIRE(N >= 0 && K >= 1, "mixture_logprob: need N >= 0, K >= 1 (N=%lld K=%d)", N, K);
   LADDER_REQUIRE(mode >= 0 && mode <= 2, "mixture_logprob: mode must be 0 (iso), 1 (diag) or 2 (full)");
   LADDER_REQUIRE((m_out == nullptr) == (s_out == nullptr), "mixture_logprob: m_out and s_out go together");
@@ -731,6 +760,7 @@ static int mixture_logprob_impl(const float* t, long long N, int D, const float*
   off = (off + 255) / 256 * 256;
   a.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + off);
   a.N = N; a.K = K; a.kc = p.kc; a.k_per_split = p.k_per_split; a.iso_scale = iso_scale; a.ref_log2 = ref_log2; a.ref_dev = ref_dev;
+  a.pstride = pstride;
   return grad ? mix_dispatch<true>(D, mode, a, p, stream) : mix_dispatch<false>(D, mode, a, p, stream);
 }
 
@@ -777,6 +807,26 @@ int ladder_mixture_diag_param_grad(const float* t, long long N, int D, const flo
     case 64: return param_grad_launch<64>(t, N, mean_dev, std_dev, K, logp, coef, dmean, dstd, stream);
     default: return fail(LADDER_ERR_ARG, "mixture_diag_param_grad: unsupported latent dim %d (1,2,3,4,8,16,32,64)", D);
   }
+}
+
+int ladder_mixture_logprob_packed(const float* t, long long N, int D, const float* table, int K, int mode, float iso_scale,
+                                  float ref_log2, float* pack, int with_grad, void* workspace, size_t workspace_bytes,
+                                  cudaStream_t stream) {
+  LADDER_REQUIRE(pack != nullptr, "mixture_logprob_packed: null output");
+  const long long W = with_grad ? 2 + D : 2;
+  return mixture_logprob_impl(t, N, D, table, K, mode, iso_scale, ref_log2, nullptr, nullptr, with_grad ? pack + 2 : nullptr, pack,
+                              pack + 1, workspace, workspace_bytes, stream, W);
+}
+
+int ladder_mixture_combine_packed(const float* parts, int P, long long N, int D, int with_grad, float* logp, float* grad_t,
+                                  cudaStream_t stream) {
+  LADDER_REQUIRE(P >= 1 && N >= 0, "mixture_combine_packed: bad sizes");
+  if (N == 0) return LADDER_OK;
+  LADDER_REQUIRE(parts && (logp || grad_t), "mixture_combine_packed: null pointer");
+  LADDER_REQUIRE(grad_t == nullptr || with_grad, "mixture_combine_packed: the partials carry no gradient");
+  const int bs = 256;
+  mix_combine_packed_kernel<<<(unsigned)ceil_div64(N, bs), bs, 0, stream>>>(parts, P, N, D, with_grad ? 2 + D : 2, logp, grad_t);
+  return check_launch("mixture combine (packed)");
 }
 
 int ladder_mixture_combine(const float* m_parts, const float* s_parts, const float* g_parts, int P,

@@ -204,6 +204,35 @@ def mixture_logprob(t, tab, want_grad=False, partial=False, out=None, exact=Fals
     return (logp, grad) if want_grad else logp
 
 
+def mixture_logprob_packed(t, tab, pack, want_grad=False):
+    """Shard partial of log p(t) under `tab` as ONE packed buffer pack [N, 2 + D] (or [N, 2]): row = (m, s, unnormalised g)."""
+    _f32(t, 't'), _f32(pack, 'pack')
+    N, D = t.shape
+    if tuple(pack.shape) != (N, 2 + D if want_grad else 2):
+        raise RuntimeError('mixture_logprob_packed: pack must be [N, %d]' % (2 + D if want_grad else 2))
+    if N == 0:
+        return pack
+    nbytes = _L().ladder_mixture_workspace_bytes(N, tab.K, D, tab.mode, int(want_grad))
+    ws = _workspace(t.device, nbytes, 'mixture')
+    _lib.check(_L().ladder_mixture_logprob_packed(_p(t), N, D, _p(tab.table), tab.K, tab.mode, tab.iso_scale, tab.ref_log2,
+                                                  _p(pack), int(want_grad), _p(ws), ws.numel(), _stream()),
+               'mixture_logprob_packed')
+    return pack
+
+
+def mixture_combine_packed(parts, D, want_grad, logp=None, grad=None):
+    """(max, sum-exp) combine of packed shard partials parts [P, N, W] -> logp [N] (and d log p / d t [N, D])."""
+    P, N, W = parts.shape
+    dev = parts.device
+    if logp is None:
+        logp = torch.empty(N, device=dev, dtype=torch.float32)
+    if want_grad and grad is None:
+        grad = torch.empty(N, D, device=dev, dtype=torch.float32)
+    _lib.check(_L().ladder_mixture_combine_packed(_p(_f32(parts)), P, N, D, int(want_grad), _p(logp), _p(grad if want_grad else None),
+                                                  _stream()), 'mixture_combine_packed')
+    return (logp, grad) if want_grad else logp
+
+
 def mixture_combine(m_parts, s_parts, g_parts=None):
     """(max, sum-exp) combine of shard partials stacked on dim 0."""
     P, N = m_parts.shape

@@ -142,8 +142,12 @@ def _shard_worker(rank, world, port, out):
     t = torch.tensor((rng.normal(size=(N, D)) * 2).astype(np.float32), device='cuda:%d' % rank)
     tab = ops.mixture_pack_diag(m, 0.5, None, 'cuda:%d' % rank)
     lp, g = parallel.sharded_mixture_logprob(t, tab, want_grad=True)
+    sm = parallel.ShardedMixture(tab, N, group=dist.group.WORLD, want_grad=True)       # one exchange, graph-captured NCCL
+    for _ in range(2):
+        lp1, g1 = sm(t)
     if rank == 0:
-        np.savez(out, lp=lp.cpu().numpy(), g=g.cpu().numpy())
+        np.savez(out, lp=lp.cpu().numpy(), g=g.cpu().numpy(), lp1=lp1.cpu().numpy(), g1=g1.cpu().numpy(),
+                 graph=np.array(sm.use_graph))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -164,3 +168,6 @@ def test_component_sharded_mixture_two_gpus(tmp_path):
     lp, g = ops.mixture_logprob(t, tab, want_grad=True)
     np.testing.assert_allclose(r['lp'], lp.cpu().numpy(), rtol=1e-5, atol=1e-4)
     np.testing.assert_allclose(r['g'], g.cpu().numpy(), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(r['lp1'], lp.cpu().numpy(), rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(r['g1'], g.cpu().numpy(), rtol=1e-3, atol=1e-3)
+    assert bool(r['graph'])

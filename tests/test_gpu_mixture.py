@@ -211,3 +211,40 @@ def test_vamp_prior_device_pack_and_param_grads(ops, D):
     np.testing.assert_allclose(ds.cpu().numpy(), sv.g, rtol=1e-3, atol=1e-5)
     tab2 = ops.mixture_pack_diag_device(md * 0 + 1, sd, tab)         # repack in place reuses the table
     assert tab2 is tab
+
+
+@pytest.mark.parametrize('D,mode', [(2, 'iso'), (2, 'full'), (16, 'diag'), (32, 'iso')])
+@pytest.mark.parametrize('want_grad', [False, True])
+def test_packed_shard_partials_combine_to_the_full_answer(D, mode, want_grad):
+    """One-exchange form of the component-sharded evaluation with the exchange done in place on one GPU: the
+    packed (m, s, g) partials of 3 component shards, stacked rank-major like the all-gather delivers them, combine to the
+    unsharded answer; `ShardedMixture` (world 1, CUDA-graph replay) returns the same."""
+    import torch
+    from ladder_latent_data_distribution_modelling_b200 import ops, parallel
+    rng = np.random.default_rng(17 + D)
+    K, N = 301, 1000
+    mean = rng.normal(size=(K, D)) * 1.5
+    if mode == 'full':
+        a = rng.normal(size=(K, D, D))
+        tab = ops.mixture_pack_full(mean, a @ a.transpose(0, 2, 1) * 0.3 + 0.1 * np.eye(D), rng.uniform(0.1, 1, size=K), 'cuda')
+    elif mode == 'diag':
+        tab = ops.mixture_pack_diag(mean, rng.uniform(0.5, 1.5, size=(K, D)), rng.uniform(0.1, 1, size=K), 'cuda')
+    else:
+        tab = ops.mixture_pack_diag(mean, 0.8, None, 'cuda')
+    t = torch.tensor(rng.normal(size=(N, D)).astype(np.float32) * 1.5, device='cuda')
+    t[:5] += 200.0                                              # far queries: the exact rescue path of every shard
+    full = ops.mixture_logprob(t, tab, want_grad=want_grad, exact=True)
+    W = 2 + D if want_grad else 2
+    parts = torch.stack([ops.mixture_logprob_packed(t, tab.shard(r, 3), torch.empty(N, W, device='cuda'), want_grad)
+                         for r in range(3)])
+    got = ops.mixture_combine_packed(parts, D, want_grad)
+    lp, lp_full = (got[0], full[0]) if want_grad else (got, full)
+    np.testing.assert_allclose(lp.cpu().numpy(), lp_full.cpu().numpy(), rtol=2e-5, atol=2e-4)
+    if want_grad:
+        np.testing.assert_allclose(got[1].cpu().numpy(), full[1].cpu().numpy(), rtol=2e-3, atol=2e-3)
+    sm = parallel.ShardedMixture(tab, N, want_grad=want_grad)
+    for _ in range(2):                                          # capture, then replay
+        out = sm(t)
+    lp2 = out[0] if want_grad else out
+    np.testing.assert_allclose(lp2.cpu().numpy(), lp_full.cpu().numpy(), rtol=2e-5, atol=2e-4)
+    assert sm.use_graph and sm._graph is not None
