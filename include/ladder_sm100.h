@@ -399,6 +399,21 @@ int ladder_philox_normal(float* out0, int outer0, int inner0, float* out1, int o
                          int inner2, int B, int B_global, int b_off, unsigned long long seed, const int* draw_ctr_dev,
                          cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Hyper-prior FITTING: one fused E + M pass of EM / variational inference for a full-covariance mixture,
+ * replacing the per-sample work of sklearn BayesianGaussianMixture.fit / GaussianMixture.fit that the reference runs on the
+ * host once per epoch (codes/base.py:93-106, 681-789, 988-1010).  params [K, ladder_gmm_param_stride(D)]: per component
+ * (mean[D] | P upper-triangular row-major [D(D+1)/2] | c) with e_nk = c_k - 1/2 ||(x_n - mean_k) P_k||^2; r_nk = softmax_k e_nk
+ * (hard = 1: one-hot argmax).  moments [K, ladder_gmm_moment_stride(D)] = (S0 | S1[D] | S2 upper[D(D+1)/2]) about the CURRENT
+ * means; scalars2 = (sum_n logsumexp_k e_nk, sum_nk r_nk log r_nk).  Both outputs are zeroed by the call.  D in {1,2,3,4,8,16}. */
+int ladder_gmm_param_stride(int D);
+int ladder_gmm_moment_stride(int D);
+int ladder_gmm_em_step(const float* x, long long N, int D, const float* params, int K, int hard, float* moments, float* scalars2,
+                       cudaStream_t stream);
+/* logp [N] = logsumexp_k e_nk (score_samples), labels [N] = argmax_k e_nk (predict); either may be NULL */
+int ladder_gmm_score(const float* x, long long N, int D, const float* params, int K, float* logp, int* labels,
+                     cudaStream_t stream);
+
 /* Diagnostic: saturate one pipe (kind 0 = FP32 FFMA, 1 = SFU MUFU.EX2).  Each of `blocks`
  * CTAs of 256 threads issues iters*64 dependent-chain ops per thread (8 chains).  Used by
  * bench.py to measure the pipe peaks the mixture kernel is compared against.            */

@@ -174,7 +174,10 @@ class BaseTrain:
             allr[self.rank] = local
             dist.all_reduce(allr, op=dist.ReduceOp.SUM, group=self.model.dist_group)
             local = allr.permute(1, 0, 2, 3).reshape(n_batch, -1, local.shape[-1])     # batch i = ranks 0..P-1 in order
-        return local.reshape(-1, local.shape[-1]).cpu().numpy().astype(np.float64)
+        flat = local.reshape(-1, local.shape[-1])
+        if hasattr(self.model.GM_prior_training, '_pass'):          # GPU estimator (host/gm_fit.py): the samples stay on the device
+            return flat.contiguous()
+        return flat.cpu().numpy().astype(np.float64)
 
     def _fit_shared(self, gm, samples):
         """Fit `gm` (a scikit-learn mixture, as in the reference) on rank 0 and hand the fitted means / covariances /
@@ -206,7 +209,7 @@ class BaseTrain:
         return idx
 
     def fit_GMM_VI(self, iterator, mode="fast", space="z"):
-        from sklearn.mixture import BayesianGaussianMixture, GaussianMixture
+        BayesianGaussianMixture, GaussianMixture = self.model.gm_classes()
         Bg = self.config['batch_size'] * self.world
         if mode == "fast":
             samples = self._collect_samples(iterator, 2000 // Bg + 1, space)

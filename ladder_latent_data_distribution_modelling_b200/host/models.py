@@ -100,8 +100,19 @@ class BaseModel:
         return self.iterator.get_next()
 
     # -- hyper-prior (base.py:88-124)
-    def define_GM_prior(self):
+    def gm_classes(self):
+        """(BayesianGaussianMixture, GaussianMixture) -- the GPU estimators of host/gm_fit.py (same constructor keywords and
+        fitted attributes, sample passes in the fused E+M kernel) unless the optional config key `gm_fit` says "sklearn" or
+        the mixture's dimension is outside the kernel's range (then scikit-learn on the host, as in the reference)."""
+        D = int(self.config['representation_size'] if self.config['prior'] == 'ours' else self.config['code_size'])
+        if self.config.get('gm_fit', 'gpu') == 'gpu' and D in (1, 2, 3, 4, 8, 16):
+            from .gm_fit import GpuBayesianGaussianMixture, GpuGaussianMixture
+            return GpuBayesianGaussianMixture, GpuGaussianMixture
         from sklearn.mixture import BayesianGaussianMixture, GaussianMixture
+        return BayesianGaussianMixture, GaussianMixture
+
+    def define_GM_prior(self):
+        BayesianGaussianMixture, GaussianMixture = self.gm_classes()
         n_mixtures = self.config['n_mixtures']
         if self.config['prior'] == 'ours':
             self.GM_prior_training = BayesianGaussianMixture(

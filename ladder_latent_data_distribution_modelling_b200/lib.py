@@ -108,6 +108,10 @@ SIGNATURES = {
     'ladder_increment': (C.c_int, [ptr, stream_t]),
     'ladder_philox_normal': (C.c_int, [ptr, C.c_int, C.c_int, ptr, C.c_int, C.c_int, ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_ulonglong, ptr, stream_t]),
+    'ladder_gmm_param_stride': (C.c_int, [C.c_int]),
+    'ladder_gmm_moment_stride': (C.c_int, [C.c_int]),
+    'ladder_gmm_em_step': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, C.c_int, C.c_int, ptr, ptr, stream_t]),
+    'ladder_gmm_score': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, C.c_int, ptr, ptr, stream_t]),
     'ladder_pipe_peak_launch': (C.c_int, [C.c_int, C.c_int, C.c_int, ptr, stream_t]),
     'ladder_mixture_tc_image_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'ladder_mixture_tc_pack_iso': (C.c_int, [c_double_p, C.c_double, c_double_p, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p]),

@@ -99,19 +99,21 @@ def _conv(P, scope, idx, x, stride=1, padding='same', act=None):
     return act(y) if act is not None else y
 
 
-def batch_norm_train(x, gamma, beta, eps=1e-3):
-    """tf.layers.batch_normalization(training=True): biased batch statistics over (N, H, W) (models.py:398-460)."""
-    mean = x.mean((0, 1, 2), keepdim=True)
-    xc = x - mean
-    var = (xc * xc).mean((0, 1, 2), keepdim=True)
-    return xc / torch.sqrt(var + eps) * gamma + beta
+def batch_norm_train(x, gamma, beta, eps=1e-3, stats_of=None):
+    """tf.layers.batch_normalization(training=True): biased batch statistics over (N, H, W) (models.py:398-460).
+    stats_of (bf16 emulation only): the tensor whose moments are used -- the engine's GEMM epilogue accumulates them from the
+    fp32 accumulators, i.e. from the conv output BEFORE it is rounded to bf16 for storage."""
+    sx = x if stats_of is None else stats_of
+    mean = sx.mean((0, 1, 2), keepdim=True)
+    var = ((sx - mean) ** 2).mean((0, 1, 2), keepdim=True)
+    return (x - mean) / torch.sqrt(var + eps) * gamma + beta
 
 
-def instance_norm(x, eps=1e-6):
+def instance_norm(x, eps=1e-6, stats_of=None):
     """tf.contrib.layers.instance_norm(center=False, scale=False): per-sample, per-channel moments over (H, W)."""
-    mean = x.mean((1, 2), keepdim=True)
-    xc = x - mean
-    return xc / torch.sqrt((xc * xc).mean((1, 2), keepdim=True) + eps)
+    sx = x if stats_of is None else stats_of
+    mean = sx.mean((1, 2), keepdim=True)
+    return (x - mean) / torch.sqrt(((sx - mean) ** 2).mean((1, 2), keepdim=True) + eps)
 
 
 def _legacy_matrix(n_in, n_out, dtype):
@@ -142,9 +144,9 @@ def encoder_celeba(cfg, P, x):
     """models.py:392-464"""
     h = x
     for i in range(6):
-        h = _st(_conv(P, 'encoder', i, h, 2 if i < 5 else 1, 'same' if i < 5 else 'valid'))
+        c = _conv(P, 'encoder', i, h, 2 if i < 5 else 1, 'same' if i < 5 else 'valid')
         bn = 'encoder/batch_normalization' if i == 0 else 'encoder/batch_normalization_%d' % i
-        h = _st(leaky(batch_norm_train(h, P[bn + '/gamma'], P[bn + '/beta'])))
+        h = _st(leaky(batch_norm_train(_st(c), P[bn + '/gamma'], P[bn + '/beta'], stats_of=c if BF16_STORED else None)))
     return h.reshape(h.shape[0], -1)
 
 
@@ -156,12 +158,17 @@ def decoder_celeba(cfg, P, z):
     for i in range(1, 9):
         dl = _dense(P, 'decoder/dense_%d' % i, dl, leaky)
     h = _st(resize_bilinear_legacy(_conv(P, 'decoder', 0, encoded.reshape(-1, 1, 1, H)), 2, 2))
-    h = _st(leaky(style_mod(P, instance_norm(_st(_conv(P, 'decoder', 1, h))), dl, 0)))
-    h = leaky(style_mod(P, instance_norm(_st(_conv(P, 'decoder', 2, h))), dl, 1))
+    def in_block(idx, num, x, epilogue_stats):
+        # conv -> instance norm -> style -> leaky; statistics out of the GEMM epilogue (fp32 accumulators) for maps of a
+        # multiple of 128 pixels, from the stored bf16 map for the 2x2 ones
+        c = _conv(P, 'decoder', idx, x)
+        return leaky(style_mod(P, instance_norm(_st(c), stats_of=c if (BF16_STORED and epilogue_stats) else None), dl, num))
+    h = _st(in_block(1, 0, h, False))
+    h = in_block(2, 1, h, False)
     h = _st(_conv(P, 'decoder', 3, _st(resize_bilinear_legacy(h, 8, 8)), act=leaky))
-    h = leaky(style_mod(P, instance_norm(_st(_conv(P, 'decoder', 4, _st(resize_bilinear_legacy(h, 16, 16))))), dl, 2))
+    h = in_block(4, 2, _st(resize_bilinear_legacy(h, 16, 16)), True)
     h = _st(_conv(P, 'decoder', 5, _st(resize_bilinear_legacy(h, 32, 32)), act=leaky))
-    h = leaky(style_mod(P, instance_norm(_st(_conv(P, 'decoder', 6, _st(resize_bilinear_legacy(h, 64, 64))))), dl, 3))
+    h = in_block(6, 3, _st(resize_bilinear_legacy(h, 64, 64)), True)
     h = _st(_conv(P, 'decoder', 7, _st(resize_bilinear_legacy(h, 128, 128)), act=leaky))
     return _conv(P, 'decoder', 8, h)
 

@@ -243,13 +243,21 @@ def test_celeba_fused_engine_matches_unfused(monkeypatch):
         eng.load_parameters(P); eng.set_feeds(**feeds); eng.set_noise(**nz)
         eng.step_ae(xd, apply=False)
         out.append((eng.scalars.cpu().numpy().copy(), {n: t.clone() for n, t in eng.named_gradients()}))
+    # Two bf16 paths that round different tensors agree like the float64 oracle agrees with itself when its operands are
+    # rounded (leaky_relu kink flips, 2x2 instance norms -- see tests/test_gpu_parity_r2.py): per tensor, that response `sens`
+    # (float64 vs float64, no kernel involved) calibrates the bound.
+    from test_gpu_parity_r2 import _oracle
+    exact, eg = _oracle(cfg, P, x, nz, feeds)
+    emu, mg = _oracle(cfg, P, x, nz, feeds, bf16=True)
     from ladder_latent_data_distribution_modelling_b200 import ops
-    for name, i in ops.O.items():
-        a, b = out[0][0][i], out[1][0][i]
-        assert abs(a - b) <= 1e-2 * max(1.0, abs(b)), (name, a, b)
+    for name in ('loss_ae', 'elbo', 'sigma', 'entropy_z', 'crossEntropy_prior', 'elbo_prior'):
+        a, b = out[0][0][ops.O[name]], out[1][0][ops.O[name]]
+        assert abs(a - b) <= 5e-3 * max(1.0, abs(b)) + 3 * abs(exact[name] - emu[name]), (name, a, b, exact[name], emu[name])
     for n in out[0][1]:
         if not (n.startswith('encoder') or n.startswith('decoder')):
             continue
-        a, b = out[0][1][n].double(), out[1][1][n].double()
-        # the two paths round different tensors to bf16, so (leaky_relu kinks) they agree like two bf16 runs do
-        assert (a - b).norm() <= 0.3 * b.norm() + 1e-6 * float(b.numel()) ** 0.5, (n, float((a - b).norm() / (b.norm() + 1e-30)))
+        a, b = out[0][1][n].double().cpu().numpy(), out[1][1][n].double().cpu().numpy()
+        e, m = np.asarray(eg['ae'][n]).reshape(a.shape), np.asarray(mg['ae'][n]).reshape(a.shape)
+        sens = np.linalg.norm(e - m) / (np.linalg.norm(e) + 1e-30)
+        assert np.linalg.norm(a - b) <= (0.08 + 2.0 * sens) * np.linalg.norm(b) + 1e-6 * np.sqrt(b.size), \
+            (n, float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)), float(sens))

@@ -88,19 +88,24 @@ def _compare(r, one, exp):
     # runs do (2^-9 per activation plus the leaky_relu kink flips it causes, see test_gpu_parity_r2); a wrong statistic count or
     # a gradient counted twice is an O(1) error and still fails
     st, gt = (2e-5, 2e-4) if exp != 'celeba_bf16' else (1e-2, 0.3)
+    # sub-steps after the first see weights that went through clip + Adam, whose first steps are sign-like: entries whose true
+    # gradient is zero (CelebA: every conv bias in front of a batch norm) move by +-lr on rounding noise alone
+    st_after = {'mnist_digit': 2e-5, 'celeba_fp32': 1e-3, 'celeba_bf16': 5e-2}[exp]
     for name in STEPS:
         a, b = one['scal_' + name], r['scal_' + name]
+        tol = st if name == 'ae' else st_after
         for k, i in ops.O.items():
-            assert abs(a[i] - b[i]) <= st * max(1.0, abs(a[i])), (name, k, a[i], b[i])
+            assert abs(a[i] - b[i]) <= tol * max(1.0, abs(a[i])), (name, k, a[i], b[i])
     for k in ('g_ae', 'g_prior'):
         if exp == 'celeba_bf16':
             assert np.linalg.norm(one[k] - r[k]) <= gt * np.linalg.norm(one[k]), (k, np.linalg.norm(one[k] - r[k]) / np.linalg.norm(one[k]))
-        else:
-            assert np.abs(one[k] - r[k]).max() <= gt * np.abs(one[k]).max(), k
+        else:                                   # g_prior is taken in the third sub-step, after two updates (see above)
+            tol = gt if (k == 'g_ae' or exp == 'mnist_digit') else 2e-2
+            assert np.abs(one[k] - r[k]).max() <= tol * np.abs(one[k]).max(), (k, np.abs(one[k] - r[k]).max() / np.abs(one[k]).max())
     if exp != 'celeba_bf16':
         for k in ('p_ae', 'p_prior'):          # after clip + Adam: sign-like first step, compare the bulk
             frac = (np.abs(one[k] - r[k]) > 1e-5).mean()
-            assert frac <= 5e-3, (k, frac)
+            assert frac <= (5e-3 if exp == 'mnist_digit' else 5e-2), (k, frac)
 
 
 @pytest.mark.parametrize('exp', ['mnist_digit', 'celeba_fp32', 'celeba_bf16'])
