@@ -26,11 +26,26 @@ sys.path.insert(0, ROOT)
 METRIC = 'train imgs/sec (ELBO fwd+bwd, 4 sub-steps per image batch)'
 
 
-# dram bytes (read+write) per launch of the roofline kernel from the committed `ncu --set full` capture (profiles/)
-TRAFFIC = {('mnist_fashion', 'bf16', 1024): 33.90e6 + 84.29e6,             # fprop: profiles/r1d_ncu_dominant_kernel.md (read + write)
-           ('mnist_fashion', 'bf16', 1024, 'dgrad'): 168.10e6 + 25.31e6}   # dgrad: profiles/r1g_ncu_dgrad_kernel.md
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a roofline kernel, read from THIS round's committed ncu
+    summary (profiles/ncu_traffic.json: {key: {"bytes": ..., "source": "profiles/<capture summary>"}}, written by
+    scripts/ncu_traffic.py from the `ncu --set full` report); None when the round has no capture of that kernel -- never a
+    constant copied from an older build."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    try:
+        with open(p) as f:
+            return json.load(f).get(key, {}).get('bytes')
+    except (OSError, ValueError):
+        return None
+
 
 WORKLOAD = 'mnist_fashion'       # set from --workload; the default is BASELINE.json configs[1]
+
+
+def workload_string(batch, epoch):
+    """config.workload of BOTH arms (the driver compares them verbatim)."""
+    return ('codes/%s_config.json @ batch %d per GPU, epoch %d (all 4 sub-steps, 50-component hyper-prior, L=100 MC samples)'
+            % (WORKLOAD, batch, epoch))
 
 
 def load_config(batch):
@@ -168,13 +183,14 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = load_config(args.batch)
-    steps = max(1, min(args.steps, 3))
-    base = cpu_reference(cfg, args.cpu_sample, steps, 1)
+    # --steps / --warmup are honoured as given; each step is ONE iteration on a bounded sample of the workload (cpu_sample
+    # images, default the full 1024-image batch: ~1.3 s per step on 16 cores), so the default run ends within a minute
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    base = cpu_reference(cfg, args.cpu_sample, steps, warmup)
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'imgs/s', 'n_gpus': args.gpus,
-            'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * base['seconds'] / steps, 'higher_is_better': True,
+            'steps': steps, 'warmup': warmup, 'ms_per_step': 1e3 * base['seconds'] / steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'codes/%s_config.json @ batch %d (CPU arm times a %d-image sample)'
-                                   % (WORKLOAD, args.batch, args.cpu_sample)},
+            'config': {'workload': workload_string(args.batch, cfg['sg_pretraining'] + 1)},
             'cpu_baseline': {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
             'e2e': {'value': base['value'], 'unit': 'imgs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -182,20 +198,28 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------ GPU arm
 def celeba_leg(args, dev, rank, world, group, B, code_size=None, steps=None):
-    """Same 4-sub-step iteration on codes/celeba_config.json (128x128x3 conv VAE + prior VAE + hyper-prior), synthetic
-    batches of B images per GPU resident in HBM; max over ranks of the CUDA-event time.  code_size overrides the JSON
+    """Same 4-sub-step iteration on codes/celeba_config.json (128x128x3 conv VAE + prior VAE + hyper-prior) through the
+    reference-facing model / trainer classes: `value` with synthetic batches of B images per GPU resident in HBM, `e2e` through
+    `CelebATrainer_joint_training.train_step_ae / train_step_prior` on pinned HOST batches (H2D copy + loss read-back inside the
+    timed region), max over ranks of the CUDA-event time, its own clock window, and (rank 0) the roofline of its dominant GEMM
+    (decoder/conv2d_7: fprop / dgrad / wgrad) and of its heaviest HBM-bound pass.  code_size overrides the JSON
     (BASELINE.json configs[4]: latent dim 128 at batch 512 per GPU)."""
+    import contextlib
     import torch
     import torch.distributed as dist
-    from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
+    from ladder_latent_data_distribution_modelling_b200 import ops
+    from ladder_latent_data_distribution_modelling_b200.host import models as hmodels, trainers as htrainers
     with open(os.path.join(ROOT, 'codes', 'celeba_config.json')) as f:
         cfg = json.load(f)
-    cfg.update(batch_size=B, seed=1234, compute_dtype=args.dtype)
+    cfg.update(batch_size=B, seed=1234, compute_dtype=args.dtype, synthetic=True, synthetic_pool=B)
+    cfg['checkpoint_dir'] = cfg['result_dir'] = tempfile.mkdtemp() + '/'
     if code_size:
         cfg['code_size'] = int(code_size)
     if args.no_graphs:
         cfg['cuda_graphs'] = False
-    eng = LadderEngine(cfg, B, dev, seed=4321 + rank, dist_group=group)
+    with contextlib.redirect_stdout(sys.stderr):
+        model = hmodels.CelebAModel_densenet(cfg, device=dev, dist_group=group)
+    eng = model.engine
     if world > 1:
         for g in eng.groups.values():
             dist.broadcast(g.param, 0)
@@ -212,29 +236,130 @@ def celeba_leg(args, dev, rank, world, group, B, code_size=None, steps=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        w0 = time.time()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), (w0, time.time())
+
+    def iteration(i):
+        for name in ('ae', 'sigma', 'prior', 'inner_sigma'):
+            eng.run_step(name, pool[i % 4])
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
     for i in range(3):
-        for name in ('ae', 'sigma', 'prior', 'inner_sigma'):
-            eng.run_step(name, pool[i % 4])
-    sync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        for name in ('ae', 'sigma', 'prior', 'inner_sigma'):
-            eng.run_step(name, pool[i % 4])
-    e1.record()
-    sync()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+        iteration(i)
+    ms, win = timed(iteration, steps)
+    windows = [win]
     fl = 3 * 10.04e9          # algorithmic fwd+bwd flop per image (one fused pass; the 4-sub-step protocol runs more)
     v = B * world * steps / (ms * 1e-3)
     out = {'workload': 'codes/celeba_config.json @ batch %d per GPU (128x128x3, H=512, C=%d), all 4 sub-steps' % (B, cfg['code_size']),
            'value': v, 'unit': 'imgs/s', 'ms_per_step': ms / steps, 'steps': steps, 'warmup': 3, 'global_batch': B * world,
-           'algorithmic_tflops': v * fl / 1e12 / world, 'loss_ae': eng.fetch(['loss_ae'])['loss_ae']}
+           'algorithmic_tflops': v * fl / 1e12 / world, 'fused_norm_layers': bool(eng.outer.fused),
+           'loss_ae': eng.fetch(['loss_ae'])['loss_ae']}
+    del pool
+    # ---- e2e: the reference-facing trainer on pinned host batches
+    try:
+        class _Data:
+            n_train, n_val = 180000, 20000
+        with contextlib.redirect_stdout(sys.stderr):
+            trainer = htrainers.CelebATrainer_joint_training(None, model, _Data(), cfg)
+        epoch = cfg['sg_pretraining'] + 1
+        trainer.cur_epoch = epoch
+        model.GM_prior_training.means_, model.GM_prior_training.covariances_, model.GM_prior_training.weights_ = gm
+        trainer._gm_version += 1
+        host_pool = [torch.rand(B, 128, 128, 3).pin_memory() for _ in range(2)]
+        trainer.compute_cur_lr()
+
+        def e2e_iteration(i):
+            loss = trainer.train_step_ae(cur_lr=trainer.cur_lr, batch_data=host_pool[i % 2])
+            trainer.train_step_prior(batch_data=host_pool[i % 2])
+            return float(loss)                       # device -> host read of the step's loss
+        for i in range(2):
+            e2e_iteration(i)
+        trainer._pending = []
+        e_steps = max(2, steps // 2)
+        e_ms, win = timed(e2e_iteration, e_steps)
+        windows.append(win)
+        out['e2e'] = {'value': B * world * e_steps / (e_ms * 1e-3), 'unit': 'imgs/s', 'ms_per_step': e_ms / e_steps,
+                      'steps': e_steps, 'h2d_bytes_per_step': B * 128 * 128 * 3 * 4, 'd2h_bytes_per_step': 4,
+                      'api': 'CelebATrainer_joint_training.train_step_ae + train_step_prior on pinned host batches'}
+        del trainer, host_pool
+    except Exception as e:                            # noqa: BLE001
+        out['e2e'] = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:200] if str(e) else '')}
+    if rank == 0:
+        out['clocks'] = sampler.summary(windows)
     eng.release_graphs()
-    del eng, pool
+    H, bf = int(cfg['num_hidden_units']), torch.bfloat16
+    del eng, model
     torch.cuda.empty_cache()
+    # ---- roofline of this leg (rank 0): the GEMMs of decoder/conv2d_7 alone, and the heaviest HBM-bound pass
+    if rank == 0 and args.dtype == 'bf16':
+        try:
+            peaks = measured_peaks()
+            c = H // 4
+            g = ops.ConvGeom(B, 128, 128, c, 3, 3, c, 1, 'same')
+            xk = torch.randn(B, 128, 128, c, device=dev).to(bf)
+            dyk = torch.randn(B, 128, 128, c, device=dev).to(bf)
+            yk = torch.empty(B, 128, 128, c, device=dev, dtype=bf)
+            wk = torch.randn(3, 3, c, c, device=dev) * 0.05
+            bk = torch.zeros(c, device=dev)
+            dwk = torch.empty(3, 3, c, c, device=dev)
+            wf, wd = ops.tma_pack(wk, g, ops.FPROP), ops.tma_pack(wk, g, ops.DGRAD)
+            flops = 2.0 * B * 128 * 128 * c * 9 * c
+            act_bytes = 2.0 * B * 128 * 128 * c
+
+            def kernel_ms(fn, reps=5):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+            rf = {}
+            for name, fn, nbytes in (
+                    ('fprop', lambda: ops.conv2d_fprop(xk, wk, bk, yk, g, 'leaky_relu', wimg=wf), 2 * act_bytes),
+                    ('dgrad', lambda: ops.conv2d_dgrad(dyk, wk, yk, g, wimg=wd), 2 * act_bytes),
+                    ('wgrad', lambda: ops.conv2d_wgrad(xk, dyk, dwk, None, g), 2 * act_bytes)):
+                t = kernel_ms(fn)
+                rf[name] = {'kernel': 'tma_kernel<%s> decoder/conv2d_7 [%d,128,128,%d] 3x3 -> %d' % (name.upper(), B, c, c),
+                            'bound': 'tensor', 'achieved': flops / (t * 1e-3) / 1e12, 'peak': peaks['bf16_tflops_sustained'],
+                            'unit': 'TFLOP/s', 'frac': flops / (t * 1e-3) / 1e12 / peaks['bf16_tflops_sustained'],
+                            'ms_per_launch': t, 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': nbytes,
+                            'traffic': ncu_traffic('celeba_bf16_b%d_conv7_%s' % (B, name)),
+                            'peak_source': peaks['source'] + ' bf16 sustained (kernel inside a long step)'}
+            del xk, dyk, dwk
+            # heaviest HBM-bound pass: instance norm + style + leaky + 64->128 resize in one pass (decoder block 6)
+            cin = torch.randn(B, 64, 64, c, device=dev).to(bf)
+            insum = torch.stack([cin.float().sum((1, 2)), (cin.float() ** 2).sum((1, 2))]).contiguous()
+            sty = torch.randn(B, 2 * c, device=dev)
+            t = kernel_ms(lambda: ops.in_style_resize16(cin, insum, sty, yk))
+            nbytes = 2.0 * B * c * (64 * 64 + 128 * 128)
+            rf['hbm_pass'] = {'kernel': 'in_style_resize16_kernel: instance norm + style + leaky + 64->128 legacy bilinear, '
+                                        '[%d,64,64,%d] -> [%d,128,128,%d] bf16' % (B, c, B, c),
+                              'bound': 'hbm', 'achieved': nbytes / (t * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                              'frac': nbytes / (t * 1e-3) / 1e9 / peaks['hbm_gbs'], 'ms_per_launch': t,
+                              'algorithmic_bytes_per_launch': nbytes, 'traffic': ncu_traffic('celeba_bf16_b%d_in_style_resize' % B),
+                              'peak_source': peaks['source'] + ' copy bandwidth'}
+            out['roofline'] = rf
+            del cin, yk, insum, sty
+            torch.cuda.empty_cache()
+        except Exception as e:                        # noqa: BLE001
+            out['roofline'] = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:200] if str(e) else '')}
     return out
 
 
@@ -445,7 +570,7 @@ def run_ours(args):
                  'tc_kernel<FPROP> (tcgen05, fp32 activations)' if args.dtype == 'bf16' else 'igemm_kernel<FPROP> (fp32 SIMT)')
         roofline = {'kernel': kname + ' %s [B,%d,%d,%d]->%d 3x3' % (dom_name, hw, hw, ci, co),
                     'bound': 'tensor', 'achieved': ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                    'frac': ach / peaks['bf16_tflops'], 'traffic': TRAFFIC.get((WORKLOAD, args.dtype, B)),
+                    'frac': ach / peaks['bf16_tflops'], 'traffic': ncu_traffic('%s_%s_b%d_fprop' % (WORKLOAD, args.dtype, B)),
                     'peak_source': peaks['source'] + ' bf16 burst (kernel timed alone)',
                     'ms_per_launch': k_ms, 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': alg_bytes,
                     'hbm_floor_ms': alg_bytes / (peaks['hbm_gbs'] * 1e9) * 1e3,
@@ -479,7 +604,7 @@ def run_ours(args):
             roofline = {'kernel': 'tma_kernel<DGRAD,64> (TMA im2col + tcgen05, bf16 in/out) %s [B,%d,%d,%d]<-%d 3x3'
                                   % (dom_name, hw, hw, ci, co),
                         'bound': 'tensor', 'achieved': d_ach, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                        'frac': d_ach / peaks['bf16_tflops'], 'traffic': TRAFFIC.get((WORKLOAD, args.dtype, B, 'dgrad')),
+                        'frac': d_ach / peaks['bf16_tflops'], 'traffic': ncu_traffic('%s_%s_b%d_dgrad' % (WORKLOAD, args.dtype, B)),
                         'peak_source': peaks['source'] + ' bf16 burst (kernel timed alone)',
                         'ms_per_launch': d_ms, 'algorithmic_flops_per_launch': flops, 'algorithmic_bytes_per_launch': d_bytes,
                         'hbm_floor_ms': d_bytes / (peaks['hbm_gbs'] * 1e9) * 1e3,
@@ -516,19 +641,20 @@ def run_ours(args):
         hyper = {'pairs_per_s_fwd': hp['fwd'], 'pairs_per_s_fwd_grad': hp['fwd_grad'], 'N': N, 'K': N, 'D': 2,
                  'bound': 'sfu (1 MUFU.EX2 per pair)', 'ex2_peak_per_s_measured': ex2_peak,
                  'frac_fwd': hp['fwd'] / ex2_peak, 'frac_fwd_grad': hp['fwd_grad'] / ex2_peak}
-        cpu = cpu_reference(cfg, args.cpu_sample, 2, 1)
+        # reported baseline, rank 0 at N = 1 only (at N > 1 the other ranks' processes would share the host cores with it)
+        cpu = cpu_reference(cfg, args.cpu_sample, 2, 1) if world == 1 else None
         line = {'metric': METRIC, 'value': value, 'unit': 'imgs/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16' if args.dtype == 'bf16' else 'f32', 'data': 'synthetic',
-                'config': {'workload': 'codes/%s_config.json @ batch %d per GPU, epoch %d (all 4 sub-steps, '
-                                       '50-component hyper-prior, L=100 MC samples)' % (WORKLOAD, B, epoch),
+                'config': {'workload': workload_string(B, epoch),
                            'global_batch': B * world, 'parallelism': 'dp%d' % world, 'cuda_graphs': bool(eng.use_graphs),
                            'l2': 'per-step activation working set (>1 GB) exceeds the 126 MB L2; 4 input batches rotate'},
                 'clocks': clocks, 'gpu_launches': launches,
                 'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': B * int(np.prod(shp)) * 4,
                         'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps,
                         'api': '*Trainer_joint_training.train_step_ae + train_step_prior on pinned host batches'},
-                'roofline': roofline, 'cpu_baseline': {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+                'roofline': roofline,
+                'cpu_baseline': {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')} if cpu else None,
                 'hyper_prior': hyper, 'hyper_prior_component_sharded': sharded, 'celeba_shape': None, 'loss_prior_last': loss_check, 'loss_ae_last_e2e': last}
     # ---- secondary workload: CelebA-shape (128x128x3) training step, BASELINE.json configs[3] per-GPU batch
     celeba = None
@@ -565,7 +691,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=None,
+                    help='timed iterations (default: 250 for the GPU arm = a timed region of about 1 s; 20 for --impl reference)')
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1024, help='images per GPU')
@@ -580,10 +707,15 @@ def main():
     ap.add_argument('--workload', default='mnist_fashion', choices=['mnist_fashion', 'mnist_digit', 'celeba'],
                     help='config file under codes/ (default: BASELINE.json configs[1])')
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 250 if args.impl == 'ours' and args.workload != 'celeba' else 20
     global WORKLOAD
     WORKLOAD = args.workload
     if args.cpu_sample <= 0:
-        args.cpu_sample = 16 if WORKLOAD == 'celeba' else min(args.batch, 1024)
+        # bounded sample: the full batch when the run is short, fewer images per step when --steps is large, so that the
+        # reference arm's whole run stays within a few minutes (~700 img/s on 16 host cores)
+        cap = max(32, int(90e3 / max(1, args.steps + args.warmup))) if args.impl == 'reference' else 1024
+        args.cpu_sample = 16 if WORKLOAD == 'celeba' else min(args.batch, 1024, cap)
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
         run_reference(args)

@@ -275,6 +275,54 @@ __global__ void __launch_bounds__(THREADS) in_style_resize16_kernel(const __nv_b
   }
 }
 
+// Scale-2 fast path of the pass above (the 16->32 and 64->128 maps, where almost all of its bytes are): one thread per INPUT
+// vector produces the 2x2 output block it owns -- legacy bilinear at scale 1/2 is src = o/2, so even outputs copy and odd outputs
+// average with the next pixel (clamped at the border); same operation order as the general kernel, so the same bits.  The
+// sample's (a, b0) coefficients are formed once per thread (grid.y = sample, thread owns channel group t % c8).
+__global__ void __launch_bounds__(THREADS) in_style_up2_kernel(const __nv_bfloat16* __restrict__ c, const float* __restrict__ insum,
+                                                               const float* __restrict__ style, __nv_bfloat16* __restrict__ out,
+                                                               int B, int H, int W, int C, float eps, float slope) {
+  const int c8 = C >> 3;
+  const int cg = threadIdx.x % c8;
+  const long long b = blockIdx.y;
+  float a[8], b0[8];
+  style_coef(insum, style, B, C, b, cg * 8, 1.f / (float)(H * W), eps, a, b0);
+  const long long n = (long long)H * W * c8, ibase = b * H * W * C, obase = b * 4 * H * W * C;
+  const int OW = 2 * W;
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * THREADS) {
+    const long long pix = i / c8;
+    const int ix = (int)(pix % W), iy = (int)(pix / W);
+    const int x1 = min(ix + 1, W - 1), y1 = min(iy + 1, H - 1);
+    float p00[8], p01[8], p10[8], p11[8], o[8];
+    ld8<true>(c, ibase + ((long long)iy * W + ix) * C + cg * 8, p00);
+    ld8<true>(c, ibase + ((long long)iy * W + x1) * C + cg * 8, p01);
+    ld8<true>(c, ibase + ((long long)y1 * W + ix) * C + cg * 8, p10);
+    ld8<true>(c, ibase + ((long long)y1 * W + x1) * C + cg * 8, p11);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float u;
+      u = fmaf(p00[t], a[t], b0[t]); p00[t] = u > 0.f ? u : u * slope;
+      u = fmaf(p01[t], a[t], b0[t]); p01[t] = u > 0.f ? u : u * slope;
+      u = fmaf(p10[t], a[t], b0[t]); p10[t] = u > 0.f ? u : u * slope;
+      u = fmaf(p11[t], a[t], b0[t]); p11[t] = u > 0.f ? u : u * slope;
+    }
+    const long long o00 = obase + ((long long)(2 * iy) * OW + 2 * ix) * C + cg * 8;
+    st8_bf16(out, o00, p00);                                               // (even, even): fx = fy = 0
+#pragma unroll
+    for (int t = 0; t < 8; ++t) o[t] = p00[t] + (p01[t] - p00[t]) * 0.5f;  // (even, odd)
+    st8_bf16(out, o00 + C, o);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {                                          // (odd, odd): top + (bot - top) / 2
+      const float bot = p10[t] + (p11[t] - p10[t]) * 0.5f;
+      o[t] = o[t] + (bot - o[t]) * 0.5f;
+    }
+    st8_bf16(out, o00 + (long long)OW * C + C, o);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) o[t] = p00[t] + (p10[t] - p00[t]) * 0.5f;  // (odd, even): fx = 0
+    st8_bf16(out, o00 + (long long)OW * C, o);
+  }
+}
+
 // dstyle[b, ch] += sum_hw g xhat ; dstyle[b, C + ch] += sum_hw g ;  g = da * leaky'(pre),  pre = xhat (s0 + 1) + s1
 // grid.y = sample, grid.x = row slices of that sample; thread owns channel group t % c8
 template <bool G16>
@@ -436,6 +484,15 @@ int ladder_in_style_resize_bf16(const void* c_bf16, const float* insum, const fl
   LADDER_REQUIRE(c_bf16 && insum && style && out_bf16 && B > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "in_style_resize_bf16: bad arguments");
   LADDER_REQUIRE(C > 0 && C % 8 == 0, "in_style_resize_bf16: C must be a multiple of 8 (got %d)", C);
   LADDER_REQUIRE(act != ACT_TANH, "in_style_resize_bf16: slope-form activations only");
+  if (OH == 2 * H && OW == 2 * W && THREADS % (C / 8) == 0) {
+    long long per_sample = ceil_div64((long long)H * W * (C / 8), THREADS);
+    const long long want = ceil_div64(8LL * num_sms(), B);
+    if (per_sample > want) per_sample = want;
+    in_style_up2_kernel<<<dim3((unsigned)per_sample, B), THREADS, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(c_bf16), insum, style, static_cast<__nv_bfloat16*>(out_bf16), B, H, W, C, eps,
+        slope_of(act));
+    return check_launch("in_style_up2_bf16");
+  }
   in_style_resize16_kernel<<<row_blocks((long long)B * OH * OW * (C / 8)), THREADS, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(c_bf16), insum, style, static_cast<__nv_bfloat16*>(out_bf16), B, H, W, C, OH, OW, eps,
       slope_of(act));

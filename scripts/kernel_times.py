@@ -33,6 +33,12 @@ def main():
     for _ in range(3):
         iteration()
     torch.cuda.synchronize()
+    if os.environ.get('LADDER_NCU') == '1':      # under `ncu --profile-from-start off`: exactly one iteration is captured
+        torch.cuda.profiler.start()
+        iteration()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(iters):

@@ -40,3 +40,23 @@ def test_gpu_arm_has_no_cpu_fallback():
         return
     r = _run(['--steps', '1'])
     assert r.returncode != 0 and 'no CPU fallback' in r.stderr
+
+
+def test_reference_arm_honours_steps_and_prints_the_gpu_arms_workload_string():
+    """`same_steps` / `same_config` -- the reference arm runs exactly --steps / --warmup and names the workload
+    with the very string the GPU arm prints (bench.workload_string)."""
+    import bench
+    r = _run(['--impl', 'reference', '--steps', '3', '--warmup', '2', '--cpu-sample', '4'])
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d['steps'] == 3 and d['warmup'] == 2
+    bench.WORKLOAD = 'mnist_fashion'
+    assert d['config']['workload'] == bench.workload_string(1024, 11)
+
+
+def test_roofline_traffic_comes_from_the_rounds_ncu_summary_or_is_null(tmp_path, monkeypatch):
+    import bench
+    monkeypatch.setattr(bench, 'ROOT', str(tmp_path))
+    assert bench.ncu_traffic('mnist_fashion_bf16_b1024_dgrad') is None
+    os.makedirs(tmp_path / 'profiles')
+    (tmp_path / 'profiles' / 'ncu_traffic.json').write_text(json.dumps({'k': {'bytes': 123.0, 'source': 'profiles/x.md'}}))
+    assert bench.ncu_traffic('k') == 123.0 and bench.ncu_traffic('other') is None

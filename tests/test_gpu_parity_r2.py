@@ -105,7 +105,8 @@ def _grad_table(group, want, depth, exact=None):
         den = max(np.linalg.norm(w), floor * np.sqrt(w.size))
         sens = 0.0 if exact is None else float(np.linalg.norm(np.asarray(exact[n]).reshape(got.shape) - w) / den)
         rows[n] = dict(l2=float(np.linalg.norm(got - w) / den), mx=float(np.abs(got - w).max() / scale), depth=int(depth[n]),
-                       sens=sens, allowed=float(BF16_C * np.sqrt(depth[n]) * BF16_EPS + sens))
+                       sens=sens, allowed=float(BF16_C * np.sqrt(depth[n]) * BF16_EPS + sens),
+                       zero=bool(np.abs(w).max() < floor))        # true gradient is zero (a conv bias in front of a batch norm)
     return rows
 
 
@@ -113,7 +114,8 @@ def _assert_table(rows, what, l2_cap=None):
     if l2_cap is not None:
         bad = {n: r for n, r in rows.items() if not r['l2'] <= l2_cap}
     else:
-        bad = {n: r for n, r in rows.items() if not (r['l2'] <= r['allowed'] and r['mx'] <= 8 * r['allowed'])}
+        # tensors whose true gradient is zero hold rounding noise only: bounded in L2 on the scale of the group's gradients
+        bad = {n: r for n, r in rows.items() if not (r['l2'] <= r['allowed'] and (r['zero'] or r['mx'] <= 8 * r['allowed']))}
     assert not bad, (what, bad)
 
 
