@@ -41,6 +41,9 @@ int ladder_version(void);
 const char* ladder_last_error(void);
 /* kernels enqueued by this library so far in this process (bench.py's gpu_launches evidence) */
 unsigned long long ladder_launch_count(void);
+/* CRC-32C of a HOST buffer (chain with the previous value, 0 first): the checksum of the TF tensor-bundle checkpoint files the
+ * reference's tf.train.Saver objects write (codes/base.py:37-48) -- used by the bundle writer of host/tf_checkpoint.py. */
+unsigned int ladder_crc32c(unsigned int crc, const void* host_data, size_t n);
 /* LADDER_OK iff `device` is compute capability 10.x (the only target); else LADDER_ERR_ARCH. */
 int ladder_device_check(int device);
 

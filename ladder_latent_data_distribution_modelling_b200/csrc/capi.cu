@@ -46,6 +46,37 @@ const char* ladder_last_error(void) { return ladder::error_buffer(); }
 
 unsigned long long ladder_launch_count(void) { return ladder::launch_counter(); }
 
+/* CRC-32C (Castagnoli, reflected polynomial 0x82F63B78), the checksum of the TF tensor-bundle files the reference's savers write
+ * (codes/base.py:37-48): host function, slicing-by-8.  `crc` chains calls (0 for the first). */
+unsigned int ladder_crc32c(unsigned int crc, const void* data, size_t n) {
+  static unsigned int table[8][256];
+  static bool ready = false;
+  if (!ready) {
+    for (unsigned int i = 0; i < 256; ++i) {
+      unsigned int c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[0][i] = c;
+    }
+    for (unsigned int i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xff];
+    ready = true;
+  }
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  unsigned int c = ~crc;
+  while (n >= 8) {
+    unsigned int lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = table[7][lo & 0xff] ^ table[6][(lo >> 8) & 0xff] ^ table[5][(lo >> 16) & 0xff] ^ table[4][lo >> 24] ^
+        table[3][hi & 0xff] ^ table[2][(hi >> 8) & 0xff] ^ table[1][(hi >> 16) & 0xff] ^ table[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = table[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+  return ~c;
+}
+
 int ladder_device_check(int device) {
   cudaDeviceProp p;
   cudaError_t e = cudaGetDeviceProperties(&p, device);

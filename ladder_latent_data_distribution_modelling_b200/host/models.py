@@ -160,19 +160,25 @@ class BaseModel:
         return out
 
     def _save(self, path, groups):
-        np.savez(path + '.npz', **{k.replace('/', '__'): v for k, v in self._group_arrays(groups).items()})
-        with open(path + '.meta', 'w') as f:      # the reference's restore test is isfile('<path>.meta')
-            f.write('ladder_b200 checkpoint: trainable variables in %s.npz\n' % os.path.basename(path))
+        """`tf.train.Saver(var_list).save(sess, path)` (base.py:50-66): the TF tensor-bundle files the reference writes --
+        <path>.index + <path>.data-00000-of-00001 + the `checkpoint` state file, same variable names, fp32 -- so either side
+        restores the other's checkpoints.  (<path>.meta, the MetaGraphDef of a TF graph that does not exist here, is a one-line
+        stub: the reference only tests its existence, base.py:72-85.)"""
+        from .tf_checkpoint import write_tf_checkpoint
+        write_tf_checkpoint(path, self._group_arrays(groups))
+        with open(path + '.meta', 'w') as f:
+            f.write('ladder_b200 checkpoint: trainable variables in the TF bundle %s.index / .data-00000-of-00001\n'
+                    % os.path.basename(path))
 
     def _load(self, path):
-        if os.path.isfile(path + '.npz'):
-            d = np.load(path + '.npz')
-            self.engine.load_parameters({k.replace('__', '/'): d[k] for k in d.files})
+        if os.path.isfile(path + '.index'):
+            # a TF bundle: written here or by the reference's tf.train.Saver (same variable names)
+            from .tf_checkpoint import read_tf_checkpoint
+            mine = {n for n, _ in self.engine.named_parameters()}
+            self.engine.load_parameters({k: v for k, v in read_tf_checkpoint(path, verify=True).items() if k in mine})
             return
-        # a checkpoint written by the reference's tf.train.Saver (<path>.index + <path>.data-00000-of-00001, same variable names)
-        from .tf_checkpoint import read_tf_checkpoint
-        mine = {n for n, _ in self.engine.named_parameters()}
-        self.engine.load_parameters({k: v for k, v in read_tf_checkpoint(path).items() if k in mine})
+        d = np.load(path + '.npz')                 # round-1 checkpoints of this repo
+        self.engine.load_parameters({k.replace('__', '/'): d[k] for k in d.files})
 
     def save(self, sess, model):
         if not self.is_main:               # data parallel: the replicas hold identical weights, rank 0 writes them
@@ -241,17 +247,26 @@ class MNISTModel_fashion(BaseModel):
 
 
 class CelebAModel_densenet(BaseModel):
-    """codes/models.py:330-598.  The reference streams `celebA_{train,val,test}.tfrecords` ('X' = raw uint8
-    128x128x3, scaled by 1/255) through tf.data; TFRecord parsing is outside the hot path, so the image pools
-    come from `<data_path>/celeba_{train,val,test}.npy` (uint8 [N,128,128,3]) when present and are synthetic
-    otherwise.  The iterator reshuffles the pool every epoch and repeats it, like `shuffle(...).repeat(8000)`."""
+    """codes/models.py:330-598.  The reference streams TFRecord files ('X' = raw uint8 128x128x3, scaled by 1/255) through
+    tf.data (models.py:346-386; `data_file` fed by trainers.py:135,145,176): the image pools come
+    from `<data_path>/celebA_{train,val,test}.tfrecords` (parsed by host/tfrecord.py, no TensorFlow) or
+    `<data_path>/celeba_{train,val,test}.npy` (uint8 [N,128,128,3]) when present and are synthetic otherwise.  The pool lives on
+    the device as uint8; the iterator reshuffles it every epoch and repeats it, like `shuffle(...).repeat(8000)`."""
 
     def _pool(self, split, n_default):
         cfg = self.config
-        path = os.path.join(cfg.get('data_path', '') or '', 'celeba_%s.npy' % split)
+        root = cfg.get('data_path', '') or ''
+        path = os.path.join(root, 'celeba_%s.npy' % split)
+        rec = os.path.join(root, 'celebA_%s.tfrecords' % split)
+        key = '_pool_' + split
+        if not cfg.get('synthetic', False) and os.path.isfile(rec):
+            if not hasattr(self, key):
+                from .tfrecord import read_images
+                shape = (int(cfg['dim_input_x']), int(cfg['dim_input_y']), int(cfg['dim_input_channel']))
+                setattr(self, key, read_images(rec, shape, limit=cfg.get('max_images_' + split)))
+            return getattr(self, key)
         if not cfg.get('synthetic', False) and os.path.isfile(path):
             return np.load(path, mmap_mode='r')        # uint8: uploaded as uint8, scaled by 1/255 per batch on the device
-        key = '_pool_' + split
         if not hasattr(self, key):
             n = int(cfg.get('synthetic_pool', n_default))
             rng = np.random.default_rng({'train': 1, 'val': 2, 'test': 3}[split])

@@ -21,6 +21,7 @@ SIGNATURES = {
     'ladder_last_error': (C.c_char_p, []),
     'ladder_launch_count': (C.c_ulonglong, []),
     'ladder_device_check': (C.c_int, [C.c_int]),
+    'ladder_crc32c': (C.c_uint, [C.c_uint, C.c_void_p, C.c_size_t]),
     'ladder_mixture_table_stride': (C.c_int, [C.c_int, C.c_int]),
     'ladder_mixture_pack_full': (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, c_float_p, c_float_p]),
     'ladder_mixture_pack_diag': (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, C.c_int,

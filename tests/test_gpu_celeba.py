@@ -258,8 +258,9 @@ def test_celeba_fused_engine_matches_unfused(monkeypatch):
             continue
         a, b = out[0][1][n].double().cpu().numpy(), out[1][1][n].double().cpu().numpy()
         e, m = np.asarray(eg['ae'][n]).reshape(a.shape), np.asarray(mg['ae'][n]).reshape(a.shape)
-        if n.endswith('/bias') and n.startswith('encoder/conv2d'):
-            continue          # a conv bias in front of a batch norm: the true gradient is zero, both paths hold rounding noise
+        if n.endswith('/bias') and (n.startswith('encoder/conv2d') or n in ('decoder/conv2d_1/bias', 'decoder/conv2d_2/bias',
+                                                                          'decoder/conv2d_4/bias', 'decoder/conv2d_6/bias')):
+            continue          # a conv bias in front of a batch / instance norm: the true gradient is zero, both paths hold noise
         sens = np.linalg.norm(e - m) / (np.linalg.norm(e) + 1e-30)
         assert np.linalg.norm(a - b) <= (0.08 + 2.0 * sens) * np.linalg.norm(b) + 1e-6 * np.sqrt(b.size), \
             (n, float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)), float(sens))
