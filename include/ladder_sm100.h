@@ -192,6 +192,11 @@ int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w /*NULL: prepacked
                             int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride, int pad_t, int pad_l,
                             int OH, int OW, int act, int out_d2s, void* workspace, size_t workspace_bytes,
                             float* stat_sums /*nullable*/, int stat_groups, cudaStream_t stream);
+/* Halo mode of the stride-1 3x3 fprop / dgrad GEMMs (maps with H % 16 == 0, W % 8 == 0): the A operand of a 64-channel chunk is
+ * fetched once as a 18 x 16-pixel halo box and the 9 filter taps read it through shifted UMMA descriptors (4x less L2 -> SM
+ * operand traffic).  Diagnostic switch: enabled 0 | 1, base_mode 0 (correct: no descriptor base offset) | 1; negative =
+ * unchanged; returns the previous `enabled`. */
+int ladder_conv2d_tma_set_halo(int enabled, int base_mode);
 int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w /*NULL: prepacked*/, const void* act_out /*nullable*/, int act_out_bf16,
                             void* dx, int dx_bf16, int B, int H, int W, int Cin, int KH, int KW, int Cout, int stride,
                             int pad_t, int pad_l, int OH, int OW, int act, int accumulate, int out_s2d,

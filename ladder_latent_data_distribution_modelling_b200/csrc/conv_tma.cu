@@ -40,6 +40,23 @@ __host__ __device__ constexpr int stages_for(int bn) {
              : (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES - STAT_BYTES) / (A_STAGE_BYTES + bn * BK * 2);
 }
 
+// ---- halo mode (stride-1 3x3 fprop / dgrad on maps with GH % 16 == 0, GW % 8 == 0)
+// The plain kernel fetches one 128-pixel x 64-channel A tile PER FILTER TAP: 9 x 16 KB per 64-channel chunk, and at N <= 128
+// the L2 -> SM operand stream (cap ~42 B/clk/SM), not the tensor pipe, bounds it (r1g: 1.77 GB per launch of the N = 64 dgrad;
+// r2e: conv2d_7 fprop at 13 TB/s of L2 reads).  In halo mode a tile is 16 rows x 8 columns of ONE image and the A operand of a
+// chunk is fetched ONCE: a {64 ch, 16 px, 18 rows} box = the tile plus its 1-pixel halo (zero filled outside the image), 36 KB
+// at a 16-pixel row pitch.  Tap (kh, kw) is then the SAME buffer read through a shifted UMMA descriptor: start + ((kh * 16 +
+// kw) * 128 B, 8-row groups 2048 B apart (one image row of the halo); the SWIZZLE_128B pattern follows the address bits, so the
+// shifted view needs no base offset.
+constexpr int HALO_TW = 8, HALO_TH = 16, HALO_PITCH = 16, HALO_ROWS = HALO_TH + 2;
+constexpr int HALO_BYTES = HALO_ROWS * HALO_PITCH * 128;      // 36 864 B per 64-channel chunk
+constexpr int HALO_STAGES = 2;
+__host__ __device__ constexpr int halo_b_stages(int bn) {
+  return (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES - STAT_BYTES - HALO_STAGES * HALO_BYTES) / (bn * BK * 2) > 10
+             ? 10        // (2 * stages + 9) mbarriers must fit the 256-byte barrier block
+             : (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES - STAT_BYTES - HALO_STAGES * HALO_BYTES) / (bn * BK * 2);
+}
+
 enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
 
 struct Args {
@@ -60,6 +77,9 @@ struct Args {
   int m_valid;               // WGRAD: rows of dw that exist (= KH*KW*C)
   int m_tiles, n_tiles, splits;
   int perm_r;                // fused depth_to_space (FPROP) / space_to_depth (DGRAD) store, 0 = off
+  int halo_ox, halo_oy;      // halo mode: source offset of the halo box origin relative to the tile origin (min over taps)
+  int halo_tiles_x, halo_tiles_per_img;
+  int halo_base_mode;        // diagnostic: 1 puts the phase kw into the descriptor's base-offset field (wrong on sm_100a), 0 = none
   float* stat;               // FPROP: per-channel (sum, sum of squares) of the output, accumulated in the epilogue (null = off):
   int stat_groups;           //   [2][groups][Ng]; groups = 1 (batch norm: all rows) or B (instance norm: rows of one sample)
   int stat_group_rows;       //   rows per group (a multiple of 128 when groups > 1, so a tile never straddles two samples)
@@ -114,8 +134,14 @@ __device__ __noinline__ void slow_store(const Args& a, float4 q, long long m, in
   for (int t = 0; t < 4; ++t) {
     if (col + t >= Ng) break;
     float e = e4[t];
-    long long oo = o + t;
-    if (MODE == FPROP && a.perm_r > 0) oo = d2s_dest(m, col + t, a.GH, a.GW, Ng, a.perm_r);
+    long long oo = o + t;                      // o: offset of column `col` of this row (row base + column offset)
+    if (MODE == FPROP && a.perm_r > 0 && t > 0) {      // depth_to_space: a 4-column group may straddle two (i, j) blocks
+      const int r = a.perm_r, Cp = Ng / (r * r), ij0 = col / Cp, ij = (col + t) / Cp;
+      if (ij != ij0) {
+        const long long off0 = ((long long)(ij0 / r) * a.GW * r + ij0 % r) * Cp + (col - ij0 * Cp);
+        oo = o - off0 + ((long long)(ij / r) * a.GW * r + ij % r) * Cp + (col + t - ij * Cp);
+      }
+    }
     if (MODE == DGRAD) {
       if (a.aux != nullptr) {
         const long long ai = arow + col + t;
@@ -146,21 +172,30 @@ __device__ __forceinline__ void stat_flush(const Args& a, float* wstat, int n_ti
   }
 }
 
-template <int MODE, int BN, bool OUT16>
+// K-major SWIZZLE_128B descriptor of a halo-buffer view: 8-row groups 2048 B apart, swizzle phase in the base-offset field
+__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, uint32_t base_offset) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((HALO_PITCH * 128) >> 4) << 32) | (1ull << 46) |
+         ((uint64_t)(base_offset & 7) << 49) | (2ull << 61);
+}
+
+template <int MODE, int BN, bool OUT16, bool HALO = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Args a) {
-  constexpr int STAGES = stages_for(BN);
+  // plain mode: STAGES x (A tile + B tile).  halo mode: HALO_STAGES halo buffers (ring `h`) + STAGES B tiles (ring `s`)
+  constexpr int STAGES = HALO ? halo_b_stages(BN) : stages_for(BN);
   constexpr int B_STAGE_BYTES = BN * BK * 2;
+  constexpr int A_REGION = HALO ? HALO_STAGES * HALO_BYTES : STAGES * A_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t sA = base, sB = base + STAGES * A_STAGE_BYTES;
-  const uint32_t bars = sB + STAGES * B_STAGE_BYTES;            // full[S], empty[S], tfull[2], tempty[2], slot
+  const uint32_t sA = base, sB = base + A_REGION;
+  const uint32_t bars = sB + STAGES * B_STAGE_BYTES;            // full[S], empty[S], tfull[2], tempty[2], slot, hfull[2], hempty[2]
   const uint32_t bar_full = bars, bar_empty = bars + STAGES * 8, bar_tfull = bars + 2 * STAGES * 8,
                  bar_tempty = bars + (2 * STAGES + 2) * 8;
   const uint32_t slot = bars + (2 * STAGES + 4) * 8;
+  const uint32_t bar_hfull = bars + (2 * STAGES + 5) * 8, bar_hempty = bars + (2 * STAGES + 7) * 8;   // <= 29 x 8 B < 256
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (slot - base));
   const uint32_t stage_off = bars + 256 - base;                 // epilogue staging (4 x 32 x 36 floats)
 
@@ -178,6 +213,8 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + i * 8, 1);
       mbar_init(bar_tempty + i * 8, 128);
+      mbar_init(bar_hfull + i * 8, 1);
+      mbar_init(bar_hempty + i * 8, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -196,8 +233,29 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       Tile T;
       decode_tile<MODE>(a, blockIdx.x, total, T);
       unsigned it = 0;
+      unsigned hit = 0;
       while (T.valid) {
-        if (MODE != WGRAD) {
+        if constexpr (HALO) {
+          // tile = 16 rows x 8 columns of image b; per 64-channel chunk ONE halo box, then the 9 weight tiles
+          const int b0 = T.m_tile / a.halo_tiles_per_img, rem = T.m_tile - b0 * a.halo_tiles_per_img;
+          const int ty = rem / a.halo_tiles_x, tx = rem - ty * a.halo_tiles_x;
+          const int hx = tx * HALO_TW + a.halo_ox, hy = ty * HALO_TH + a.halo_oy;
+          int kb = 0;
+          for (int c0 = 0; c0 < a.C; c0 += BK, ++hit) {
+            const int h = hit % HALO_STAGES;
+            mbar_wait(bar_hempty + h * 8, ((hit / HALO_STAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_hfull + h * 8, HALO_BYTES);
+            tma_load_4d(sA + h * HALO_BYTES, &mapA, c0, hx, hy, b0, bar_hfull + h * 8);
+            for (int tap = 0; tap < taps; ++tap, ++kb, ++it) {
+              const int s = it % STAGES;
+              mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
+              mbar_arrive_expect_tx(bar_full + s * 8, B_STAGE_BYTES);
+              tma_bulk_g2s(sB + s * B_STAGE_BYTES,
+                           reinterpret_cast<const uint8_t*>(a.wt) + ((size_t)T.n_tile * T.nkb + kb) * B_STAGE_BYTES,
+                           B_STAGE_BYTES, bar_full + s * 8);
+            }
+          }
+        } else if (MODE != WGRAD) {
           const unsigned m0 = (unsigned)T.m_tile * BM;
           const int x0 = (int)(m0 % (unsigned)a.GW);
           const unsigned r = m0 / (unsigned)a.GW;
@@ -257,12 +315,41 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       constexpr uint32_t idesc = make_idesc(BM, BN, MODE == WGRAD);
       Tile T;
       decode_tile<MODE>(a, blockIdx.x, total, T);
-      unsigned it = 0, j = 0;
+      unsigned it = 0, j = 0, hit = 0;
       while (T.valid) {
         const uint32_t acc = j & 1;
         mbar_wait(bar_tempty + acc * 8, ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        if constexpr (HALO) {
+          const int taps = a.KH * a.KW;
+          int kb = 0;
+          for (int c0 = 0; c0 < a.C; c0 += BK, ++hit) {
+            const int h = hit % HALO_STAGES;
+            mbar_wait(bar_hfull + h * 8, (hit / HALO_STAGES) & 1);
+            tc_fence_after();
+            int kh = 0, kw = 0;
+            for (int tap = 0; tap < taps; ++tap, ++kb, ++it) {
+              const int s = it % STAGES;
+              mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
+              tc_fence_after();
+              // halo coordinates of this tap's view: (off + sign * k) - origin
+              const int vy = a.off_y + a.sign * kh - a.halo_oy, vx = a.off_x + a.sign * kw - a.halo_ox;
+              const uint32_t tA = sA + h * HALO_BYTES + (uint32_t)(vy * HALO_PITCH + vx) * 128u, tB = sB + s * B_STAGE_BYTES;
+              const uint32_t bo = a.halo_base_mode ? (uint32_t)vx : 0u;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(tmem_d, make_desc_halo(tA + k * 32, bo), make_desc(tB + k * 32), idesc, (kb | k) != 0);
+              umma_commit(bar_empty + s * 8);
+              if (++kw == a.KW) { kw = 0; ++kh; }
+            }
+            umma_commit(bar_hempty + h * 8);
+          }
+          umma_commit(bar_tfull + acc * 8);
+          ++j;
+          decode_tile<MODE>(a, T.t + gridDim.x, total, T);
+          continue;
+        }
         for (int kb = 0; kb < T.nkb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
@@ -310,7 +397,7 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     // decomposition is done ONCE per tile, one row per lane, with 32-bit divisions; the store loop fetches a row's offset
     // with a warp shuffle.  Calling d2s_dest / s2d_dest per (row, column chunk) -- four 64-bit divisions each -- made the
     // epilogue, not the MMA mainloop, the critical path of every decoder layer (4x on the 16x16 conv).
-    const bool need_bhw = MODE != WGRAD && (a.perm_r > 0 || (MODE == DGRAD && a.os > 1));
+    const bool need_bhw = HALO || (MODE != WGRAD && (a.perm_r > 0 || (MODE == DGRAD && a.os > 1)));
     const int pr = a.perm_r > 0 ? a.perm_r : 1;
     const int rsh = (pr & (pr - 1)) == 0 ? __ffs(pr) - 1 : -1;
     const int GHr = a.GH / pr, GWr = a.GW / pr, Cp_d2s = Ng / (pr * pr);
@@ -328,7 +415,8 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         bias_tile = T.n_tile;
       }
       if (do_stat) {                                 // running sums follow (n_tile, group): flush when either changes
-        const int grp = a.stat_groups > 1 ? (int)(((long long)T.m_tile * BM) / a.stat_group_rows) : 0;
+        const int grp = a.stat_groups > 1 ? (HALO ? T.m_tile / a.halo_tiles_per_img
+                                                  : (int)(((long long)T.m_tile * BM) / a.stat_group_rows)) : 0;
         if (stat_tile >= 0 && (stat_tile != T.n_tile || stat_group != grp)) stat_flush<BN>(a, wstat, stat_tile, stat_group, lane);
         stat_tile = T.n_tile;
         stat_group = grp;
@@ -339,10 +427,19 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       // lane L owns the addressing of row L of this warp's 32-row slab; the store loop fetches it with a shuffle
       long long my_o = 0, my_arow = 0;
       if (need_bhw) {                                // rows < 2^31 (checked by ladder_conv2d_tma_supported)
-        const unsigned mu = (unsigned)(mrow0 + lane);
-        const int pw = (int)(mu % (unsigned)a.GW);
-        const unsigned rq = mu / (unsigned)a.GW;
-        const int ph = (int)(rq % (unsigned)a.GH), pb = (int)(rq / (unsigned)a.GH);
+        int pw, ph, pb;
+        if constexpr (HALO) {                        // row r of the tile is pixel (ty * 16 + r / 8, tx * 8 + r % 8) of image pb
+          pb = T.m_tile / a.halo_tiles_per_img;
+          const int rem = T.m_tile - pb * a.halo_tiles_per_img, ty = rem / a.halo_tiles_x, r = quad * 32 + lane;
+          ph = ty * HALO_TH + (r >> 3);
+          pw = (rem - ty * a.halo_tiles_x) * HALO_TW + (r & 7);
+        } else {
+          const unsigned mu = (unsigned)(mrow0 + lane);
+          pw = (int)(mu % (unsigned)a.GW);
+          const unsigned rq = mu / (unsigned)a.GW;
+          ph = (int)(rq % (unsigned)a.GH);
+          pb = (int)(rq / (unsigned)a.GH);
+        }
         my_arow = (((long long)pb * a.GH + ph) * a.GW + pw) * Ng;
         if (MODE == DGRAD && a.os > 1)               // parity class of a strided dgrad: scatter into the full map
           my_arow = (((long long)pb * a.OHf + ph * a.os + a.opy) * a.OWf + pw * a.os + a.opx) * Ng;
@@ -356,6 +453,15 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           }
         }
       }
+      // tcgen05.ld hands this thread ONE accumulator row (32 columns per chunk): it is finished and stored from registers,
+      // 64 (bf16) / 128 (fp32) contiguous bytes per thread and chunk.  (r1 transposed every chunk through shared memory so that
+      // 8 lanes shared a row: ~110 SASS instructions per 4-row store iteration, 10.9 k cycles per 128x128 tile against 4.6 k
+      // of MMA -- gpurun_out/r2f_conv7.ncu-rep -- i.e. the epilogue, not the tensor pipe, bounded every large conv.)
+      const long long m_row = mrow0 + lane;
+      const bool row_ok = HALO || m_row < Mg;
+      const long long o_row = need_bhw ? my_o : m_row * Ng, a_row = need_bhw ? my_arow : m_row * Ng;
+      const bool perm_f = MODE == FPROP && a.perm_r > 0;
+      const bool fast_n = (Ng & 7) == 0 && (!perm_f || (Cp_d2s & 7) == 0);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
@@ -373,12 +479,12 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
             for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
           }
         }
+        if (do_stat) {                               // column sums need the transpose: lane = column over this warp's rows
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        __syncwarp();
-        if (do_stat) {                               // lane = column: sum the fp32 values of this warp's (valid) rows
-          const long long left = Mg - mrow0;
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(stage + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          __syncwarp();
+          const long long left = HALO ? 32 : Mg - mrow0;
           const int rows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
           float s1 = 0.f, s2 = 0.f;
           for (int r = 0; r < rows; ++r) {
@@ -388,73 +494,75 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           }
           wstat[c0 + lane] += s1;
           wstat[256 + c0 + lane] += s2;
+          __syncwarp();
         }
-        const int col = nb + c4;
-        bool vec_ok = (Ng & 3) == 0 && col + 4 <= Ng;
-        long long coloff = col;
-        if (MODE == FPROP && a.perm_r > 0) {
-          const int r = a.perm_r, Cp = Ng / (r * r), ij = col / Cp, c = col % Cp;
-          coloff = ((long long)(ij / r) * a.GW * r + ij % r) * Cp + c;
-          vec_ok = vec_ok && (Cp & 3) == 0;
-        }
-#pragma unroll 2
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + sub;
-          const long long m = mrow0 + r;
-          const float4 q = *reinterpret_cast<const float4*>(stage + r * 36 + c4);
-          long long o, arow;                             // output row / row of the saved activation (aux)
-          if (!need_bhw) {
-            o = arow = m * Ng;
-          } else {                                       // warp-uniform branch: every lane takes part in the shuffles
-            o = __shfl_sync(0xffffffffu, my_o, r);
-            arow = MODE == DGRAD ? __shfl_sync(0xffffffffu, my_arow, r) : o;
-          }
-          if (m >= Mg || col >= Ng) continue;
-          o += coloff;
-          if (!vec_ok) {
-            slow_store<MODE, OUT16>(a, q, m, col, o, arow, slope, is_tanh);
-            continue;
-          }
-          float e[4] = {q.x, q.y, q.z, q.w};
-          if (MODE == DGRAD) {
-            if (a.aux != nullptr) {
-              float ax[4];
-              const long long ai = arow + col;
-              if (a.aux_bf16) {
-                const uint2 u = __ldg(reinterpret_cast<const uint2*>(auxh + ai));
-                ax[0] = bf16_bits_to_float(u.x & 0xffffu); ax[1] = bf16_bits_to_float(u.x >> 16);
-                ax[2] = bf16_bits_to_float(u.y & 0xffffu); ax[3] = bf16_bits_to_float(u.y >> 16);
-              } else {
-                const float4 f = __ldg(reinterpret_cast<const float4*>(auxf + ai));
-                ax[0] = f.x; ax[1] = f.y; ax[2] = f.z; ax[3] = f.w;
-              }
+        if (!row_ok) continue;
+        if (fast_n && nb + 32 <= Ng) {
+          // ---- 4 groups of 8 columns; a depth_to_space store re-bases each group (C' % 8 == 0)
 #pragma unroll
-              for (int t = 0; t < 4; ++t) e[t] *= is_tanh ? 1.f - ax[t] * ax[t] : (ax[t] > 0.f ? 1.f : slope);
+          for (int q = 0; q < 4; ++q) {
+            const int col = nb + 8 * q;
+            long long coloff = col;
+            if (perm_f) {
+              const int r = a.perm_r, ij = col / Cp_d2s, c = col - ij * Cp_d2s;
+              coloff = ((long long)(ij / r) * a.GW * r + ij % r) * Cp_d2s + c;
             }
-            if (a.accumulate) {
-              if (OUT16) {
-                const uint2 u = *reinterpret_cast<const uint2*>(outh + o);
-                e[0] += bf16_bits_to_float(u.x & 0xffffu); e[1] += bf16_bits_to_float(u.x >> 16);
-                e[2] += bf16_bits_to_float(u.y & 0xffffu); e[3] += bf16_bits_to_float(u.y >> 16);
-              } else {
-                const float4 f = *reinterpret_cast<const float4*>(outf + o);
-                e[0] += f.x; e[1] += f.y; e[2] += f.z; e[3] += f.w;
+            float e[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) e[t] = v[8 * q + t];
+            if (MODE == DGRAD) {
+              if (a.aux != nullptr) {
+                float ax[8];
+                if (a.aux_bf16) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(auxh + a_row + col));
+                  const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) { ax[2 * t] = bf16_bits_to_float(w4[t] & 0xffffu); ax[2 * t + 1] = bf16_bits_to_float(w4[t] >> 16); }
+                } else {
+                  const float4 f0 = __ldg(reinterpret_cast<const float4*>(auxf + a_row + col)),
+                               f1 = __ldg(reinterpret_cast<const float4*>(auxf + a_row + col + 4));
+                  ax[0] = f0.x; ax[1] = f0.y; ax[2] = f0.z; ax[3] = f0.w; ax[4] = f1.x; ax[5] = f1.y; ax[6] = f1.z; ax[7] = f1.w;
+                }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) e[t] *= is_tanh ? 1.f - ax[t] * ax[t] : (ax[t] > 0.f ? 1.f : slope);
+              }
+              if (a.accumulate) {
+                if (OUT16) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(outh + o_row + coloff);
+                  const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) { e[2 * t] += bf16_bits_to_float(w4[t] & 0xffffu); e[2 * t + 1] += bf16_bits_to_float(w4[t] >> 16); }
+                } else {
+                  const float4 f0 = *reinterpret_cast<const float4*>(outf + o_row + coloff),
+                               f1 = *reinterpret_cast<const float4*>(outf + o_row + coloff + 4);
+                  e[0] += f0.x; e[1] += f0.y; e[2] += f0.z; e[3] += f0.w; e[4] += f1.x; e[5] += f1.y; e[6] += f1.z; e[7] += f1.w;
+                }
               }
             }
+            if (MODE == WGRAD) {
+              atomicAdd(reinterpret_cast<float4*>(outf + o_row + coloff), make_float4(e[0], e[1], e[2], e[3]));   // red.global.add.v4.f32
+              atomicAdd(reinterpret_cast<float4*>(outf + o_row + coloff + 4), make_float4(e[4], e[5], e[6], e[7]));
+            } else if (OUT16) {
+              *reinterpret_cast<uint4*>(outh + o_row + coloff) = pack8(e);
+            } else {
+              *reinterpret_cast<float4*>(outf + o_row + coloff) = make_float4(e[0], e[1], e[2], e[3]);
+              *reinterpret_cast<float4*>(outf + o_row + coloff + 4) = make_float4(e[4], e[5], e[6], e[7]);
+            }
           }
-          if (MODE == WGRAD) {
-            atomicAdd(reinterpret_cast<float4*>(outf + o), make_float4(e[0], e[1], e[2], e[3]));   // red.global.add.v4.f32
-          } else if (OUT16) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(e[0], e[1]), p1 = __floats2bfloat162_rn(e[2], e[3]);
-            uint2 u;
-            u.x = *reinterpret_cast<uint32_t*>(&p0);
-            u.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(outh + o) = u;
-          } else {
-            *reinterpret_cast<float4*>(outf + o) = make_float4(e[0], e[1], e[2], e[3]);
+        } else {
+          // ---- ragged N / narrow depth_to_space groups: 4 columns at a time through the scalar path
+          for (int q = 0; q < 8; ++q) {
+            const int col = nb + 4 * q;
+            if (col >= Ng) break;
+            long long coloff = col;
+            if (perm_f) {
+              const int r = a.perm_r, ij = col / Cp_d2s, c = col - ij * Cp_d2s;
+              coloff = ((long long)(ij / r) * a.GW * r + ij % r) * Cp_d2s + c;
+            }
+            slow_store<MODE, OUT16>(a, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), m_row, col, o_row + coloff,
+                                    a_row, slope, is_tanh);
           }
         }
-        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + acc * 8);
@@ -523,7 +631,33 @@ static void dense_as_row(int& B, int& H, int& W, int KH, int KW, int& OH, int& O
 }
 
 // bf16 NHWC tensor [B, SH, SW, C] as a 4-D tensor map {C, SW, SH, B}, SWIZZLE_128B, zero fill outside
-static int make_map(CUtensorMap* map, const void* ptr, int B, int SH, int SW, int C, int bw, int bh, int bb, int es = 1) {
+static int make_map(CUtensorMap* map, const void* ptr, int B, int SH, int SW, int C, int bw, int bh, int bb, int es = 1);
+
+// halo mode: environment switches (diagnostics): LADDER_HALO=0 disables it, LADDER_HALO_BASE=0 leaves the descriptor's
+// base-offset field zero
+static int g_halo_on = -1, g_halo_base = -1;       // -1: from the environment on first use; set by ladder_conv2d_tma_set_halo
+static bool halo_enabled() {
+  if (g_halo_on < 0) { const char* e = getenv("LADDER_HALO"); g_halo_on = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1); }
+  return g_halo_on != 0;
+}
+static int halo_base_mode() {
+  // measured (scripts/halo_probe.py, r2f): the hardware applies SWIZZLE_128B to the ADDRESS bits of every row it reads, so a
+  // view that starts kw rows into an atom needs NO base offset (base_mode 0 is bit-exact against the per-tap kernel, 1 is wrong)
+  if (g_halo_base < 0) { const char* e = getenv("LADDER_HALO_BASE"); g_halo_base = (e && e[0] == '1') ? 1 : 0; }
+  return g_halo_base;
+}
+// stride-1 3x3 layer over a [B, GH, GW] pixel grid whose epilogue never needs the scalar slow path
+static bool halo_ok(int mode, int GH, int GW, int C, int KH, int KW, int stride, int Ng, int perm_r) {
+  // measured (scripts/halo_probe.py, r2g): +6 % at N = 256 (fashion decoder fprop, 854 -> 903 TFLOP/s), -4 .. -8 % at N <= 128,
+  // where the 9 weight tiles per chunk, not the activation tile, are the longer stream: automatic use is limited to N >= 256
+  // (LADDER_HALO=2 / ladder_conv2d_tma_set_halo(2, .) forces it everywhere, for tests and probes)
+  if (!halo_enabled() || (g_halo_on != 2 && Ng < 256)) return false;
+  if (stride != 1 || KH != 3 || KW != 3 || GH % HALO_TH || GW % HALO_TW || C % BK || (Ng & 3)) return false;
+  if (perm_r > 0 && mode == FPROP && ((Ng / (perm_r * perm_r)) & 3)) return false;
+  return true;
+}
+
+static int make_map(CUtensorMap* map, const void* ptr, int B, int SH, int SW, int C, int bw, int bh, int bb, int es) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(LADDER_ERR_CUDA, "conv2d_tma: cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)SW, (cuuint64_t)SH, (cuuint64_t)B};
@@ -538,7 +672,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int B, int SH, int SW, in
   return LADDER_OK;
 }
 
-template <int MODE>
+template <int MODE, bool HALO = false>
 static int launch(const CUtensorMap& mA, const CUtensorMap& mB, Args& a, long long Mg, int bn, cudaStream_t st) {
   a.m_tiles = (int)ceil_div64(Mg, BM);
   a.n_tiles = ceil_div(a.Ng, bn);
@@ -546,10 +680,30 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, Args& a, long lo
   const int sms = num_sms();
   const unsigned grid = (unsigned)(total < sms ? total : sms);
   auto go = [&](auto kern, int BNv) {
-    const size_t smem = (size_t)stages_for(BNv) * (A_STAGE_BYTES + BNv * BK * 2) + 1024 + 256 + EPI_BYTES + BIAS_BYTES + STAT_BYTES;
+    const size_t ab = HALO ? (size_t)HALO_STAGES * HALO_BYTES + (size_t)halo_b_stages(BNv) * BNv * BK * 2
+                           : (size_t)stages_for(BNv) * (A_STAGE_BYTES + BNv * BK * 2);
+    const size_t smem = ab + 1024 + 256 + EPI_BYTES + BIAS_BYTES + STAT_BYTES;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, NTHREADS, smem, st>>>(mA, mB, a);
   };
+  if constexpr (HALO) {
+    if (a.out_bf16) {
+      switch (bn) {
+        case 32: go(tma_kernel<MODE, 32, true, true>, 32); break;
+        case 64: go(tma_kernel<MODE, 64, true, true>, 64); break;
+        case 128: go(tma_kernel<MODE, 128, true, true>, 128); break;
+        default: go(tma_kernel<MODE, 256, true, true>, 256); break;
+      }
+    } else {
+      switch (bn) {
+        case 32: go(tma_kernel<MODE, 32, false, true>, 32); break;
+        case 64: go(tma_kernel<MODE, 64, false, true>, 64); break;
+        case 128: go(tma_kernel<MODE, 128, false, true>, 128); break;
+        default: go(tma_kernel<MODE, 256, false, true>, 256); break;
+      }
+    }
+    return check_launch("tcgen05 TMA conv kernel (halo)");
+  }
   if (a.out_bf16) {
     if constexpr (MODE != WGRAD) {
       switch (bn) {
@@ -660,6 +814,16 @@ size_t ladder_conv2d_tma_workspace_bytes(int Cin, int KH, int KW, int Cout) {
   return m + 256 + 64 * 1024;    // + alignment slack of the per-class images of a strided dgrad
 }
 
+/* diagnostic switch of the halo mode of the stride-1 3x3 fprop / dgrad kernels (see conv_tma.cu): enabled 0 / 1, base_mode 0 / 1
+ * (negative: leave unchanged); returns the previous `enabled`.  Defaults: LADDER_HALO / LADDER_HALO_BASE, both 1. */
+int ladder_conv2d_tma_set_halo(int enabled, int base_mode) {
+  const int prev = halo_enabled() ? 1 : 0;
+  halo_base_mode();
+  if (enabled >= 0) g_halo_on = enabled > 2 ? 1 : enabled;
+  if (base_mode >= 0) g_halo_base = base_mode ? 1 : 0;
+  return prev;
+}
+
 /* N tile width the TMA launcher uses for GEMM `mode` of this geometry (the packed weight image depends on it) */
 int ladder_conv2d_tma_bn(int mode, int B, int H, int W, int Cin, int Cout, int OH, int OW) {
   switch (mode) {
@@ -736,10 +900,11 @@ int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bia
   else if (workspace == nullptr || workspace_bytes < tc::pack_bytes(Cout, KH * KW * Cin, bn))
     rc = fail(LADDER_ERR_WORKSPACE, "conv2d_fprop_tma: packed weight image too small");
   if (rc) return rc;
+  const bool halo = halo_ok(FPROP, OH, OW, Cin, KH, KW, stride, Cout, out_d2s) && H == OH && W == OW;
   int bw, bh, bb;
   pixel_box(OW, OH, B, BM, bw, bh, bb);
   CUtensorMap mA;
-  rc = make_map(&mA, x_bf16, B, H, W, Cin, bw, bh, bb, stride);
+  rc = halo ? make_map(&mA, x_bf16, B, H, W, Cin, HALO_PITCH, HALO_ROWS, 1) : make_map(&mA, x_bf16, B, H, W, Cin, bw, bh, bb, stride);
   if (rc) return rc;
   Args a;
   memset(&a, 0, sizeof(a));
@@ -750,6 +915,12 @@ int ladder_conv2d_fprop_tma(const void* x_bf16, const float* w, const float* bia
   a.off_y = -pad_t; a.off_x = -pad_l; a.sign = 1;
   a.Ng = Cout; a.act = act; a.nkb = KH * KW * (Cin / BK); a.splits = 1; a.perm_r = out_d2s;
   a.stat = stat_sums; a.stat_groups = stat_sums ? stat_groups : 0; a.stat_group_rows = stat_group_rows;
+  if (halo) {
+    a.halo_ox = -pad_l; a.halo_oy = -pad_t;                   // taps read offsets off + k, k = 0..2: the origin is tap 0
+    a.halo_tiles_x = OW / HALO_TW; a.halo_tiles_per_img = (OH / HALO_TH) * (OW / HALO_TW);
+    a.halo_base_mode = halo_base_mode();
+    return launch<FPROP, true>(mA, mA, a, (long long)B * OH * OW, bn, stream);
+  }
   return launch<FPROP>(mA, mA, a, (long long)B * OH * OW, bn, stream);
 }
 
@@ -807,10 +978,11 @@ int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w, const void* act
   else if (workspace == nullptr || workspace_bytes < tc::pack_bytes(Cin, KH * KW * Cout, bn))
     rc = fail(LADDER_ERR_WORKSPACE, "conv2d_dgrad_tma: packed weight image too small");
   if (rc) return rc;
+  const bool halo = halo_ok(DGRAD, H, W, Cout, KH, KW, 1, Cin, out_s2d) && H == OH && W == OW;
   int bw, bh, bb;
   pixel_box(W, H, B, BM, bw, bh, bb);
   CUtensorMap mA;
-  rc = make_map(&mA, dy_bf16, B, OH, OW, Cout, bw, bh, bb);
+  rc = halo ? make_map(&mA, dy_bf16, B, OH, OW, Cout, HALO_PITCH, HALO_ROWS, 1) : make_map(&mA, dy_bf16, B, OH, OW, Cout, bw, bh, bb);
   if (rc) return rc;
   Args a;
   memset(&a, 0, sizeof(a));
@@ -820,6 +992,12 @@ int ladder_conv2d_dgrad_tma(const void* dy_bf16, const float* w, const void* act
   a.GW = W; a.GH = H; a.B = B; a.C = Cout; a.KH = KH; a.KW = KW;
   a.off_y = pad_t; a.off_x = pad_l; a.sign = -1;       // dx(y, x) += dy(y + pad_t - kh, x + pad_l - kw) . w(kh, kw)
   a.Ng = Cin; a.act = act; a.accumulate = accumulate; a.nkb = KH * KW * (Cout / BK); a.splits = 1; a.perm_r = out_s2d;
+  if (halo) {
+    a.halo_ox = pad_l - (KW - 1); a.halo_oy = pad_t - (KH - 1);    // taps read offsets pad - k: the origin is the LAST tap
+    a.halo_tiles_x = W / HALO_TW; a.halo_tiles_per_img = (H / HALO_TH) * (W / HALO_TW);
+    a.halo_base_mode = halo_base_mode();
+    return launch<DGRAD, true>(mA, mA, a, (long long)B * H * W, bn, stream);
+  }
   return launch<DGRAD>(mA, mA, a, (long long)B * H * W, bn, stream);
 }
 

@@ -54,6 +54,7 @@ SIGNATURES = {
     'ladder_conv2d_tma_pack': (C.c_int, [ptr, ptr, C.c_size_t] + [C.c_int] * 6 + [stream_t]),
     'ladder_pack_weights_multi': (C.c_int, [ptr, ptr, ptr, C.c_int, C.c_longlong, stream_t]),
     'ladder_conv2d_fprop_tma': (C.c_int, [ptr, ptr, ptr, ptr, C.c_int] + [C.c_int] * 14 + [ptr, C.c_size_t, ptr, C.c_int, stream_t]),
+    'ladder_conv2d_tma_set_halo': (C.c_int, [C.c_int, C.c_int]),
     'ladder_conv2d_dgrad_tma': (C.c_int, [ptr, ptr, ptr, C.c_int, ptr, C.c_int] + [C.c_int] * 15 + [ptr, C.c_size_t, stream_t]),
     'ladder_conv2d_wgrad_tma': (C.c_int, [ptr, ptr, ptr] + [C.c_int] * 12 + [stream_t]),
     'ladder_tap_dgrad': (C.c_int, [ptr, ptr, ptr, C.c_int, ptr, C.c_int] + [C.c_int] * 14 + [stream_t]),

@@ -550,6 +550,11 @@ def _tma_ws(x, g):
     return ws, ws.numel()
 
 
+def set_halo(enabled=-1, base_mode=-1):
+    """Diagnostic switch of the halo mode of the TMA-fed 3x3 GEMMs (ladder_conv2d_tma_set_halo); returns the previous state."""
+    return int(_L().ladder_conv2d_tma_set_halo(int(enabled), int(base_mode)))
+
+
 def colsum(dy, rows, cols, out):
     if dy.dtype == torch.bfloat16:
         _lib.check(_L().ladder_colsum_bf16(_p(dy), rows, cols, _p(out), _stream()), 'colsum_bf16')

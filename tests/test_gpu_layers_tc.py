@@ -341,3 +341,45 @@ def test_multi_tensor_weight_pack_matches_single_layer_pack(ops):
         for mode in (ops.FPROP, ops.DGRAD):
             if c.tma[mode] and c.wimg[mode] is not None:       # strided dgrad packs per parity class at call time
                 assert torch.equal(c.wimg[mode], ops.tma_pack(c.w, c.geom, mode)), (n, mode)
+
+
+@pytest.mark.parametrize('B,HW,Cin,Cout', [(2, 16, 64, 64), (3, 16, 256, 64), (2, 32, 128, 128), (4, 16, 64, 256), (1, 48, 64, 128)])
+def test_halo_mode_is_bit_exact_against_the_per_tap_kernel(B, HW, Cin, Cout):
+    """Halo mode of the stride-1 3x3 GEMMs (one 18 x 16-pixel halo box per 64-channel chunk, the 9 taps as shifted UMMA
+    descriptors on the swizzled buffer) against the per-tap TMA kernel: same MMAs in the same order, so the same bits --
+    fprop with bias + leaky_relu and the fused depth_to_space store, dgrad with the producer's activation derivative and the
+    space_to_depth scatter, and the epilogue statistics."""
+    import torch
+    from ladder_latent_data_distribution_modelling_b200 import ops
+    ops.set_math_mode('bf16')
+    bf = torch.bfloat16
+    torch.manual_seed(B * 1000 + HW)
+    g = ops.ConvGeom(B, HW, HW, Cin, 3, 3, Cout, 1, 'same')
+    x = torch.randn(B, HW, HW, Cin, device='cuda').to(bf)
+    w = torch.randn(3, 3, Cin, Cout, device='cuda') * 0.05
+    b = torch.randn(Cout, device='cuda')
+    dy = torch.randn(B, HW, HW, Cout, device='cuda').to(bf)
+    aux = torch.randn(B, HW, HW, Cin, device='cuda').to(bf)
+    out = {}
+    prev = ops.set_halo(-1, -1)
+    try:
+        for mode in (0, 2):
+            ops.set_halo(mode, 0)
+            y = torch.empty(B, HW, HW, Cout, device='cuda', dtype=bf)
+            ops.conv2d_fprop(x, w, b, y, g, 'leaky_relu')
+            yd = torch.empty(B, 2 * HW, 2 * HW, Cout // 4, device='cuda', dtype=bf)
+            ops.conv2d_fprop(x, w, b, yd, g, 'leaky_relu', out_d2s=2)
+            y32 = torch.empty(B, HW, HW, Cout, device='cuda')
+            sums = torch.zeros(2, 1, Cout, device='cuda')
+            ops.conv2d_fprop(x, w, b, y32.to(bf), g, None, stats=(sums, 1))
+            dx = torch.empty(B, HW, HW, Cin, device='cuda', dtype=bf)
+            ops.conv2d_dgrad(dy, w, dx, g, act_out=aux, act='leaky_relu')
+            dxs = torch.empty(B, HW // 2, HW // 2, Cin * 4, device='cuda')
+            ops.conv2d_dgrad(dy, w, dxs, g, act_out=aux, act='leaky_relu', out_s2d=2)
+            torch.cuda.synchronize()
+            out[mode] = (y, yd, dx, dxs, sums)
+    finally:
+        ops.set_halo(prev, 0)
+    for a, c in zip(out[0][:4], out[2][:4]):
+        assert torch.equal(a, c)
+    assert torch.allclose(out[0][4], out[2][4], rtol=1e-5, atol=1e-3)       # fp32 atomics: order only
