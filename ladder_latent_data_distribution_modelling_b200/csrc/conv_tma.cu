@@ -50,11 +50,14 @@ __host__ __device__ constexpr int stages_for(int bn) {
 // shifted view needs no base offset.
 constexpr int HALO_TW = 8, HALO_TH = 16, HALO_PITCH = 16, HALO_ROWS = HALO_TH + 2;
 constexpr int HALO_BYTES = HALO_ROWS * HALO_PITCH * 128;      // 36 864 B per 64-channel chunk
-constexpr int HALO_STAGES = 2;
+// One halo buffer feeds 9 taps x 4 MMAs: 1152 / 2304 / 4608 tensor-pipe cycles at N = 64 / 128 / 256, against ~2-3 k cycles of
+// loaded TMA latency for the 36 KB box: the narrower the tile, the more halo buffers must be in flight (r2g: with 2 buffers the
+// N <= 128 kernels stalled on the halo ring at every chunk boundary and ran 4-8 % SLOWER than the per-tap kernel).
+__host__ __device__ constexpr int halo_stages(int bn) { return bn <= 64 ? 4 : (bn <= 128 ? 3 : 2); }
 __host__ __device__ constexpr int halo_b_stages(int bn) {
-  return (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES - STAT_BYTES - HALO_STAGES * HALO_BYTES) / (bn * BK * 2) > 10
-             ? 10        // (2 * stages + 9) mbarriers must fit the 256-byte barrier block
-             : (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES - STAT_BYTES - HALO_STAGES * HALO_BYTES) / (bn * BK * 2);
+  return (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES - STAT_BYTES - halo_stages(bn) * HALO_BYTES) / (bn * BK * 2) > 9
+             ? 9         // (2 * stages + 13) mbarriers must fit the 256-byte barrier block
+             : (232448 - 1024 - 256 - EPI_BYTES - BIAS_BYTES - STAT_BYTES - halo_stages(bn) * HALO_BYTES) / (bn * BK * 2);
 }
 
 enum { FPROP = 0, DGRAD = 1, WGRAD = 2 };
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Args a) {
   // plain mode: STAGES x (A tile + B tile).  halo mode: HALO_STAGES halo buffers (ring `h`) + STAGES B tiles (ring `s`)
   constexpr int STAGES = HALO ? halo_b_stages(BN) : stages_for(BN);
+  constexpr int HALO_STAGES = halo_stages(BN);
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   constexpr int A_REGION = HALO ? HALO_STAGES * HALO_BYTES : STAGES * A_STAGE_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
@@ -195,7 +199,7 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   const uint32_t bar_full = bars, bar_empty = bars + STAGES * 8, bar_tfull = bars + 2 * STAGES * 8,
                  bar_tempty = bars + (2 * STAGES + 2) * 8;
   const uint32_t slot = bars + (2 * STAGES + 4) * 8;
-  const uint32_t bar_hfull = bars + (2 * STAGES + 5) * 8, bar_hempty = bars + (2 * STAGES + 7) * 8;   // <= 29 x 8 B < 256
+  const uint32_t bar_hfull = bars + (2 * STAGES + 5) * 8, bar_hempty = bars + (2 * STAGES + 9) * 8;   // <= 31 x 8 B <= 256
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (slot - base));
   const uint32_t stage_off = bars + 256 - base;                 // epilogue staging (4 x 32 x 36 floats)
 
@@ -213,6 +217,8 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + i * 8, 1);
       mbar_init(bar_tempty + i * 8, 128);
+    }
+    for (int i = 0; i < 4; ++i) {
       mbar_init(bar_hfull + i * 8, 1);
       mbar_init(bar_hempty + i * 8, 1);
     }
@@ -680,7 +686,7 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, Args& a, long lo
   const int sms = num_sms();
   const unsigned grid = (unsigned)(total < sms ? total : sms);
   auto go = [&](auto kern, int BNv) {
-    const size_t ab = HALO ? (size_t)HALO_STAGES * HALO_BYTES + (size_t)halo_b_stages(BNv) * BNv * BK * 2
+    const size_t ab = HALO ? (size_t)halo_stages(BNv) * HALO_BYTES + (size_t)halo_b_stages(BNv) * BNv * BK * 2
                            : (size_t)stages_for(BNv) * (A_STAGE_BYTES + BNv * BK * 2);
     const size_t smem = ab + 1024 + 256 + EPI_BYTES + BIAS_BYTES + STAT_BYTES;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
