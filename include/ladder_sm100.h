@@ -82,6 +82,13 @@ size_t ladder_mixture_tc_workspace_bytes(long long N, int K);
 int ladder_mixture_logprob_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
                               float iso_scale, float ref_log2, float* logp, void* workspace,
                               size_t workspace_bytes, cudaStream_t stream);
+/* Forward AND gradient on the tensor cores (same isotropic D in {32, 64} image): d log p / d t_n = -2 ln2 a' (t'_n - sum_k p_nk
+ * mu'_k); the second sum is a second contraction W . mu whose A operand W = exp2(scores) stays in TMEM (written in place of the
+ * scores) and whose B operand is the same component tile read MN-major.  grad_t [N, D]; logp may be NULL.                   */
+size_t ladder_mixture_tc_grad_workspace_bytes(long long N, int K, int D);
+int ladder_mixture_logprob_grad_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
+                                   float iso_scale, float ref_log2, float* logp /*nullable*/, float* grad_t, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t stream);
 /* VampPrior mixture (codes/base.py:215-254): K diagonal Gaussians with equal weights whose means / stds are device
  * tensors produced by the shared encoder from the trainable pseudo-inputs.
  *  - ladder_mixture_pack_diag_device packs the mode-1 table and its log2 frame ON THE DEVICE (no host round trip, graph

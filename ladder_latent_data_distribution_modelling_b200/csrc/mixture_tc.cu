@@ -265,6 +265,293 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_kernel(Args a) {
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ forward + gradient
+// d log p / d t_n = -2 ln2 a' (t'_n - sum_k p_nk mu'_k),  p_nk = w_nk / S_n,  w_nk = 2^(e2_nk - M): the second sum is ANOTHER
+// contraction, G'_n = sum_k w_nk (2 mu'_k) = W [N x K] . (2 mu') [K x D], fed from where the first one ends:
+//   * the consumers overwrite each S accumulator column IN PLACE with w = ex2(S + ck - tn) (tcgen05.st; same lane = query row,
+//     same column = component), so W is already the TMEM-resident A operand of a kind::tf32 MMA (M = 128 queries, K = 128
+//     components, no shared-memory round trip, the N x K matrix still never leaves the SM);
+//   * its B operand is the SAME component tile the first MMA read: [128 components x D] with D contiguous is K-major for
+//     t . mu^T and MN-major for W . mu (descriptor `make_desc_mn`, 8 component rows = one K step);
+//   * G' [128 x D] accumulates in TMEM across all component chunks of the unit and is read once at the end.
+// TMEM: S0 | S1 (2 query sub-tiles x 128 columns, single-buffered: the two sub-tiles ping-pong between the tensor pipe and the
+// SFU as in flash-attention) | G'0 | G'1 (2 x D columns).  Per pair: 2 D tf32 flops (t.mu) + 2 D (W.mu) + 1 MUFU.EX2.
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc], tf32
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+// MN-major SWIZZLE_128B descriptor (32 fp32 = 128 B contiguous along MN per K row, 8 K rows per 1024-byte atom, next MN block LBO away)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// a = b = TF32, A K-major (TMEM), B MN-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32_bmn(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct GradArgs {
+  const float* t;
+  const float* bimg;
+  float* part_s;         // [splits, N]
+  float* part_g;         // [splits, N, D]  sum_k w_nk (2 mu'_k)
+  long long N;
+  int n_chunks, chunks_per_split, splits;
+  float iso_scale;
+};
+
+constexpr int GSTAGES = 3;
+
+template <int D>
+__global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
+  constexpr int ATOMS = D / 32;
+  constexpr int A_BYTES = 2 * ATOMS * 128 * 128;
+  constexpr int B_BYTES = ATOMS * BN * 128;
+  constexpr int B_STAGE = B_BYTES + BN * 4;
+  constexpr int B_STRIDE = (B_STAGE + 1023) / 1024 * 1024;
+  constexpr uint32_t G_COL = 256;                       // TMEM columns: S0 [0,128) S1 [128,256) G0 [256,256+D) G1 [256+D, 256+2D)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + A_BYTES;
+  const uint32_t bars = sB + GSTAGES * B_STRIDE;
+  const uint32_t bar_full = bars, bar_empty = bars + GSTAGES * 8, bar_sfull = bars + 2 * GSTAGES * 8, bar_sfree = bar_sfull + 16,
+                 bar_wfull = bar_sfree + 16, bar_gfull = bar_wfull + 16, bar_gfree = bar_gfull + 16, bar_a = bar_gfree + 16,
+                 bar_adone = bar_a + 8;
+  const uint32_t slot = bar_adone + 8;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (slot - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long row_tiles = (a.N + QROWS - 1) / QROWS;
+  const long long units = row_tiles * a.splits;
+
+  if (tid == 0) {
+    for (int s = 0; s < GSTAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1 + 8);            // commit after the stage's last MMA + one lane of each consumer warp (ck)
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_sfull + i * 8, 1);                // MMA1 of the sub-tile retired: S readable
+      mbar_init(bar_sfree + i * 8, 1);                // MMA2 of the sub-tile retired: S / W columns reusable
+      mbar_init(bar_wfull + i * 8, 128);              // the sub-tile's 4 consumer warps wrote W
+      mbar_init(bar_gfull + i * 8, 1);                // last MMA2 of the unit retired: G' readable
+      mbar_init(bar_gfree + i * 8, 128);              // consumers read G'
+    }
+    mbar_init(bar_a, 256);
+    mbar_init(bar_adone, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      unsigned it = 0;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const int split = (int)(u % a.splits);
+        const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
+        for (int c = c_lo; c < c_hi; ++c, ++it) {
+          const int s = it % GSTAGES;
+          mbar_wait(bar_empty + s * 8, ((it / GSTAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full + s * 8, B_STAGE);
+          tma_bulk_g2s(sB + s * B_STRIDE, reinterpret_cast<const uint8_t*>(a.bimg) + (size_t)c * B_STAGE, B_STAGE, bar_full + s * 8);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc_tf32(128, BN), idesc2 = make_idesc_tf32_bmn(128, D);
+      unsigned it = 0, g = 0, un = 0;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x, ++un) {
+        const int split = (int)(u % a.splits);
+        const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
+        mbar_wait(bar_a, un & 1);
+        fence_proxy_async();
+        for (int c = c_lo; c < c_hi; ++c, ++it, ++g) {
+          const int s = it % GSTAGES;
+          mbar_wait(bar_full + s * 8, (it / GSTAGES) & 1);
+          tc_fence_after();
+          const uint32_t tB = sB + s * B_STRIDE;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {           // S_sub = t' . (2 mu')^T
+            mbar_wait(bar_sfree + sub * 8, (g & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_s = tmem_base + sub * BN;
+#pragma unroll
+            for (int k = 0; k < D / 8; ++k) {
+              const int atom = k / 4, kk = k % 4;
+              umma_tf32(tmem_s, make_desc(sA + (sub * ATOMS + atom) * (128 * 128) + kk * 32),
+                        make_desc(tB + atom * (BN * 128) + kk * 32), idesc1, k != 0);
+            }
+            umma_commit(bar_sfull + sub * 8);
+          }
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {           // G'_sub += W_sub . (2 mu')
+            if (c == c_lo) {                            // first chunk of the unit overwrites G': the previous unit's was read
+              mbar_wait(bar_gfree + sub * 8, (un & 1) ^ 1);
+            }
+            mbar_wait(bar_wfull + sub * 8, g & 1);
+            tc_fence_after();
+            const uint32_t tmem_g = tmem_base + G_COL + sub * D, tmem_w = tmem_base + sub * BN;
+#pragma unroll
+            for (int k = 0; k < BN / 8; ++k)            // 8 components (rows of the tile, 1024 B) per K step
+              umma_tf32_ts(tmem_g, tmem_w + k * 8, make_desc_mn(tB + k * 1024, BN * 128), idesc2, (c != c_lo) | (k != 0));
+            umma_commit(bar_sfree + sub * 8);
+            if (c == c_hi - 1) umma_commit(bar_gfull + sub * 8);
+          }
+          umma_commit(bar_empty + s * 8);
+        }
+        umma_commit(bar_adone);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int sub = (warp - 4) >> 2, quad = warp & 3;
+    const int row = sub * 128 + quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    unsigned it = 0, g = 0, un = 0;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x, ++un) {
+      const long long rt = u / a.splits;
+      const int split = (int)(u % a.splits);
+      const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
+      const long long n = rt * QROWS + row;
+      if (un > 0) mbar_wait(bar_adone, (un - 1) & 1);
+      float tn = 0.f;
+      {
+        const int r = quad * 32 + lane;
+#pragma unroll
+        for (int atom = 0; atom < ATOMS; ++atom) {
+          const uint32_t rowaddr = sA + (sub * ATOMS + atom) * (128 * 128) + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < a.N) v = __ldg(reinterpret_cast<const float4*>(a.t + n * D + atom * 32 + j * 4));
+            v.x *= a.iso_scale; v.y *= a.iso_scale; v.z *= a.iso_scale; v.w *= a.iso_scale;
+            tn = fmaf(v.x, v.x, tn); tn = fmaf(v.y, v.y, tn); tn = fmaf(v.z, v.z, tn); tn = fmaf(v.w, v.w, tn);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((j ^ (r & 7)) << 4)), "f"(v.x), "f"(v.y),
+                         "f"(v.z), "f"(v.w) : "memory");
+          }
+        }
+      }
+      mbar_arrive(bar_a);
+      float S = 0.f;
+      for (int c = c_lo; c < c_hi; ++c, ++it, ++g) {
+        const int s = it % GSTAGES;
+        const float* ck = reinterpret_cast<const float*>(smem + (sB + s * B_STRIDE + B_BYTES - base));
+        mbar_wait(bar_full + s * 8, (it / GSTAGES) & 1);
+        mbar_wait(bar_sfull + sub * 8, g & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(lane_base + sub * BN + c0, v);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(ck + c0 + i);
+            v[i] = ex2((v[i] + k4.x) - tn);
+            v[i + 1] = ex2((v[i + 1] + k4.y) - tn);
+            v[i + 2] = ex2((v[i + 2] + k4.z) - tn);
+            v[i + 3] = ex2((v[i + 3] + k4.w) - tn);
+            S += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+          }
+          tmem_st32(lane_base + sub * BN + c0, v);       // W in place of S: the A operand of the second MMA
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(bar_wfull + sub * 8);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + s * 8);
+      }
+      // ---- the unit's G' row
+      mbar_wait(bar_gfull + sub * 8, un & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        float v[32];
+        tmem_ld32(lane_base + G_COL + sub * D + c0, v);
+        if (n < a.N) {
+          float* dst = a.part_g + ((size_t)split * a.N + n) * D + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_gfree + sub * 8);
+      if (n < a.N) a.part_s[(size_t)split * a.N + n] = S;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// log p and d log p / d t from the split partials; underflowed rows are recomputed exactly (two passes over all components)
+template <int D>
+__global__ void mix_tc_grad_finalize_kernel(const float* __restrict__ part_s, const float* __restrict__ part_g, int splits,
+                                            long long N, const float* __restrict__ t, const float* __restrict__ table, int K,
+                                            float iso_scale, float ref_log2, float* __restrict__ logp, float* __restrict__ grad) {
+  constexpr int STRIDE = (D + 1 + 3) / 4 * 4;
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int i = 0; i < splits; ++i) s += part_s[(size_t)i * N + n];
+  const float gc = -2.f * LN2 * iso_scale;
+  if (s >= 1e-30f) {
+    if (logp != nullptr) logp[n] = LN2 * (ref_log2 + log2f(s));
+    const float inv = 0.5f / s;                         // G' carries 2 mu'
+    for (int d = 0; d < D; ++d) {
+      float gsum = 0.f;
+      for (int i = 0; i < splits; ++i) gsum += part_g[((size_t)i * N + n) * D + d];
+      grad[n * D + d] = gc * (t[n * D + d] * iso_scale - gsum * inv);
+    }
+    return;
+  }
+  float mx = -INFINITY;
+  for (int k = 0; k < K; ++k) {
+    const float* c = table + (size_t)k * STRIDE;
+    float e = c[D];
+    for (int d = 0; d < D; ++d) { const float y = t[n * D + d] * iso_scale - c[d]; e = fmaf(-y, y, e); }
+    mx = fmaxf(mx, e);
+  }
+  for (int d = 0; d < D; ++d) grad[n * D + d] = 0.f;
+  s = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float* c = table + (size_t)k * STRIDE;
+    float e = c[D];
+    for (int d = 0; d < D; ++d) { const float y = t[n * D + d] * iso_scale - c[d]; e = fmaf(-y, y, e); }
+    const float p = exp2f(e - mx);
+    s += p;
+    for (int d = 0; d < D; ++d) grad[n * D + d] += p * c[d];
+  }
+  if (logp != nullptr) logp[n] = LN2 * (ref_log2 + mx + log2f(s));
+  for (int d = 0; d < D; ++d) grad[n * D + d] = gc * (t[n * D + d] * iso_scale - grad[n * D + d] / s);
+}
+
 // log p = ln2 * (M + log2 sum_splits S); rows that underflowed the fixed frame are recomputed exactly (two-pass)
 // from the SIMT table (iso layout [mu'(D), c2'], stride padded to 4).
 template <int D>
@@ -401,6 +688,59 @@ int ladder_mixture_logprob_tc(const float* t, long long N, int D, const float* i
   if (D == 32) mix_tc_finalize_kernel<32><<<fb, 256, 0, stream>>>(a.part, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp);
   else mix_tc_finalize_kernel<64><<<fb, 256, 0, stream>>>(a.part, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp);
   return check_launch("mixture tc finalize");
+}
+
+size_t ladder_mixture_tc_grad_workspace_bytes(long long N, int K, int D) {
+  const int n_chunks = (K + BN - 1) / BN;
+  const long long row_tiles = (N + QROWS - 1) / QROWS;
+  long long splits = ceil_div64(2LL * num_sms(), row_tiles > 0 ? row_tiles : 1);
+  if (splits > n_chunks) splits = n_chunks;
+  if (splits < 1) splits = 1;
+  return (size_t)splits * (N > 0 ? N : 1) * (size_t)(1 + D) * sizeof(float) + 256;
+}
+
+/* log p(t_n) AND d log p / d t_n for an isotropic mixture with D in {32, 64} on the tensor cores: t . mu^T (kind::tf32), the
+ * exponentials written back into TMEM in place of the scores, and W . mu (kind::tf32, A from TMEM, B = the same component tile
+ * read MN-major) -- see mix_tc_grad_kernel.  logp may be NULL.                                                                */
+int ladder_mixture_logprob_grad_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
+                                   float iso_scale, float ref_log2, float* logp, float* grad_t, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t stream) {
+  LADDER_REQUIRE(D == 32 || D == 64, "mixture_logprob_grad_tc: D must be 32 or 64 (got %d)", D);
+  LADDER_REQUIRE(N >= 0 && K >= 1, "mixture_logprob_grad_tc: bad sizes");
+  if (N == 0) return LADDER_OK;
+  LADDER_REQUIRE(t && image && simt_table && grad_t, "mixture_logprob_grad_tc: null pointer");
+  LADDER_REQUIRE(((uintptr_t)image & 127) == 0 && ((uintptr_t)t & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+                 "mixture_logprob_grad_tc: misaligned input");
+  const int n_chunks = (K + BN - 1) / BN;
+  const long long row_tiles = (N + QROWS - 1) / QROWS;
+  const int sms = num_sms();
+  long long splits = ceil_div64(2LL * sms, row_tiles);
+  if (splits > n_chunks) splits = n_chunks;
+  if (splits < 1) splits = 1;
+  const int cps = ceil_div(n_chunks, (int)splits);
+  splits = ceil_div(n_chunks, cps);
+  const size_t need = (size_t)splits * N * (size_t)(1 + D) * sizeof(float);
+  if (workspace == nullptr || workspace_bytes < need)
+    return fail(LADDER_ERR_WORKSPACE, "mixture_logprob_grad_tc: workspace %zu < %zu bytes", workspace_bytes, need);
+  float* part_g = static_cast<float*>(workspace);
+  float* part_s = part_g + (size_t)splits * N * D;
+  GradArgs a{t, image, part_s, part_g, N, n_chunks, cps, (int)splits, iso_scale};
+  const long long units = row_tiles * splits;
+  const unsigned grid = (unsigned)(units < sms ? units : sms);
+  auto go = [&](auto kern, int Dv) {
+    const int atoms = Dv / 32;
+    const size_t b_stride = ((size_t)atoms * BN * 128 + BN * 4 + 1023) / 1024 * 1024;
+    const size_t smem = (size_t)2 * atoms * 128 * 128 + GSTAGES * b_stride + 1024 + 256;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, NTHREADS, smem, stream>>>(a);
+  };
+  if (D == 32) go(mix_tc_grad_kernel<32>, 32); else go(mix_tc_grad_kernel<64>, 64);
+  int rc = check_launch("mixture tc grad kernel");
+  if (rc) return rc;
+  const unsigned fb = (unsigned)ceil_div64(N, 128);
+  if (D == 32) mix_tc_grad_finalize_kernel<32><<<fb, 128, 0, stream>>>(part_s, part_g, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp, grad_t);
+  else mix_tc_grad_finalize_kernel<64><<<fb, 128, 0, stream>>>(part_s, part_g, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp, grad_t);
+  return check_launch("mixture tc grad finalize");
 }
 
 }  // extern "C"

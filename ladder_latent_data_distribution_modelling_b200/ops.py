@@ -151,6 +151,7 @@ def mixture_diag_param_grad(t, mean, std, logp, coef, dmean, dstd):
 
 
 MIXTURE_TC = True      # use the tcgen05 kernel for isotropic D in {32, 64} forward evaluations
+MIXTURE_TC_GRAD = os.environ.get('LADDER_MIX_TC_GRAD', '1') != '0'      # ... and for forward + gradient (second MMA from TMEM)
 
 
 def mixture_logprob(t, tab, want_grad=False, partial=False, out=None, exact=False):
@@ -175,6 +176,15 @@ def mixture_logprob(t, tab, want_grad=False, partial=False, out=None, exact=Fals
                                                   tab.ref_log2, _p(logp), _p(ws), ws.numel(), _stream()),
                    'mixture_logprob_tc')
         return logp
+    if (MIXTURE_TC and MIXTURE_TC_GRAD and not exact and want_grad and not partial and tab.tc_image is not None and N > 0):
+        logp = out.get('logp') if 'logp' in out else torch.empty(N, device=dev, dtype=torch.float32)
+        grad = out.get('grad') if 'grad' in out else torch.empty_like(t)
+        nbytes = _L().ladder_mixture_tc_grad_workspace_bytes(N, tab.K, D)
+        ws = _workspace(dev, nbytes, 'mixture_tc_grad')
+        _lib.check(_L().ladder_mixture_logprob_grad_tc(_p(t), N, D, _p(tab.tc_image), _p(tab.table), tab.K, tab.iso_scale,
+                                                       tab.ref_log2, _p(logp), _p(grad), _p(ws), ws.numel(), _stream()),
+                   'mixture_logprob_grad_tc')
+        return logp, grad
     if N == 0:                       # empty batch: nothing to launch
         e = torch.empty(0, device=dev, dtype=torch.float32)
         if partial:

@@ -65,3 +65,27 @@ def test_decoder_only_paths_and_embeddings(exp):
     assert np.abs(ez - o2['code_mean'].v).max() <= 2e-4 * max(1.0, np.abs(o2['code_mean'].v).max())
     et = eng.embed(xs, 't')
     assert et.shape == (n, R) and torch.isfinite(et).all()
+
+
+def test_shortest_likelihood_path_on_the_fused_kernel_matches_the_oracle_run():
+    """Notebook cells 17-21 end to end: `optimise_shortest_likelihood_path` with the prior's log-density and gradient coming
+    from the fused mixture kernel, against the same loop driven by the float64 oracle mixture (reference fixture
+    GM_prior_info.npz as the prior)."""
+    import os
+    import numpy as np
+    from ladder_latent_data_distribution_modelling_b200.host import demo_tools
+    from oracle import mixture as OM
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'gm_prior_golden.npz'))
+    prior = demo_tools.MixtureDistribution.full(d['m_full'], d['K_full'], d['w_full'], 'cuda')
+
+    class OraclePrior:
+        c = OM.canonical_from_full(d['m_full'], d['K_full'], d['w_full'])
+
+        def log_prob_grad(self, x):
+            return OM.mixture_logprob(np.asarray(x, dtype=np.float64), *self.c, with_grad=True)
+    start, end = d['m_full'][3], d['m_full'][17]
+    got, rec = demo_tools.optimise_shortest_likelihood_path(prior, start, end, n_step=8, n_iter=200, record=True)
+    want, rec_o = demo_tools.optimise_shortest_likelihood_path(OraclePrior(), start, end, n_step=8, n_iter=200, record=True)
+    assert rec['loss'][-1] < rec['loss'][0]
+    np.testing.assert_allclose(rec['loss'][:50], rec_o['loss'][:50], rtol=2e-4, atol=2e-3)
+    assert np.abs(got - want).max() < 5e-2 * np.abs(end - start).max()

@@ -173,6 +173,45 @@ def test_tensor_core_path_iso(ops, D):
         assert torch.equal(lp_tc, lp2)                               # deterministic
 
 
+@pytest.mark.parametrize('D', [32, 64])
+def test_tensor_core_forward_and_gradient(ops, D):
+    """tcgen05 forward + gradient for isotropic D in {32, 64}: scores t.mu^T on kind::tf32, the exponentials written back into
+    TMEM in place of the scores, and the gradient's contraction W.mu as a second kind::tf32 MMA whose A operand is that
+    TMEM-resident W and whose B operand is the same component tile read MN-major -- against the float64 oracle and the exact
+    fp32 SIMT kernel.  Stated tolerance: |d logp| <= 5e-2 as for the forward kernel; the gradient (= -(t - sum_k p_k mu_k) /
+    sigma^2, both operands of the second contraction rounded to tf32's 11 bits) within 2e-3 of its largest entry per call,
+    5e-4 relative L2."""
+    rng = np.random.default_rng(100 + D)
+    for N, K in ((1000, 777), (4096, 4096), (257, 129), (300, 5000)):
+        m = rng.normal(size=(K, D)); t = rng.normal(size=(N, D)).astype(np.float32)
+        w = rng.uniform(0.1, 1.0, size=K)
+        tab = ops.mixture_pack_diag(m, 0.9, w, 'cuda')
+        lp_tc, g_tc = ops.mixture_logprob(_dev(t), tab, want_grad=True)
+        lp_ex, g_ex = ops.mixture_logprob(_dev(t), tab, want_grad=True, exact=True)
+        if N * K <= 2_000_000:
+            mu, A, c = OM.canonical_from_diag(m, 0.9, w)
+            ref, gref = OM.mixture_logprob(t.astype(np.float64), mu, A, c, with_grad=True, chunk=128)
+            np.testing.assert_allclose(g_ex.cpu().numpy(), gref, rtol=2e-3, atol=2e-3)
+        else:                        # the float64 oracle materialises [N, K, D]: at this size the exact fp32 kernel is the checker
+            ref, gref = lp_ex.cpu().numpy().astype(np.float64), g_ex.cpu().numpy().astype(np.float64)
+        assert torch.isfinite(lp_tc).all() and torch.isfinite(g_tc).all()
+        assert np.abs(lp_tc.cpu().numpy() - ref).max() < 5e-2
+        g = g_tc.cpu().numpy().astype(np.float64)
+        assert np.abs(g - gref).max() <= 2e-3 * np.abs(gref).max(), np.abs(g - gref).max() / np.abs(gref).max()
+        assert np.linalg.norm(g - gref) <= 5e-4 * np.linalg.norm(gref), np.linalg.norm(g - gref) / np.linalg.norm(gref)
+        lp2, g2 = ops.mixture_logprob(_dev(t), tab, want_grad=True)
+        assert torch.equal(lp_tc, lp2) and torch.equal(g_tc, g2)             # deterministic (split partials summed in order)
+    # far queries: the fixed-frame sum underflows, the finalising kernel recomputes log p and the gradient exactly
+    t = (rng.normal(size=(64, D)) * 30).astype(np.float32)
+    m = rng.normal(size=(300, D))
+    tab = ops.mixture_pack_diag(m, 0.5, None, 'cuda')
+    lp, g = ops.mixture_logprob(_dev(t), tab, want_grad=True)
+    mu, A, c = OM.canonical_from_diag(m, 0.5)
+    ref, gref = OM.mixture_logprob(t.astype(np.float64), mu, A, c, with_grad=True)
+    np.testing.assert_allclose(lp.cpu().numpy(), ref, rtol=2e-5)
+    np.testing.assert_allclose(g.cpu().numpy(), gref, rtol=1e-3, atol=1e-3 * np.abs(gref).max())
+
+
 def test_tensor_core_path_far_queries_rescued(ops):
     rng = np.random.default_rng(9)
     D, K, N = 32, 300, 512
