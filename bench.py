@@ -378,6 +378,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     group = None
     if world > 1:
+        os.environ['NCCL_DEBUG'] = os.environ.get('LADDER_NCCL_DEBUG', 'WARN')     # NCCL's version banner goes to STDOUT otherwise
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
         group = dist.group.WORLD
     dev = torch.device('cuda', local)
@@ -615,22 +616,9 @@ def run_ours(args):
                                 'leaky_relu\'%s; bound by L2->SM operand traffic at N = 64 (profiles/r1g_ncu_dgrad_kernel.md)'
                                 % (' + space_to_depth(2) scatter' if d2s else ''),
                         'roofline_fprop': roofline_fprop}
-        # ---- hyper-prior micro-benchmark (second half of the metric): 65 536 x 65 536 pairs, D = 2
-        rng = np.random.default_rng(1234)
-        N = 65536
-        tq = torch.tensor(rng.normal(size=(N, 2)).astype(np.float32), device=dev)
-        tab = ops.mixture_pack_diag(rng.normal(size=(N, 2)), 1.0, None, dev)
-        hp = {}
-        for grad in (False, True):
-            for _ in range(3):
-                ops.mixture_logprob(tq, tab, want_grad=grad)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(5):
-                ops.mixture_logprob(tq, tab, want_grad=grad)
-            e1.record()
-            torch.cuda.synchronize()
-            hp['fwd_grad' if grad else 'fwd'] = N * N / (e0.elapsed_time(e1) / 5 * 1e-3)
+        # ---- hyper-prior micro-benchmark (second half of the metric, BASELINE.json configs[2]): 65 536 x 65 536 pairs at
+        # D = 2 (register / SIMT kernel) and D = 32, 64 (tcgen05 kernels: scores on kind::tf32, exponentials out of TMEM; the
+        # gradient's second contraction W . mu with W kept in TMEM), forward and forward + gradient
         n_ex2 = ops.pipe_peak(1, 148 * 8, 512)
         torch.cuda.synchronize()
         e0.record()
@@ -638,9 +626,29 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         ex2_peak = n_ex2 / (e0.elapsed_time(e1) * 1e-3)
-        hyper = {'pairs_per_s_fwd': hp['fwd'], 'pairs_per_s_fwd_grad': hp['fwd_grad'], 'N': N, 'K': N, 'D': 2,
-                 'bound': 'sfu (1 MUFU.EX2 per pair)', 'ex2_peak_per_s_measured': ex2_peak,
-                 'frac_fwd': hp['fwd'] / ex2_peak, 'frac_fwd_grad': hp['fwd_grad'] / ex2_peak}
+        N = 65536
+        hyper = {'N': N, 'K': N, 'bound': 'sfu (1 MUFU.EX2 per pair)', 'ex2_peak_per_s_measured': ex2_peak}
+        for D in (2, 32, 64):
+            rng = np.random.default_rng(1234 + D)
+            sc = 1.0 if D == 2 else 1.0 / np.sqrt(D / 2.0)           # keep |t - mu|^2 ~ O(1) so the sums stay in fp32 range
+            tq = torch.tensor((rng.normal(size=(N, D)) * sc).astype(np.float32), device=dev)
+            tab = ops.mixture_pack_diag(rng.normal(size=(N, D)) * sc, 1.0, None, dev)
+            for grad in (False, True):
+                for _ in range(3):
+                    ops.mixture_logprob(tq, tab, want_grad=grad)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(5):
+                    ops.mixture_logprob(tq, tab, want_grad=grad)
+                e1.record()
+                torch.cuda.synchronize()
+                rate = N * N / (e0.elapsed_time(e1) / 5 * 1e-3)
+                key = ('fwd_grad' if grad else 'fwd') + ('' if D == 2 else '_D%d' % D)
+                hyper['pairs_per_s_' + key] = rate
+                hyper['frac_' + key] = rate / ex2_peak
+            del tq, tab
+        hyper['D'] = 2
+        hyper['kernels'] = {'D2': 'mix_kernel (registers, fp32)', 'D32_D64': 'mix_tc_kernel / mix_tc_grad_kernel (tcgen05 kind::tf32, TMEM)'}
         # reported baseline, rank 0 at N = 1 only (at N > 1 the other ranks' processes would share the host cores with it)
         cpu = cpu_reference(cfg, args.cpu_sample, 2, 1) if world == 1 else None
         line = {'metric': METRIC, 'value': value, 'unit': 'imgs/s', 'n_gpus': world, 'steps': args.steps,

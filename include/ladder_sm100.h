@@ -84,7 +84,11 @@ int ladder_mixture_logprob_tc(const float* t, long long N, int D, const float* i
                               size_t workspace_bytes, cudaStream_t stream);
 /* Forward AND gradient on the tensor cores (same isotropic D in {32, 64} image): d log p / d t_n = -2 ln2 a' (t'_n - sum_k p_nk
  * mu'_k); the second sum is a second contraction W . mu whose A operand W = exp2(scores) stays in TMEM (written in place of the
- * scores) and whose B operand is the same component tile read MN-major.  grad_t [N, D]; logp may be NULL.                   */
+ * scores) and whose B operand is the transposed component tile; `image` is the one ladder_mixture_tc_pack_iso_grad builds
+ * (per chunk: (2 mu') | (2 mu')^T | ck).  grad_t [N, D]; logp may be NULL.                                                  */
+size_t ladder_mixture_tc_grad_image_bytes(int K, int D);
+int ladder_mixture_tc_pack_iso_grad(const double* mean_host, double std_, const double* weight_host /*nullable*/, int K, int D,
+                                    float* image_host, float* ref_log2, float* iso_scale);
 size_t ladder_mixture_tc_grad_workspace_bytes(long long N, int K, int D);
 int ladder_mixture_logprob_grad_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
                                    float iso_scale, float ref_log2, float* logp /*nullable*/, float* grad_t, void* workspace,

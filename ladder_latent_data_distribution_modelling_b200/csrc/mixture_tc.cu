@@ -271,8 +271,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_kernel(Args a) {
 //   * the consumers overwrite each S accumulator column IN PLACE with w = ex2(S + ck - tn) (tcgen05.st; same lane = query row,
 //     same column = component), so W is already the TMEM-resident A operand of a kind::tf32 MMA (M = 128 queries, K = 128
 //     components, no shared-memory round trip, the N x K matrix still never leaves the SM);
-//   * its B operand is the SAME component tile the first MMA read: [128 components x D] with D contiguous is K-major for
-//     t . mu^T and MN-major for W . mu (descriptor `make_desc_mn`, 8 component rows = one K step);
+//   * its B operand is the TRANSPOSED component tile (2 mu')^T [D x 128 components], K-major like every other operand here and
+//     shipped in the same bulk copy as the first tile.  (Reading the first tile MN-major instead would save the second image,
+//     but kind::tf32 accepts MN-major operands only in the 32-bit-granular SWIZZLE_128B_BASE32B layout, which the first MMA's
+//     K-major view of the same bytes cannot share -- measured r2l: with the plain SWIZZLE_128B descriptor the MMA returns 0.)
 //   * G' [128 x D] accumulates in TMEM across all component chunks of the unit and is read once at the end.
 // TMEM: S0 | S1 (2 query sub-tiles x 128 columns, single-buffered: the two sub-tiles ping-pong between the tensor pipe and the
 // SFU as in flash-attention) | G'0 | G'1 (2 x D columns).  Per pair: 2 D tf32 flops (t.mu) + 2 D (W.mu) + 1 MUFU.EX2.
@@ -318,14 +320,15 @@ struct GradArgs {
   float iso_scale;
 };
 
-constexpr int GSTAGES = 3;
+constexpr int GSTAGES = 2;       // D = 64: 2 x 64.5 KB of component tiles + 64 KB of query tiles
 
 template <int D>
 __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
   constexpr int ATOMS = D / 32;
   constexpr int A_BYTES = 2 * ATOMS * 128 * 128;
-  constexpr int B_BYTES = ATOMS * BN * 128;
-  constexpr int B_STAGE = B_BYTES + BN * 4;
+  constexpr int B_BYTES = ATOMS * BN * 128;             // (2 mu') [128 components x D], K-major for t . mu^T
+  constexpr int B2_BYTES = (BN / 32) * D * 128;         // (2 mu')^T [D x 128 components], K-major for W . mu (4 atoms of 32 components)
+  constexpr int B_STAGE = B_BYTES + B2_BYTES + BN * 4;  // + ck
   constexpr int B_STRIDE = (B_STAGE + 1023) / 1024 * 1024;
   constexpr uint32_t G_COL = 256;                       // TMEM columns: S0 [0,128) S1 [128,256) G0 [256,256+D) G1 [256+D, 256+2D)
   extern __shared__ uint8_t smem_raw[];
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_tf32(128, BN), idesc2 = make_idesc_tf32_bmn(128, D);
+      constexpr uint32_t idesc1 = make_idesc_tf32(128, BN), idesc2 = make_idesc_tf32(128, D);
       unsigned it = 0, g = 0, un = 0;
       for (long long u = blockIdx.x; u < units; u += gridDim.x, ++un) {
         const int split = (int)(u % a.splits);
@@ -419,8 +422,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
             tc_fence_after();
             const uint32_t tmem_g = tmem_base + G_COL + sub * D, tmem_w = tmem_base + sub * BN;
 #pragma unroll
-            for (int k = 0; k < BN / 8; ++k)            // 8 components (rows of the tile, 1024 B) per K step
-              umma_tf32_ts(tmem_g, tmem_w + k * 8, make_desc_mn(tB + k * 1024, BN * 128), idesc2, (c != c_lo) | (k != 0));
+            for (int k = 0; k < BN / 8; ++k) {          // 8 components per K step: 32 B inside a 128-byte atom of 32 components
+              const int atom = k / 4, kk = k % 4;
+              umma_tf32_ts(tmem_g, tmem_w + k * 8, make_desc(tB + B_BYTES + atom * (D * 128) + kk * 32), idesc2,
+                           (c != c_lo) | (k != 0));
+            }
             umma_commit(bar_sfree + sub * 8);
             if (c == c_hi - 1) umma_commit(bar_gfull + sub * 8);
           }
@@ -462,7 +468,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
       float S = 0.f;
       for (int c = c_lo; c < c_hi; ++c, ++it, ++g) {
         const int s = it % GSTAGES;
-        const float* ck = reinterpret_cast<const float*>(smem + (sB + s * B_STRIDE + B_BYTES - base));
+        const float* ck = reinterpret_cast<const float*>(smem + (sB + s * B_STRIDE + B_BYTES + B2_BYTES - base));
         mbar_wait(bar_full + s * 8, (it / GSTAGES) & 1);
         mbar_wait(bar_sfull + sub * 8, g & 1);
         tc_fence_after();
@@ -690,6 +696,57 @@ int ladder_mixture_logprob_tc(const float* t, long long N, int D, const float* i
   return check_launch("mixture tc finalize");
 }
 
+/* component image of the forward + gradient kernel: per chunk of 128 components [ (2 mu') K-major | (2 mu')^T K-major | ck ] */
+size_t ladder_mixture_tc_grad_image_bytes(int K, int D) {
+  if (D != 32 && D != 64) return 0;
+  const size_t chunks = (size_t)(K + BN - 1) / BN;
+  return chunks * ((size_t)(D / 32) * BN * 128 + (size_t)(BN / 32) * D * 128 + BN * 4);
+}
+
+int ladder_mixture_tc_pack_iso_grad(const double* mean, double std_, const double* weight, int K, int D, float* image,
+                                    float* ref_log2, float* iso_scale) {
+  LADDER_REQUIRE(mean && image && ref_log2 && iso_scale && K >= 1, "mixture_tc_pack_iso_grad: bad arguments");
+  LADDER_REQUIRE(D == 32 || D == 64, "mixture_tc_pack_iso_grad: D must be 32 or 64 (got %d)", D);
+  LADDER_REQUIRE(std_ > 0, "mixture_tc_pack_iso_grad: std must be positive");
+  const double LOG2E = 1.4426950408889634, HALF_LOG_2PI = 0.9189385332046727;
+  const double sc = std::sqrt(0.5 * LOG2E) / std_;
+  double wsum = 0;
+  for (int k = 0; k < K; ++k) wsum += weight ? weight[k] : 1.0;
+  std::vector<double> c2(K);
+  double M = -INFINITY;
+  for (int k = 0; k < K; ++k) {
+    const double w = weight ? weight[k] : 1.0;
+    c2[k] = (std::log(w / wsum) - D * HALF_LOG_2PI - D * std::log(std_)) * LOG2E;
+    if (c2[k] > M) M = c2[k];
+  }
+  if (!(M > -INFINITY)) return fail(LADDER_ERR_ARG, "mixture_tc_pack_iso_grad: all weights are zero");
+  const int atoms = D / 32, chunks = (K + BN - 1) / BN;
+  const size_t b1 = (size_t)atoms * BN * 32, b2 = (size_t)(BN / 32) * D * 32, stage_floats = b1 + b2 + BN;
+  for (int c = 0; c < chunks; ++c) {
+    float* img = image + (size_t)c * stage_floats;
+    float* img2 = img + b1;
+    float* ck = img2 + b2;
+    for (int r = 0; r < BN; ++r) {
+      const int k = c * BN + r;
+      double m2 = 0;
+      for (int d = 0; d < D; ++d) {
+        const double mu = k < K ? sc * mean[(size_t)k * D + d] : 0.0;
+        m2 += mu * mu;
+        // tile 1: row = component r, K = d
+        const int atom = d / 32, e = d % 32;
+        img[(size_t)atom * BN * 32 + r * 32 + (((e / 4) ^ (r & 7)) << 2) + (e & 3)] = (float)(2.0 * mu);
+        // tile 2: row = d, K = component r (atom of 32 components, 16-byte chunk swizzled by the row)
+        const int atom2 = r / 32, e2 = r % 32;
+        img2[(size_t)atom2 * D * 32 + d * 32 + (((e2 / 4) ^ (d & 7)) << 2) + (e2 & 3)] = (float)(2.0 * mu);
+      }
+      ck[r] = k < K ? (float)(c2[k] - M - m2) : -1e30f;
+    }
+  }
+  *ref_log2 = (float)M;
+  *iso_scale = (float)sc;
+  return LADDER_OK;
+}
+
 size_t ladder_mixture_tc_grad_workspace_bytes(long long N, int K, int D) {
   const int n_chunks = (K + BN - 1) / BN;
   const long long row_tiles = (N + QROWS - 1) / QROWS;
@@ -700,8 +757,8 @@ size_t ladder_mixture_tc_grad_workspace_bytes(long long N, int K, int D) {
 }
 
 /* log p(t_n) AND d log p / d t_n for an isotropic mixture with D in {32, 64} on the tensor cores: t . mu^T (kind::tf32), the
- * exponentials written back into TMEM in place of the scores, and W . mu (kind::tf32, A from TMEM, B = the same component tile
- * read MN-major) -- see mix_tc_grad_kernel.  logp may be NULL.                                                                */
+ * exponentials written back into TMEM in place of the scores, and W . mu (kind::tf32, A from TMEM, B = the transposed component
+ * tile of the same image) -- see mix_tc_grad_kernel.  `image` from ladder_mixture_tc_pack_iso_grad.  logp may be NULL.       */
 int ladder_mixture_logprob_grad_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
                                    float iso_scale, float ref_log2, float* logp, float* grad_t, void* workspace,
                                    size_t workspace_bytes, cudaStream_t stream) {
@@ -729,7 +786,7 @@ int ladder_mixture_logprob_grad_tc(const float* t, long long N, int D, const flo
   const unsigned grid = (unsigned)(units < sms ? units : sms);
   auto go = [&](auto kern, int Dv) {
     const int atoms = Dv / 32;
-    const size_t b_stride = ((size_t)atoms * BN * 128 + BN * 4 + 1023) / 1024 * 1024;
+    const size_t b_stride = ((size_t)atoms * BN * 128 + (size_t)(BN / 32) * Dv * 128 + BN * 4 + 1023) / 1024 * 1024;
     const size_t smem = (size_t)2 * atoms * 128 * 128 + GSTAGES * b_stride + 1024 + 256;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, NTHREADS, smem, stream>>>(a);

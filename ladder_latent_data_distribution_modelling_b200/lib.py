@@ -121,6 +121,8 @@ SIGNATURES = {
     'ladder_mixture_logprob_tc': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, ptr, C.c_int, C.c_float, C.c_float, ptr, ptr, C.c_size_t, stream_t]),
     'ladder_mixture_logprob_packed': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, C.c_int, C.c_int, C.c_float, C.c_float, ptr, C.c_int,
                                                 ptr, C.c_size_t, stream_t]),
+    'ladder_mixture_tc_grad_image_bytes': (C.c_size_t, [C.c_int, C.c_int]),
+    'ladder_mixture_tc_pack_iso_grad': (C.c_int, [c_double_p, C.c_double, c_double_p, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p]),
     'ladder_mixture_tc_grad_workspace_bytes': (C.c_size_t, [C.c_longlong, C.c_int, C.c_int]),
     'ladder_mixture_logprob_grad_tc': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, ptr, C.c_int, C.c_float, C.c_float, ptr, ptr, ptr,
                                                  C.c_size_t, stream_t]),

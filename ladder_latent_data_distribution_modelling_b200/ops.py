@@ -70,11 +70,12 @@ def _workspace(device, nbytes, tag):
 class MixtureTable:
     """Packed canonical form of a Gaussian mixture on the device (see csrc/mixture.cu)."""
 
-    def __init__(self, table, K, D, mode, iso_scale, ref_log2, tc_image=None):
+    def __init__(self, table, K, D, mode, iso_scale, ref_log2, tc_image=None, tc_image_grad=None):
         self.table, self.K, self.D, self.mode = table, K, D, mode
         self.iso_scale, self.ref_log2 = iso_scale, ref_log2
         self.ref_dev = None               # device-resident frame (tables packed by mixture_pack_diag_device)
-        self.tc_image = tc_image          # tensor-core operand image (isotropic, D in {32, 64}); forward only
+        self.tc_image = tc_image          # tensor-core operand image (isotropic, D in {32, 64}): forward kernel
+        self.tc_image_grad = tc_image_grad   # ... forward + gradient kernel (adds the transposed component tiles)
 
     def shard(self, rank, world):
         """Contiguous component shard for rank `rank` of `world` (same frame)."""
@@ -125,6 +126,12 @@ def mixture_pack_diag(mean, std, weight=None, device='cuda'):
                                                    img.ctypes.data_as(_lib.c_float_p), C.byref(ref2), C.byref(iso2)),
                    'mixture_tc_pack_iso')
         tc_image = torch.from_numpy(img).to(device)
+        img2 = np.zeros(_L().ladder_mixture_tc_grad_image_bytes(K, D) // 4, dtype=np.float32)
+        _lib.check(_L().ladder_mixture_tc_pack_iso_grad(_dptr(mean), float(std[0]), _dptr(w) if w is not None else None, K, D,
+                                                        img2.ctypes.data_as(_lib.c_float_p), C.byref(ref2), C.byref(iso2)),
+                   'mixture_tc_pack_iso_grad')
+        tc_image_grad = torch.from_numpy(img2).to(device)
+        return MixtureTable(torch.from_numpy(table).to(device), K, D, mode, iso.value, ref.value, tc_image, tc_image_grad)
     return MixtureTable(torch.from_numpy(table).to(device), K, D, mode, iso.value, ref.value, tc_image)
 
 
@@ -176,12 +183,12 @@ def mixture_logprob(t, tab, want_grad=False, partial=False, out=None, exact=Fals
                                                   tab.ref_log2, _p(logp), _p(ws), ws.numel(), _stream()),
                    'mixture_logprob_tc')
         return logp
-    if (MIXTURE_TC and MIXTURE_TC_GRAD and not exact and want_grad and not partial and tab.tc_image is not None and N > 0):
+    if (MIXTURE_TC and MIXTURE_TC_GRAD and not exact and want_grad and not partial and tab.tc_image_grad is not None and N > 0):
         logp = out.get('logp') if 'logp' in out else torch.empty(N, device=dev, dtype=torch.float32)
         grad = out.get('grad') if 'grad' in out else torch.empty_like(t)
         nbytes = _L().ladder_mixture_tc_grad_workspace_bytes(N, tab.K, D)
         ws = _workspace(dev, nbytes, 'mixture_tc_grad')
-        _lib.check(_L().ladder_mixture_logprob_grad_tc(_p(t), N, D, _p(tab.tc_image), _p(tab.table), tab.K, tab.iso_scale,
+        _lib.check(_L().ladder_mixture_logprob_grad_tc(_p(t), N, D, _p(tab.tc_image_grad), _p(tab.table), tab.K, tab.iso_scale,
                                                        tab.ref_log2, _p(logp), _p(grad), _p(ws), ws.numel(), _stream()),
                    'mixture_logprob_grad_tc')
         return logp, grad
