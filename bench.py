@@ -688,6 +688,12 @@ def run_ours(args):
         line['celeba_shape'] = celeba
     try:
         if world > 1:
+            eng.release_graphs()             # captured graphs hold NCCL kernels: drop them before the group goes away
+            try:
+                model.engine.release_graphs()
+            except NameError:                # already deleted in front of the CelebA legs
+                pass
+            torch.cuda.synchronize()
             dist.barrier()
             dist.destroy_process_group()
     except Exception:                                 # noqa: BLE001

@@ -74,6 +74,10 @@ class ShardedMixture:
         self._graph = None
         self.use_graph = bool(graph) and dev.type == 'cuda'
 
+    def release(self):
+        """Drop the captured graph (it holds an NCCL kernel: do this before destroying the process group)."""
+        self._graph = None
+
     def _launch(self):
         ops = self.ops
         ops.mixture_logprob_packed(self.t, self.shard, self.pack, self.want_grad)

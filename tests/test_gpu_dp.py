@@ -59,6 +59,11 @@ def _run(cfg, P, x, feeds, epoch, B, dev, graphs, group=None):
     out['p_ae'] = eng.ae.param.cpu().numpy()
     out['p_prior'] = eng.prior_g.param.cpu().numpy()
     out['graphs'] = np.array(len(eng._graphs))
+    # captured graphs hold NCCL kernels: drop them before the process group goes away (destroy_process_group blocks otherwise,
+    # gpurun_out/r2m_hang.log)
+    eng.release_graphs()
+    del eng
+    torch.cuda.synchronize()
     return out
 
 
@@ -161,6 +166,8 @@ def _shard_worker(rank, world, port, out):
     if rank == 0:
         np.savez(out, lp=lp.cpu().numpy(), g=g.cpu().numpy(), lp1=lp1.cpu().numpy(), g1=g1.cpu().numpy(),
                  graph=np.array(sm.use_graph))
+    del sm, lp1, g1                      # the captured all-gather must be gone before the process group is destroyed
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -60,6 +60,8 @@ def main():
         if config['num_epochs'] > 0:
             trainer_VAE.train()
     if dist_group is not None:
+        model.engine.release_graphs()      # captured sub-step graphs hold NCCL kernels: drop them before the group goes away
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 
