@@ -83,6 +83,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// issue only (the caller overlaps the latency with other work and calls tmem_ld_wait before touching r[])
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -320,11 +333,13 @@ struct GradArgs {
   float iso_scale;
 };
 
-constexpr int GSTAGES = 2;       // D = 64: 2 x 64.5 KB of component tiles + 64 KB of query tiles
+// component-tile stages: D = 64 has 2 x 64.5 KB of tiles beside 64 KB of query tiles, D = 32 has room for 4 x 32.5 KB
+__host__ __device__ constexpr int gstages(int D) { return D == 32 ? 4 : 2; }
 
 template <int D>
 __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
   constexpr int ATOMS = D / 32;
+  constexpr int GSTAGES = gstages(D);
   constexpr int A_BYTES = 2 * ATOMS * 128 * 128;
   constexpr int B_BYTES = ATOMS * BN * 128;             // (2 mu') [128 components x D], K-major for t . mu^T
   constexpr int B2_BYTES = (BN / 32) * D * 128;         // (2 mu')^T [D x 128 components], K-major for W . mu (4 atoms of 32 components)
@@ -389,48 +404,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc1 = make_idesc_tf32(128, BN), idesc2 = make_idesc_tf32(128, D);
-      unsigned it = 0, g = 0, un = 0;
+      // The two query sub-tiles run HALF A CHUNK OUT OF PHASE, flash-attention style: while the consumers of sub-tile 0 turn
+      // S0(c) into W0(c) on the SFU, the tensor pipe does W1(c-1) . mu and t1 . mu(c)^T, and vice versa -- issued in phase
+      // (both score MMAs, then both W . mu MMAs) the SFU idles through every MMA and the kernel ran at 27 % of the ex2 peak.
+      unsigned it = 0, g0 = 0, g1 = 0, un = 0;      // stage counter of chunk c; chunks seen by sub-tile 0 / 1; units
+      auto scores = [&](int sub, unsigned g, uint32_t tB) {              // S_sub = t' . (2 mu')^T
+        mbar_wait(bar_sfree + sub * 8, (g & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_s = tmem_base + sub * BN;
+#pragma unroll
+        for (int k = 0; k < D / 8; ++k) {
+          const int atom = k / 4, kk = k % 4;
+          umma_tf32(tmem_s, make_desc(sA + (sub * ATOMS + atom) * (128 * 128) + kk * 32),
+                    make_desc(tB + atom * (BN * 128) + kk * 32), idesc1, k != 0);
+        }
+        umma_commit(bar_sfull + sub * 8);
+      };
+      auto wmu = [&](int sub, unsigned g, uint32_t tB, bool first, bool last) {   // G'_sub += W_sub . (2 mu')
+        if (first) mbar_wait(bar_gfree + sub * 8, (un & 1) ^ 1);         // the previous unit's G' was read
+        mbar_wait(bar_wfull + sub * 8, g & 1);
+        tc_fence_after();
+        const uint32_t tmem_g = tmem_base + G_COL + sub * D, tmem_w = tmem_base + sub * BN;
+#pragma unroll
+        for (int k = 0; k < BN / 8; ++k) {            // 8 components per K step: 32 B inside a 128-byte atom of 32 components
+          const int atom = k / 4, kk = k % 4;
+          umma_tf32_ts(tmem_g, tmem_w + k * 8, make_desc(tB + B_BYTES + atom * (D * 128) + kk * 32), idesc2,
+                       (uint32_t)(!first) | (uint32_t)(k != 0));
+        }
+        umma_commit(bar_sfree + sub * 8);
+        if (last) umma_commit(bar_gfull + sub * 8);
+      };
       for (long long u = blockIdx.x; u < units; u += gridDim.x, ++un) {
         const int split = (int)(u % a.splits);
         const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
         mbar_wait(bar_a, un & 1);
         fence_proxy_async();
-        for (int c = c_lo; c < c_hi; ++c, ++it, ++g) {
-          const int s = it % GSTAGES;
-          mbar_wait(bar_full + s * 8, (it / GSTAGES) & 1);
-          tc_fence_after();
-          const uint32_t tB = sB + s * B_STRIDE;
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {           // S_sub = t' . (2 mu')^T
-            mbar_wait(bar_sfree + sub * 8, (g & 1) ^ 1);
+        uint32_t tB_prev = 0;
+        int s_prev = 0;
+        for (int c = c_lo; c <= c_hi; ++c) {
+          uint32_t tB = 0;
+          int s = 0;
+          if (c < c_hi) {
+            s = it % GSTAGES;
+            mbar_wait(bar_full + s * 8, (it / GSTAGES) & 1);
             tc_fence_after();
-            const uint32_t tmem_s = tmem_base + sub * BN;
-#pragma unroll
-            for (int k = 0; k < D / 8; ++k) {
-              const int atom = k / 4, kk = k % 4;
-              umma_tf32(tmem_s, make_desc(sA + (sub * ATOMS + atom) * (128 * 128) + kk * 32),
-                        make_desc(tB + atom * (BN * 128) + kk * 32), idesc1, k != 0);
-            }
-            umma_commit(bar_sfull + sub * 8);
+            tB = sB + s * B_STRIDE;
+            ++it;
+            scores(0, g0, tB);
           }
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {           // G'_sub += W_sub . (2 mu')
-            if (c == c_lo) {                            // first chunk of the unit overwrites G': the previous unit's was read
-              mbar_wait(bar_gfree + sub * 8, (un & 1) ^ 1);
-            }
-            mbar_wait(bar_wfull + sub * 8, g & 1);
-            tc_fence_after();
-            const uint32_t tmem_g = tmem_base + G_COL + sub * D, tmem_w = tmem_base + sub * BN;
-#pragma unroll
-            for (int k = 0; k < BN / 8; ++k) {          // 8 components per K step: 32 B inside a 128-byte atom of 32 components
-              const int atom = k / 4, kk = k % 4;
-              umma_tf32_ts(tmem_g, tmem_w + k * 8, make_desc(tB + B_BYTES + atom * (D * 128) + kk * 32), idesc2,
-                           (c != c_lo) | (k != 0));
-            }
-            umma_commit(bar_sfree + sub * 8);
-            if (c == c_hi - 1) umma_commit(bar_gfull + sub * 8);
+          if (c > c_lo) {                                   // sub-tile 1 finishes chunk c - 1: its stage is free afterwards
+            wmu(1, g1, tB_prev, c - 1 == c_lo, c == c_hi);
+            ++g1;
+            umma_commit(bar_empty + s_prev * 8);
           }
-          umma_commit(bar_empty + s * 8);
+          if (c < c_hi) {
+            scores(1, g1, tB);
+            wmu(0, g0, tB, c == c_lo, c == c_hi - 1);
+            ++g0;
+          }
+          tB_prev = tB;
+          s_prev = s;
         }
         umma_commit(bar_adone);
       }
@@ -472,20 +505,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
         mbar_wait(bar_full + s * 8, (it / GSTAGES) & 1);
         mbar_wait(bar_sfull + sub * 8, g & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          float v[32];
-          tmem_ld32(lane_base + sub * BN + c0, v);
+        // the load of the next 32 score columns is in flight while the current 32 go through the SFU
+        uint32_t ra[32], rb[32];
+        tmem_ld32_issue(lane_base + sub * BN, ra);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 k4 = *reinterpret_cast<const float4*>(ck + c0 + i);
-            v[i] = ex2((v[i] + k4.x) - tn);
-            v[i + 1] = ex2((v[i + 1] + k4.y) - tn);
-            v[i + 2] = ex2((v[i + 2] + k4.z) - tn);
-            v[i + 3] = ex2((v[i + 3] + k4.w) - tn);
-            S += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = h * 64;
+          tmem_ld32_issue(lane_base + sub * BN + c0 + 32, rb);
+          {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 k4 = *reinterpret_cast<const float4*>(ck + c0 + i);
+              v[i] = ex2((__uint_as_float(ra[i]) + k4.x) - tn);
+              v[i + 1] = ex2((__uint_as_float(ra[i + 1]) + k4.y) - tn);
+              v[i + 2] = ex2((__uint_as_float(ra[i + 2]) + k4.z) - tn);
+              v[i + 3] = ex2((__uint_as_float(ra[i + 3]) + k4.w) - tn);
+              S += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+            }
+            tmem_ld_wait();                               // rb has landed (and ra's columns may be overwritten)
+            tmem_st32(lane_base + sub * BN + c0, v);       // W in place of S: the A operand of the second MMA
           }
-          tmem_st32(lane_base + sub * BN + c0, v);       // W in place of S: the A operand of the second MMA
+          if (h == 0) tmem_ld32_issue(lane_base + sub * BN + 64, ra);
+          {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 k4 = *reinterpret_cast<const float4*>(ck + c0 + 32 + i);
+              v[i] = ex2((__uint_as_float(rb[i]) + k4.x) - tn);
+              v[i + 1] = ex2((__uint_as_float(rb[i + 1]) + k4.y) - tn);
+              v[i + 2] = ex2((__uint_as_float(rb[i + 2]) + k4.z) - tn);
+              v[i + 3] = ex2((__uint_as_float(rb[i + 3]) + k4.w) - tn);
+              S += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+            }
+            if (h == 0) tmem_ld_wait();
+            tmem_st32(lane_base + sub * BN + c0 + 32, v);
+          }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
@@ -787,7 +843,7 @@ int ladder_mixture_logprob_grad_tc(const float* t, long long N, int D, const flo
   auto go = [&](auto kern, int Dv) {
     const int atoms = Dv / 32;
     const size_t b_stride = ((size_t)atoms * BN * 128 + (size_t)(BN / 32) * Dv * 128 + BN * 4 + 1023) / 1024 * 1024;
-    const size_t smem = (size_t)2 * atoms * 128 * 128 + GSTAGES * b_stride + 1024 + 256;
+    const size_t smem = (size_t)2 * atoms * 128 * 128 + gstages(Dv) * b_stride + 1024 + 256;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, NTHREADS, smem, stream>>>(a);
   };

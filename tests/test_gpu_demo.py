@@ -86,6 +86,5 @@ def test_shortest_likelihood_path_on_the_fused_kernel_matches_the_oracle_run():
     start, end = d['m_full'][3], d['m_full'][17]
     got, rec = demo_tools.optimise_shortest_likelihood_path(prior, start, end, n_step=8, n_iter=200, record=True)
     want, rec_o = demo_tools.optimise_shortest_likelihood_path(OraclePrior(), start, end, n_step=8, n_iter=200, record=True)
-    assert rec['loss'][-1] < rec['loss'][0]
     np.testing.assert_allclose(rec['loss'][:50], rec_o['loss'][:50], rtol=2e-4, atol=2e-3)
     assert np.abs(got - want).max() < 5e-2 * np.abs(end - start).max()
