@@ -93,6 +93,22 @@ size_t ladder_mixture_tc_grad_workspace_bytes(long long N, int K, int D);
 int ladder_mixture_logprob_grad_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
                                    float iso_scale, float ref_log2, float* logp /*nullable*/, float* grad_t, void* workspace,
                                    size_t workspace_bytes, cudaStream_t stream);
+/* Component-shard partial of the tensor-core kernels as ONE packed row (m, s[, unnormalised g]) per query -- the row format
+ * of ladder_mixture_logprob_packed, combined by ladder_mixture_combine_packed (SURVEY 8e-2 at D in {32, 64}).  `image` is the
+ * shard's ..._pack_iso_grad image when with_grad, else its ..._pack_iso image (chunks of 128 components: a shard is a
+ * chunk-aligned slice of the full image, the frame ref_log2 is the full mixture's); workspace sized accordingly.            */
+int ladder_mixture_logprob_tc_packed(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
+                                     float iso_scale, float ref_log2, float* pack, int with_grad, void* workspace,
+                                     size_t workspace_bytes, cudaStream_t stream);
+/* Full-covariance mixture at LARGE latent dimension (32 <= D <= 256, D % 32 == 0): the z-space mixture of prior = "GMM" on
+ * the CelebA model (codes/base.py:323-329 with codes/celeba_config.json code_size 256 / 128) -- csrc/mixture_bigd.cu, fp32
+ * SGEMM-tiled.  Table row per component (ladder_mixture_bigd_table_stride(D) floats): [ P (D x D row-major, upper-triangular
+ * precision Cholesky factor, Sigma^-1 = P P^T) | Lambda = P P^T (D x D) | mu (D) | c = log w + sum log diag P - D/2 log 2 pi,
+ * 0, 0, 0 ].  logp [N] and grad_t [N, D] may each be NULL (not both); workspace >= ladder_mixture_bigd_workspace_bytes(N, K). */
+size_t ladder_mixture_bigd_table_stride(int D);
+size_t ladder_mixture_bigd_workspace_bytes(long long N, int K);
+int ladder_mixture_logprob_bigd(const float* t, long long N, int D, const float* table, int K, float* logp /*nullable*/,
+                                float* grad_t /*nullable*/, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 /* VampPrior mixture (codes/base.py:215-254): K diagonal Gaussians with equal weights whose means / stds are device
  * tensors produced by the shared encoder from the trainable pseudo-inputs.
  *  - ladder_mixture_pack_diag_device packs the mode-1 table and its log2 frame ON THE DEVICE (no host round trip, graph

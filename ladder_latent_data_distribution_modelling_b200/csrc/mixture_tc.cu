@@ -576,20 +576,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
 template <int D>
 __global__ void mix_tc_grad_finalize_kernel(const float* __restrict__ part_s, const float* __restrict__ part_g, int splits,
                                             long long N, const float* __restrict__ t, const float* __restrict__ table, int K,
-                                            float iso_scale, float ref_log2, float* __restrict__ logp, float* __restrict__ grad) {
+                                            float iso_scale, float ref_log2, float* __restrict__ logp, float* __restrict__ grad,
+                                            float* __restrict__ pack) {
+  // pack != null: emit the component-shard partial row (m, s, unnormalised g) of csrc/mixture.cu instead of (logp, grad)
   constexpr int STRIDE = (D + 1 + 3) / 4 * 4;
+  constexpr int W = 2 + D;
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
   for (int i = 0; i < splits; ++i) s += part_s[(size_t)i * N + n];
   const float gc = -2.f * LN2 * iso_scale;
   if (s >= 1e-30f) {
-    if (logp != nullptr) logp[n] = LN2 * (ref_log2 + log2f(s));
+    if (pack != nullptr) {
+      pack[n * W] = LN2 * ref_log2;
+      pack[n * W + 1] = s;
+    } else if (logp != nullptr) logp[n] = LN2 * (ref_log2 + log2f(s));
     const float inv = 0.5f / s;                         // G' carries 2 mu'
     for (int d = 0; d < D; ++d) {
       float gsum = 0.f;
       for (int i = 0; i < splits; ++i) gsum += part_g[((size_t)i * N + n) * D + d];
-      grad[n * D + d] = gc * (t[n * D + d] * iso_scale - gsum * inv);
+      if (pack != nullptr) pack[n * W + 2 + d] = gc * (t[n * D + d] * iso_scale * s - 0.5f * gsum);
+      else grad[n * D + d] = gc * (t[n * D + d] * iso_scale - gsum * inv);
     }
     return;
   }
@@ -600,7 +607,8 @@ __global__ void mix_tc_grad_finalize_kernel(const float* __restrict__ part_s, co
     for (int d = 0; d < D; ++d) { const float y = t[n * D + d] * iso_scale - c[d]; e = fmaf(-y, y, e); }
     mx = fmaxf(mx, e);
   }
-  for (int d = 0; d < D; ++d) grad[n * D + d] = 0.f;
+  float* acc = pack != nullptr ? pack + n * W + 2 : grad + n * D;      // scratch: this row's own output slots
+  for (int d = 0; d < D; ++d) acc[d] = 0.f;
   s = 0.f;
   for (int k = 0; k < K; ++k) {
     const float* c = table + (size_t)k * STRIDE;
@@ -608,10 +616,16 @@ __global__ void mix_tc_grad_finalize_kernel(const float* __restrict__ part_s, co
     for (int d = 0; d < D; ++d) { const float y = t[n * D + d] * iso_scale - c[d]; e = fmaf(-y, y, e); }
     const float p = exp2f(e - mx);
     s += p;
-    for (int d = 0; d < D; ++d) grad[n * D + d] += p * c[d];
+    for (int d = 0; d < D; ++d) acc[d] += p * c[d];
+  }
+  if (pack != nullptr) {
+    pack[n * W] = LN2 * (ref_log2 + mx);
+    pack[n * W + 1] = s;
+    for (int d = 0; d < D; ++d) acc[d] = gc * (t[n * D + d] * iso_scale * s - acc[d]);
+    return;
   }
   if (logp != nullptr) logp[n] = LN2 * (ref_log2 + mx + log2f(s));
-  for (int d = 0; d < D; ++d) grad[n * D + d] = gc * (t[n * D + d] * iso_scale - grad[n * D + d] / s);
+  for (int d = 0; d < D; ++d) acc[d] = gc * (t[n * D + d] * iso_scale - acc[d] / s);
 }
 
 // log p = ln2 * (M + log2 sum_splits S); rows that underflowed the fixed frame are recomputed exactly (two-pass)
@@ -619,7 +633,7 @@ __global__ void mix_tc_grad_finalize_kernel(const float* __restrict__ part_s, co
 template <int D>
 __global__ void mix_tc_finalize_kernel(const float* __restrict__ part, int splits, long long N, const float* __restrict__ t,
                                        const float* __restrict__ table, int K, float iso_scale, float ref_log2,
-                                       float* __restrict__ logp) {
+                                       float* __restrict__ logp, float* __restrict__ pack) {
   constexpr int STRIDE = (D + 1 + 3) / 4 * 4;
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -642,6 +656,11 @@ __global__ void mix_tc_finalize_kernel(const float* __restrict__ part, int split
       }
     }
     frame += mx;
+  }
+  if (pack != nullptr) {                 // component-shard partial row (m, s)
+    pack[n * 2] = LN2 * frame;
+    pack[n * 2 + 1] = s;
+    return;
   }
   logp[n] = LN2 * (frame + log2f(s));
 }
@@ -714,13 +733,13 @@ size_t ladder_mixture_tc_workspace_bytes(long long N, int K) {
 /* log p(t_n) for an isotropic mixture with D in {32, 64} on the tensor cores.  `image` from
  * ladder_mixture_tc_pack_iso (device copy), `simt_table` the mode-0 table of ladder_mixture_pack_diag (for the
  * exact rescue of underflowed rows).                                                              */
-int ladder_mixture_logprob_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
-                              float iso_scale, float ref_log2, float* logp, void* workspace, size_t workspace_bytes,
-                              cudaStream_t stream) {
+static int run_tc_forward(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
+                          float iso_scale, float ref_log2, float* logp, float* pack, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream) {
   LADDER_REQUIRE(D == 32 || D == 64, "mixture_logprob_tc: D must be 32 or 64 (got %d)", D);
   LADDER_REQUIRE(N >= 0 && K >= 1, "mixture_logprob_tc: bad sizes");
   if (N == 0) return LADDER_OK;
-  LADDER_REQUIRE(t && image && simt_table && logp, "mixture_logprob_tc: null pointer");
+  LADDER_REQUIRE(t && image && simt_table && (logp || pack), "mixture_logprob_tc: null pointer");
   LADDER_REQUIRE(((uintptr_t)image & 127) == 0 && ((uintptr_t)t & 15) == 0, "mixture_logprob_tc: misaligned input");
   const int n_chunks = (K + BN - 1) / BN;
   const long long row_tiles = (N + QROWS - 1) / QROWS;
@@ -747,9 +766,16 @@ int ladder_mixture_logprob_tc(const float* t, long long N, int D, const float* i
   int rc = check_launch("mixture tc kernel");
   if (rc) return rc;
   const unsigned fb = (unsigned)ceil_div64(N, 256);
-  if (D == 32) mix_tc_finalize_kernel<32><<<fb, 256, 0, stream>>>(a.part, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp);
-  else mix_tc_finalize_kernel<64><<<fb, 256, 0, stream>>>(a.part, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp);
+  if (D == 32) mix_tc_finalize_kernel<32><<<fb, 256, 0, stream>>>(a.part, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp, pack);
+  else mix_tc_finalize_kernel<64><<<fb, 256, 0, stream>>>(a.part, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp, pack);
   return check_launch("mixture tc finalize");
+}
+
+int ladder_mixture_logprob_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
+                              float iso_scale, float ref_log2, float* logp, void* workspace, size_t workspace_bytes,
+                              cudaStream_t stream) {
+  LADDER_REQUIRE(logp != nullptr || N == 0, "mixture_logprob_tc: null output");
+  return run_tc_forward(t, N, D, image, simt_table, K, iso_scale, ref_log2, logp, nullptr, workspace, workspace_bytes, stream);
 }
 
 /* component image of the forward + gradient kernel: per chunk of 128 components [ (2 mu') K-major | (2 mu')^T K-major | ck ] */
@@ -815,13 +841,13 @@ size_t ladder_mixture_tc_grad_workspace_bytes(long long N, int K, int D) {
 /* log p(t_n) AND d log p / d t_n for an isotropic mixture with D in {32, 64} on the tensor cores: t . mu^T (kind::tf32), the
  * exponentials written back into TMEM in place of the scores, and W . mu (kind::tf32, A from TMEM, B = the transposed component
  * tile of the same image) -- see mix_tc_grad_kernel.  `image` from ladder_mixture_tc_pack_iso_grad.  logp may be NULL.       */
-int ladder_mixture_logprob_grad_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
-                                   float iso_scale, float ref_log2, float* logp, float* grad_t, void* workspace,
-                                   size_t workspace_bytes, cudaStream_t stream) {
+static int run_tc_forward_grad(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
+                               float iso_scale, float ref_log2, float* logp, float* grad_t, float* pack, void* workspace,
+                               size_t workspace_bytes, cudaStream_t stream) {
   LADDER_REQUIRE(D == 32 || D == 64, "mixture_logprob_grad_tc: D must be 32 or 64 (got %d)", D);
   LADDER_REQUIRE(N >= 0 && K >= 1, "mixture_logprob_grad_tc: bad sizes");
   if (N == 0) return LADDER_OK;
-  LADDER_REQUIRE(t && image && simt_table && grad_t, "mixture_logprob_grad_tc: null pointer");
+  LADDER_REQUIRE(t && image && simt_table && (grad_t || pack), "mixture_logprob_grad_tc: null pointer");
   LADDER_REQUIRE(((uintptr_t)image & 127) == 0 && ((uintptr_t)t & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
                  "mixture_logprob_grad_tc: misaligned input");
   const int n_chunks = (K + BN - 1) / BN;
@@ -851,9 +877,31 @@ int ladder_mixture_logprob_grad_tc(const float* t, long long N, int D, const flo
   int rc = check_launch("mixture tc grad kernel");
   if (rc) return rc;
   const unsigned fb = (unsigned)ceil_div64(N, 128);
-  if (D == 32) mix_tc_grad_finalize_kernel<32><<<fb, 128, 0, stream>>>(part_s, part_g, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp, grad_t);
-  else mix_tc_grad_finalize_kernel<64><<<fb, 128, 0, stream>>>(part_s, part_g, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp, grad_t);
+  if (D == 32) mix_tc_grad_finalize_kernel<32><<<fb, 128, 0, stream>>>(part_s, part_g, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp, grad_t, pack);
+  else mix_tc_grad_finalize_kernel<64><<<fb, 128, 0, stream>>>(part_s, part_g, (int)splits, N, t, simt_table, K, iso_scale, ref_log2, logp, grad_t, pack);
   return check_launch("mixture tc grad finalize");
+}
+
+int ladder_mixture_logprob_grad_tc(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
+                                   float iso_scale, float ref_log2, float* logp, float* grad_t, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t stream) {
+  LADDER_REQUIRE(grad_t != nullptr || N == 0, "mixture_logprob_grad_tc: null output");
+  return run_tc_forward_grad(t, N, D, image, simt_table, K, iso_scale, ref_log2, logp, grad_t, nullptr, workspace,
+                             workspace_bytes, stream);
+}
+
+/* Component-shard partial of the two tensor-core kernels as ONE packed buffer pack [N, 2 + D] (with_grad) or [N, 2]:
+ * row = (m, s, unnormalised g), the row format of ladder_mixture_logprob_packed, combined by ladder_mixture_combine_packed.
+ * `image` is the shard's ladder_mixture_tc_pack_iso_grad image when with_grad, else its ladder_mixture_tc_pack_iso image;
+ * workspace sized by ladder_mixture_tc_grad_workspace_bytes / ladder_mixture_tc_workspace_bytes accordingly.             */
+int ladder_mixture_logprob_tc_packed(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
+                                     float iso_scale, float ref_log2, float* pack, int with_grad, void* workspace,
+                                     size_t workspace_bytes, cudaStream_t stream) {
+  LADDER_REQUIRE(pack != nullptr || N == 0, "mixture_logprob_tc_packed: null output");
+  if (with_grad)
+    return run_tc_forward_grad(t, N, D, image, simt_table, K, iso_scale, ref_log2, nullptr, nullptr, pack, workspace,
+                               workspace_bytes, stream);
+  return run_tc_forward(t, N, D, image, simt_table, K, iso_scale, ref_log2, nullptr, pack, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -78,10 +78,20 @@ class MixtureTable:
         self.tc_image_grad = tc_image_grad   # ... forward + gradient kernel (adds the transposed component tiles)
 
     def shard(self, rank, world):
-        """Contiguous component shard for rank `rank` of `world` (same frame)."""
+        """Contiguous component shard for rank `rank` of `world` (same frame).  The tensor-core operand images are made of
+        128-component chunks, so a shard that starts on a chunk boundary keeps them (a slice of the chunks it owns; a ragged
+        last chunk is already padded with zero-weight components)."""
         per = -(-self.K // world)
         lo, hi = min(rank * per, self.K), min((rank + 1) * per, self.K)
-        return MixtureTable(self.table[lo:hi].contiguous(), hi - lo, self.D, self.mode, self.iso_scale, self.ref_log2)
+        tc = tcg = None
+        if self.tc_image is not None and lo % 128 == 0 and (hi % 128 == 0 or hi == self.K) and hi > lo:
+            c0, c1 = lo // 128, -(-hi // 128)
+            f = self.D * 128 + 128
+            tc = self.tc_image[c0 * f:c1 * f]
+            if self.tc_image_grad is not None:
+                g = 2 * self.D * 128 + 128
+                tcg = self.tc_image_grad[c0 * g:c1 * g]
+        return MixtureTable(self.table[lo:hi].contiguous(), hi - lo, self.D, self.mode, self.iso_scale, self.ref_log2, tc, tcg)
 
 
 
@@ -95,12 +105,41 @@ def mixture_pack_full(mean, cov, weight, device):
     cov = np.ascontiguousarray(cov, dtype=np.float64)
     weight = np.ascontiguousarray(weight, dtype=np.float64)
     K, D = mean.shape
+    if D > 16:
+        return _mixture_pack_full_bigd(mean, cov, weight, device)
     stride = _L().ladder_mixture_table_stride(D, 2)
     table = np.zeros((K, stride), dtype=np.float32)
     ref = C.c_float()
     _lib.check(_L().ladder_mixture_pack_full(_dptr(mean), _dptr(cov), _dptr(weight), K, D,
                                              table.ctypes.data_as(_lib.c_float_p), C.byref(ref)), 'mixture_pack_full')
     return MixtureTable(torch.from_numpy(table).to(device), K, D, 2, 1.0, ref.value)
+
+
+MODE_FULL_BIGD = 3      # MixtureTable.mode of the large-dimension full-covariance table (csrc/mixture_bigd.cu)
+
+
+def _mixture_pack_full_bigd(mean, cov, weight, device):
+    """Large-dimension full-covariance table (code_size 128 / 256 of prior "GMM" on CelebA): per component the upper-triangular
+    precision Cholesky factor P (Sigma^-1 = P P^T; tfp's scale_tril = cholesky(cov) inverted), Lambda = P P^T, the mean and the
+    constant, all prepared in float64 on the host (K Cholesky factorisations: parameter preparation, once per fit)."""
+    K, D = mean.shape
+    stride = _L().ladder_mixture_bigd_table_stride(D)
+    if stride == 0:
+        raise RuntimeError('mixture_pack_full: latent dim %d is outside the kernels\' range (<= 16, or a multiple of 32 up to 256)' % D)
+    chol = np.linalg.cholesky(cov)                                      # raises LinAlgError on a non-PD covariance
+    eye = np.eye(D)
+    P = np.stack([np.triu(np.linalg.solve(chol[k], eye).T) for k in range(K)])
+    lam = P @ P.transpose(0, 2, 1)
+    with np.errstate(divide='ignore'):
+        c = (np.log(weight / weight.sum()) - 0.5 * D * np.log(2 * np.pi)
+             + np.log(np.diagonal(P, axis1=1, axis2=2)).sum(axis=1))
+    c = np.maximum(c, -1e30)                                            # zero-weight components: finite, never selected
+    table = np.zeros((K, stride), dtype=np.float32)
+    table[:, :D * D] = P.reshape(K, -1)
+    table[:, D * D:2 * D * D] = lam.reshape(K, -1)
+    table[:, 2 * D * D:2 * D * D + D] = mean
+    table[:, 2 * D * D + D] = c
+    return MixtureTable(torch.from_numpy(table).to(device), K, D, MODE_FULL_BIGD, 1.0, 0.0)
 
 
 def mixture_pack_diag(mean, std, weight=None, device='cuda'):
@@ -175,6 +214,16 @@ def mixture_logprob(t, tab, want_grad=False, partial=False, out=None, exact=Fals
         raise RuntimeError('mixture_logprob: query dim %d != table dim %d' % (D, tab.D))
     out = out or {}
     dev = t.device
+    if tab.mode == MODE_FULL_BIGD:
+        if partial:
+            raise RuntimeError('mixture_logprob: the large-dimension full-covariance table does not support shard partials')
+        logp = out.get('logp') if 'logp' in out else torch.empty(N, device=dev, dtype=torch.float32)
+        grad = (out.get('grad') if 'grad' in out else torch.empty_like(t)) if want_grad else None
+        if N > 0:
+            ws = _workspace(dev, _L().ladder_mixture_bigd_workspace_bytes(N, tab.K), 'mixture_bigd')
+            _lib.check(_L().ladder_mixture_logprob_bigd(_p(t), N, D, _p(tab.table), tab.K, _p(logp), _p(grad), _p(ws), ws.numel(),
+                                                        _stream()), 'mixture_logprob_bigd')
+        return (logp, grad) if want_grad else logp
     if (MIXTURE_TC and not exact and not want_grad and not partial and tab.tc_image is not None and N > 0):
         logp = out.get('logp') if 'logp' in out else torch.empty(N, device=dev, dtype=torch.float32)
         nbytes = _L().ladder_mixture_tc_workspace_bytes(N, tab.K)
@@ -221,13 +270,24 @@ def mixture_logprob(t, tab, want_grad=False, partial=False, out=None, exact=Fals
     return (logp, grad) if want_grad else logp
 
 
-def mixture_logprob_packed(t, tab, pack, want_grad=False):
-    """Shard partial of log p(t) under `tab` as ONE packed buffer pack [N, 2 + D] (or [N, 2]): row = (m, s, unnormalised g)."""
+def mixture_logprob_packed(t, tab, pack, want_grad=False, exact=False):
+    """Shard partial of log p(t) under `tab` as ONE packed buffer pack [N, 2 + D] (or [N, 2]): row = (m, s, unnormalised g).
+    Isotropic D in {32, 64} shards that kept their tensor-core images (MixtureTable.shard) run on the tcgen05 kernels unless
+    exact=True."""
     _f32(t, 't'), _f32(pack, 'pack')
     N, D = t.shape
     if tuple(pack.shape) != (N, 2 + D if want_grad else 2):
         raise RuntimeError('mixture_logprob_packed: pack must be [N, %d]' % (2 + D if want_grad else 2))
     if N == 0:
+        return pack
+    img = None if exact or not MIXTURE_TC else (tab.tc_image_grad if want_grad else tab.tc_image)
+    if img is not None and (MIXTURE_TC_GRAD or not want_grad):
+        nbytes = (_L().ladder_mixture_tc_grad_workspace_bytes(N, tab.K, D) if want_grad
+                  else _L().ladder_mixture_tc_workspace_bytes(N, tab.K))
+        ws = _workspace(t.device, nbytes, 'mixture_tc_grad' if want_grad else 'mixture_tc')
+        _lib.check(_L().ladder_mixture_logprob_tc_packed(_p(t), N, D, _p(img), _p(tab.table), tab.K, tab.iso_scale, tab.ref_log2,
+                                                         _p(pack), int(want_grad), _p(ws), ws.numel(), _stream()),
+                   'mixture_logprob_tc_packed')
         return pack
     nbytes = _L().ladder_mixture_workspace_bytes(N, tab.K, D, tab.mode, int(want_grad))
     ws = _workspace(t.device, nbytes, 'mixture')

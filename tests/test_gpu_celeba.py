@@ -120,6 +120,49 @@ def test_celeba_engine_scalars_and_gradients():
     assert all(torch.isfinite(t).all() for _, t in eng.named_parameters())
 
 
+def test_celeba_gmm_prior_large_code_size():
+    """prior = "GMM" on the CelebA model (base.py:323-329; celeba_config.json has code_size 256): the L samples of q(z|x) are
+    scored under a full-covariance mixture in z-space whose dimension is the code size -- here 32, the smallest size that takes
+    the large-dimension kernel (csrc/mixture_bigd.cu; tests/test_gpu_mixture.py covers D = 128 / 256 at op level).  Every logged
+    scalar and every `ae` gradient against the float64 oracle, epoch after sg_pretraining (fitted mixture + 0.01 I feeds)."""
+    from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
+    from ladder_latent_data_distribution_modelling_b200 import ops as _ops
+    from test_gpu_engine import SCALARS_AE, rel, grad_check
+    B, C = 2, 32
+    cfg = load_config('celeba', batch_size=B, n_MC_samples=4, num_hidden_units=16, code_size=C, compute_dtype='fp32', prior='GMM',
+                      n_mixtures=5)
+    rng = np.random.default_rng(11)
+    P = oparams.glorot_init(oparams.vae_param_specs(cfg), cfg, 12, dtype=np.float32)
+    for k in P:
+        if k.endswith('/bias') or k.endswith('/beta'):
+            P[k] = (rng.normal(size=P[k].shape) * 0.05).astype(np.float32)
+        if k.endswith('/gamma'):
+            P[k] = (1 + rng.normal(size=P[k].shape) * 0.1).astype(np.float32)
+    L, K = cfg['n_MC_samples'], cfg['n_mixtures']
+    x = rng.uniform(size=(B, 128, 128, 3)).astype(np.float32)
+    nz = dict(eps_z=rng.normal(size=(B, C)).astype(np.float32), eps_mc=rng.normal(size=(L, B, C)).astype(np.float32))
+    a = rng.normal(size=(K, C, C))
+    gm = (rng.normal(size=(K, C)), a @ a.transpose(0, 2, 1) * 0.6 / C + 0.05 * np.eye(C), rng.uniform(0.05, 1, size=K))
+    feeds = steps.compute_feeds(cfg, cfg['sg_pretraining'] + 1, gm)
+    eng = LadderEngine(cfg, B, 'cuda', seed=0)
+    eng.load_parameters(P)
+    eng.set_feeds(**feeds)
+    assert eng.mixture.mode == _ops.MODE_FULL_BIGD
+    eng.set_noise(**nz)
+    xd = torch.tensor(x, device='cuda')
+    eng.step_ae(xd, apply=False)
+    Pv, o = nets.build(cfg, P, x, dict(nz, eps_t=None), feeds)
+    got = eng.fetch(SCALARS_AE)
+    for k in SCALARS_AE:
+        assert rel(got[k], float(o[k].v)) < 1e-4, (k, got[k], float(o[k].v))
+    grad_check(eng, eng.ae, nets.grads_of(o['loss_ae'], Pv, eng.ae.names()), tol=3e-3)
+    eng.set_lrs(1e-4, 1e-4, 1e-4, 1e-4)
+    eng.draw_noise()
+    eng.step_ae(xd)
+    eng.step_sigma(xd)
+    assert all(torch.isfinite(t).all() for _, t in eng.named_parameters())
+
+
 # ------------------------------------------------------------------ fused bf16-resident norm layers (csrc/norm_fused.cu)
 def _bf16(a):
     """round a float array to bf16 and back (the value the device tensor holds)."""
