@@ -109,6 +109,13 @@ size_t ladder_mixture_bigd_table_stride(int D);
 size_t ladder_mixture_bigd_workspace_bytes(long long N, int K);
 int ladder_mixture_logprob_bigd(const float* t, long long N, int D, const float* table, int K, float* logp /*nullable*/,
                                 float* grad_t /*nullable*/, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* Diagonal equal-weight mixture with device-resident mean / std [K, D] for any D (VampPrior at the CelebA code sizes 128 /
+ * 256, codes/base.py:215-254): log p, d log p / d t (nullable) and the responsibilities resp [N, K], from which
+ * ..._param_grad forms d(coef * sum_n log p(t_n)) / d(mean, std) (overwrites dmean, dstd [K, D]).                           */
+int ladder_mixture_diag_bigd(const float* t, long long N, int D, const float* mean_dev, const float* std_dev, int K, float* logp,
+                             float* grad_t /*nullable*/, float* resp, cudaStream_t stream);
+int ladder_mixture_diag_bigd_param_grad(const float* t, long long N, int D, const float* mean_dev, const float* std_dev, int K,
+                                        const float* resp, float coef, float* dmean, float* dstd, cudaStream_t stream);
 /* VampPrior mixture (codes/base.py:215-254): K diagonal Gaussians with equal weights whose means / stds are device
  * tensors produced by the shared encoder from the trainable pseudo-inputs.
  *  - ladder_mixture_pack_diag_device packs the mode-1 table and its log2 frame ON THE DEVICE (no host round trip, graph

@@ -188,6 +188,69 @@ __global__ void __launch_bounds__(THREADS, 1) grad_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Diagonal equal-weight mixture whose means / standard deviations are DEVICE tensors, any D (used for D > 64): the VampPrior
+// of the CelebA model (codes/base.py:215-254 with code_size 128 / 256), where the register-resident kernel of csrc/mixture.cu
+// (D <= 64) does not apply.  Work is N K D multiply-adds (no contraction to tile): one warp per (query, component) pair with
+// the lanes striding the latent dimension, the same exact log-sum-exp, then one thread per output element for d/dt, d/dmean,
+// d/dstd (sums over K resp. N in a fixed order: deterministic).
+//   e_nk = -log K - D/2 log 2 pi - sum_d [ log sd_kd + 1/2 ((t_nd - mu_kd) / sd_kd)^2 ]
+__global__ void diag_scores_kernel(const float* __restrict__ t, long long N, int D, const float* __restrict__ mean,
+                                   const float* __restrict__ sd, int K, float* __restrict__ E) {
+  const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pair >= N * K) return;
+  const int lane = threadIdx.x & 31;
+  const long long n = pair / K;
+  const int k = (int)(pair % K);
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float s = __ldg(sd + (size_t)k * D + d);
+    const float y = (__ldg(t + n * D + d) - __ldg(mean + (size_t)k * D + d)) / s;
+    acc += logf(s) + 0.5f * y * y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) E[pair] = -logf((float)K) - 0.9189385332046727f * (float)D - acc;
+}
+
+// grad_t[n, d] = sum_k r_nk (mu_kd - t_nd) / sd_kd^2
+__global__ void diag_grad_t_kernel(const float* __restrict__ t, long long N, int D, const float* __restrict__ mean,
+                                   const float* __restrict__ sd, int K, const float* __restrict__ R, float* __restrict__ grad) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * D) return;
+  const long long n = idx / D;
+  const int d = (int)(idx % D);
+  const float tv = __ldg(t + idx);
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float s = __ldg(sd + (size_t)k * D + d);
+    acc = fmaf(__ldg(R + n * K + k), (__ldg(mean + (size_t)k * D + d) - tv) / (s * s), acc);
+  }
+  grad[idx] = acc;
+}
+
+// dmean[k, d] = coef sum_n r_nk (t_nd - mu_kd) / sd_kd^2;  dstd[k, d] = coef sum_n r_nk ((t_nd - mu_kd)^2 / sd_kd^3 - 1 / sd_kd)
+__global__ void diag_param_grad_kernel(const float* __restrict__ t, long long N, int D, const float* __restrict__ mean,
+                                       const float* __restrict__ sd, int K, const float* __restrict__ R, float coef,
+                                       float* __restrict__ dmean, float* __restrict__ dstd) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * D) return;
+  const int k = idx / D, d = idx % D;
+  const float mu = __ldg(mean + idx), s = __ldg(sd + idx);
+  float a1 = 0.f, a2 = 0.f, a0 = 0.f;
+#pragma unroll 4
+  for (long long n = 0; n < N; ++n) {
+    const float r = __ldg(R + n * K + k);
+    const float u = __ldg(t + n * D + d) - mu;
+    a0 += r;
+    a1 = fmaf(r, u, a1);
+    a2 = fmaf(r * u, u, a2);
+  }
+  const float is = 1.f / s;
+  dmean[idx] = coef * a1 * is * is;
+  dstd[idx] = coef * (a2 * is * is * is - a0 * is);
+}
+
 }  // namespace bigd
 }  // namespace ladder
 
@@ -225,6 +288,33 @@ int ladder_mixture_logprob_bigd(const float* t, long long N, int D, const float*
   cudaFuncSetAttribute(grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
   grad_kernel<<<row_tiles, THREADS, smem_g, stream>>>(t, N, D, table, K, E, grad_t);
   return check_launch("mixture bigd gradient");
+}
+
+/* Diagonal equal-weight mixture with device-resident mean / std [K, D] (VampPrior, codes/base.py:241-254), any D >= 1 (the
+ * engine uses it for D > 64).  resp [N, K] receives the responsibilities r_nk (input of ladder_mixture_diag_bigd_param_grad);
+ * logp [N]; grad_t [N, D] may be NULL.                                                                                     */
+int ladder_mixture_diag_bigd(const float* t, long long N, int D, const float* mean_dev, const float* std_dev, int K, float* logp,
+                             float* grad_t, float* resp, cudaStream_t stream) {
+  LADDER_REQUIRE(N >= 0 && K >= 1 && D >= 1, "mixture_diag_bigd: bad sizes");
+  if (N == 0) return LADDER_OK;
+  LADDER_REQUIRE(t && mean_dev && std_dev && logp && resp, "mixture_diag_bigd: null pointer");
+  diag_scores_kernel<<<(unsigned)ceil_div64(N * K, 8), 256, 0, stream>>>(t, N, D, mean_dev, std_dev, K, resp);
+  int rc = check_launch("mixture diag bigd scores");
+  if (rc) return rc;
+  lse_kernel<<<(unsigned)ceil_div64(N, 128), 128, 0, stream>>>(resp, N, K, logp, 1);
+  rc = check_launch("mixture diag bigd lse");
+  if (rc || grad_t == nullptr) return rc;
+  diag_grad_t_kernel<<<(unsigned)ceil_div64(N * D, 256), 256, 0, stream>>>(t, N, D, mean_dev, std_dev, K, resp, grad_t);
+  return check_launch("mixture diag bigd grad_t");
+}
+
+/* d(coef * sum_n log p(t_n)) / d(mean, std) from the responsibilities ladder_mixture_diag_bigd left in resp (overwrites) */
+int ladder_mixture_diag_bigd_param_grad(const float* t, long long N, int D, const float* mean_dev, const float* std_dev, int K,
+                                        const float* resp, float coef, float* dmean, float* dstd, cudaStream_t stream) {
+  LADDER_REQUIRE(N >= 0 && K >= 1 && D >= 1, "mixture_diag_bigd_param_grad: bad sizes");
+  LADDER_REQUIRE(mean_dev && std_dev && dmean && dstd && (N == 0 || (t && resp)), "mixture_diag_bigd_param_grad: null pointer");
+  diag_param_grad_kernel<<<(unsigned)ceil_div(K * D, 128), 128, 0, stream>>>(t, N, D, mean_dev, std_dev, K, resp, coef, dmean, dstd);
+  return check_launch("mixture diag bigd param grad");
 }
 
 }  // extern "C"

@@ -495,7 +495,7 @@ class CelebAOuterVAE:
     Set LADDER_FUSED_NORM=0 to force the latter."""
     last_act = None
 
-    def __init__(self, config, group, B, device, allreduce, world):
+    def __init__(self, config, group, B, device, allreduce, world, encoder_only=False):
         self.cfg, self.group, self.B, self.dev, self.world = config, group, B, device, world
         H, C, k = int(config['num_hidden_units']), int(config['code_size']), int(config['kernel_size'])
         ch, S = int(config['dim_input_channel']), int(config['dim_input_x'])
@@ -514,8 +514,9 @@ class CelebAOuterVAE:
         self.fused = (os.environ.get('LADDER_FUSED_NORM', '1') != '0' and ops.MATH_MODE == 'bf16'
                       and all(fwd_ok(g) and ops.norm_fused_ok(g.Cout) for g in egeoms)
                       and all(ops.tma_supported(g, ops.DGRAD) and ops.tma_supported(g, ops.WGRAD) for g in egeoms[1:])
-                      and all(ops.tma_supported(g, ops.FPROP) and ops.tma_supported(g, ops.DGRAD)
-                              and ops.tma_supported(g, ops.WGRAD) and ops.norm_fused_ok(g.Cout) for g in sgeoms.values()))
+                      and (encoder_only or all(ops.tma_supported(g, ops.FPROP) and ops.tma_supported(g, ops.DGRAD)
+                                               and ops.tma_supported(g, ops.WGRAD) and ops.norm_fused_ok(g.Cout)
+                                               for g in sgeoms.values())))
         fused = self.fused
         self.enc = [(BNBlock16 if fused else BNBlock)(group, i, g, device, allreduce) for i, g in enumerate(egeoms)]
         self.flat, self.C, self.H = hw * hw * cin, C, H
@@ -524,6 +525,9 @@ class CelebAOuterVAE:
         self.mean = self.head_mean.y.view(B, C)
         self.std = self.head_std.y.view(B, C)
         self.z = torch.empty(B, C, device=device)
+        self.decoded = None
+        if encoder_only:                                   # VampPrior pseudo-input path (base.py:228-238)
+            return
         # decoder
         self.dec_dense = Conv(group, 'decoder/dense', G.dense(B, C, H), LEAKY, device)
         self.mapping = [Conv(group, 'decoder/dense_%d' % i, G.dense(B, H, H), LEAKY, device) for i in range(1, 9)]
@@ -651,7 +655,9 @@ class CelebAOuterVAE:
         self.dec_dense.backward(d_enc, dx=dz.view(B, 1, 1, self.C), wgrad=wgrad)
         return dz
 
-    def encode_backward(self, dz, c_entropy, c_sg, dmean_add=None, dstd_add=None):
+    def encode_backward(self, dz, c_entropy, c_sg, dmean_add=None, dstd_add=None, wgrad=True, dx_image=None):
+        """dx_image [B, S, S, ch]: also return the gradient w.r.t. the input images (VampPrior pseudo-inputs).  `wgrad` is
+        accepted for interface parity with MnistOuterVAE; the batch-norm blocks always produce their weight gradients."""
         B, C = self.B, self.C
         floor = float(self.cfg['latent_variance_precision'])
         dmean, dstd = self.buf.get('dmean', B, C), self.buf.get('dstd', B, C)
@@ -673,14 +679,14 @@ class CelebAOuterVAE:
                     blk.backward(gcur, dx, self.world, producer=(prev.y, LEAKY))
                 else:
                     dx = None
-                    blk.backward(gcur, None, self.world)
+                    blk.backward(gcur, dx_image, self.world)
                 gcur = dx
             return
         self.head_mean.backward(dmean.view(B, 1, 1, C), dx=dflat)
         self.head_std.backward(dstd.view(B, 1, 1, C), dx=dflat, accumulate=True)
         dout = dflat.view(*self.enc[-1].y.shape)
         for i in range(len(self.enc) - 1, -1, -1):
-            dx = self.buf.get('de%d' % i, *self.enc[i - 1].y.shape) if i > 0 else None
+            dx = self.buf.get('de%d' % i, *self.enc[i - 1].y.shape) if i > 0 else dx_image
             self.enc[i].backward(dout, dx, self.world)
             dout = dx
 
@@ -879,8 +885,6 @@ class LadderEngine:
             self.inner_sigma = ParamGroup('inner_sigma', [('inner_sigma/Variable', ())], dev)
             self.groups.update(prior=self.prior_g, inner_sigma=self.inner_sigma)
         if self.prior == 'vampPrior':
-            if config['exp_name'] == 'celeba':
-                raise NotImplementedError('prior=vampPrior is built for the MNIST models (28x28x1 pseudo-inputs) only')
             # the K trainable pseudo-inputs, the only variable of scope `prior` (base.py:224-225, 424-429)
             self.prior_g = ParamGroup('prior', [('prior/Variable', (self.K, int(config['dim_input_x']),
                                                                     int(config['dim_input_y']),
@@ -902,7 +906,12 @@ class LadderEngine:
         if self.prior == 'vampPrior':
             # define_vampPrior (base.py:215-254): the shared encoder + heads on the K pseudo-inputs
             self.shared = SharedGroup(self.ae)
-            self.pseudo = MnistOuterVAE(config, self.shared, self.K, dev, encoder_only=True)
+            if config['exp_name'] == 'celeba':
+                # the pseudo-inputs are replicated parameters: their batch-norm statistics are the K pseudo-images' own on
+                # every rank (no cross-replica reduction); the shared-weight gradient is all-reduced with the rest of `ae`
+                self.pseudo = CelebAOuterVAE(config, self.shared, self.K, dev, lambda t: t, 1, encoder_only=True)
+            else:
+                self.pseudo = MnistOuterVAE(config, self.shared, self.K, dev, encoder_only=True)
         for grp in list(self.groups.values()) + ([self.shared] if self.shared is not None else []):
             grp.plan_packs()
         self.scalars = torch.zeros(ops.SCALARS_LEN, device=dev)
@@ -928,6 +937,9 @@ class LadderEngine:
             self.dmean_p = torch.empty(K, C, device=dev)
             self.dstd_p = torch.empty(K, C, device=dev)
             self.vamp_tab = None
+            # code sizes beyond the register-resident mixture kernel (CelebA: 128 / 256): csrc/mixture_bigd.cu, which keeps
+            # the responsibilities [L B, K] for the parameter gradients
+            self.vamp_resp = torch.empty(self.L * B, K, device=dev) if C > 64 else None
         if self.prior in ('GMM', 'vampPrior'):
             # prior "GMM" (base.py:323-329): L samples of q(z|x) scored under a full-covariance mixture in z-space (D = C)
             self.eps_mc = torch.zeros(self.L, B, self.C, device=dev)
@@ -1058,10 +1070,13 @@ class LadderEngine:
             if mix and not self.use_sg:                  # tf.cond(use_standard_gaussian_prior): branch not taken
                 self.shared.repack()
                 self.pseudo.encode(self.prior_g.p('prior/Variable'), self.pseudo_eps, self.pseudo_stats)
-                self.vamp_tab = ops.mixture_pack_diag_device(self.pseudo.mean, self.pseudo.std, self.vamp_tab)
                 ops.mc_sample(self.outer.mean, self.outer.std, self.eps_mc, self.t_mc)
-                ops.mixture_logprob(self.t_mc, self.vamp_tab, want_grad=True,
-                                    out={'logp': self.logp_mc, 'grad': self.g_mc})
+                if self.vamp_resp is not None:
+                    ops.mixture_diag_bigd(self.t_mc, self.pseudo.mean, self.pseudo.std, self.logp_mc, self.g_mc, self.vamp_resp)
+                else:
+                    self.vamp_tab = ops.mixture_pack_diag_device(self.pseudo.mean, self.pseudo.std, self.vamp_tab)
+                    ops.mixture_logprob(self.t_mc, self.vamp_tab, want_grad=True,
+                                        out={'logp': self.logp_mc, 'grad': self.g_mc})
                 ops.sum_into(self.logp_mc, s[11:12])
         self._allreduce(s[:12])            # batch-global sums (sigma, means) across data-parallel ranks
         cfg = self.cfg
@@ -1124,6 +1139,15 @@ class LadderEngine:
         else:
             self.pvae.backward(self.dzhat, None, None, -1.0 / Bg, 1.0 / Bg, dz=dz, wgrad=wgrad)
 
+    def _vamp_param_grad(self, coef):
+        """d(coef * sum log p(t_mc)) / d(pseudo code_mean, code_std_dev) -> dmean_p, dstd_p"""
+        if self.vamp_resp is not None:
+            ops.mixture_diag_bigd_param_grad(self.t_mc, self.pseudo.mean, self.pseudo.std, self.vamp_resp, coef, self.dmean_p,
+                                             self.dstd_p)
+        else:
+            ops.mixture_diag_param_grad(self.t_mc, self.pseudo.mean, self.pseudo.std, self.logp_mc, coef, self.dmean_p,
+                                        self.dstd_p)
+
     # ---- the four sess.run equivalents (codes/base.py:583-641)
     def step_ae(self, x, apply=True):
         """train_step_ae: forward everything, d loss_ae / d (encoder, decoder), clip + Adam."""
@@ -1137,8 +1161,7 @@ class LadderEngine:
             coef = -1.0 / (self.L * Bg)
             ops.mc_reduce(self.g_mc, self.eps_mc, coef, self.dmu_add, self.dsd_add)
             # the shared encoder also receives the gradient that reaches it through the pseudo-input mixture
-            ops.mixture_diag_param_grad(self.t_mc, self.pseudo.mean, self.pseudo.std, self.logp_mc, coef, self.dmean_p,
-                                        self.dstd_p)
+            self._vamp_param_grad(coef)
             self.pseudo.encode_backward(self.pseudo_dz, 0.0, 0.0, self.dmean_p, self.dstd_p)
             self.outer.encode_backward(self.dz, -1.0 / Bg, 0.0, self.dmu_add, self.dsd_add)
             ops.axpy(self.ae.grad, self.shared.grad, 1.0)
@@ -1167,8 +1190,7 @@ class LadderEngine:
             if self.use_sg:
                 pg.zero_()
             else:
-                ops.mixture_diag_param_grad(self.t_mc, self.pseudo.mean, self.pseudo.std, self.logp_mc,
-                                            -1.0 / (self.L * self.B_global), self.dmean_p, self.dstd_p)
+                self._vamp_param_grad(-1.0 / (self.L * self.B_global))
                 self.pseudo.encode_backward(self.pseudo_dz, 0.0, 0.0, self.dmean_p, self.dstd_p, wgrad=False, dx_image=pg)
             self._allreduce(self.prior_g.grad)
             if apply:

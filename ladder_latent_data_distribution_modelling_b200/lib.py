@@ -131,6 +131,9 @@ SIGNATURES = {
     'ladder_mixture_bigd_table_stride': (C.c_size_t, [C.c_int]),
     'ladder_mixture_bigd_workspace_bytes': (C.c_size_t, [C.c_longlong, C.c_int]),
     'ladder_mixture_logprob_bigd': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, C.c_int, ptr, ptr, ptr, C.c_size_t, stream_t]),
+    'ladder_mixture_diag_bigd': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, ptr, C.c_int, ptr, ptr, ptr, stream_t]),
+    'ladder_mixture_diag_bigd_param_grad': (C.c_int, [ptr, C.c_longlong, C.c_int, ptr, ptr, C.c_int, ptr, C.c_float, ptr, ptr,
+                                                      stream_t]),
     'ladder_mixture_combine_packed': (C.c_int, [ptr, C.c_int, C.c_longlong, C.c_int, C.c_int, ptr, ptr, stream_t]),
     'ladder_mixture_combine': (C.c_int, [ptr, ptr, ptr, C.c_int, C.c_longlong, C.c_int, ptr, ptr, stream_t]),
 }

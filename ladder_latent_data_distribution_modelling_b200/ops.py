@@ -196,6 +196,26 @@ def mixture_diag_param_grad(t, mean, std, logp, coef, dmean, dstd):
                'mixture_diag_param_grad')
 
 
+def mixture_diag_bigd(t, mean, std, logp, grad, resp):
+    """Diagonal equal-weight mixture with device mean / std [K, D] at any D (VampPrior on the CelebA model, D = 128 / 256):
+    logp [N], grad [N, D] (or None) and the responsibilities resp [N, K] that mixture_diag_bigd_param_grad consumes."""
+    N, D = t.shape
+    K = mean.shape[0]
+    if tuple(resp.shape) != (N, K):
+        raise RuntimeError('mixture_diag_bigd: resp must be [N, K]')
+    _lib.check(_L().ladder_mixture_diag_bigd(_p(_f32(t)), N, D, _p(_f32(mean)), _p(_f32(std)), K, _p(_f32(logp)),
+                                             _p(_f32(grad) if grad is not None else None), _p(_f32(resp)), _stream()),
+               'mixture_diag_bigd')
+    return (logp, grad) if grad is not None else logp
+
+
+def mixture_diag_bigd_param_grad(t, mean, std, resp, coef, dmean, dstd):
+    N, D = t.shape
+    _lib.check(_L().ladder_mixture_diag_bigd_param_grad(_p(_f32(t)), N, D, _p(_f32(mean)), _p(_f32(std)), mean.shape[0],
+                                                        _p(_f32(resp)), float(coef), _p(_f32(dmean)), _p(_f32(dstd)), _stream()),
+               'mixture_diag_bigd_param_grad')
+
+
 MIXTURE_TC = True      # use the tcgen05 kernel for isotropic D in {32, 64} forward evaluations
 MIXTURE_TC_GRAD = os.environ.get('LADDER_MIX_TC_GRAD', '1') != '0'      # ... and for forward + gradient (second MMA from TMEM)
 

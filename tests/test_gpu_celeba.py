@@ -163,6 +163,57 @@ def test_celeba_gmm_prior_large_code_size():
     assert all(torch.isfinite(t).all() for _, t in eng.named_parameters())
 
 
+@pytest.mark.parametrize('C', [8, 128])
+def test_celeba_vamp_prior(C):
+    """prior = "vampPrior" on the CelebA model (base.py:215-254): the K pseudo-images go through the SHARED batch-norm encoder
+    (their own batch statistics) to a diagonal mixture in z-space; code_size 8 takes the register-resident mixture kernel,
+    128 the large-dimension kernels.  Scalars, every `ae` gradient (direct + through the pseudo path) and the pseudo-input
+    gradient of loss_prior = -elbo against the float64 oracle."""
+    from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
+    from test_gpu_engine import SCALARS_AE, rel, grad_check
+    B, K, L = 2, 3, 4
+    cfg = load_config('celeba', batch_size=B, n_MC_samples=L, num_hidden_units=16, code_size=C, compute_dtype='fp32',
+                      prior='vampPrior', n_mixtures=K)
+    rng = np.random.default_rng(21 + C)
+    P = oparams.glorot_init(oparams.vae_param_specs(cfg) + oparams.prior_param_specs(cfg), cfg, 22, dtype=np.float32)
+    for k in P:
+        if k.endswith('/bias') or k.endswith('/beta'):
+            P[k] = (rng.normal(size=P[k].shape) * 0.05).astype(np.float32)
+        if k.endswith('/gamma'):
+            P[k] = (1 + rng.normal(size=P[k].shape) * 0.1).astype(np.float32)
+    # stds of the image batch and of the K = 3 pseudo-images (batch norm over 3 samples saturates) away from the 1e-3 floor
+    P['encoder/code_std_dev/kernel'] = (0.1 * P['encoder/code_std_dev/kernel']).astype(np.float32)
+    P['encoder/code_std_dev/bias'] = P['encoder/code_std_dev/bias'] + np.float32(0.7)
+    P['prior/Variable'] = rng.uniform(size=P['prior/Variable'].shape).astype(np.float32)
+    assert P['prior/Variable'].shape == (K, 128, 128, 3)
+    x = rng.uniform(size=(B, 128, 128, 3)).astype(np.float32)
+    nz = dict(eps_z=rng.normal(size=(B, C)).astype(np.float32), eps_mc=rng.normal(size=(L, B, C)).astype(np.float32))
+    feeds = steps.compute_feeds(cfg, cfg['sg_pretraining'] + 1, None)
+    assert not feeds['use_standard_gaussian_prior']
+    eng = LadderEngine(cfg, B, 'cuda', seed=0)
+    eng.load_parameters(P)
+    eng.set_feeds(**feeds)
+    eng.set_noise(**nz)
+    assert (eng.vamp_resp is not None) == (C > 64)
+    xd = torch.tensor(x, device='cuda')
+    eng.step_ae(xd, apply=False)
+    Pv, o = nets.build(cfg, P, x, dict(nz, eps_t=None), feeds)
+    got = eng.fetch(SCALARS_AE)
+    for k in SCALARS_AE:
+        assert rel(got[k], float(o[k].v)) < 1e-4, (k, got[k], float(o[k].v))
+    grad_check(eng, eng.ae, nets.grads_of(o['loss_ae'], Pv, eng.ae.names()), tol=3e-3)
+    eng.step_prior(xd, apply=False)
+    g = nets.grads_of(o['loss_prior'], Pv, ['prior/Variable'])['prior/Variable']
+    gg = eng.prior_g.g('prior/Variable').cpu().numpy()
+    assert np.abs(g).max() > 0
+    assert np.abs(gg - g).max() <= 3e-3 * np.abs(g).max(), (np.abs(gg - g).max(), np.abs(g).max())
+    eng.set_lrs(1e-4, 1e-4, 1e-4, 1e-4)
+    for fn in (eng.step_ae, eng.step_sigma, eng.step_prior):
+        eng.draw_noise()
+        fn(xd)
+    assert all(torch.isfinite(t).all() for _, t in eng.named_parameters())
+
+
 # ------------------------------------------------------------------ fused bf16-resident norm layers (csrc/norm_fused.cu)
 def _bf16(a):
     """round a float array to bf16 and back (the value the device tensor holds)."""

@@ -362,3 +362,29 @@ def test_full_cov_unsupported_dim_raises(ops):
     rng = np.random.default_rng(0)
     with pytest.raises(RuntimeError):
         ops.mixture_pack_full(rng.normal(size=(3, 24)), np.tile(np.eye(24), (3, 1, 1)), np.ones(3), 'cuda')
+
+
+@pytest.mark.parametrize('D', [128, 256, 40])
+def test_vamp_prior_large_dims(ops, D):
+    """VampPrior mixture at the CelebA code sizes (base.py:241-254 with code_size 128 / 256; D = 40 checks a dimension that is
+    not a lane multiple): log p, d/dt, and d/d mean, d/d std of coef * sum_n log p(t_n) from csrc/mixture_bigd.cu's diagonal
+    kernels against the float64 oracle."""
+    from oracle import tape as T
+    rng = np.random.default_rng(D)
+    K, N = 9, 301
+    mean = rng.normal(size=(K, D)); std = rng.uniform(0.5, 1.5, size=(K, D))
+    t = rng.normal(size=(N, D)) * 1.2
+    tv, mv, sv = T.Var(t), T.Var(mean), T.Var(std)
+    lp = OM.diag_mixture_logprob_var(tv, mv, sv)
+    coef = -1.0 / N
+    T.backward(T.reduce_sum(lp) * coef)
+    md, sd, td = _dev(mean.astype(np.float32)), _dev(std.astype(np.float32)), _dev(t.astype(np.float32))
+    logp, g, resp = torch.empty(N, device='cuda'), torch.empty(N, D, device='cuda'), torch.empty(N, K, device='cuda')
+    ops.mixture_diag_bigd(td, md, sd, logp, g, resp)
+    np.testing.assert_allclose(logp.cpu().numpy(), lp.v, rtol=2e-5, atol=2e-3)
+    np.testing.assert_allclose(resp.sum(1).cpu().numpy(), np.ones(N), rtol=1e-4)
+    np.testing.assert_allclose(g.cpu().numpy() * coef, tv.g, rtol=2e-3, atol=2e-3 / N)
+    dm, ds = torch.full((K, D), 7.0, device='cuda'), torch.full((K, D), 7.0, device='cuda')
+    ops.mixture_diag_bigd_param_grad(td, md, sd, resp, coef, dm, ds)
+    np.testing.assert_allclose(dm.cpu().numpy(), mv.g, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(ds.cpu().numpy(), sv.g, rtol=1e-3, atol=2e-5)
