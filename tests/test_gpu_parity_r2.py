@@ -179,6 +179,78 @@ def test_celeba_engine_bf16_real_widths(H, C, B):
     _assert_table(rows_px, 'prior vs exact', KINK_L2)
 
 
+@pytest.mark.parametrize('prior', ['GMM', 'vampPrior'])
+def test_celeba_engine_bf16_mixture_priors(prior):
+    """The z-space mixture branches on the PRODUCTION realisation of the CelebA model (bf16 tcgen05 GEMMs, fused bf16-resident
+    norm layers; 64-aligned widths so the VampPrior pseudo-encoder takes the fused blocks too; code_size 128 = the
+    large-dimension mixture kernels of csrc/mixture_bigd.cu): logged terms and every gradient -- `ae` (for the VampPrior also
+    through the pseudo path) and the pseudo-images -- under the same per-tensor tolerance model as test (a), then CUDA-graph
+    replays of every sub-step stay finite."""
+    from ladder_latent_data_distribution_modelling_b200.engine import LadderEngine
+    B, K, L, C, H = 4, 4, 4, 128, 256
+    cfg = load_config('celeba', batch_size=B, n_MC_samples=L, num_hidden_units=H, code_size=C, compute_dtype='bf16', prior=prior,
+                      n_mixtures=K)
+    rng = np.random.default_rng(41)
+    spec = oparams.vae_param_specs(cfg) + (oparams.prior_param_specs(cfg) if prior == 'vampPrior' else [])
+    P = oparams.glorot_init(spec, cfg, 42, dtype=np.float32)
+    for k in P:
+        if k.endswith('/bias') or k.endswith('/beta'):
+            P[k] = (rng.normal(size=P[k].shape) * 0.05).astype(np.float32)
+        if k.endswith('/gamma'):
+            P[k] = (1 + rng.normal(size=P[k].shape) * 0.1).astype(np.float32)
+    # code standard deviations (image batch and pseudo-images) away from the relu + 1e-3 floor
+    P['encoder/code_std_dev/kernel'] = (0.1 * P['encoder/code_std_dev/kernel']).astype(np.float32)
+    P['encoder/code_std_dev/bias'] = P['encoder/code_std_dev/bias'] + np.float32(0.7)
+
+    def smooth(n):
+        low = rng.uniform(size=(n, 16, 16, 3))
+        return np.clip(np.repeat(np.repeat(low, 8, 1), 8, 2) + 0.05 * rng.normal(size=(n, 128, 128, 3)), 0, 1).astype(np.float32)
+    x = smooth(B)
+    if prior == 'vampPrior':
+        P['prior/Variable'] = smooth(K)
+    nz = dict(eps_z=rng.normal(size=(B, C)).astype(np.float32), eps_mc=rng.normal(size=(L, B, C)).astype(np.float32))
+    a = rng.normal(size=(K, C, C))
+    gm = (rng.normal(size=(K, C)), a @ a.transpose(0, 2, 1) * 0.6 / C + 0.05 * np.eye(C), rng.uniform(0.05, 1, size=K))
+    feeds = steps.compute_feeds(cfg, cfg['sg_pretraining'] + 1, gm if prior == 'GMM' else None)
+    exact, egrads = _oracle(cfg, P, x, nz, feeds)
+    want, wgrads = _oracle(cfg, P, x, nz, feeds, bf16=True)
+    eng = LadderEngine(cfg, B, 'cuda', seed=0)
+    assert eng.outer.fused and (prior != 'vampPrior' or eng.pseudo.fused)
+    eng.load_parameters(P)
+    eng.set_feeds(**feeds)
+    eng.set_noise(**nz)
+    xd = torch.tensor(x, device='cuda')
+    eng.step_ae(xd, apply=False)
+    names = ['loss_ae', 'elbo', 'sigma', 'entropy_z', 'crossEntropy_prior']
+    got = eng.fetch(names)
+    d_ae = _depths(cfg, eng.ae.names())
+    rows, rows_x = _grad_table(eng.ae, wgrads['ae'], d_ae, egrads['ae']), _grad_table(eng.ae, egrads['ae'], d_ae)
+    table = {'scalars': {k: [got[k], want[k], exact[k]] for k in names}, 'ae': rows, 'ae_vs_exact': rows_x}
+    if prior == 'vampPrior':
+        eng.step_prior(xd, apply=False)
+        d_pr = {'prior/Variable': max(d_ae.values()) + 2}           # behind the whole encoder, through the mixture and back
+        table['prior'] = _grad_table(eng.prior_g, wgrads['prior'], d_pr, egrads['prior'])
+        table['prior_vs_exact'] = _grad_table(eng.prior_g, egrads['prior'], d_pr)
+    _dump('celeba_%s' % prior, table)
+    for k in names:
+        assert abs(got[k] - want[k]) <= 3e-3 * max(1.0, abs(want[k])) + abs(exact[k] - want[k]), (k, got[k], want[k], exact[k])
+        assert abs(got[k] - exact[k]) <= 1e-2 * max(1.0, abs(exact[k])), (k, got[k], exact[k])
+    # batch norm over 4 samples: the float64 oracle's own encoder gradients move by 0.33-0.44 (relative L2) under operand
+    # rounding in this case, so against the EXACT graph only "same order" is asserted
+    _assert_table(rows, 'ae')
+    _assert_table(rows_x, 'ae vs exact', 1.0)
+    if prior == 'vampPrior':
+        _assert_table(table['prior'], 'pseudo-inputs')
+        _assert_table(table['prior_vs_exact'], 'pseudo-inputs vs exact', 1.0)
+    eng.set_lrs(1e-4, 1e-4, 1e-4, 1e-4)
+    for _ in range(2):
+        for name in ('ae', 'sigma') + (('prior',) if prior == 'vampPrior' else ()):
+            eng.run_step(name, xd)
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(t).all() for _, t in eng.named_parameters())
+    eng.release_graphs()
+
+
 def mnist_case(exp, B, seed, **over):
     from test_gpu_engine import make_case
     return make_case(exp, B, seed, **over)

@@ -63,6 +63,42 @@ def test_two_epochs_through_the_reference_interface(prior, tmp_path):
         assert torch.equal(model.engine.ae.p(n), model2.engine.ae.p(n)), n
 
 
+@pytest.mark.parametrize('prior', ['ours', 'GMM', 'vampPrior'])
+def test_celeba_two_epochs_through_the_reference_interface(prior, tmp_path):
+    """The CelebA classes (codes/models.py:330-598, codes/trainers.py:110-249) on a narrow model for the three mixture priors:
+    "GMM" fits a full-covariance mixture in z-space at code_size 32 (scikit-learn on the host: the GPU estimator covers D <= 16)
+    and feeds the large-dimension mixture kernel; "vampPrior" runs the shared batch-norm encoder on the pseudo-images."""
+    from codes.data_loader import DataGenerator
+    from codes.models import CelebAModel_densenet
+    from codes.trainers import CelebATrainer_joint_training
+    B = 8
+    cfg = load_config('celeba', batch_size=B, prior=prior, num_epochs=2, sg_pretraining=1, n_mixtures=2, n_MC_samples=4,
+                      num_hidden_units=32, code_size=32, synthetic=True, synthetic_n_train=4 * B, synthetic_n_val=2 * B,
+                      synthetic_pool=4 * B, num_iter_to_plot=1, use_mask_start=2, GM_fit_restart=1, seed=3)
+    cfg['result_dir'] = str(tmp_path / 'result') + '/'
+    cfg['checkpoint_dir'] = str(tmp_path / 'checkpoint') + '/'
+    os.makedirs(cfg['result_dir']); os.makedirs(cfg['checkpoint_dir'])
+    data = DataGenerator(cfg, None)
+    model = CelebAModel_densenet(cfg, device='cuda')
+    trainer = CelebATrainer_joint_training(None, model, data, cfg)
+    before = {n: t.clone() for n, t in model.engine.named_parameters()}
+    trainer.train()
+    torch.cuda.synchronize()
+    assert trainer.cur_epoch == 2 and len(trainer.train_loss) == 2 * 4
+    assert np.all(np.isfinite(trainer.train_loss)) and np.all(np.isfinite(trainer.val_loss))
+    for n, t in model.engine.named_parameters():
+        assert torch.isfinite(t).all(), n
+    moved = {n for n, t in model.engine.named_parameters() if not torch.equal(t, before[n])}
+    assert 'encoder/conv2d/kernel' in moved and 'decoder/conv2d_7/kernel' in moved
+    if prior == 'vampPrior':
+        assert 'prior/Variable' in moved
+    if prior == 'GMM':
+        from ladder_latent_data_distribution_modelling_b200 import ops
+        assert model.GM_prior_training.means_.shape == (2, 32)
+        assert model.engine.mixture.mode == ops.MODE_FULL_BIGD and model.engine.mixture.K == 2
+    assert os.path.isfile(cfg['result_dir'] + 'celeba-result.npz')
+
+
 def _train_two_epochs(cfg, device, dist_group=None):
     from codes.data_loader import DataGenerator
     from codes.models import MNISTModel_digit
