@@ -532,6 +532,9 @@ def run_ours(args):
                     sharded['graph'] = bool(sm.use_graph)
                     del sm
             sharded['D'] = 2
+            sharded['kernels'] = {'D2': 'mix_kernel (registers, fp32), packed (m, s, g) partial',
+                                  'D32_D64': 'mix_tc_kernel / mix_tc_grad_kernel (tcgen05 kind::tf32) on the rank\'s slice of the '
+                                             'operand images, packed partial from the finalising kernel'}
         except Exception as e:                                       # noqa: BLE001
             sharded = {'error': '%s: %s' % (type(e).__name__, str(e).splitlines()[0][:200] if str(e) else '')}
 
