@@ -364,38 +364,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(TcArgs a) {
       load(vb); advance_load();
     }
   } else if (warp == MMA_WARP) {
-    // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, MODE == WGRAD);
-      Tile T;
-      decode_tile<MODE>(a, blockIdx.x, total, pixels, T);
-      unsigned it = 0, j = 0;
-      while (T.valid) {
-        const uint32_t acc = j & 1;
-        mbar_wait(bar_tempty + acc * 8, ((j >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+    // ===================================================== MMA issuer (converged warp, one elected lane issues: see conv_tma.cu)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc(BM, BN, MODE == WGRAD);
+    Tile T;
+    decode_tile<MODE>(a, blockIdx.x, total, pixels, T);
+    uint32_t s = 0, ph = 0;
+    unsigned j = 0;
+    while (T.valid) {
+      const uint32_t acc = j & 1;
+      mbar_wait(bar_tempty + acc * 8, ((j >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < T.nkb; ++kb) {
+        mbar_wait(bar_full + s * 8, ph);                    // acquire: all producers' st.shared of this stage
+        if (!(a.debug & 8)) fence_proxy_async();            // ... made visible to the async proxy (tcgen05.mma reads)
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = 0; kb < T.nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(bar_full + s * 8, (it / STAGES) & 1);   // acquire: all producers' st.shared of this stage
-          if (!(a.debug & 8)) fence_proxy_async();            // ... made visible to the async proxy (tcgen05.mma reads)
-          tc_fence_after();
-          const uint32_t tA = sA + s * A_STAGE_BYTES, tB = sB + s * B_STAGE_BYTES;
+        const uint32_t tA = sA + s * A_STAGE_BYTES, tB = sB + s * B_STAGE_BYTES;
+        if (leader) {
+          if (MODE == WGRAD) {     // 16 pixels = two 8-row groups = 2048 B per K step; 64-element MN blocks 8192 B apart
+            const uint64_t dA = make_desc_mn(tA, 8192), dB = make_desc_mn(tB, 8192);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            if (MODE == WGRAD)     // 16 pixels = two 8-row groups = 2048 B per K step; 64-element MN blocks 8192 B apart
-              umma_bf16(tmem_d, make_desc_mn(tA + k * 2048, 8192), make_desc_mn(tB + k * 2048, 8192), idesc, (kb | k) != 0);
-            else                   // +32 bytes per 16-element K step inside the swizzle atom
-              umma_bf16(tmem_d, make_desc(tA + k * 32), make_desc(tB + k * 32), idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, dA + 128 * k, dB + 128 * k, idesc, (kb | k) != 0);
+          } else {                 // +32 bytes per 16-element K step inside the swizzle atom
+            const uint64_t dA = make_desc(tA), dB = make_desc(tB);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(bar_empty + s * 8);          // stage is free once these MMAs retire
         }
-        umma_commit(bar_tfull + acc * 8);          // accumulator complete
-        ++j;
-        decode_tile<MODE>(a, T.t + gridDim.x, total, pixels, T);
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
+      if (leader) umma_commit(bar_tfull + acc * 8);          // accumulator complete
+      __syncwarp();
+      ++j;
+      decode_tile<MODE>(a, T.t + gridDim.x, total, pixels, T);
     }
-    __syncwarp();
   } else {
     // ===================================================== epilogue (TMEM -> registers -> smem transpose -> global)
     // tcgen05.ld hands every thread one accumulator ROW; stores of that shape are 32 scattered 16-byte pieces per

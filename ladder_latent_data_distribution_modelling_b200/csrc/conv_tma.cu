@@ -230,77 +230,95 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *slot_ptr;
 
+  // Warps 0 and 1 run their loops CONVERGED (all 32 lanes wait on the barriers and keep the counters) and one elected lane
+  // issues the TMA / tcgen05 instructions.  r2w: with the loops inside `if (lane == 0)` ptxas cannot prove the operands
+  // warp-uniform, moves every descriptor through R2UR and wraps each UTCHMMA / UTMALDG / UBLKCP / UTCBAR in an
+  // ELECT .. BRA.U.ANY waterfall loop: ~16 dependent SASS instructions (+ a division in the producer) per MMA, 95-135 clk
+  // of issue time against 32 / 64 clk of tensor time at N = 64 / 128 -- the issue warps, not the tensor pipe, set the pace of
+  // every N <= 128 layer.  Converged, the operands live in uniform registers and the 4 MMAs of a k-block issue back to back.
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    const bool leader = elect_one();
+    if (leader) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
       if (MODE == WGRAD) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-      const int taps = a.KH * a.KW;
-      Tile T;
-      decode_tile<MODE>(a, blockIdx.x, total, T);
-      unsigned it = 0;
-      unsigned hit = 0;
-      while (T.valid) {
-        if constexpr (HALO) {
-          // tile = 16 rows x 8 columns of image b; per 64-channel chunk ONE halo box, then the 9 weight tiles
-          const int b0 = T.m_tile / a.halo_tiles_per_img, rem = T.m_tile - b0 * a.halo_tiles_per_img;
-          const int ty = rem / a.halo_tiles_x, tx = rem - ty * a.halo_tiles_x;
-          const int hx = tx * HALO_TW + a.halo_ox, hy = ty * HALO_TH + a.halo_oy;
-          int kb = 0;
-          for (int c0 = 0; c0 < a.C; c0 += BK, ++hit) {
-            const int h = hit % HALO_STAGES;
-            mbar_wait(bar_hempty + h * 8, ((hit / HALO_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    Tile T;
+    decode_tile<MODE>(a, blockIdx.x, total, T);
+    uint32_t s = 0, ph = 1;                      // ring slot and the parity of its "empty" barrier to wait for
+    uint32_t h = 0, hph = 1;                     // halo ring
+    while (T.valid) {
+      if constexpr (HALO) {
+        // tile = 16 rows x 8 columns of image b; per 64-channel chunk ONE halo box, then the 9 weight tiles
+        const int taps = a.KH * a.KW;
+        const int b0 = T.m_tile / a.halo_tiles_per_img, rem = T.m_tile - b0 * a.halo_tiles_per_img;
+        const int ty = rem / a.halo_tiles_x, tx = rem - ty * a.halo_tiles_x;
+        const int hx = tx * HALO_TW + a.halo_ox, hy = ty * HALO_TH + a.halo_oy;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wt) + (size_t)T.n_tile * T.nkb * B_STAGE_BYTES;
+        for (int c0 = 0; c0 < a.C; c0 += BK) {
+          mbar_wait(bar_hempty + h * 8, hph);
+          if (leader) {
             mbar_arrive_expect_tx(bar_hfull + h * 8, HALO_BYTES);
             tma_load_4d(sA + h * HALO_BYTES, &mapA, c0, hx, hy, b0, bar_hfull + h * 8);
-            for (int tap = 0; tap < taps; ++tap, ++kb, ++it) {
-              const int s = it % STAGES;
-              mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
+          }
+          __syncwarp();
+          if (++h == HALO_STAGES) { h = 0; hph ^= 1; }
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(bar_empty + s * 8, ph);
+            if (leader) {
               mbar_arrive_expect_tx(bar_full + s * 8, B_STAGE_BYTES);
-              tma_bulk_g2s(sB + s * B_STAGE_BYTES,
-                           reinterpret_cast<const uint8_t*>(a.wt) + ((size_t)T.n_tile * T.nkb + kb) * B_STAGE_BYTES,
-                           B_STAGE_BYTES, bar_full + s * 8);
+              tma_bulk_g2s(sB + s * B_STAGE_BYTES, wsrc, B_STAGE_BYTES, bar_full + s * 8);
             }
+            __syncwarp();
+            wsrc += B_STAGE_BYTES;
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
-        } else if (MODE != WGRAD) {
-          const unsigned m0 = (unsigned)T.m_tile * BM;
-          const int x0 = (int)(m0 % (unsigned)a.GW);
-          const unsigned r = m0 / (unsigned)a.GW;
-          const int y0 = (int)(r % (unsigned)a.GH), b0 = (int)(r / (unsigned)a.GH);
-          int tap = 0, c0 = 0;
-          for (int kb = 0; kb < T.nkb; ++kb, ++it) {
-            const int s = it % STAGES;
-            mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
-            const int kh = tap / a.KW, kw = tap - kh * a.KW;
+        }
+      } else if (MODE != WGRAD) {
+        const unsigned m0 = (unsigned)T.m_tile * BM;
+        const int x0 = (int)(m0 % (unsigned)a.GW);
+        const unsigned r = m0 / (unsigned)a.GW;
+        const int y0 = (int)(r % (unsigned)a.GH), b0 = (int)(r / (unsigned)a.GH);
+        const int xb = x0 * a.stride + a.off_x, yb = y0 * a.stride + a.off_y;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wt) + (size_t)T.n_tile * T.nkb * B_STAGE_BYTES;
+        int kh = 0, kw = 0, c0 = 0;              // K order: 64-channel chunk major, tap minor
+        for (int kb = 0; kb < T.nkb; ++kb) {
+          mbar_wait(bar_empty + s * 8, ph);
+          if (leader) {
             mbar_arrive_expect_tx(bar_full + s * 8, A_STAGE_BYTES + B_STAGE_BYTES);
-            tma_load_4d(sA + s * A_STAGE_BYTES, &mapA, c0, x0 * a.stride + a.off_x + a.sign * kw, y0 * a.stride + a.off_y + a.sign * kh, b0,
-                        bar_full + s * 8);
-            tma_bulk_g2s(sB + s * B_STAGE_BYTES,
-                         reinterpret_cast<const uint8_t*>(a.wt) + ((size_t)T.n_tile * T.nkb + kb) * B_STAGE_BYTES,
-                         B_STAGE_BYTES, bar_full + s * 8);
-            if (++tap == taps) { tap = 0; c0 += BK; }      // K order: 64-channel chunk major, tap minor
+            tma_load_4d(sA + s * A_STAGE_BYTES, &mapA, c0, xb + a.sign * kw, yb + a.sign * kh, b0, bar_full + s * 8);
+            tma_bulk_g2s(sB + s * B_STAGE_BYTES, wsrc, B_STAGE_BYTES, bar_full + s * 8);
           }
-        } else {
-          // rows of dw: patch entries (tap, ci); a 128-row tile = two 64-channel blocks (possibly of different taps)
-          int oy[2], ox[2], cc[2];
-          bool on[2];
+          __syncwarp();
+          wsrc += B_STAGE_BYTES;
+          if (++kw == a.KW) { kw = 0; if (++kh == a.KH) { kh = 0; c0 += BK; } }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      } else {
+        // rows of dw: patch entries (tap, ci); a 128-row tile = two 64-channel blocks (possibly of different taps)
+        int oy[2], ox[2], cc[2];
+        bool on[2];
 #pragma unroll
-          for (int mb = 0; mb < 2; ++mb) {
-            const int kd0 = T.m_tile * BM + mb * 64;
-            on[mb] = kd0 < a.m_valid;
-            const int tp = kd0 / a.C;
-            cc[mb] = kd0 - tp * a.C;
-            const int kh = tp / a.KW, kw = tp - kh * a.KW;
-            oy[mb] = a.off_y + a.sign * kh;
-            ox[mb] = a.off_x + a.sign * kw;
-          }
-          const uint32_t bytes = (uint32_t)((on[0] ? 8192 : 0) + (on[1] ? 8192 : 0) + B_STAGE_BYTES);
-          for (int kb = 0; kb < T.nkb; ++kb, ++it) {
-            const int s = it % STAGES;
-            mbar_wait(bar_empty + s * 8, ((it / STAGES) & 1) ^ 1);
-            const unsigned p0 = (unsigned)(T.k_lo + kb) * BK;
-            const int x0 = (int)(p0 % (unsigned)a.GW);
-            const unsigned r = p0 / (unsigned)a.GW;
-            const int y0 = (int)(r % (unsigned)a.GH), b0 = (int)(r / (unsigned)a.GH);
+        for (int mb = 0; mb < 2; ++mb) {
+          const int kd0 = T.m_tile * BM + mb * 64;
+          on[mb] = kd0 < a.m_valid;
+          const int tp = kd0 / a.C;
+          cc[mb] = kd0 - tp * a.C;
+          const int kh = tp / a.KW, kw = tp - kh * a.KW;
+          oy[mb] = a.off_y + a.sign * kh;
+          ox[mb] = a.off_x + a.sign * kw;
+        }
+        const uint32_t bytes = (uint32_t)((on[0] ? 8192 : 0) + (on[1] ? 8192 : 0) + B_STAGE_BYTES);
+        // pixel position of the slice's first 64-pixel k-block, then stepped by 64 pixels per k-block without divisions
+        const unsigned p0 = (unsigned)T.k_lo * BK;
+        int x0 = (int)(p0 % (unsigned)a.GW);
+        const unsigned r = p0 / (unsigned)a.GW;
+        int y0 = (int)(r % (unsigned)a.GH), b0 = (int)(r / (unsigned)a.GH);
+        const int step_y = BK / a.GW, step_x = BK - step_y * a.GW;
+        for (int kb = 0; kb < T.nkb; ++kb) {
+          mbar_wait(bar_empty + s * 8, ph);
+          if (leader) {
             mbar_arrive_expect_tx(bar_full + s * 8, bytes);
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb)
@@ -310,72 +328,85 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
             for (int nb = 0; nb < BN / 64; ++nb)
               tma_load_4d(sB + s * B_STAGE_BYTES + nb * 8192, &mapB, T.n_tile * BN + nb * 64, x0, y0, b0, bar_full + s * 8);
           }
+          __syncwarp();
+          x0 += step_x;
+          y0 += step_y;
+          if (x0 >= a.GW) { x0 -= a.GW; ++y0; }
+          while (y0 >= a.GH) { y0 -= a.GH; ++b0; }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        decode_tile<MODE>(a, T.t + gridDim.x, total, T);
       }
+      decode_tile<MODE>(a, T.t + gridDim.x, total, T);
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, MODE == WGRAD);
-      Tile T;
-      decode_tile<MODE>(a, blockIdx.x, total, T);
-      unsigned it = 0, j = 0, hit = 0;
-      while (T.valid) {
-        const uint32_t acc = j & 1;
-        mbar_wait(bar_tempty + acc * 8, ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        if constexpr (HALO) {
-          const int taps = a.KH * a.KW;
-          int kb = 0;
-          for (int c0 = 0; c0 < a.C; c0 += BK, ++hit) {
-            const int h = hit % HALO_STAGES;
-            mbar_wait(bar_hfull + h * 8, (hit / HALO_STAGES) & 1);
-            tc_fence_after();
-            int kh = 0, kw = 0;
-            for (int tap = 0; tap < taps; ++tap, ++kb, ++it) {
-              const int s = it % STAGES;
-              mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
+    // ===================================================== MMA issuer (one elected lane, converged warp)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc(BM, BN, MODE == WGRAD);
+    Tile T;
+    decode_tile<MODE>(a, blockIdx.x, total, T);
+    uint32_t s = 0, ph = 0;                      // ring slot and the parity of its "full" barrier
+    uint32_t h = 0, hph = 0;
+    unsigned j = 0;
+    while (T.valid) {
+      const uint32_t acc = j & 1;
+      mbar_wait(bar_tempty + acc * 8, ((j >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      if constexpr (HALO) {
+        int kb = 0;
+        for (int c0 = 0; c0 < a.C; c0 += BK) {
+          mbar_wait(bar_hfull + h * 8, hph);
+          tc_fence_after();
+          for (int kh = 0; kh < a.KH; ++kh) {
+            for (int kw = 0; kw < a.KW; ++kw, ++kb) {
+              mbar_wait(bar_full + s * 8, ph);
               tc_fence_after();
               // halo coordinates of this tap's view: (off + sign * k) - origin
               const int vy = a.off_y + a.sign * kh - a.halo_oy, vx = a.off_x + a.sign * kw - a.halo_ox;
               const uint32_t tA = sA + h * HALO_BYTES + (uint32_t)(vy * HALO_PITCH + vx) * 128u, tB = sB + s * B_STAGE_BYTES;
               const uint32_t bo = a.halo_base_mode ? (uint32_t)vx : 0u;
+              if (leader) {
+                const uint64_t dA = make_desc_halo(tA, bo), dB = make_desc(tB);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                umma_bf16(tmem_d, make_desc_halo(tA + k * 32, bo), make_desc(tB + k * 32), idesc, (kb | k) != 0);
-              umma_commit(bar_empty + s * 8);
-              if (++kw == a.KW) { kw = 0; ++kh; }
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(bar_empty + s * 8);
+              }
+              __syncwarp();
+              if (++s == STAGES) { s = 0; ph ^= 1; }
             }
-            umma_commit(bar_hempty + h * 8);
           }
-          umma_commit(bar_tfull + acc * 8);
-          ++j;
-          decode_tile<MODE>(a, T.t + gridDim.x, total, T);
-          continue;
+          if (leader) umma_commit(bar_hempty + h * 8);
+          __syncwarp();
+          if (++h == HALO_STAGES) { h = 0; hph ^= 1; }
         }
-        for (int kb = 0; kb < T.nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
+      } else {
+        for (int kb = 0; kb < T.nkb; ++kb) {
+          mbar_wait(bar_full + s * 8, ph);
           tc_fence_after();
           const uint32_t tA = sA + s * A_STAGE_BYTES, tB = sB + s * B_STAGE_BYTES;
+          if (leader) {
+            // the 4 K steps of a k-block advance the 14-bit start-address field by 32 B (K-major) / 2048 B (MN-major): the tiles
+            // are 1024-byte aligned inside a < 256 KB window, so the field never carries into its neighbours
+            if (MODE == WGRAD) {
+              const uint64_t dA = make_desc_mn(tA, 8192), dB = make_desc_mn(tB, 8192);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            if (MODE == WGRAD)
-              umma_bf16(tmem_d, make_desc_mn(tA + k * 2048, 8192), make_desc_mn(tB + k * 2048, 8192), idesc, (kb | k) != 0);
-            else
-              umma_bf16(tmem_d, make_desc(tA + k * 32), make_desc(tB + k * 32), idesc, (kb | k) != 0);
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, dA + 128 * k, dB + 128 * k, idesc, (kb | k) != 0);
+            } else {
+              const uint64_t dA = make_desc(tA), dB = make_desc(tB);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(bar_empty + s * 8);
           }
-          umma_commit(bar_empty + s * 8);
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_tfull + acc * 8);
-        ++j;
-        decode_tile<MODE>(a, T.t + gridDim.x, total, T);
       }
+      if (leader) umma_commit(bar_tfull + acc * 8);
+      __syncwarp();
+      ++j;
+      decode_tile<MODE>(a, T.t + gridDim.x, total, T);
     }
-    __syncwarp();
   } else {
     // ===================================================== epilogue
     // tcgen05.ld hands every thread one accumulator ROW.  FPROP applies bias + activation right there (the bias tile

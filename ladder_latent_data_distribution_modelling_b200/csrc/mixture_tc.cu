@@ -55,6 +55,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   } while (!ok);
 }
+// one lane of a converged warp (elect.sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -180,40 +186,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_kernel(Args a) {
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, BN);
-      unsigned it = 0, g = 0, un = 0;     // stage counter, accumulator-use counter, unit counter
-      for (long long u = blockIdx.x; u < units; u += gridDim.x, ++un) {
-        const int split = (int)(u % a.splits);
-        const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
-        mbar_wait(bar_a, un & 1);                          // query tile staged by the consumers (generic proxy)
-        fence_proxy_async();
-        for (int c = c_lo; c < c_hi; ++c, ++it, ++g) {
-          const int s = it % STAGES;
-          const uint32_t buf = g & 1;
-          mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
-          tc_fence_after();
+    // ===================================================== MMA issuer: converged warp, one elected lane issues (see conv_tma.cu)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_tf32(128, BN);
+    unsigned it = 0, g = 0, un = 0;     // stage counter, accumulator-use counter, unit counter
+    for (long long u = blockIdx.x; u < units; u += gridDim.x, ++un) {
+      const int split = (int)(u % a.splits);
+      const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
+      mbar_wait(bar_a, un & 1);                          // query tile staged by the consumers (generic proxy)
+      fence_proxy_async();
+      for (int c = c_lo; c < c_hi; ++c, ++it, ++g) {
+        const int s = it % STAGES;
+        const uint32_t buf = g & 1;
+        mbar_wait(bar_full + s * 8, (it / STAGES) & 1);
+        tc_fence_after();
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            mbar_wait(bar_tempty + (sub * 2 + buf) * 8, ((g >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (sub * 2 + buf) * BN;
+        for (int sub = 0; sub < 2; ++sub) {
+          mbar_wait(bar_tempty + (sub * 2 + buf) * 8, ((g >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (sub * 2 + buf) * BN;
+          if (leader) {
 #pragma unroll
             for (int k = 0; k < D / 8; ++k) {
               const int atom = k / 4, kk = k % 4;          // 4 k-steps of 8 tf32 (32 B) per 128-byte atom
-              const uint64_t ad = make_desc(sA + (sub * ATOMS + atom) * (128 * 128) + kk * 32);
-              const uint64_t bd = make_desc(sB + s * B_STRIDE + atom * (BN * 128) + kk * 32);
+              const uint64_t ad = make_desc(sA + (sub * ATOMS + atom) * (128 * 128)) + 2 * kk;
+              const uint64_t bd = make_desc(sB + s * B_STRIDE + atom * (BN * 128)) + 2 * kk;
               umma_tf32(tmem_d, ad, bd, idesc, k != 0);
             }
             umma_commit(bar_tfull + (sub * 2 + buf) * 8);
           }
-          umma_commit(bar_empty + s * 8);
+          __syncwarp();
         }
-        umma_commit(bar_adone);                            // all MMAs reading this unit's A tile have retired
+        if (leader) umma_commit(bar_empty + s * 8);
+        __syncwarp();
       }
+      if (leader) umma_commit(bar_adone);                  // all MMAs reading this unit's A tile have retired
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ===================================================== consumers: one query row per thread
     const int sub = (warp - 4) >> 2, quad = warp & 3;
@@ -252,19 +261,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_kernel(Args a) {
         mbar_wait(bar_full + s * 8, (it / STAGES) & 1);             // the stage's ck constants (async-proxy write) are visible
         mbar_wait(bar_tfull + (sub * 2 + buf) * 8, (g >> 1) & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (sub * 2 + buf) * BN + c0, v);
+        // software pipeline: the tcgen05.ld of the next 32 score columns is in flight while the current 32 go through the SFU
+        // (r2w: once the MMA warp stopped staggering the two sub-tiles, the exposed load latency cost 4 %)
+        const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (sub * 2 + buf) * BN;
+        uint32_t ra[32], rb[32];
+        auto sfu32 = [&](const uint32_t (&r)[32], int c0) {
+          float s0 = 0.f, s1 = 0.f;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 k4 = *reinterpret_cast<const float4*>(ck + c0 + i);
-            S += ex2((v[i] + k4.x) - tn);
-            S += ex2((v[i + 1] + k4.y) - tn);
-            S += ex2((v[i + 2] + k4.z) - tn);
-            S += ex2((v[i + 3] + k4.w) - tn);
+            s0 += ex2((__uint_as_float(r[i]) + k4.x) - tn);
+            s1 += ex2((__uint_as_float(r[i + 1]) + k4.y) - tn);
+            s0 += ex2((__uint_as_float(r[i + 2]) + k4.z) - tn);
+            s1 += ex2((__uint_as_float(r[i + 3]) + k4.w) - tn);
           }
-        }
+          S += s0 + s1;
+        };
+        tmem_ld32_issue(tcol, ra);
+        tmem_ld_wait();
+        tmem_ld32_issue(tcol + 32, rb);
+        sfu32(ra, 0);
+        tmem_ld_wait();
+        tmem_ld32_issue(tcol + 64, ra);
+        sfu32(rb, 32);
+        tmem_ld_wait();
+        tmem_ld32_issue(tcol + 96, rb);
+        sfu32(ra, 64);
+        tmem_ld_wait();
+        sfu32(rb, 96);
         tc_fence_before();
         mbar_arrive(bar_tempty + (sub * 2 + buf) * 8);
         __syncwarp();
@@ -331,6 +355,7 @@ struct GradArgs {
   long long N;
   int n_chunks, chunks_per_split, splits;
   float iso_scale;
+  int order;             // issue order of the MMA warp (see the kernel): 0 per sub-tile, 1 sub-tiles alternating
 };
 
 // component-tile stages: D = 64 has 2 x 64.5 KB of tiles beside 64 KB of query tiles, D = 32 has room for 4 x 32.5 KB
@@ -345,16 +370,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
   constexpr int B2_BYTES = (BN / 32) * D * 128;         // (2 mu')^T [D x 128 components], K-major for W . mu (4 atoms of 32 components)
   constexpr int B_STAGE = B_BYTES + B2_BYTES + BN * 4;  // + ck
   constexpr int B_STRIDE = (B_STAGE + 1023) / 1024 * 1024;
-  constexpr uint32_t G_COL = 256;                       // TMEM columns: S0 [0,128) S1 [128,256) G0 [256,256+D) G1 [256+D, 256+2D)
+  // TMEM columns: S0 [0,128) S1 [128,256) | NACC partial G' accumulators per sub-tile, D columns each, from column 256.  The
+  // K steps of W . mu (8 components each, N = D: tiny MMAs) rotate over the NACC accumulators: consecutive tcgen05.mma that
+  // accumulate into the SAME TMEM tile serialise on its latency (measured r2u: ~135 clk per MMA whatever its size), independent
+  // ones pipeline; the epilogue adds the partial accumulators.
+  constexpr int NACC = D == 32 ? 4 : 2;
+  constexpr uint32_t G_COL = 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t sA = base, sB = base + A_BYTES;
   const uint32_t bars = sB + GSTAGES * B_STRIDE;
-  const uint32_t bar_full = bars, bar_empty = bars + GSTAGES * 8, bar_sfull = bars + 2 * GSTAGES * 8, bar_sfree = bar_sfull + 16,
-                 bar_wfull = bar_sfree + 16, bar_gfull = bar_wfull + 16, bar_gfree = bar_gfull + 16, bar_a = bar_gfree + 16,
-                 bar_adone = bar_a + 8;
+  // sfull / wfull: one barrier per (sub-tile, 64-column half) -- index sub * 2 + h
+  const uint32_t bar_full = bars, bar_empty = bars + GSTAGES * 8, bar_sfull = bars + 2 * GSTAGES * 8, bar_wfull = bar_sfull + 32,
+                 bar_gfull = bar_wfull + 32, bar_gfree = bar_gfull + 16, bar_a = bar_gfree + 16, bar_adone = bar_a + 8;
   const uint32_t slot = bar_adone + 8;
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + (slot - base));
 
@@ -367,10 +397,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
       mbar_init(bar_full + s * 8, 1);
       mbar_init(bar_empty + s * 8, 1 + 8);            // commit after the stage's last MMA + one lane of each consumer warp (ck)
     }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar_sfull + i * 8, 1);                // score MMA of (sub-tile, half) retired: 64 S columns readable
+      mbar_init(bar_wfull + i * 8, 128);              // the sub-tile's 4 consumer warps wrote that half of W
+    }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_sfull + i * 8, 1);                // MMA1 of the sub-tile retired: S readable
-      mbar_init(bar_sfree + i * 8, 1);                // MMA2 of the sub-tile retired: S / W columns reusable
-      mbar_init(bar_wfull + i * 8, 128);              // the sub-tile's 4 consumer warps wrote W
       mbar_init(bar_gfull + i * 8, 1);                // last MMA2 of the unit retired: G' readable
       mbar_init(bar_gfree + i * 8, 128);              // consumers read G'
     }
@@ -402,73 +433,119 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc_tf32(128, BN), idesc2 = make_idesc_tf32(128, D);
-      // The two query sub-tiles run HALF A CHUNK OUT OF PHASE, flash-attention style: while the consumers of sub-tile 0 turn
-      // S0(c) into W0(c) on the SFU, the tensor pipe does W1(c-1) . mu and t1 . mu(c)^T, and vice versa -- issued in phase
-      // (both score MMAs, then both W . mu MMAs) the SFU idles through every MMA and the kernel ran at 27 % of the ex2 peak.
-      unsigned it = 0, g0 = 0, g1 = 0, un = 0;      // stage counter of chunk c; chunks seen by sub-tile 0 / 1; units
-      auto scores = [&](int sub, unsigned g, uint32_t tB) {              // S_sub = t' . (2 mu')^T
-        mbar_wait(bar_sfree + sub * 8, (g & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_s = tmem_base + sub * BN;
+    // MMA warp: all 32 lanes run the loop and wait on the barriers, ONE elected lane issues (see conv_tma.cu: inside
+    // `if (lane == 0)` every tcgen05.mma cost ~135 clk of R2UR + ELECT .. BRA.U.ANY issue code, r2u / r2v, which made the 40-48
+    // small MMAs of a chunk -- not the SFU -- the pace of this kernel).
+    const bool leader = elect_one();
+    constexpr uint32_t idesc1 = make_idesc_tf32(128, BN / 2), idesc2 = make_idesc_tf32(128, D);
+    // Software pipeline at HALF-CHUNK granularity (64 components), both query sub-tiles alike.  tcgen05.mma instructions
+    // execute in issue order, so the score MMA of chunk c + 1 may overwrite the 64 S / W columns of a half as soon as it is
+    // issued BEHIND the W . mu MMA that reads them -- no "S free" barrier.  Per half h:
+    //     wait W(c, h) written -> issue G' += W(c, h) . mu(c, h) -> issue S(c + 1, h) = t . mu(c + 1, h)^T -> commit "S(c+1, h) full".
+    // While the consumers exponentiate half 1 of chunk c the tensor pipe finishes half 0 of chunk c + 1, and vice versa.
+    unsigned it = 0, g = 0, un = 0;               // stage counter of the NEXT chunk to score; chunks finished; units
+    auto score_step = [&](int sub, int h, int k, uint32_t tB) {       // one K step (8 dims) of S_sub[:, 64 h : 64 h + 64]
+      const int atom = k / 4, kk = k % 4;
+      umma_tf32(tmem_base + sub * BN + h * 64, make_desc(sA + (sub * ATOMS + atom) * (128 * 128)) + 2 * kk,
+                make_desc(tB + atom * (BN * 128) + h * (64 * 128)) + 2 * kk, idesc1, k != 0);
+    };
+    auto wmu_step = [&](int sub, int h, int j, uint32_t tB, bool first) {   // K step j (8 components) of G'_sub (+)= W_sub[:, 64 h ...] . (2 mu')
+      const int k = h * 8 + j, atom = k / 4, kk = k % 4;
+      umma_tf32_ts(tmem_base + G_COL + (sub * NACC + j % NACC) * D, tmem_base + sub * BN + k * 8,
+                   make_desc(tB + B_BYTES + atom * (D * 128)) + 2 * kk, idesc2, (uint32_t)(!first) | (uint32_t)(j >= NACC));
+    };
+    for (long long u = blockIdx.x; u < units; u += gridDim.x, ++un) {
+      const int split = (int)(u % a.splits);
+      const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
+      mbar_wait(bar_a, un & 1);
+      fence_proxy_async();
+      // prologue: the scores of the unit's first chunk (the S columns are free: every earlier MMA that read them was issued before)
+      int s_cur = it % GSTAGES;
+      mbar_wait(bar_full + s_cur * 8, (it / GSTAGES) & 1);
+      tc_fence_after();
+      ++it;
+      uint32_t tB = sB + s_cur * B_STRIDE;
+      if (leader) {
 #pragma unroll
-        for (int k = 0; k < D / 8; ++k) {
-          const int atom = k / 4, kk = k % 4;
-          umma_tf32(tmem_s, make_desc(sA + (sub * ATOMS + atom) * (128 * 128) + kk * 32),
-                    make_desc(tB + atom * (BN * 128) + kk * 32), idesc1, k != 0);
-        }
-        umma_commit(bar_sfull + sub * 8);
-      };
-      auto wmu = [&](int sub, unsigned g, uint32_t tB, bool first, bool last) {   // G'_sub += W_sub . (2 mu')
-        if (first) mbar_wait(bar_gfree + sub * 8, (un & 1) ^ 1);         // the previous unit's G' was read
-        mbar_wait(bar_wfull + sub * 8, g & 1);
-        tc_fence_after();
-        const uint32_t tmem_g = tmem_base + G_COL + sub * D, tmem_w = tmem_base + sub * BN;
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int k = 0; k < BN / 8; ++k) {            // 8 components per K step: 32 B inside a 128-byte atom of 32 components
-          const int atom = k / 4, kk = k % 4;
-          umma_tf32_ts(tmem_g, tmem_w + k * 8, make_desc(tB + B_BYTES + atom * (D * 128) + kk * 32), idesc2,
-                       (uint32_t)(!first) | (uint32_t)(k != 0));
+          for (int k = 0; k < D / 8; ++k) {
+            score_step(0, h, k, tB);
+            score_step(1, h, k, tB);
+          }
+          umma_commit(bar_sfull + (0 * 2 + h) * 8);
+          umma_commit(bar_sfull + (1 * 2 + h) * 8);
         }
-        umma_commit(bar_sfree + sub * 8);
-        if (last) umma_commit(bar_gfull + sub * 8);
-      };
-      for (long long u = blockIdx.x; u < units; u += gridDim.x, ++un) {
-        const int split = (int)(u % a.splits);
-        const int c_lo = split * a.chunks_per_split, c_hi = min(a.n_chunks, c_lo + a.chunks_per_split);
-        mbar_wait(bar_a, un & 1);
-        fence_proxy_async();
-        uint32_t tB_prev = 0;
-        int s_prev = 0;
-        for (int c = c_lo; c <= c_hi; ++c) {
-          uint32_t tB = 0;
-          int s = 0;
-          if (c < c_hi) {
-            s = it % GSTAGES;
-            mbar_wait(bar_full + s * 8, (it / GSTAGES) & 1);
-            tc_fence_after();
-            tB = sB + s * B_STRIDE;
-            ++it;
-            scores(0, g0, tB);
-          }
-          if (c > c_lo) {                                   // sub-tile 1 finishes chunk c - 1: its stage is free afterwards
-            wmu(1, g1, tB_prev, c - 1 == c_lo, c == c_hi);
-            ++g1;
-            umma_commit(bar_empty + s_prev * 8);
-          }
-          if (c < c_hi) {
-            scores(1, g1, tB);
-            wmu(0, g0, tB, c == c_lo, c == c_hi - 1);
-            ++g0;
-          }
-          tB_prev = tB;
-          s_prev = s;
-        }
-        umma_commit(bar_adone);
       }
+      __syncwarp();
+      for (int c = c_lo; c < c_hi; ++c, ++g) {
+        const bool next = c + 1 < c_hi;
+        uint32_t tB_next = 0;
+        int s_next = 0;
+        if (next) {
+          s_next = it % GSTAGES;
+          mbar_wait(bar_full + s_next * 8, (it / GSTAGES) & 1);
+          ++it;
+          tB_next = sB + s_next * B_STRIDE;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const bool first = c == c_lo && h == 0;
+          if (a.order == 0) {                     // per sub-tile: its 8 W . mu steps, then its D / 8 score steps
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              if (first) mbar_wait(bar_gfree + sub * 8, (un & 1) ^ 1);      // the previous unit's G' was read
+              mbar_wait(bar_wfull + (sub * 2 + h) * 8, g & 1);
+              tc_fence_after();
+              if (leader) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wmu_step(sub, h, j, tB, first);
+                if (next) {
+#pragma unroll
+                  for (int k = 0; k < D / 8; ++k) score_step(sub, h, k, tB_next);
+                  umma_commit(bar_sfull + (sub * 2 + h) * 8);
+                }
+              }
+              __syncwarp();
+            }
+          } else {                                // the two sub-tiles step by step alternately
+            if (first) { mbar_wait(bar_gfree, (un & 1) ^ 1); mbar_wait(bar_gfree + 8, (un & 1) ^ 1); }
+            mbar_wait(bar_wfull + (0 * 2 + h) * 8, g & 1);
+            mbar_wait(bar_wfull + (1 * 2 + h) * 8, g & 1);
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                wmu_step(0, h, j, tB, first);
+                wmu_step(1, h, j, tB, first);
+              }
+              if (next) {
+#pragma unroll
+                for (int k = 0; k < D / 8; ++k) {
+                  score_step(0, h, k, tB_next);
+                  score_step(1, h, k, tB_next);
+                }
+                umma_commit(bar_sfull + (0 * 2 + h) * 8);
+                umma_commit(bar_sfull + (1 * 2 + h) * 8);
+              }
+            }
+            __syncwarp();
+          }
+        }
+        if (leader) {
+          umma_commit(bar_empty + s_cur * 8);           // every MMA that reads chunk c's tiles has been issued
+          if (!next) {
+            umma_commit(bar_gfull);
+            umma_commit(bar_gfull + 8);
+          }
+        }
+        __syncwarp();
+        tB = tB_next;
+        s_cur = s_next;
+      }
+      if (leader) umma_commit(bar_adone);
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp >= 4) {
     const int sub = (warp - 4) >> 2, quad = warp & 3;
     const int row = sub * 128 + quad * 32 + lane;
@@ -503,15 +580,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
         const int s = it % GSTAGES;
         const float* ck = reinterpret_cast<const float*>(smem + (sB + s * B_STRIDE + B_BYTES + B2_BYTES - base));
         mbar_wait(bar_full + s * 8, (it / GSTAGES) & 1);
-        mbar_wait(bar_sfull + sub * 8, g & 1);
-        tc_fence_after();
-        // the load of the next 32 score columns is in flight while the current 32 go through the SFU
-        uint32_t ra[32], rb[32];
-        tmem_ld32_issue(lane_base + sub * BN, ra);
-        tmem_ld_wait();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = h * 64;
+          mbar_wait(bar_sfull + (sub * 2 + h) * 8, g & 1);
+          tc_fence_after();
+          // the load of the half's second 32 score columns is in flight while the first 32 go through the SFU
+          uint32_t ra[32], rb[32];
+          tmem_ld32_issue(lane_base + sub * BN + c0, ra);
+          tmem_ld_wait();
           tmem_ld32_issue(lane_base + sub * BN + c0 + 32, rb);
           {
             float v[32];
@@ -524,10 +601,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
               v[i + 3] = ex2((__uint_as_float(ra[i + 3]) + k4.w) - tn);
               S += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
             }
-            tmem_ld_wait();                               // rb has landed (and ra's columns may be overwritten)
+            tmem_ld_wait();                               // rb has landed
             tmem_st32(lane_base + sub * BN + c0, v);       // W in place of S: the A operand of the second MMA
           }
-          if (h == 0) tmem_ld32_issue(lane_base + sub * BN + 64, ra);
           {
             float v[32];
 #pragma unroll
@@ -539,13 +615,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
               v[i + 3] = ex2((__uint_as_float(rb[i + 3]) + k4.w) - tn);
               S += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
             }
-            if (h == 0) tmem_ld_wait();
             tmem_st32(lane_base + sub * BN + c0 + 32, v);
           }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          mbar_arrive(bar_wfull + (sub * 2 + h) * 8);
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        mbar_arrive(bar_wfull + sub * 8);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + s * 8);
       }
@@ -555,7 +630,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mix_tc_grad_kernel(GradArgs a) {
 #pragma unroll
       for (int c0 = 0; c0 < D; c0 += 32) {
         float v[32];
-        tmem_ld32(lane_base + G_COL + sub * D + c0, v);
+        tmem_ld32(lane_base + G_COL + sub * (NACC * D) + c0, v);
+#pragma unroll
+        for (int j = 1; j < NACC; ++j) {
+          float w[32];
+          tmem_ld32(lane_base + G_COL + (sub * NACC + j) * D + c0, w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += w[i];
+        }
         if (n < a.N) {
           float* dst = a.part_g + ((size_t)split * a.N + n) * D + c0;
 #pragma unroll
@@ -841,6 +923,12 @@ size_t ladder_mixture_tc_grad_workspace_bytes(long long N, int K, int D) {
 /* log p(t_n) AND d log p / d t_n for an isotropic mixture with D in {32, 64} on the tensor cores: t . mu^T (kind::tf32), the
  * exponentials written back into TMEM in place of the scores, and W . mu (kind::tf32, A from TMEM, B = the transposed component
  * tile of the same image) -- see mix_tc_grad_kernel.  `image` from ladder_mixture_tc_pack_iso_grad.  logp may be NULL.       */
+static int grad_issue_order() {
+  static int order = -1;
+  if (order < 0) { const char* e = getenv("LADDER_MIX_ORDER"); order = e ? atoi(e) : 1; if (order < 0 || order > 1) order = 1; }
+  return order;
+}
+
 static int run_tc_forward_grad(const float* t, long long N, int D, const float* image, const float* simt_table, int K,
                                float iso_scale, float ref_log2, float* logp, float* grad_t, float* pack, void* workspace,
                                size_t workspace_bytes, cudaStream_t stream) {
@@ -863,7 +951,7 @@ static int run_tc_forward_grad(const float* t, long long N, int D, const float* 
     return fail(LADDER_ERR_WORKSPACE, "mixture_logprob_grad_tc: workspace %zu < %zu bytes", workspace_bytes, need);
   float* part_g = static_cast<float*>(workspace);
   float* part_s = part_g + (size_t)splits * N * D;
-  GradArgs a{t, image, part_s, part_g, N, n_chunks, cps, (int)splits, iso_scale};
+  GradArgs a{t, image, part_s, part_g, N, n_chunks, cps, (int)splits, iso_scale, grad_issue_order()};
   const long long units = row_tiles * splits;
   const unsigned grid = (unsigned)(units < sms ? units : sms);
   auto go = [&](auto kern, int Dv) {
