@@ -246,8 +246,14 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     __syncwarp();
     Tile T;
     decode_tile<MODE>(a, blockIdx.x, total, T);
-    uint32_t s = 0, ph = 1;                      // ring slot and the parity of its "empty" barrier to wait for
+    // Ring protocol (plain mode): EVERY TILE STARTS AT SLOT 0 and walks the slots in order, so the slot index is a compile-time
+    // constant of the unrolled loops below (barrier and tile addresses become base + immediate; the ring position no longer
+    // travels through R2UR every k-block); each slot keeps its own barrier parity bit.  Slots skipped at the end of a tile's
+    // last pass are simply not used that round.  Halo mode keeps running counters (its weight ring is nested in the halo ring).
+    uint32_t empty_par = (1u << STAGES) - 1u;    // bit s: parity of slot s's "empty" barrier to wait for
+    uint32_t s = 0, ph = 1;                      // halo mode: weight-ring slot and parity
     uint32_t h = 0, hph = 1;                     // halo ring
+    (void)empty_par; (void)s; (void)ph; (void)h; (void)hph;
     while (T.valid) {
       if constexpr (HALO) {
         // tile = 16 rows x 8 columns of image b; per 64-channel chunk ONE halo box, then the 9 weight tiles
@@ -283,17 +289,22 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         const int xb = x0 * a.stride + a.off_x, yb = y0 * a.stride + a.off_y;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wt) + (size_t)T.n_tile * T.nkb * B_STAGE_BYTES;
         int kh = 0, kw = 0, c0 = 0;              // K order: 64-channel chunk major, tap minor
-        for (int kb = 0; kb < T.nkb; ++kb) {
-          mbar_wait(bar_empty + s * 8, ph);
-          if (leader) {
-            mbar_arrive_expect_tx(bar_full + s * 8, A_STAGE_BYTES + B_STAGE_BYTES);
-            tma_load_4d(sA + s * A_STAGE_BYTES, &mapA, c0, xb + a.sign * kw, yb + a.sign * kh, b0, bar_full + s * 8);
-            tma_bulk_g2s(sB + s * B_STAGE_BYTES, wsrc, B_STAGE_BYTES, bar_full + s * 8);
+        for (int kb0 = 0; kb0 < T.nkb; kb0 += STAGES) {
+#pragma unroll
+          for (int s = 0; s < STAGES; ++s) {     // slot index is a compile-time constant: barrier / tile addresses are base + immediate
+            if (kb0 + s < T.nkb) {
+              mbar_wait(bar_empty + s * 8, (empty_par >> s) & 1u);
+              empty_par ^= 1u << s;
+              if (leader) {
+                mbar_arrive_expect_tx(bar_full + s * 8, A_STAGE_BYTES + B_STAGE_BYTES);
+                tma_load_4d(sA + s * A_STAGE_BYTES, &mapA, c0, xb + a.sign * kw, yb + a.sign * kh, b0, bar_full + s * 8);
+                tma_bulk_g2s(sB + s * B_STAGE_BYTES, wsrc, B_STAGE_BYTES, bar_full + s * 8);
+              }
+              __syncwarp();
+              wsrc += B_STAGE_BYTES;
+              if (++kw == a.KW) { kw = 0; if (++kh == a.KH) { kh = 0; c0 += BK; } }
+            }
           }
-          __syncwarp();
-          wsrc += B_STAGE_BYTES;
-          if (++kw == a.KW) { kw = 0; if (++kh == a.KH) { kh = 0; c0 += BK; } }
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       } else {
         // rows of dw: patch entries (tap, ci); a 128-row tile = two 64-channel blocks (possibly of different taps)
@@ -316,24 +327,29 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
         const unsigned r = p0 / (unsigned)a.GW;
         int y0 = (int)(r % (unsigned)a.GH), b0 = (int)(r / (unsigned)a.GH);
         const int step_y = BK / a.GW, step_x = BK - step_y * a.GW;
-        for (int kb = 0; kb < T.nkb; ++kb) {
-          mbar_wait(bar_empty + s * 8, ph);
-          if (leader) {
-            mbar_arrive_expect_tx(bar_full + s * 8, bytes);
+        for (int kb0 = 0; kb0 < T.nkb; kb0 += STAGES) {
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb)
-              if (on[mb])
-                tma_load_4d(sA + s * A_STAGE_BYTES + mb * 8192, &mapA, cc[mb], x0 * a.stride + ox[mb], y0 * a.stride + oy[mb], b0, bar_full + s * 8);
+          for (int s = 0; s < STAGES; ++s) {
+            if (kb0 + s < T.nkb) {
+              mbar_wait(bar_empty + s * 8, (empty_par >> s) & 1u);
+              empty_par ^= 1u << s;
+              if (leader) {
+                mbar_arrive_expect_tx(bar_full + s * 8, bytes);
 #pragma unroll
-            for (int nb = 0; nb < BN / 64; ++nb)
-              tma_load_4d(sB + s * B_STAGE_BYTES + nb * 8192, &mapB, T.n_tile * BN + nb * 64, x0, y0, b0, bar_full + s * 8);
+                for (int mb = 0; mb < 2; ++mb)
+                  if (on[mb])
+                    tma_load_4d(sA + s * A_STAGE_BYTES + mb * 8192, &mapA, cc[mb], x0 * a.stride + ox[mb], y0 * a.stride + oy[mb], b0, bar_full + s * 8);
+#pragma unroll
+                for (int nb = 0; nb < BN / 64; ++nb)
+                  tma_load_4d(sB + s * B_STAGE_BYTES + nb * 8192, &mapB, T.n_tile * BN + nb * 64, x0, y0, b0, bar_full + s * 8);
+              }
+              __syncwarp();
+              x0 += step_x;
+              y0 += step_y;
+              if (x0 >= a.GW) { x0 -= a.GW; ++y0; }
+              while (y0 >= a.GH) { y0 -= a.GH; ++b0; }
+            }
           }
-          __syncwarp();
-          x0 += step_x;
-          y0 += step_y;
-          if (x0 >= a.GW) { x0 -= a.GW; ++y0; }
-          while (y0 >= a.GH) { y0 -= a.GH; ++b0; }
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
       decode_tile<MODE>(a, T.t + gridDim.x, total, T);
@@ -344,8 +360,10 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     constexpr uint32_t idesc = make_idesc(BM, BN, MODE == WGRAD);
     Tile T;
     decode_tile<MODE>(a, blockIdx.x, total, T);
-    uint32_t s = 0, ph = 0;                      // ring slot and the parity of its "full" barrier
+    uint32_t full_par = 0;                       // plain mode: bit s = parity of slot s's "full" barrier (every tile starts at slot 0)
+    uint32_t s = 0, ph = 0;                      // halo mode: weight-ring slot and the parity of its "full" barrier
     uint32_t h = 0, hph = 0;
+    (void)full_par; (void)s; (void)ph; (void)h; (void)hph;
     unsigned j = 0;
     while (T.valid) {
       const uint32_t acc = j & 1;
@@ -380,26 +398,31 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
           if (++h == HALO_STAGES) { h = 0; hph ^= 1; }
         }
       } else {
-        for (int kb = 0; kb < T.nkb; ++kb) {
-          mbar_wait(bar_full + s * 8, ph);
-          tc_fence_after();
-          const uint32_t tA = sA + s * A_STAGE_BYTES, tB = sB + s * B_STAGE_BYTES;
-          if (leader) {
-            // the 4 K steps of a k-block advance the 14-bit start-address field by 32 B (K-major) / 2048 B (MN-major): the tiles
-            // are 1024-byte aligned inside a < 256 KB window, so the field never carries into its neighbours
-            if (MODE == WGRAD) {
-              const uint64_t dA = make_desc_mn(tA, 8192), dB = make_desc_mn(tB, 8192);
+        for (int kb0 = 0; kb0 < T.nkb; kb0 += STAGES) {
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, dA + 128 * k, dB + 128 * k, idesc, (kb | k) != 0);
-            } else {
-              const uint64_t dA = make_desc(tA), dB = make_desc(tB);
+          for (int s = 0; s < STAGES; ++s) {     // compile-time slot (see the producer): descriptors are base + immediate
+            if (kb0 + s < T.nkb) {
+              mbar_wait(bar_full + s * 8, (full_par >> s) & 1u);
+              full_par ^= 1u << s;
+              tc_fence_after();
+              if (leader) {
+                // the 4 K steps of a k-block advance the 14-bit start-address field by 32 B (K-major) / 2048 B (MN-major): the
+                // tiles are 1024-byte aligned inside a < 256 KB window, so the field never carries into its neighbours
+                const uint32_t first = s == 0 ? (uint32_t)(kb0 != 0) : 1u;
+                if (MODE == WGRAD) {
+                  const uint64_t dA = make_desc_mn(sA + s * A_STAGE_BYTES, 8192), dB = make_desc_mn(sB + s * B_STAGE_BYTES, 8192);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, idesc, (kb | k) != 0);
+                  for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, dA + 128 * k, dB + 128 * k, idesc, k == 0 ? first : 1u);
+                } else {
+                  const uint64_t dA = make_desc(sA + s * A_STAGE_BYTES), dB = make_desc(sB + s * B_STAGE_BYTES);
+#pragma unroll
+                  for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_d, dA + 2 * k, dB + 2 * k, idesc, k == 0 ? first : 1u);
+                }
+                umma_commit(bar_empty + s * 8);
+              }
+              __syncwarp();
             }
-            umma_commit(bar_empty + s * 8);
           }
-          __syncwarp();
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
       if (leader) umma_commit(bar_tfull + acc * 8);
