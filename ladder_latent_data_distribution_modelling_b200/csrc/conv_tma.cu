@@ -31,7 +31,7 @@ constexpr int BK = 64;
 constexpr int NTHREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int EPI_BYTES = 4 * 32 * 36 * 4;
-constexpr int BIAS_BYTES = 256 * 4;
+constexpr int BIAS_BYTES = 256 * 4 + 32 * 4;   // bias tile + depth_to_space column offsets of the tile's 8-column groups
 constexpr int STAT_BYTES = 4 * 2 * 256 * 4;     // per epilogue warp: running (sum, sum of squares) of up to 256 output columns
 __host__ __device__ constexpr int stages_for(int bn) {
   // 227 KB - alignment slack - barriers - epilogue staging - statistics, divided by the stage size
@@ -440,6 +440,7 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
     const int quad = warp & 3;                     // tcgen05.ld: warp w may touch TMEM lanes 32*(w%4)..+31
     float* stage = reinterpret_cast<float*>(smem + stage_off) + quad * (32 * 36);
     float* sbias = reinterpret_cast<float*>(smem + stage_off + EPI_BYTES);
+    int* scol = reinterpret_cast<int*>(sbias + 256);   // depth_to_space: element offset of column group (n0 + 8 i) inside a row's block
     float* wstat = reinterpret_cast<float*>(smem + stage_off + EPI_BYTES + BIAS_BYTES) + quad * (2 * 256);   // this warp's sums
     const bool do_stat = MODE == FPROP && a.stat != nullptr;
     if (do_stat)
@@ -471,6 +472,10 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
       if (MODE == FPROP && bias_tile != T.n_tile) {          // (re)load the bias tile; uniform across the 4 warps
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int i = etid; i < BN; i += 128) sbias[i] = (a.bias != nullptr && n0 + i < Ng) ? __ldg(a.bias + n0 + i) : 0.f;
+        if (a.perm_r > 0 && etid < BN / 8) {         // once per n-tile instead of three divisions per (row, 8-column group)
+          const int col = n0 + 8 * etid, r = a.perm_r, ij = col / Cp_d2s, c = col - ij * Cp_d2s;
+          scol[etid] = ((ij / r) * a.GW * r + ij % r) * Cp_d2s + c;
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         bias_tile = T.n_tile;
       }
@@ -562,11 +567,7 @@ tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUt
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col = nb + 8 * q;
-            long long coloff = col;
-            if (perm_f) {
-              const int r = a.perm_r, ij = col / Cp_d2s, c = col - ij * Cp_d2s;
-              coloff = ((long long)(ij / r) * a.GW * r + ij % r) * Cp_d2s + c;
-            }
+            const long long coloff = perm_f ? (long long)scol[(c0 >> 3) + q] : (long long)col;
             float e[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) e[t] = v[8 * q + t];
