@@ -105,12 +105,15 @@ __global__ void __launch_bounds__(256) tap_dgrad_kernel(TapArgs a) {
   }
 }
 
-// DYS[p, tap] (bf16, leading dimension ld, zero padded): one thread = one input pixel x 8 taps
+// DYS[p, tap] (bf16, leading dimension ld, zero padded): one thread = one input pixel x 8 taps.  KWC > 0: filter width known
+// at compile time (the two divisions per tap by a runtime KW made this pass instruction bound: r2x, 136 us for 134 MB).
+template <int KWC>
 __global__ void __launch_bounds__(256) tap_scatter_bf16_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dys,
-                                                               int ld, int B, int H, int W, int KH, int KW, int pad_t,
+                                                               int ld, int B, int H, int W, int KH, int KW_rt, int pad_t,
                                                                int pad_l, int OH, int OW) {
+  const int KW = KWC > 0 ? KWC : KW_rt;
   const int T = KH * KW;
-  const unsigned l8 = ld / 8;
+  const unsigned l8 = KWC > 0 ? 8u : (unsigned)ld / 8;            // the compile-time forms are launched with ld == 64 only
   const unsigned total = (unsigned)B * H * W * l8;                 // < 2^31 (checked on the host): 32-bit index arithmetic
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int t0 = (int)(i % l8) * 8;
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(256) tap_scatter_bf16_kernel(const float* __re
       v[j] = 0.f;
       if (tap < T) {
         const int ny = y + pad_t - tap / KW, nx = x + pad_l - tap % KW;
-        if (ny >= 0 && nx >= 0 && ny < OH && nx < OW) v[j] = __ldg(dy + (b * OH + ny) * OW + nx);
+        if ((unsigned)ny < (unsigned)OH && (unsigned)nx < (unsigned)OW) v[j] = __ldg(dy + (b * OH + ny) * OW + nx);
       }
     }
     uint4 u;
@@ -259,6 +262,72 @@ __global__ void __launch_bounds__(256) thin_k_fprop_kernel(ThinK a) {
   }
 }
 
+// Single-input-channel KH x KW conv (the MNIST encoders' first layer): the grid-stride loop keeps a thread's 8 output channels
+// fixed (gridDim * blockDim is a multiple of Cout / 8), so its KH*KW x 8 weights and 8 biases live in REGISTERS for the whole
+// launch; the taps are compile-time, one (broadcast) image load per tap.  r2x: the generic kernel above re-fetched 18 LDG.128
+// of weights per work item and ran at ~0.6 TB/s of output; this is the same arithmetic without those loads.
+template <int KH, int KW>
+__global__ void __launch_bounds__(256) thin_k_c1_fprop_kernel(ThinK a) {
+  constexpr int T = KH * KW;
+  const unsigned n8 = a.Cout / 8;
+  const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned pstep = gridDim.x * blockDim.x / n8;
+  const int n0 = (int)(i0 % n8) * 8;
+  float w[T][8], bs[8];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.w + (size_t)t * a.Cout + n0));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.w + (size_t)t * a.Cout + n0 + 4));
+    w[t][0] = w0.x; w[t][1] = w0.y; w[t][2] = w0.z; w[t][3] = w0.w; w[t][4] = w1.x; w[t][5] = w1.y; w[t][6] = w1.z; w[t][7] = w1.w;
+  }
+  if (a.bias != nullptr) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + n0)), b1 = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + 4));
+    bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+  } else {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) bs[t] = 0.f;
+  }
+  const unsigned P = (unsigned)a.B * a.OH * a.OW;                 // < 2^31 (checked on the host)
+  const float slope = a.act == ACT_LEAKY ? 0.2f : (a.act == ACT_RELU ? 0.f : 1.f);
+  for (unsigned p = i0 / n8; p < P; p += pstep) {
+    const int ox = (int)(p % (unsigned)a.OW);
+    const unsigned r = p / (unsigned)a.OW;
+    const int oy = (int)(r % (unsigned)a.OH);
+    const float* xb = a.x + (size_t)(r / (unsigned)a.OH) * a.H * a.W;
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = bs[t];
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh) {
+      const int iy = oy * a.stride - a.pad_t + kh;
+      const bool row_ok = (unsigned)iy < (unsigned)a.H;
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ix = ox * a.stride - a.pad_l + kw;
+        float xv = 0.f;
+        if (row_ok && (unsigned)ix < (unsigned)a.W) xv = __ldg(xb + iy * a.W + ix);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = fmaf(xv, w[kh * KW + kw][t], acc[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = a.act == ACT_TANH ? tanhf(acc[t]) : (acc[t] > 0.f ? acc[t] : acc[t] * slope);
+    const long long o = (long long)p * a.Cout + n0;
+    if (a.out_bf16) {
+      uint4 u;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[0], acc[1]), p1 = __floats2bfloat162_rn(acc[2], acc[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(acc[4], acc[5]), p3 = __floats2bfloat162_rn(acc[6], acc[7]);
+      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.y) + o) = u;
+    } else {
+      float* q = reinterpret_cast<float*>(a.y) + o;
+      *reinterpret_cast<float4*>(q) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(q + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
 // dw[k, n] = sum_p patch(p)[k] dy[p, n], db[n] = sum_p dy[p, n] for K <= KMAX.  Thread = 4 output channels x a strided set of
 // pixels of this block's pixel range; accumulators in registers; per-k block reduction through a small smem tile, then one
 // red.global.add per (k, n) per block.  dw / db must be zero on entry (the host wrapper clears them).
@@ -320,6 +389,67 @@ __global__ void __launch_bounds__(256) thin_k_wgrad_kernel(ThinK a, const float*
       }
       __syncthreads();
     }
+  }
+}
+
+// Weight gradient of the single-input-channel KH x KW conv (MNIST encoders' first layer): compile-time taps, one thread = 8
+// output channels x a strided set of this block's pixels (the generic kernel above spends ~18 instructions per (tap, pixel,
+// 4 channels) on offset decoding; r2ab: 117 us for 71 MB).  Same reduction scheme: registers -> smem -> one red.add per block.
+template <int KH, int KW>
+__global__ void __launch_bounds__(256) thin_k_c1_wgrad_kernel(ThinK a, const float* __restrict__ dy, float* __restrict__ dw,
+                                                              float* __restrict__ db, long long per) {
+  constexpr int T = KH * KW;
+  extern __shared__ float red[];                    // [lanes][Cout]
+  const int n8 = a.Cout / 8, lanes = blockDim.x / n8;
+  const int ng = threadIdx.x % n8, pl = threadIdx.x / n8;
+  const long long P = (long long)a.B * a.OH * a.OW;
+  const long long lo = (long long)blockIdx.x * per, hi = min(P, lo + per);
+  float acc[T + 1][8];                              // row T: the bias gradient
+#pragma unroll
+  for (int k = 0; k <= T; ++k)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[k][t] = 0.f;
+  if (pl < lanes) {
+    for (long long p = lo + pl; p < hi; p += lanes) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(dy + p * a.Cout + ng * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(dy + p * a.Cout + ng * 8 + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[T][t] += g[t];
+      const unsigned pu = (unsigned)p;                               // P < 2^31 (checked on the host)
+      const int ox = (int)(pu % (unsigned)a.OW);
+      const unsigned r = pu / (unsigned)a.OW;
+      const int oy = (int)(r % (unsigned)a.OH);
+      const float* xb = a.x + (size_t)(r / (unsigned)a.OH) * a.H * a.W;
+#pragma unroll
+      for (int kh = 0; kh < KH; ++kh) {
+        const int iy = oy * a.stride - a.pad_t + kh;
+        const bool row_ok = (unsigned)iy < (unsigned)a.H;
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw) {
+          const int ix = ox * a.stride - a.pad_l + kw;
+          float xv = 0.f;
+          if (row_ok && (unsigned)ix < (unsigned)a.W) xv = __ldg(xb + iy * a.W + ix);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc[kh * KW + kw][t] = fmaf(xv, g[t], acc[kh * KW + kw][t]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k <= T; ++k) {
+    if (pl < lanes) {
+      *reinterpret_cast<float4*>(red + (size_t)pl * a.Cout + ng * 8) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+      *reinterpret_cast<float4*>(red + (size_t)pl * a.Cout + ng * 8 + 4) = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < a.Cout; n += blockDim.x) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[(size_t)l * a.Cout + n];
+      if (k == T) { if (db != nullptr) atomicAdd(db + n, s); }
+      else atomicAdd(dw + (size_t)k * a.Cout + n, s);
+    }
+    __syncthreads();
   }
 }
 
@@ -437,7 +567,10 @@ int ladder_thin_k_fprop(const float* x, const float* w, const float* bias, void*
   ThinK a{x, w, bias, y, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, act, y_bf16};
   long long blocks = ceil_div64((long long)B * OH * OW * (Cout / 8), 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  thin_k_fprop_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+  if (Cin == 1 && KH == 3 && KW == 3 && 256 % (Cout / 8) == 0)
+    thin_k_c1_fprop_kernel<3, 3><<<(unsigned)blocks, 256, 0, stream>>>(a);
+  else
+    thin_k_fprop_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
   return check_launch("thin_k_fprop");
 }
 
@@ -452,11 +585,21 @@ int ladder_thin_k_wgrad(const float* x, const float* dy, float* dw, float* dbias
   if (e == cudaSuccess && dbias != nullptr) e = cudaMemsetAsync(dbias, 0, (size_t)Cout * sizeof(float), stream);
   if (e != cudaSuccess) return fail(LADDER_ERR_CUDA, "thin_k_wgrad memset: %s", cudaGetErrorString(e));
   ThinK a{x, nullptr, nullptr, nullptr, B, H, W, Cin, KH, KW, Cout, stride, pad_t, pad_l, OH, OW, 0, 0};
+  if (Cin == 1 && KH == 3 && KW == 3 && 256 % (Cout / 8) == 0) {
+    const int lanes8 = 256 / (Cout / 8);
+    const long long P8 = (long long)B * OH * OW;
+    long long blocks8 = 148 * 8;
+    long long per8 = ceil_div64(P8, blocks8);
+    if (per8 < 4LL * lanes8) per8 = 4LL * lanes8;
+    blocks8 = ceil_div64(P8, per8);
+    thin_k_c1_wgrad_kernel<3, 3><<<(unsigned)blocks8, 256, (size_t)lanes8 * Cout * sizeof(float), stream>>>(a, dy, dw, dbias, per8);
+    return check_launch("thin_k_wgrad");
+  }
   const int n4 = Cout / 4;
   const int threads = n4 >= 256 ? n4 : 256 / n4 * n4;            // whole pixel lanes only
   const int lanes = threads / n4;
   const long long P = (long long)B * OH * OW;
-  long long blocks = 148 * 2;
+  long long blocks = 148 * 8;                    // r2x: 2 blocks per SM left the dependent x / dy loads of every pixel exposed (139 us for 71 MB)
   long long per = ceil_div64(P, blocks);
   if (per < 4LL * lanes) per = 4LL * lanes;
   blocks = ceil_div64(P, per);
@@ -497,8 +640,10 @@ int ladder_tap_scatter_bf16(const float* dy, void* dys_bf16, int ld, int B, int 
   LADDER_REQUIRE((long long)B * H * W * (ld / 8) < (1LL << 31), "tap_scatter_bf16: more than 2^31 work items");
   long long blocks = ceil_div64((long long)B * H * W * (ld / 8), 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  tap_scatter_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dy, static_cast<__nv_bfloat16*>(dys_bf16), ld, B, H, W, KH, KW,
-                                                                pad_t, pad_l, OH, OW);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(dys_bf16);
+  if (KW == 5 && ld == 64) tap_scatter_bf16_kernel<5><<<(unsigned)blocks, 256, 0, stream>>>(dy, out, ld, B, H, W, KH, KW, pad_t, pad_l, OH, OW);
+  else if (KW == 3 && ld == 64) tap_scatter_bf16_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(dy, out, ld, B, H, W, KH, KW, pad_t, pad_l, OH, OW);
+  else tap_scatter_bf16_kernel<0><<<(unsigned)blocks, 256, 0, stream>>>(dy, out, ld, B, H, W, KH, KW, pad_t, pad_l, OH, OW);
   return check_launch("tap_scatter_bf16");
 }
 
