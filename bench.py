@@ -615,8 +615,9 @@ def run_ours(args):
                         'tensor_floor_ms': flops / (peaks['bf16_tflops'] * 1e12) * 1e3,
                         'timed': 'CUDA events on the launch stream around %d back-to-back launches; dy + aux + dx = %d MB (%s the '
                                  '126 MB L2)' % (reps, d_bytes >> 20, 'exceeds' if d_bytes > 126 << 20 else 'FITS in'),
-                        'note': 'largest launch of the largest kernel of the step (15-17 %% of the step, profiles/); fused producer '
-                                'leaky_relu\'%s; bound by L2->SM operand traffic at N = 64 (profiles/r1g_ncu_dgrad_kernel.md)'
+                        'note': 'largest launch of the largest kernel of the step (11-12 %% of the step, profiles/r2ac_kernel_times_fashion.txt); '
+                                'fused producer leaky_relu\'%s; issue warps run converged with one elected lane since r2w '
+                                '(profiles/r2w_issue_warp_analysis.md); what remains is the L2->SM operand stream at N = 64'
                                 % (' + space_to_depth(2) scatter' if d2s else ''),
                         'roofline_fprop': roofline_fprop}
         # ---- hyper-prior micro-benchmark (second half of the metric, BASELINE.json configs[2]): 65 536 x 65 536 pairs at

@@ -803,12 +803,35 @@ int ladder_mixture_tc_pack_iso(const double* mean, double std_, const double* we
   return LADDER_OK;
 }
 
+
+/* Split of the component chunks of a query tile into `splits` work units of `cps` chunks each.  The persistent grid runs
+ * ceil(units / SMs) rounds of units that each take `cps` chunks, so the makespan is rounds * cps: r2y's fixed "2 units per SM"
+ * rule gave 512 units on 148 SMs at 65 536 x 65 536 -- 4 rounds where 3.46 were needed, 14 % of every kernel lost to the tail.
+ * Pick the smallest split count (at most 4x the old rule: the partial buffers grow with it) that minimises rounds * cps. */
+static void pick_splits(long long row_tiles, int n_chunks, int sms, int* splits_out, int* cps_out) {
+  if (row_tiles < 1) row_tiles = 1;
+  long long s0 = ceil_div64(2LL * sms, row_tiles);
+  if (s0 > n_chunks) s0 = n_chunks;
+  if (s0 < 1) s0 = 1;
+  long long smax = 4 * s0 < n_chunks ? 4 * s0 : n_chunks;
+  long long best_cost = -1;
+  int best_s = 1, best_cps = n_chunks;
+  for (long long sp = 1; sp <= smax; ++sp) {
+    const int cps = ceil_div(n_chunks, (int)sp);
+    const int se = ceil_div(n_chunks, cps);
+    const long long rounds = ceil_div64(row_tiles * se, sms);
+    const long long cost = rounds * cps * 64 + se;             // makespan first, fewer partial buffers second
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = se; best_cps = cps; }
+  }
+  *splits_out = best_s;
+  *cps_out = best_cps;
+}
+
 size_t ladder_mixture_tc_workspace_bytes(long long N, int K) {
   const int n_chunks = (K + BN - 1) / BN;
   const long long row_tiles = (N + QROWS - 1) / QROWS;
-  long long splits = ceil_div64(2LL * num_sms(), row_tiles > 0 ? row_tiles : 1);
-  if (splits > n_chunks) splits = n_chunks;
-  if (splits < 1) splits = 1;
+  int splits, cps;
+  pick_splits(row_tiles, n_chunks, num_sms(), &splits, &cps);
   return (size_t)splits * (N > 0 ? N : 1) * sizeof(float) + 256;
 }
 
@@ -826,16 +849,13 @@ static int run_tc_forward(const float* t, long long N, int D, const float* image
   const int n_chunks = (K + BN - 1) / BN;
   const long long row_tiles = (N + QROWS - 1) / QROWS;
   const int sms = num_sms();
-  long long splits = ceil_div64(2LL * sms, row_tiles);
-  if (splits > n_chunks) splits = n_chunks;
-  if (splits < 1) splits = 1;
-  const int cps = ceil_div(n_chunks, (int)splits);
-  splits = ceil_div(n_chunks, cps);
+  int splits, cps;
+  pick_splits(row_tiles, n_chunks, sms, &splits, &cps);
   const size_t need = (size_t)splits * N * sizeof(float);
   if (workspace == nullptr || workspace_bytes < need)
     return fail(LADDER_ERR_WORKSPACE, "mixture_logprob_tc: workspace %zu < %zu bytes", workspace_bytes, need);
   Args a{t, image, static_cast<float*>(workspace), N, n_chunks, cps, (int)splits, iso_scale};
-  const long long units = row_tiles * splits;
+  const long long units = row_tiles * (long long)splits;
   const unsigned grid = (unsigned)(units < sms ? units : sms);
   auto go = [&](auto kern, int Dv) {
     const int atoms = Dv / 32;
@@ -914,9 +934,8 @@ int ladder_mixture_tc_pack_iso_grad(const double* mean, double std_, const doubl
 size_t ladder_mixture_tc_grad_workspace_bytes(long long N, int K, int D) {
   const int n_chunks = (K + BN - 1) / BN;
   const long long row_tiles = (N + QROWS - 1) / QROWS;
-  long long splits = ceil_div64(2LL * num_sms(), row_tiles > 0 ? row_tiles : 1);
-  if (splits > n_chunks) splits = n_chunks;
-  if (splits < 1) splits = 1;
+  int splits, cps;
+  pick_splits(row_tiles, n_chunks, num_sms(), &splits, &cps);
   return (size_t)splits * (N > 0 ? N : 1) * (size_t)(1 + D) * sizeof(float) + 256;
 }
 
@@ -941,18 +960,15 @@ static int run_tc_forward_grad(const float* t, long long N, int D, const float* 
   const int n_chunks = (K + BN - 1) / BN;
   const long long row_tiles = (N + QROWS - 1) / QROWS;
   const int sms = num_sms();
-  long long splits = ceil_div64(2LL * sms, row_tiles);
-  if (splits > n_chunks) splits = n_chunks;
-  if (splits < 1) splits = 1;
-  const int cps = ceil_div(n_chunks, (int)splits);
-  splits = ceil_div(n_chunks, cps);
+  int splits, cps;
+  pick_splits(row_tiles, n_chunks, sms, &splits, &cps);
   const size_t need = (size_t)splits * N * (size_t)(1 + D) * sizeof(float);
   if (workspace == nullptr || workspace_bytes < need)
     return fail(LADDER_ERR_WORKSPACE, "mixture_logprob_grad_tc: workspace %zu < %zu bytes", workspace_bytes, need);
   float* part_g = static_cast<float*>(workspace);
   float* part_s = part_g + (size_t)splits * N * D;
   GradArgs a{t, image, part_s, part_g, N, n_chunks, cps, (int)splits, iso_scale, grad_issue_order()};
-  const long long units = row_tiles * splits;
+  const long long units = row_tiles * (long long)splits;
   const unsigned grid = (unsigned)(units < sms ? units : sms);
   auto go = [&](auto kern, int Dv) {
     const int atoms = Dv / 32;

@@ -118,6 +118,10 @@ __global__ void __launch_bounds__(256) tap_scatter_bf16_kernel(const float* __re
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int t0 = (int)(i % l8) * 8;
     const unsigned mu = i / l8;
+    if (t0 >= T) {                                                 // zero padding columns beyond the last tap: nothing to gather
+      *reinterpret_cast<uint4*>(dys + (size_t)mu * ld + t0) = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
     const int x = (int)(mu % (unsigned)W);
     const unsigned r = mu / (unsigned)W;
     const int y = (int)(r % (unsigned)H);
