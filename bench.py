@@ -710,7 +710,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None,
-                    help='timed iterations (default: 250 for the GPU arm = a timed region of about 1 s; 20 for --impl reference)')
+                    help='timed iterations (default: 320 for the GPU arm = a timed region of about 1 s at 3.2 ms per iteration; 20 for --impl reference)')
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1024, help='images per GPU')
@@ -726,7 +726,7 @@ def main():
                     help='config file under codes/ (default: BASELINE.json configs[1])')
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 250 if args.impl == 'ours' and args.workload != 'celeba' else 20
+        args.steps = 320 if args.impl == 'ours' and args.workload != 'celeba' else 20
     global WORKLOAD
     WORKLOAD = args.workload
     if args.cpu_sample <= 0:
