@@ -292,7 +292,7 @@ def celeba_leg(args, dev, rank, world, group, B, code_size=None, steps=None):
         e_ms, win = timed(e2e_iteration, e_steps)
         windows.append(win)
         out['e2e'] = {'value': B * world * e_steps / (e_ms * 1e-3), 'unit': 'imgs/s', 'ms_per_step': e_ms / e_steps,
-                      'steps': e_steps, 'h2d_bytes_per_step': B * 128 * 128 * 3 * 4, 'd2h_bytes_per_step': 4,
+                      'steps': e_steps, 'h2d_bytes_per_step': 2 * B * 128 * 128 * 3 * 4, 'd2h_bytes_per_step': 4,
                       'api': 'CelebATrainer_joint_training.train_step_ae + train_step_prior on pinned host batches'}
         del trainer, host_pool
     except Exception as e:                            # noqa: BLE001
@@ -662,7 +662,7 @@ def run_ours(args):
                            'global_batch': B * world, 'parallelism': 'dp%d' % world, 'cuda_graphs': bool(eng.use_graphs),
                            'l2': 'per-step activation working set (>1 GB) exceeds the 126 MB L2; 4 input batches rotate'},
                 'clocks': clocks, 'gpu_launches': launches,
-                'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': B * int(np.prod(shp)) * 4,
+                'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': 2 * B * int(np.prod(shp)) * 4,
                         'd2h_bytes_per_step': 4, 'ms_per_step': e2e_ms / args.steps,
                         'api': '*Trainer_joint_training.train_step_ae + train_step_prior on pinned host batches'},
                 'roofline': roofline,

@@ -49,6 +49,20 @@ class BaseTrain:
         """Host batches go through one pinned staging buffer; device tensors pass through."""
         if isinstance(batch_data, torch.Tensor) and batch_data.is_cuda:
             return batch_data
+        if isinstance(batch_data, torch.Tensor) and batch_data.dtype == torch.float32 and batch_data.is_contiguous():
+            # a batch that already sits in PINNED host memory (DataLoader(pin_memory=True), bench.py's host pool) is copied
+            # from where it is: the staging memcpy below would only add ~0.2 ms of host time per 3 MB batch.  As with any
+            # non_blocking copy from pinned memory, the caller must not overwrite the batch before the step has consumed it.
+            try:
+                pinned = batch_data.is_pinned()
+            except RuntimeError:
+                pinned = False
+            if pinned:
+                if getattr(self, '_staged', None) is None or self._staged.shape != batch_data.shape:
+                    self._staged = torch.empty(batch_data.shape, dtype=torch.float32, device=self.model.device)
+                    self._pinned = None
+                self._staged.copy_(batch_data, non_blocking=True)
+                return self._staged
         arr = torch.as_tensor(np.asarray(batch_data), dtype=torch.float32)
         if self._pinned is None or self._pinned.shape != arr.shape:
             self._pinned = torch.empty(arr.shape, dtype=torch.float32).pin_memory()
